@@ -1,0 +1,125 @@
+"""On-disk formats shared by the CUDA decoder, the oracle and the reference harness.
+
+* newfst graph file — the reference's flat HCLG format, read by ``Fst::ReadFst``
+  (reference ``src/newfst/optimize-fst.h:226-280``):
+  six int32 ``start, final_state, total_states, total_arcs, total_niepsilons,
+  total_noepsilons``; ``total_states x {u32 num_arcs, niepsilons, noepsilons}``;
+  ``total_arcs x {i32 ilabel, i32 olabel, f32 weight, i32 nextstate}``.
+* loglikes file — ours: int32 magic ``0x4c4c5341``, int32 n_utt, then per
+  utterance int32 T, int32 P, float32[T*P]; column = ilabel - 1, the convention of
+  Kaldi's ``DecodableMatrixScaled`` that the reference's bins use
+  (``src/kaldi-nnet3bin/kaldi-hclg-my-decoder.cc:107``).
+"""
+from __future__ import annotations
+
+import dataclasses
+import numpy as np
+
+ARC_DTYPE = np.dtype([("ilabel", "<i4"), ("olabel", "<i4"), ("weight", "<f4"), ("nextstate", "<i4")])
+STATEINFO_DTYPE = np.dtype([("num_arcs", "<u4"), ("niepsilons", "<u4"), ("noepsilons", "<u4")])
+LL_MAGIC = 0x4C4C5341
+
+
+@dataclasses.dataclass
+class Fst:
+    """Host mirror of the reference ``Fst`` (``src/newfst/optimize-fst.h:53-307``):
+    two flat arrays plus start / super-final ids.  ``arcs`` is the 16-byte record
+    array verbatim; ``row_off`` is the exclusive prefix sum of ``num_arcs``."""
+
+    start: int
+    final_state: int
+    arcs: np.ndarray        # ARC_DTYPE [A]
+    num_arcs: np.ndarray    # u32 [S]
+    niepsilons: np.ndarray  # u32 [S]
+    noepsilons: np.ndarray  # u32 [S]
+
+    @property
+    def total_states(self) -> int:
+        return int(self.num_arcs.shape[0])
+
+    @property
+    def total_arcs(self) -> int:
+        return int(self.arcs.shape[0])
+
+    @property
+    def row_off(self) -> np.ndarray:
+        off = np.zeros(self.total_states + 1, dtype=np.int64)
+        np.cumsum(self.num_arcs, out=off[1:])
+        return off
+
+    # Fst::Start / IsFinal / NumInputEpsilons (optimize-fst.h:169-192)
+    def Start(self) -> int:
+        return self.start
+
+    def IsFinal(self, s: int) -> bool:
+        return s == self.final_state
+
+    def NumInputEpsilons(self, s: int) -> int:
+        return int(self.niepsilons[s])
+
+    def eps_first(self) -> bool:
+        """True when every state's input-epsilon arcs form a prefix of its row — the
+        layout ``convert_fst`` / ``Fst(const ConstFst&)`` produce and the layout the
+        device kernels rely on to split eps / emitting spans without a scan."""
+        off = self.row_off
+        il = self.arcs["ilabel"]
+        is_eps = (il == 0).astype(np.int64)
+        csum = np.concatenate([[0], np.cumsum(is_eps)])
+        n_eps_row = csum[off[1:]] - csum[off[:-1]]
+        if not np.array_equal(n_eps_row, self.niepsilons.astype(np.int64)):
+            return False
+        # eps count inside the first niepsilons arcs of each row must equal niepsilons
+        head_end = off[:-1] + self.niepsilons.astype(np.int64)
+        n_eps_head = csum[head_end] - csum[off[:-1]]
+        return bool(np.array_equal(n_eps_head, n_eps_row))
+
+
+def write_fst(path: str, fst: Fst) -> None:
+    hdr = np.array(
+        [fst.start, fst.final_state, fst.total_states, fst.total_arcs,
+         int(fst.niepsilons.sum()), int(fst.noepsilons.sum())], dtype="<i4")
+    info = np.empty(fst.total_states, dtype=STATEINFO_DTYPE)
+    info["num_arcs"] = fst.num_arcs
+    info["niepsilons"] = fst.niepsilons
+    info["noepsilons"] = fst.noepsilons
+    with open(path, "wb") as f:
+        f.write(hdr.tobytes())
+        f.write(info.tobytes())
+        f.write(np.ascontiguousarray(fst.arcs).tobytes())
+
+
+def read_fst(path: str) -> Fst:
+    with open(path, "rb") as f:
+        hdr = np.frombuffer(f.read(24), dtype="<i4")
+        start, final_state, n_states, n_arcs = (int(x) for x in hdr[:4])
+        info = np.frombuffer(f.read(12 * n_states), dtype=STATEINFO_DTYPE)
+        arcs = np.frombuffer(f.read(16 * n_arcs), dtype=ARC_DTYPE)
+    if info.shape[0] != n_states or arcs.shape[0] != n_arcs:
+        raise IOError(f"{path}: truncated newfst file")
+    if int(info["num_arcs"].sum()) != n_arcs:
+        raise IOError(f"{path}: state arc counts do not sum to total_arcs")
+    return Fst(start, final_state, arcs.copy(), info["num_arcs"].copy(),
+               info["niepsilons"].copy(), info["noepsilons"].copy())
+
+
+def write_loglikes(path: str, utts) -> None:
+    """``utts``: iterable of float32 [T, P] matrices."""
+    utts = list(utts)
+    with open(path, "wb") as f:
+        f.write(np.array([LL_MAGIC, len(utts)], dtype="<i4").tobytes())
+        for m in utts:
+            m = np.ascontiguousarray(m, dtype="<f4")
+            f.write(np.array([m.shape[0], m.shape[1]], dtype="<i4").tobytes())
+            f.write(m.tobytes())
+
+
+def read_loglikes(path: str):
+    out = []
+    with open(path, "rb") as f:
+        magic, n = np.frombuffer(f.read(8), dtype="<i4")
+        if int(magic) != LL_MAGIC:
+            raise IOError(f"{path}: bad loglikes magic")
+        for _ in range(int(n)):
+            t, p = (int(x) for x in np.frombuffer(f.read(8), dtype="<i4"))
+            out.append(np.frombuffer(f.read(4 * t * p), dtype="<f4").reshape(t, p).copy())
+    return out
