@@ -1,0 +1,568 @@
+// Host side of the C ABI (include/asrd.h).  Thin: validates arguments, owns device
+// memory, uploads the graph, sequences the per-frame kernels.  No CPU fallback: every
+// search step runs in the kernels of asrd_kernels.cuh.
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "asrd_kernels.cuh"
+
+using namespace asrd;
+
+namespace {
+
+std::atomic<long long> g_launches{0};
+thread_local std::string g_last_error;
+
+#define CU_CHECK(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t e__ = (expr);                                                            \
+    if (e__ != cudaSuccess) {                                                            \
+      g_last_error = std::string(#expr) + ": " + cudaGetErrorString(e__);                \
+      fprintf(stderr, "[asrd] CUDA error %s at %s:%d\n", g_last_error.c_str(), __FILE__, \
+              __LINE__);                                                                 \
+      return ASRD_ERR_CUDA;                                                              \
+    }                                                                                    \
+  } while (0)
+
+int g_num_sms = 0;
+
+int EnsureDevice(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    g_last_error = "no CUDA device";
+    return ASRD_ERR_CUDA;
+  }
+  if (device < 0 || device >= n) return ASRD_ERR_BAD_ARG;
+  CU_CHECK(cudaSetDevice(device));
+  if (!g_num_sms) {
+    cudaDeviceProp p;
+    CU_CHECK(cudaGetDeviceProperties(&p, device));
+    g_num_sms = p.multiProcessorCount;
+  }
+  return ASRD_OK;
+}
+
+uint32_t NextPow2(uint64_t v) {
+  uint32_t p = 1;
+  while (p < v && p < (1u << 30)) p <<= 1;
+  return p;
+}
+
+struct Scratch {  // stream-ordered device scratch released on scope exit
+  cudaStream_t s;
+  std::vector<void *> ptrs;
+  explicit Scratch(cudaStream_t st) : s(st) {}
+  ~Scratch() {
+    for (void *p : ptrs) cudaFreeAsync(p, s);
+  }
+  template <typename T>
+  cudaError_t Alloc(T **out, size_t count) {
+    void *p = nullptr;
+    cudaError_t e = cudaMallocAsync(&p, std::max<size_t>(count * sizeof(T), 16), s);
+    if (e == cudaSuccess) ptrs.push_back(p);
+    *out = (T *)p;
+    return e;
+  }
+};
+
+int UploadStreams(asrd_decoder *const *decs, int n, cudaStream_t s, Scratch &sc, StreamState ***out) {
+  std::vector<StreamState *> h(n);
+  for (int i = 0; i < n; ++i) h[i] = decs[i]->d_state;
+  StreamState **d = nullptr;
+  CU_CHECK(sc.Alloc(&d, (size_t)n));
+  CU_CHECK(cudaMemcpyAsync(d, h.data(), sizeof(StreamState *) * n, cudaMemcpyHostToDevice, s));
+  *out = d;
+  return ASRD_OK;
+}
+
+DecoderConfigDev DevCfg(const asrd_decoder *d) {
+  DecoderConfigDev c;
+  c.beam = d->cfg.beam;
+  c.max_active = d->cfg.max_active;
+  c.min_active = d->cfg.min_active;
+  c.lattice_beam = d->cfg.lattice_beam;
+  c.beam_delta = d->cfg.beam_delta;
+  c.collect_stats = d->opts.collect_stats;
+  return c;
+}
+
+int CheckBatch(asrd_decoder *const *decs, int n) {
+  if (!decs || n <= 0 || n > kMaxBatch) return ASRD_ERR_BAD_ARG;
+  for (int i = 0; i < n; ++i) {
+    if (!decs[i]) return ASRD_ERR_BAD_ARG;
+    if (decs[i]->graph != decs[0]->graph) return ASRD_ERR_BAD_ARG;  // one graph per launch
+    if (memcmp(&decs[i]->cfg, &decs[0]->cfg, sizeof(asrd_config)) != 0) return ASRD_ERR_BAD_ARG;
+  }
+  return ASRD_OK;
+}
+
+int ExpandGrid() { return g_num_sms * 8; }
+
+}  // namespace
+
+extern "C" {
+
+const char *asrd_strerror(int status) {
+  switch (status) {
+    case ASRD_OK: return "ok";
+    case ASRD_ERR_BAD_ARG: return "bad argument";
+    case ASRD_ERR_CUDA: return g_last_error.empty() ? "CUDA error" : g_last_error.c_str();
+    case ASRD_ERR_NOMEM: return "out of memory";
+    case ASRD_ERR_HASH_OVERFLOW: return "state->token map overflow (raise hash_capacity)";
+    case ASRD_ERR_ARENA_OVERFLOW: return "token arena overflow (raise token_capacity)";
+    case ASRD_ERR_FRAMES_OVERFLOW: return "more frames than max_frames";
+    case ASRD_ERR_NO_TOKENS: return "no surviving tokens / nothing decoded";
+    case ASRD_ERR_PATH_OVERFLOW: return "best path longer than the output buffer";
+    case ASRD_ERR_STATE: return "call order violated";
+    case ASRD_ERR_IO: return "I/O error";
+  }
+  return "unknown status";
+}
+
+int asrd_abi_version(void) { return ASRD_ABI_VERSION; }
+
+int asrd_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return ASRD_ERR_CUDA;
+  int ok = 0;
+  for (int i = 0; i < n; ++i) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major >= 10) ++ok;
+  }
+  return ok;
+}
+
+int64_t asrd_launch_count(void) { return g_launches.load(); }
+
+// ------------------------------------------------------------------------- graph
+
+int asrd_graph_create(const asrd_arc *arcs, const uint32_t *num_arcs, const uint32_t *niepsilons,
+                      int32_t total_states, int64_t total_arcs, int32_t start, int32_t final_state,
+                      int device, asrd_graph **out) {
+  if (!arcs || !num_arcs || !niepsilons || !out || total_states <= 0 || total_arcs < 0 ||
+      total_arcs >= 0xFFFFFFFFll || start < 0 || start >= total_states)
+    return ASRD_ERR_BAD_ARG;
+  int rc = EnsureDevice(device);
+  if (rc) return rc;
+  const int32_t S = total_states;
+  const int64_t A = total_arcs;
+  std::vector<uint2> rows((size_t)S + 1);
+  std::vector<asrd_arc> parc((size_t)std::max<int64_t>(A, 1));
+  std::vector<uint32_t> src((size_t)std::max<int64_t>(A, 1));
+  std::vector<uint32_t> par((size_t)(A + 31) / 32 + 1, 0u);
+  std::vector<std::pair<int32_t, uint32_t>> tmp;
+  int64_t off = 0;
+  for (int32_t s = 0; s < S; ++s) {
+    const uint32_t n = num_arcs[s];
+    if (off + n > A) return ASRD_ERR_BAD_ARG;
+    // stable partition: input-epsilon arcs first (no-op for convert_fst / Fst(ConstFst) graphs,
+    // reference src/newfst/optimize-fst.h:107-119)
+    uint32_t ne = 0;
+    for (uint32_t k = 0; k < n; ++k)
+      if (arcs[off + k].ilabel == 0) parc[off + ne++] = arcs[off + k];
+    uint32_t w = ne;
+    for (uint32_t k = 0; k < n; ++k)
+      if (arcs[off + k].ilabel != 0) parc[off + w++] = arcs[off + k];
+    rows[s] = make_uint2((uint32_t)off, (uint32_t)(off + ne));
+    for (uint32_t k = 0; k < n; ++k) {
+      src[off + k] = (uint32_t)s;
+      const asrd_arc &a = parc[off + k];
+      if (a.nextstate < 0 || a.nextstate >= S || a.ilabel < 0) return ASRD_ERR_BAD_ARG;
+    }
+    // sibling flags: same class (eps / emitting), same destination
+    for (int cls = 0; cls < 2; ++cls) {
+      const uint32_t b = cls == 0 ? 0 : ne, e = cls == 0 ? ne : n;
+      if (e - b < 2) continue;
+      tmp.clear();
+      for (uint32_t k = b; k < e; ++k) tmp.emplace_back(parc[off + k].nextstate, (uint32_t)(off + k));
+      std::sort(tmp.begin(), tmp.end());
+      for (size_t k = 0; k + 1 < tmp.size(); ++k)
+        if (tmp[k].first == tmp[k + 1].first) {
+          par[tmp[k].second >> 5] |= 1u << (tmp[k].second & 31);
+          par[tmp[k + 1].second >> 5] |= 1u << (tmp[k + 1].second & 31);
+        }
+    }
+    off += n;
+  }
+  if (off != A) return ASRD_ERR_BAD_ARG;
+  rows[S] = make_uint2((uint32_t)A, (uint32_t)A);
+
+  asrd_graph *g = new asrd_graph();
+  memset(g, 0, sizeof(*g));
+  g->device = device;
+  g->total_arcs = A;
+  const size_t b_arcs = sizeof(asrd_arc) * parc.size(), b_rows = sizeof(uint2) * rows.size(),
+               b_src = sizeof(uint32_t) * src.size(), b_par = sizeof(uint32_t) * par.size();
+  if (cudaMalloc(&g->d_arcs, b_arcs) != cudaSuccess || cudaMalloc(&g->d_rows, b_rows) != cudaSuccess ||
+      cudaMalloc(&g->d_arc_src, b_src) != cudaSuccess || cudaMalloc(&g->d_par, b_par) != cudaSuccess) {
+    asrd_graph_destroy(g);
+    return ASRD_ERR_NOMEM;
+  }
+  CU_CHECK(cudaMemcpy(g->d_arcs, parc.data(), b_arcs, cudaMemcpyHostToDevice));
+  CU_CHECK(cudaMemcpy(g->d_rows, rows.data(), b_rows, cudaMemcpyHostToDevice));
+  CU_CHECK(cudaMemcpy(g->d_arc_src, src.data(), b_src, cudaMemcpyHostToDevice));
+  CU_CHECK(cudaMemcpy(g->d_par, par.data(), b_par, cudaMemcpyHostToDevice));
+  g->device_bytes = (int64_t)(b_arcs + b_rows + b_src + b_par);
+  g->view.arcs = (const int4 *)g->d_arcs;
+  g->view.rows = (const uint2 *)g->d_rows;
+  g->view.arc_src = (const uint32_t *)g->d_arc_src;
+  g->view.par_bits = (const uint32_t *)g->d_par;
+  g->view.n_states = S;
+  g->view.n_arcs = (uint32_t)A;
+  g->view.start = start;
+  g->view.final_state = final_state;
+  *out = g;
+  return ASRD_OK;
+}
+
+int asrd_graph_read(const char *path, int device, asrd_graph **out) {
+  // Fst::ReadFst, src/newfst/optimize-fst.h:226-280
+  if (!path || !out) return ASRD_ERR_BAD_ARG;
+  FILE *fp = fopen(path, "rb");
+  if (!fp) return ASRD_ERR_IO;
+  int32_t hdr[6];
+  if (fread(hdr, 4, 6, fp) != 6 || hdr[2] <= 0 || hdr[3] < 0) {
+    fclose(fp);
+    return ASRD_ERR_IO;
+  }
+  const int32_t S = hdr[2];
+  const int64_t A = hdr[3];
+  std::vector<uint32_t> info((size_t)S * 3);
+  std::vector<asrd_arc> arcs((size_t)std::max<int64_t>(A, 1));
+  bool ok = fread(info.data(), 12, (size_t)S, fp) == (size_t)S &&
+            fread(arcs.data(), 16, (size_t)A, fp) == (size_t)A;
+  fclose(fp);
+  if (!ok) return ASRD_ERR_IO;
+  std::vector<uint32_t> na(S), ne(S);
+  for (int32_t s = 0; s < S; ++s) {
+    na[s] = info[(size_t)s * 3];
+    ne[s] = info[(size_t)s * 3 + 1];
+  }
+  return asrd_graph_create(arcs.data(), na.data(), ne.data(), S, A, hdr[0], hdr[1], device, out);
+}
+
+int asrd_graph_destroy(asrd_graph *g) {
+  if (!g) return ASRD_OK;
+  cudaSetDevice(g->device);
+  cudaFree(g->d_arcs);
+  cudaFree(g->d_rows);
+  cudaFree(g->d_arc_src);
+  cudaFree(g->d_par);
+  delete g;
+  return ASRD_OK;
+}
+
+int asrd_graph_info(const asrd_graph *g, int32_t *total_states, int64_t *total_arcs, int32_t *start,
+                    int32_t *final_state, int64_t *device_bytes) {
+  if (!g) return ASRD_ERR_BAD_ARG;
+  if (total_states) *total_states = g->view.n_states;
+  if (total_arcs) *total_arcs = g->total_arcs;
+  if (start) *start = g->view.start;
+  if (final_state) *final_state = g->view.final_state;
+  if (device_bytes) *device_bytes = g->device_bytes;
+  return ASRD_OK;
+}
+
+// ------------------------------------------------------------------------- decoder
+
+int asrd_decoder_create(asrd_graph *g, const asrd_config *cfg, const asrd_device_options *opts,
+                        asrd_decoder **out) {
+  if (!g || !cfg || !out) return ASRD_ERR_BAD_ARG;
+  // LatticeFasterDecoderConfig::Check, src/my-decoder/lattice-faster-decoder-conf.h:62-67
+  if (!(cfg->beam > 0.0f && cfg->max_active > 1 && cfg->lattice_beam > 0.0f && cfg->beam_delta > 0.0f) ||
+      cfg->min_active < 0)
+    return ASRD_ERR_BAD_ARG;
+  int rc = EnsureDevice(g->device);
+  if (rc) return rc;
+  asrd_decoder *d = new asrd_decoder();
+  memset((void *)d, 0, sizeof(*d));
+  d->graph = g;
+  d->cfg = *cfg;
+  if (opts) d->opts = *opts;
+  asrd_device_options &o = d->opts;
+  if (o.hash_capacity <= 0) {
+    // every surviving token can fan out; 8x max_active keeps the load factor low
+    uint64_t want = (uint64_t)std::min<int64_t>((int64_t)cfg->max_active, 1 << 20) * 8;
+    o.hash_capacity = (int32_t)std::min<uint64_t>(std::max<uint64_t>(NextPow2(want), 4096), 1u << 24);
+  } else {
+    o.hash_capacity = (int32_t)NextPow2((uint64_t)o.hash_capacity);
+  }
+  if (o.max_frames <= 0) o.max_frames = 2048;
+  if (o.token_capacity <= 0)  // 16 bytes per token record; ~1.5 x max_active survivors per frame
+    o.token_capacity = std::min<int64_t>((int64_t)o.max_frames * std::min<int64_t>(cfg->max_active, 1 << 16) * 3 / 2,
+                                         (int64_t)1 << 23);
+  if (o.token_capacity >= 0xFFFFFFF0ll) return ASRD_ERR_BAD_ARG;
+  const size_t H = (size_t)o.hash_capacity;
+  auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t b_hash = align(H * sizeof(HashEntry)), b_list = align(H * 4),
+               b_tok = align((size_t)o.token_capacity * 8), b_off = align(((size_t)o.max_frames + 2) * 4),
+               b_stats = o.collect_stats ? align(((size_t)o.max_frames + 1) * sizeof(asrd_frame_stat)) : 0,
+               b_state = align(sizeof(StreamState));
+  const size_t total = b_state + 2 * b_hash + 4 * b_list + 2 * b_tok + b_off + b_stats;
+  if (cudaMalloc(&d->slab, total) != cudaSuccess) {
+    cudaGetLastError();
+    delete d;
+    return ASRD_ERR_NOMEM;
+  }
+  d->slab_bytes = (int64_t)total;
+  char *p = (char *)d->slab;
+  StreamState &h = d->h_state;
+  memset(&h, 0, sizeof(h));
+  d->d_state = (StreamState *)p; p += b_state;
+  h.hash[0] = (HashEntry *)p; p += b_hash;
+  h.hash[1] = (HashEntry *)p; p += b_hash;
+  for (int i = 0; i < 2; ++i) { h.slots[i] = (uint32_t *)p; p += b_list; }
+  for (int i = 0; i < 2; ++i) { h.queue[i] = (uint32_t *)p; p += b_list; }
+  h.tok_sc = (uint2 *)p; p += b_tok;
+  h.tok_aa = (uint2 *)p; p += b_tok;
+  h.frame_off = (uint32_t *)p; p += b_off;
+  h.stats = o.collect_stats ? (asrd_frame_stat *)p : nullptr;
+  h.hash_mask = (uint32_t)H - 1;
+  uint32_t lg = 0;
+  while ((1u << lg) < H) ++lg;
+  h.hash_shift = 32 - lg;
+  h.token_capacity = (uint32_t)o.token_capacity;
+  h.max_frames = o.max_frames;
+  // empty maps: key = 0xFFFFFFFF, val = +inf
+  if (cudaMemset(h.hash[0], 0xFF, 2 * b_hash) != cudaSuccess ||
+      cudaMemcpy(d->d_state, &h, sizeof(h), cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaFree(d->slab);
+    delete d;
+    return ASRD_ERR_CUDA;
+  }
+  *out = d;
+  return ASRD_OK;
+}
+
+int asrd_decoder_destroy(asrd_decoder *d) {
+  if (!d) return ASRD_OK;
+  cudaSetDevice(d->graph->device);
+  cudaFree(d->slab);
+  delete d;
+  return ASRD_OK;
+}
+
+int asrd_init_decoding(asrd_decoder *const *decs, int32_t n, void *stream) {
+  int rc = CheckBatch(decs, n);
+  if (rc) return rc;
+  if ((rc = EnsureDevice(decs[0]->graph->device))) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  Scratch sc(s);
+  StreamState **d_streams;
+  if ((rc = UploadStreams(decs, n, s, sc, &d_streams))) return rc;
+  k_boundary<<<n, kBoundaryThreads, 0, s>>>(d_streams, decs[0]->graph->view, DevCfg(decs[0]), kModeInit);
+  ++g_launches;
+  CU_CHECK(cudaGetLastError());
+  for (int i = 0; i < n; ++i) {
+    decs[i]->frames_decoded = 0;
+    decs[i]->finalized = 0;
+    decs[i]->initialized = 1;
+  }
+  return ASRD_OK;
+}
+
+int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *const *loglikes,
+                          const int32_t *n_frames, const int32_t *stride, int32_t num_indices,
+                          int32_t max_num_frames, int32_t on_device, void *stream) {
+  int rc = CheckBatch(decs, n);
+  if (rc) return rc;
+  if (!loglikes || !n_frames || !stride || num_indices <= 0) return ASRD_ERR_BAD_ARG;
+  if ((rc = EnsureDevice(decs[0]->graph->device))) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  std::vector<int32_t> nf(n);
+  int32_t max_nf = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!decs[i]->initialized || decs[i]->finalized) return ASRD_ERR_STATE;  // inl.h:634-635
+    if (n_frames[i] < 0 || stride[i] < num_indices || (n_frames[i] > 0 && !loglikes[i])) return ASRD_ERR_BAD_ARG;
+    nf[i] = n_frames[i];
+    if (max_num_frames >= 0) nf[i] = std::min(nf[i], max_num_frames);  // inl.h:643-648
+    nf[i] = std::min(nf[i], decs[i]->opts.max_frames - decs[i]->frames_decoded);
+    max_nf = std::max(max_nf, nf[i]);
+  }
+  if (max_nf == 0) return ASRD_OK;
+  const GraphView gv = decs[0]->graph->view;
+  const DecoderConfigDev cfg = DevCfg(decs[0]);
+  Scratch sc(s);
+  StreamState **d_streams;
+  if ((rc = UploadStreams(decs, n, s, sc, &d_streams))) return rc;
+  AdvanceParams *d_params;
+  CU_CHECK(sc.Alloc(&d_params, (size_t)n));
+  const int grid = ExpandGrid();
+  const size_t dyn = sizeof(uint32_t) * ((size_t)n + 1);
+
+  // Host log-likelihoods are staged chunk by chunk so the staging buffer stays small.
+  const int32_t chunk = on_device ? max_nf : std::min<int32_t>(max_nf, 64);
+  float *d_stage = nullptr;
+  const size_t row = (size_t)num_indices;
+  if (!on_device) CU_CHECK(sc.Alloc(&d_stage, (size_t)n * chunk * row));
+  std::vector<AdvanceParams> hp(n);
+  for (int32_t f0 = 0; f0 < max_nf; f0 += chunk) {
+    int32_t steps = 0;
+    for (int i = 0; i < n; ++i) {
+      const int32_t c = std::max(0, std::min(chunk, nf[i] - f0));
+      steps = std::max(steps, c);
+      hp[i].n_frames = c;
+      if (on_device) {
+        hp[i].ll = loglikes[i] + (size_t)f0 * stride[i];
+        hp[i].stride = stride[i];
+      } else {
+        hp[i].ll = d_stage + (size_t)i * chunk * row;
+        hp[i].stride = num_indices;
+        if (c > 0)
+          CU_CHECK(cudaMemcpy2DAsync(d_stage + (size_t)i * chunk * row, row * 4,
+                                     loglikes[i] + (size_t)f0 * stride[i], (size_t)stride[i] * 4, row * 4,
+                                     (size_t)c, cudaMemcpyHostToDevice, s));
+      }
+    }
+    CU_CHECK(cudaMemcpyAsync(d_params, hp.data(), sizeof(AdvanceParams) * n, cudaMemcpyHostToDevice, s));
+    k_begin_advance<<<(n + 127) / 128, 128, 0, s>>>(d_streams, d_params, n);
+    k_boundary<<<n, kBoundaryThreads, 0, s>>>(d_streams, gv, cfg, kModePro);
+    g_launches += 2;
+    for (int32_t f = 0; f < steps; ++f) {
+      k_expand<<<grid, kExpandThreads, dyn, s>>>(d_streams, n, gv);
+      k_boundary<<<n, kBoundaryThreads, 0, s>>>(d_streams, gv, cfg, kModeEpi | (f + 1 < steps ? kModePro : 0));
+      g_launches += 2;
+    }
+    CU_CHECK(cudaGetLastError());
+  }
+  for (int i = 0; i < n; ++i) decs[i]->frames_decoded += nf[i];
+  return ASRD_OK;
+}
+
+int asrd_finalize_decoding(asrd_decoder *const *decs, int32_t n, void *stream) {
+  (void)stream;
+  int rc = CheckBatch(decs, n);
+  if (rc) return rc;
+  for (int i = 0; i < n; ++i) {
+    if (!decs[i]->initialized) return ASRD_ERR_STATE;
+    decs[i]->finalized = 1;
+  }
+  return ASRD_OK;
+}
+
+int32_t asrd_num_frames_decoded(const asrd_decoder *d) { return d ? d->frames_decoded : ASRD_ERR_BAD_ARG; }
+
+int asrd_get_best_path(asrd_decoder *const *decs, int32_t n, int32_t use_final_probs, int32_t cap,
+                       int32_t *ilabel, int32_t *olabel, float *graph, float *acoustic, int32_t *n_arcs,
+                       int32_t *status, void *stream) {
+  int rc = CheckBatch(decs, n);
+  if (rc) return rc;
+  if (cap <= 0 || !ilabel || !olabel || !graph || !acoustic || !n_arcs || !status) return ASRD_ERR_BAD_ARG;
+  for (int i = 0; i < n; ++i) {
+    if (!decs[i]->initialized) return ASRD_ERR_STATE;
+    if (decs[i]->finalized && !use_final_probs) return ASRD_ERR_STATE;  // inl.h:1100-1102
+  }
+  if ((rc = EnsureDevice(decs[0]->graph->device))) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  Scratch sc(s);
+  StreamState **d_streams;
+  if ((rc = UploadStreams(decs, n, s, sc, &d_streams))) return rc;
+  const size_t tot = (size_t)n * cap;
+  int32_t *d_il, *d_ol, *d_n, *d_st;
+  float *d_gr, *d_ac;
+  CU_CHECK(sc.Alloc(&d_il, tot));
+  CU_CHECK(sc.Alloc(&d_ol, tot));
+  CU_CHECK(sc.Alloc(&d_gr, tot));
+  CU_CHECK(sc.Alloc(&d_ac, tot));
+  CU_CHECK(sc.Alloc(&d_n, (size_t)n));
+  CU_CHECK(sc.Alloc(&d_st, (size_t)n));
+  k_best_path<<<n, 256, 0, s>>>(d_streams, decs[0]->graph->view, use_final_probs, cap, d_il, d_ol, d_gr,
+                                d_ac, d_n, d_st);
+  ++g_launches;
+  CU_CHECK(cudaGetLastError());
+  CU_CHECK(cudaMemcpyAsync(n_arcs, d_n, 4 * (size_t)n, cudaMemcpyDeviceToHost, s));
+  CU_CHECK(cudaMemcpyAsync(status, d_st, 4 * (size_t)n, cudaMemcpyDeviceToHost, s));
+  CU_CHECK(cudaStreamSynchronize(s));
+  // arcs come back end -> start; copy only what each stream produced and flip to path order
+  for (int i = 0; i < n; ++i) {
+    const int32_t m = std::max(0, std::min(n_arcs[i], cap));
+    const size_t b = (size_t)i * cap;
+    if (m == 0) continue;
+    CU_CHECK(cudaMemcpyAsync(ilabel + b, d_il + b, 4 * (size_t)m, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(cudaMemcpyAsync(olabel + b, d_ol + b, 4 * (size_t)m, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(cudaMemcpyAsync(graph + b, d_gr + b, 4 * (size_t)m, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(cudaMemcpyAsync(acoustic + b, d_ac + b, 4 * (size_t)m, cudaMemcpyDeviceToHost, s));
+  }
+  CU_CHECK(cudaStreamSynchronize(s));
+  for (int i = 0; i < n; ++i) {
+    const int32_t m = std::max(0, std::min(n_arcs[i], cap));
+    const size_t b = (size_t)i * cap;
+    std::reverse(ilabel + b, ilabel + b + m);
+    std::reverse(olabel + b, olabel + b + m);
+    std::reverse(graph + b, graph + b + m);
+    std::reverse(acoustic + b, acoustic + b + m);
+  }
+  return ASRD_OK;
+}
+
+int asrd_path_to_vector(const int32_t *ilabel, const int32_t *olabel, const float *graph,
+                        const float *acoustic, int32_t n_arcs, int32_t *words, int32_t *n_words,
+                        int32_t *alignment, int32_t *n_alignment, float *tot_score, float *lm_score) {
+  // LatticeToVector, src/newfst/lattice-functions.cc:179-217
+  if (n_arcs < 0 || !n_words || !n_alignment || !tot_score || !lm_score) return ASRD_ERR_BAD_ARG;
+  float tot = 0.f, lm = 0.f;
+  int32_t nw = 0, na = 0;
+  for (int32_t i = 0; i < n_arcs; ++i) {
+    if (ilabel[i] != 0 && alignment) alignment[na] = ilabel[i];
+    if (ilabel[i] != 0) ++na;
+    if (olabel[i] != 0 && words) words[nw] = olabel[i];
+    if (olabel[i] != 0) ++nw;
+    lm += graph[i];
+    tot += graph[i] + acoustic[i];
+  }
+  *n_words = nw;
+  *n_alignment = na;
+  *tot_score = tot;
+  *lm_score = lm;
+  return ASRD_OK;
+}
+
+int32_t asrd_frame_stats(asrd_decoder *d, asrd_frame_stat *out, int32_t cap, void *stream) {
+  if (!d) return ASRD_ERR_BAD_ARG;
+  if (!d->opts.collect_stats) return 0;
+  const int32_t n = d->initialized ? d->frames_decoded + 1 : 0;
+  if (out && cap > 0 && n > 0) {
+    if (EnsureDevice(d->graph->device)) return ASRD_ERR_CUDA;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (cudaMemcpyAsync(out, d->h_state.stats, sizeof(asrd_frame_stat) * (size_t)std::min(n, cap),
+                        cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess)
+      return ASRD_ERR_CUDA;
+  }
+  return n;
+}
+
+int asrd_decoder_status(asrd_decoder *d, void *stream) {
+  if (!d) return ASRD_ERR_BAD_ARG;
+  int rc = EnsureDevice(d->graph->device);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  int32_t st = 0;
+  CU_CHECK(cudaMemcpyAsync(&st, &d->d_state->status, 4, cudaMemcpyDeviceToHost, s));
+  CU_CHECK(cudaStreamSynchronize(s));
+  return st;
+}
+
+int asrd_synchronize(void *stream) {
+  CU_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+  return ASRD_OK;
+}
+
+int asrd_host_alloc(void **ptr, int64_t bytes) {
+  if (!ptr || bytes <= 0) return ASRD_ERR_BAD_ARG;
+  CU_CHECK(cudaHostAlloc(ptr, (size_t)bytes, cudaHostAllocDefault));
+  return ASRD_OK;
+}
+
+int asrd_host_free(void *ptr) {
+  if (ptr) CU_CHECK(cudaFreeHost(ptr));
+  return ASRD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,133 @@
+// Internal device/host structures of the B200 WFST decoder.  Not part of the ABI.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "asrd.h"
+
+namespace asrd {
+
+constexpr uint32_t kEmptyKey = 0xFFFFFFFFu;
+constexpr uint32_t kNoArc = 0xFFFFFFFFu;
+constexpr unsigned long long kInfVal = 0xFFFFFFFFFFFFFFFFull;
+constexpr uint32_t kOrdInf = 0xFF800000u;  // f2ord(+inf)
+
+constexpr int kExpandThreads = 256;   // CTA size of the expand kernel
+constexpr int kTileTokens = 256;      // tokens staged per CTA tile
+constexpr int kBoundaryThreads = 512; // CTA size of the per-stream frame-boundary kernel
+constexpr int kMaxBatch = 8192;       // streams per launch (tile prefix lives in shared memory)
+
+// One slot of the per-frame state->token map.  val = (ordered cost << 32) | global arc id,
+// recombined with a single 64-bit atomicMin: lowest cost wins, equal cost -> lowest arc id.
+struct __align__(16) HashEntry {
+  uint32_t key;             // state id, kEmptyKey when free
+  uint32_t aux;             // eps-closure round stamp (de-duplicates the frontier queue)
+  unsigned long long val;
+};
+
+// Device-resident graph: the reference's two flat arrays (src/newfst/optimize-fst.h:60-61)
+// as CSR.  arcs[] are the 16-byte StdArc records verbatim (eps arcs first in every row).
+struct GraphView {
+  const int4 *arcs;        // {ilabel, olabel, weight bits, nextstate}
+  const uint2 *rows;       // [S+1] {row_off, emit_off}: eps span [x, y), emitting span [y, rows[s+1].x)
+  const uint32_t *arc_src; // [A] source state of every arc
+  const uint32_t *par_bits;// [ceil(A/32)] arc has a same-class sibling with the same (src, dst)
+  int32_t n_states;
+  uint32_t n_arcs;
+  int32_t start;
+  int32_t final_state;
+};
+
+// Per-stream (per decoder object) state, resident in HBM.
+struct StreamState {
+  // ---- buffers
+  HashEntry *hash[2];   // state->token maps; frame f lives in hash[f & 1]
+  uint32_t *slots[2];   // claimed-slot lists of the two maps
+  uint32_t *queue[2];   // eps-closure frontier queues
+  uint2 *tok_sc;        // token arena: {state, cost bits}
+  uint2 *tok_aa;        // token arena: {reported arc id, acoustic cost bits}
+  uint32_t *frame_off;  // [max_frames + 2] arena offset of every frame's token span
+  asrd_frame_stat *stats;  // [max_frames + 1] or null
+  uint32_t hash_mask;
+  uint32_t hash_shift;  // 32 - log2(capacity)
+  uint32_t token_capacity;
+  int32_t max_frames;
+  // ---- search state
+  int32_t frame;        // frames decoded so far == index of the current token span
+  int32_t status;       // sticky ASRD_ERR_* raised by kernels
+  uint32_t n_slots[2];
+  uint32_t n_cur;       // tokens in the current frame
+  float cur_cut;        // GetCutoff result for the current frame
+  float abeam;          // adaptive beam for the current frame
+  uint32_t next_cut_bits;  // running next_cutoff (ordered uint, atomicMin)
+  uint32_t arcs_expanded;
+  uint32_t arcs_admitted;
+  uint32_t tiles;       // expand tiles of the current frame (0 when the stream is idle)
+  int32_t finalized;
+  // ---- this AdvanceDecoding call
+  const float *ll_base; // row of frame ll_frame0
+  int32_t ll_stride;
+  int32_t ll_frame0;
+  int32_t target_frame; // decode while frame < target_frame
+  int32_t pad0;
+};
+
+struct AdvanceParams {
+  const float *ll;
+  int32_t stride;
+  int32_t n_frames;
+};
+
+struct DecoderConfigDev {
+  float beam;
+  int32_t max_active;
+  int32_t min_active;
+  float lattice_beam;
+  float beam_delta;
+  int32_t collect_stats;
+};
+
+// order-preserving float <-> uint32 map (handles negative costs)
+__host__ __device__ inline uint32_t f2ord(float f) {
+#ifdef __CUDA_ARCH__
+  uint32_t u = __float_as_uint(f);
+#else
+  uint32_t u;
+  memcpy(&u, &f, 4);
+#endif
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ inline float ord2f(uint32_t o) {
+  uint32_t u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+#endif
+}
+
+}  // namespace asrd
+
+struct asrd_graph {
+  int device;
+  asrd::GraphView view;
+  void *d_arcs, *d_rows, *d_arc_src, *d_par;
+  int64_t device_bytes;
+  int64_t total_arcs;
+};
+
+struct asrd_decoder {
+  asrd_graph *graph;
+  asrd_config cfg;
+  asrd_device_options opts;
+  asrd::StreamState *d_state;  // device copy
+  asrd::StreamState h_state;   // host mirror of the static fields
+  void *slab;                  // one allocation carved into the buffers above
+  int64_t slab_bytes;
+  int32_t frames_decoded;      // host-side mirror of StreamState::frame
+  int32_t finalized;
+  int32_t initialized;
+};

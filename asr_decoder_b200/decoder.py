@@ -1,0 +1,319 @@
+"""Host-side mirror of the reference decoder interface, over the C ABI.
+
+Names, argument meaning and error behaviour follow the reference:
+
+* ``LatticeFasterDecoderConfig`` — ``src/my-decoder/lattice-faster-decoder-conf.h:8-69``
+* ``CudaLatticeDecoder`` — the ``DecoderItf`` surface (``src/my-decoder/decoder-itf.h:10-25``):
+  ``InitDecoding / AdvanceDecoding / FinalizeDecoding / NumFramesDecoded / Decode /
+  GetBestPath``; constructed from ``(graph, config)`` like
+  ``OnlineLatticeDecoderBase(FST*, const LatticeFasterDecoderConfig&)``
+  (``online-decoder-base.h:95``).
+* ``CudaDecoderBatch`` — the same calls over N decoder objects at once (one launch
+  sequence steps every stream): what replaces the reference's one-decoder-per-pthread
+  deployment (``src/v2-asrbin/v2-asr-service.cc:95-104``).
+* ``LatticeToVector`` — ``src/newfst/lattice-functions.cc:179-217``.
+
+All search work happens in the CUDA library; this module only marshals buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import asrd_config, asrd_device_options, asrd_frame_stat, check
+from .fstio import Fst, read_fst
+
+FRAME_STAT_DTYPE = np.dtype([("n_in", "<u4"), ("cur_cutoff", "<f4"), ("abeam", "<f4"),
+                             ("next_cutoff", "<f4"), ("n_tokens", "<u4"), ("best", "<f4"),
+                             ("arcs_expanded", "<u4"), ("arcs_admitted", "<u4")])
+
+
+@dataclasses.dataclass
+class LatticeFasterDecoderConfig:
+    """Defaults are the reference's (lattice-faster-decoder-conf.h:35-44)."""
+    beam: float = 16.0
+    max_active: int = 2 ** 31 - 1
+    min_active: int = 200
+    lattice_beam: float = 10.0
+    prune_interval: int = 25
+    determinize_lattice: bool = True
+    beam_delta: float = 0.5
+    hash_ratio: float = 2.0
+    prune_scale: float = 0.1
+
+    def Check(self) -> None:
+        # lattice-faster-decoder-conf.h:62-67 (the reference asserts)
+        assert (self.beam > 0.0 and self.max_active > 1 and self.lattice_beam > 0.0
+                and self.prune_interval > 0 and self.beam_delta > 0.0 and self.hash_ratio >= 1.0
+                and 0.0 < self.prune_scale < 1.0)
+
+    def to_c(self) -> asrd_config:
+        return asrd_config(self.beam, self.max_active, self.min_active, self.lattice_beam,
+                           self.prune_interval, self.beam_delta, self.hash_ratio, self.prune_scale)
+
+
+@dataclasses.dataclass
+class BestPath:
+    """The linear lattice GetBestPath fills (one arc per back-trace step, path order),
+    plus its LatticeToVector view."""
+    ok: bool
+    status: int
+    ilabel: np.ndarray
+    olabel: np.ndarray
+    graph: np.ndarray
+    acoustic: np.ndarray
+    words: List[int]
+    ali: List[int]
+    tot: float
+    lm: float
+
+    @property
+    def tot_bits(self) -> int:
+        return int(np.float32(self.tot).view(np.uint32))
+
+
+def LatticeToVector(ilabel, olabel, graph, acoustic):
+    """words, alignment, tot_score, lm_score of a best path (lattice-functions.cc:179-217)."""
+    L = _lib.lib()
+    il = np.ascontiguousarray(ilabel, np.int32)
+    ol = np.ascontiguousarray(olabel, np.int32)
+    g = np.ascontiguousarray(graph, np.float32)
+    a = np.ascontiguousarray(acoustic, np.float32)
+    n = il.shape[0]
+    words = np.zeros(max(n, 1), np.int32)
+    ali = np.zeros(max(n, 1), np.int32)
+    nw, na = C.c_int32(0), C.c_int32(0)
+    tot, lm = C.c_float(0), C.c_float(0)
+    check(L.asrd_path_to_vector(il.ctypes.data, ol.ctypes.data, g.ctypes.data, a.ctypes.data, n,
+                                words.ctypes.data, C.byref(nw), ali.ctypes.data, C.byref(na),
+                                C.byref(tot), C.byref(lm)), "asrd_path_to_vector")
+    return words[:nw.value].tolist(), ali[:na.value].tolist(), float(tot.value), float(lm.value)
+
+
+class CudaFst:
+    """Device-resident HCLG (the reference's ``Fst``, optimize-fst.h:53-307, as CSR in HBM)."""
+
+    def __init__(self, fst: Fst, device: int = 0):
+        L = _lib.lib()
+        self.host = fst
+        self.device = device
+        arcs = np.ascontiguousarray(fst.arcs)
+        na = np.ascontiguousarray(fst.num_arcs, np.uint32)
+        ne = np.ascontiguousarray(fst.niepsilons, np.uint32)
+        h = C.c_void_p()
+        check(L.asrd_graph_create(arcs.ctypes.data, na.ctypes.data, ne.ctypes.data, fst.total_states,
+                                  fst.total_arcs, fst.start, fst.final_state, device, C.byref(h)),
+              "asrd_graph_create")
+        self.h = h
+        self.max_ilabel = int(fst.arcs["ilabel"].max()) if fst.total_arcs else 0
+
+    @classmethod
+    def ReadFst(cls, path: str, device: int = 0) -> "CudaFst":
+        """``Fst::ReadFst`` (optimize-fst.h:208-280)."""
+        return cls(read_fst(path), device)
+
+    def device_bytes(self) -> int:
+        b = C.c_int64(0)
+        check(_lib.lib().asrd_graph_info(self.h, None, None, None, None, C.byref(b)), "asrd_graph_info")
+        return b.value
+
+    def close(self):
+        if getattr(self, "h", None):
+            _lib.lib().asrd_graph_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _as_ptr_and_keep(x):
+    """(device?, pointer, n_frames, stride, keepalive) for a numpy array or a torch tensor."""
+    if isinstance(x, np.ndarray):
+        a = x if (x.dtype == np.float32 and x.flags.c_contiguous) else np.ascontiguousarray(x, np.float32)
+        return False, a.ctypes.data, a.shape[0], a.shape[1], a
+    # torch tensor (CUDA or pinned/pageable CPU)
+    t = x
+    assert t.dim() == 2 and t.dtype.is_floating_point and t.element_size() == 4
+    if t.stride(1) != 1:
+        t = t.contiguous()
+    return bool(t.is_cuda), int(t.data_ptr()), int(t.shape[0]), int(t.stride(0)), t
+
+
+class CudaDecoderBatch:
+    """N decoder objects stepped together.  ``decoders[i]`` is one stream."""
+
+    def __init__(self, graph: CudaFst, config: LatticeFasterDecoderConfig, n: int,
+                 max_frames: int = 0, hash_capacity: int = 0, token_capacity: int = 0,
+                 collect_stats: bool = False):
+        config.Check()
+        L = _lib.lib()
+        self.graph = graph
+        self.config = config
+        self.n = n
+        cfg = config.to_c()
+        opts = asrd_device_options(hash_capacity, token_capacity, max_frames, int(collect_stats))
+        self.handles = (C.c_void_p * n)()
+        self._created = 0
+        for i in range(n):
+            h = C.c_void_p()
+            check(L.asrd_decoder_create(graph.h, C.byref(cfg), C.byref(opts), C.byref(h)),
+                  "asrd_decoder_create")
+            self.handles[i] = h
+            self._created += 1
+        self.collect_stats = collect_stats
+
+    def close(self):
+        L = _lib.lib()
+        for i in range(self._created):
+            if self.handles[i]:
+                L.asrd_decoder_destroy(self.handles[i])
+                self.handles[i] = None
+        self._created = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- DecoderItf, batched
+    def InitDecoding(self, stream: int = 0) -> None:
+        check(_lib.lib().asrd_init_decoding(self.handles, self.n, stream), "asrd_init_decoding")
+
+    def AdvanceDecoding(self, loglikes: Sequence, max_num_frames: int = -1, stream: int = 0) -> None:
+        """``loglikes[i]``: rows for the not-yet-decoded frames of stream i — a numpy
+        ``[T, P]`` array (host) or a torch tensor (CUDA or CPU); all on the same side."""
+        assert len(loglikes) == self.n
+        ptrs = (C.c_void_p * self.n)()
+        nfr = (C.c_int32 * self.n)()
+        strides = (C.c_int32 * self.n)()
+        keep = []
+        dev = None
+        P = None
+        for i, x in enumerate(loglikes):
+            on_dev, p, t, s, k = _as_ptr_and_keep(x)
+            if dev is None:
+                dev = on_dev
+            assert dev == on_dev, "all log-likelihood buffers must live on the same side"
+            cols = int(x.shape[1])
+            P = cols if P is None else P
+            assert cols == P
+            ptrs[i], nfr[i], strides[i] = p, t, s
+            keep.append(k)
+        if P < self.graph.max_ilabel:
+            raise _lib.AsrdError(-1, f"log-likelihood matrix has {P} columns but the graph uses "
+                                     f"ilabels up to {self.graph.max_ilabel}")
+        self._keep = keep  # host rows must stay alive until the stream is synchronised
+        check(_lib.lib().asrd_advance_decoding(self.handles, self.n, ptrs, nfr, strides, P,
+                                               max_num_frames, int(dev), stream), "asrd_advance_decoding")
+
+    def AdvanceDecodingRaw(self, ptrs, n_frames, strides, num_indices: int, on_device: bool,
+                           max_num_frames: int = -1, stream: int = 0) -> None:
+        """Same, with prebuilt ctypes arrays (no per-call marshalling)."""
+        check(_lib.lib().asrd_advance_decoding(self.handles, self.n, ptrs, n_frames, strides, num_indices,
+                                               max_num_frames, int(on_device), stream), "asrd_advance_decoding")
+
+    def FinalizeDecoding(self, stream: int = 0) -> None:
+        check(_lib.lib().asrd_finalize_decoding(self.handles, self.n, stream), "asrd_finalize_decoding")
+
+    def NumFramesDecoded(self, i: int = 0) -> int:
+        return _lib.lib().asrd_num_frames_decoded(self.handles[i])
+
+    def Synchronize(self, stream: int = 0) -> None:
+        check(_lib.lib().asrd_synchronize(stream), "asrd_synchronize")
+
+    def GetBestPath(self, use_final_probs: bool = True, stream: int = 0, vectors: bool = True) -> List[BestPath]:
+        L = _lib.lib()
+        maxf = max(self.NumFramesDecoded(i) for i in range(self.n))
+        cap = 4 * maxf + 64
+        while True:
+            il = np.zeros((self.n, cap), np.int32)
+            ol = np.zeros((self.n, cap), np.int32)
+            gr = np.zeros((self.n, cap), np.float32)
+            ac = np.zeros((self.n, cap), np.float32)
+            na = np.zeros(self.n, np.int32)
+            st = np.zeros(self.n, np.int32)
+            check(L.asrd_get_best_path(self.handles, self.n, int(use_final_probs), cap, il.ctypes.data,
+                                       ol.ctypes.data, gr.ctypes.data, ac.ctypes.data, na.ctypes.data,
+                                       st.ctypes.data, stream), "asrd_get_best_path")
+            if (st == -8).any():  # ASRD_ERR_PATH_OVERFLOW
+                cap *= 4
+                continue
+            break
+        out = []
+        for i in range(self.n):
+            m = int(na[i])
+            ok = st[i] == 0 and m > 0
+            if ok and vectors:
+                words, ali, tot, lm = LatticeToVector(il[i, :m], ol[i, :m], gr[i, :m], ac[i, :m])
+            else:
+                words, ali, tot, lm = [], [], 0.0, 0.0
+            out.append(BestPath(bool(ok), int(st[i]), il[i, :m].copy(), ol[i, :m].copy(), gr[i, :m].copy(),
+                                ac[i, :m].copy(), words, ali, tot, lm))
+        return out
+
+    def frame_stats(self, i: int = 0, stream: int = 0) -> np.ndarray:
+        L = _lib.lib()
+        n = L.asrd_frame_stats(self.handles[i], None, 0, stream)
+        if n < 0:
+            raise _lib.AsrdError(n, "asrd_frame_stats")
+        out = np.zeros(n, FRAME_STAT_DTYPE)
+        if n:
+            L.asrd_frame_stats(self.handles[i], out.ctypes.data, n, stream)
+        return out
+
+    def status(self, i: int = 0, stream: int = 0) -> int:
+        return _lib.lib().asrd_decoder_status(self.handles[i], stream)
+
+    def Decode(self, loglikes: Sequence, stream: int = 0) -> List[BestPath]:
+        """InitDecoding -> AdvanceDecoding -> FinalizeDecoding -> GetBestPath — the sequence
+        every reference caller uses (kaldi-hclg-my-decoder.cc:97-122).  The reference's own
+        ``Decode()`` reads one frame past the end (inl.h:615) and is
+        not reproduced."""
+        self.InitDecoding(stream)
+        self.AdvanceDecoding(loglikes, stream=stream)
+        self.FinalizeDecoding(stream)
+        return self.GetBestPath(True, stream)
+
+
+class CudaLatticeDecoder:
+    """Single-stream drop-in with the ``DecoderItf`` call surface."""
+
+    def __init__(self, graph: CudaFst, config: LatticeFasterDecoderConfig, **device_options):
+        self._b = CudaDecoderBatch(graph, config, 1, **device_options)
+
+    def InitDecoding(self) -> None:
+        self._b.InitDecoding()
+
+    def AdvanceDecoding(self, loglikes, max_num_frames: int = -1) -> None:
+        self._b.AdvanceDecoding([loglikes], max_num_frames)
+
+    def FinalizeDecoding(self) -> None:
+        self._b.FinalizeDecoding()
+
+    def NumFramesDecoded(self) -> int:
+        return self._b.NumFramesDecoded(0)
+
+    def GetBestPath(self, use_final_probs: bool = True) -> BestPath:
+        return self._b.GetBestPath(use_final_probs)[0]
+
+    def Decode(self, loglikes) -> bool:
+        bp = self._b.Decode([loglikes])[0]
+        self._last = bp
+        return bp.ok
+
+    def frame_stats(self) -> np.ndarray:
+        return self._b.frame_stats(0)
+
+    def status(self) -> int:
+        return self._b.status(0)
+
+    def close(self):
+        self._b.close()

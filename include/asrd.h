@@ -1,0 +1,178 @@
+/* asrd.h — C ABI of the B200-native WFST token-passing beam-search decoder.
+ *
+ * This is the drop-in boundary for the hot path of datemoon/ASR-decoder's `my-decoder`
+ * (SURVEY.md §8b).  Every entry point names the reference interface it replaces
+ * (paths relative to the reference's src/).  Plain pointers and sizes only — no torch,
+ * no C++ types.  The library is CUDA-only: there is no CPU fallback; every call fails
+ * with ASRD_ERR_CUDA when no sm_100 device is usable.
+ *
+ * Threading: calls on DIFFERENT decoder handles may run concurrently; one host thread
+ * can step thousands of streams through the batched entry points (the reference uses
+ * one decoder object per pthread, src/v2-asrbin/v2-asr-service.cc:95-104).
+ *
+ * Semantics: the reference's per-frame token set depends on its hash-list visiting
+ * order.  This library implements the order-independent
+ * ("canonical") semantics: an arc is admitted iff its cost is below the frame's FINAL
+ * next_cutoff; equal-cost recombination prefers the lowest arc index.  On inputs where
+ * the reference agrees with itself under different token orders, one-best words and
+ * alignment are bit-identical to the reference's.
+ */
+#ifndef ASRD_H_
+#define ASRD_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ASRD_ABI_VERSION 1
+
+/* status codes (reference: bool returns / LOG_ERR throw / LOG_ASSERT abort,
+ * src/util/log-message.cc:122-144) */
+enum {
+  ASRD_OK = 0,
+  ASRD_ERR_BAD_ARG = -1,
+  ASRD_ERR_CUDA = -2,         /* CUDA runtime error or no usable device */
+  ASRD_ERR_NOMEM = -3,
+  ASRD_ERR_HASH_OVERFLOW = -4,  /* per-frame state->token map full (raise hash_capacity) */
+  ASRD_ERR_ARENA_OVERFLOW = -5, /* token / link arena full (raise token_capacity) */
+  ASRD_ERR_FRAMES_OVERFLOW = -6,/* more frames than max_frames */
+  ASRD_ERR_NO_TOKENS = -7,      /* reference: GetBestPath returns false (inl.h:1078-1079) */
+  ASRD_ERR_PATH_OVERFLOW = -8,  /* best path longer than the caller's buffer */
+  ASRD_ERR_STATE = -9,          /* call order violated (e.g. Advance after Finalize, inl.h:634) */
+  ASRD_ERR_IO = -10
+};
+
+/* newfst StdArc, src/newfst/arc.h:23-26 (16 bytes, kept verbatim in HBM) */
+typedef struct {
+  int32_t ilabel;
+  int32_t olabel;
+  float weight;
+  int32_t nextstate;
+} asrd_arc;
+
+/* LatticeFasterDecoderConfig, src/my-decoder/lattice-faster-decoder-conf.h:21-44.
+ * hash_ratio only shapes the reference's HashList and has no effect here. */
+typedef struct {
+  float beam;
+  int32_t max_active;
+  int32_t min_active;
+  float lattice_beam;
+  int32_t prune_interval;
+  float beam_delta;
+  float hash_ratio;
+  float prune_scale;
+} asrd_config;
+
+/* Device-side sizing; zero means "choose from the config". No reference counterpart
+ * (the reference grows heap structures on demand). */
+typedef struct {
+  int32_t hash_capacity;   /* state->token slots per frame, rounded up to a power of two */
+  int64_t token_capacity;  /* token records kept per utterance (all frames) */
+  int32_t max_frames;      /* frames per utterance */
+  int32_t collect_stats;   /* keep per-frame statistics for asrd_frame_stats */
+  int32_t reserved[4];
+} asrd_device_options;
+
+/* per-frame statistics; index 0 = after InitDecoding (what the reference logs under
+ * VLOG_COM(2), src/my-decoder/online-decoder-base-inl.h:306-308) */
+typedef struct {
+  uint32_t n_in;         /* tokens seen by GetCutoff for the frame that produced this one */
+  float cur_cutoff;      /* GetCutoff result (inl.h:267) */
+  float abeam;           /* adaptive beam */
+  float next_cutoff;     /* final next_cutoff = cutoff of the eps closure */
+  uint32_t n_tokens;     /* tokens alive after the closure (all have cost < next_cutoff) */
+  float best;            /* best cost after the closure */
+  uint32_t arcs_expanded;/* emitting arcs fetched for tokens with cost <= cur_cutoff */
+  uint32_t arcs_admitted;/* ... whose cost was below the running cutoff when scored */
+} asrd_frame_stat;
+
+typedef struct asrd_graph asrd_graph;
+typedef struct asrd_decoder asrd_decoder;
+
+const char *asrd_strerror(int status);
+int asrd_abi_version(void);
+/* number of usable sm_100 devices; 0 or a negative status when none */
+int asrd_device_count(void);
+
+/* ---- graph: replaces Fst (src/newfst/optimize-fst.h:53-307) -------------------------- */
+
+/* From the in-memory form Fst::ReadFst builds: per-state {num_arcs, niepsilons}
+ * (StateInfo, optimize-fst.h:220-225) and the flat arc array.  Rows whose input-epsilon
+ * arcs are not a prefix are stably partitioned on upload (relative order kept). */
+int asrd_graph_create(const asrd_arc *arcs, const uint32_t *num_arcs, const uint32_t *niepsilons,
+                      int32_t total_states, int64_t total_arcs, int32_t start, int32_t final_state,
+                      int device, asrd_graph **out);
+/* Fst::ReadFst(const char*), optimize-fst.h:208-219: same file format */
+int asrd_graph_read(const char *path, int device, asrd_graph **out);
+int asrd_graph_destroy(asrd_graph *g);
+int asrd_graph_info(const asrd_graph *g, int32_t *total_states, int64_t *total_arcs,
+                    int32_t *start, int32_t *final_state, int64_t *device_bytes);
+
+/* ---- decoder: replaces OnlineLatticeDecoderMempool behind DecoderItf ----------------- */
+
+/* OnlineLatticeDecoderBase(FST*, const LatticeFasterDecoderConfig&), online-decoder-base.h:95.
+ * The graph is shared and not owned (inl.h:24, _delete_fst(false)). */
+int asrd_decoder_create(asrd_graph *g, const asrd_config *cfg, const asrd_device_options *opts,
+                        asrd_decoder **out);
+int asrd_decoder_destroy(asrd_decoder *d);
+
+/* DecoderItf::InitDecoding (decoder-itf.h:15; inl.h:41-67), batched over n handles.
+ * `stream` is a cudaStream_t (NULL = default stream). */
+int asrd_init_decoding(asrd_decoder *const *decs, int32_t n, void *stream);
+
+/* DecoderItf::AdvanceDecoding (decoder-itf.h:16; inl.h:630-668), batched.
+ * loglikes[i] points at the row of frame NumFramesDecoded(i) of stream i — what
+ * AmInterface::LogLikelihood(frame, index) would return for index = column + 1
+ * (src/itf/decodable-itf.h:55-62; caller inl.h:295,326).  n_frames[i] rows with
+ * row pitch stride[i] (floats) are available; all of them are decoded, at most
+ * max_num_frames when that is >= 0.  num_indices = columns per row.
+ * on_device != 0: the pointers are device pointers valid on `stream`.
+ * on_device == 0: host pointers; rows are copied inside the call (asynchronously when the
+ * memory is pinned) — the caller must not touch them before asrd_synchronize. */
+int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *const *loglikes,
+                          const int32_t *n_frames, const int32_t *stride, int32_t num_indices,
+                          int32_t max_num_frames, int32_t on_device, void *stream);
+
+/* DecoderItf::FinalizeDecoding (decoder-itf.h:17; inl.h:829-847).  One-best mode keeps no
+ * forward links on the device, so this only freezes the streams and picks the final token
+ * (ComputeFinalCosts, inl.h:670-720). */
+int asrd_finalize_decoding(asrd_decoder *const *decs, int32_t n, void *stream);
+
+/* DecoderItf::NumFramesDecoded (decoder-itf.h:18) */
+int32_t asrd_num_frames_decoded(const asrd_decoder *d);
+
+/* DecoderItf::GetBestPath (decoder-itf.h:22; inl.h:1071-1200), batched.  For stream i the
+ * arcs of the linear best-path lattice are written in path order (start -> end) to
+ * ilabel/olabel/graph/acoustic[i*cap .. i*cap + n_arcs[i]), including the label-free arc
+ * of the start token (inl.h:1193-1198).  status[i] receives the per-stream status
+ * (ASRD_ERR_NO_TOKENS = the reference's `false`).  Synchronises `stream`. */
+int asrd_get_best_path(asrd_decoder *const *decs, int32_t n, int32_t use_final_probs, int32_t cap,
+                       int32_t *ilabel, int32_t *olabel, float *graph, float *acoustic,
+                       int32_t *n_arcs, int32_t *status, void *stream);
+
+/* LatticeToVector (src/newfst/lattice-functions.cc:179-217) over one best path. */
+int asrd_path_to_vector(const int32_t *ilabel, const int32_t *olabel, const float *graph,
+                        const float *acoustic, int32_t n_arcs, int32_t *words, int32_t *n_words,
+                        int32_t *alignment, int32_t *n_alignment, float *tot_score, float *lm_score);
+
+/* per-frame statistics (needs collect_stats); returns the number of entries available */
+int32_t asrd_frame_stats(asrd_decoder *d, asrd_frame_stat *out, int32_t cap, void *stream);
+
+/* sticky per-stream status (overflow flags raised by kernels); synchronises `stream` */
+int asrd_decoder_status(asrd_decoder *d, void *stream);
+
+int asrd_synchronize(void *stream);
+
+/* pinned host memory for log-likelihood staging */
+int asrd_host_alloc(void **ptr, int64_t bytes);
+int asrd_host_free(void *ptr);
+
+/* number of kernels launched by this library since load (bench.py "gpu_launches") */
+int64_t asrd_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASRD_H_ */

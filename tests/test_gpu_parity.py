@@ -1,0 +1,115 @@
+"""GPU parity: the CUDA path (through the C ABI) against the canonical-mode oracle.
+
+Bit-exact bar: one-best words, alignment and cost bits, per-frame token counts, cutoffs,
+adaptive beams and emitting-arc counts.  The oracle is the checker only.
+"""
+import numpy as np
+import pytest
+
+from asr_decoder_b200 import synth
+from asr_decoder_b200.decoder import CudaDecoderBatch, CudaFst, LatticeFasterDecoderConfig
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfg(**kw):
+    base = dict(beam=13.0, max_active=7000, min_active=200, lattice_beam=8.0)
+    base.update(kw)
+    return LatticeFasterDecoderConfig(**base)
+
+
+def _oracle_decode(O, og, cfg, ll, finalize=True):
+    d = O.OracleDecoder(og, O.make_config(cfg.beam, cfg.max_active, cfg.min_active, cfg.lattice_beam,
+                                          cfg.prune_interval, cfg.beam_delta, cfg.hash_ratio,
+                                          cfg.prune_scale), O.MODE_CANONICAL)
+    r = d.decode(ll, finalize=finalize)
+    return r, d.frame_stats()
+
+
+def _compare(bp, st, ref, rst, tag=""):
+    assert bp.ok == ref.ok, tag
+    assert bp.words == ref.words, tag
+    assert bp.ali == ref.ali, tag
+    assert bp.tot_bits == ref.tot_bits, (tag, bp.tot, ref.tot)
+    assert np.array_equal(bp.ilabel, ref.ilabel) and np.array_equal(bp.olabel, ref.olabel), tag
+    assert np.array_equal(bp.graph.view(np.uint32), ref.graph.view(np.uint32)), tag
+    assert np.array_equal(bp.acoustic.view(np.uint32), ref.acoustic.view(np.uint32)), tag
+    if st is not None:
+        assert len(st) == len(rst), tag
+        assert np.array_equal(st["n_tokens"], rst["n_raw"]), tag
+        assert np.array_equal(rst["n_raw"], rst["n_within"]), tag
+        for a, b in (("cur_cutoff", "cur_cutoff"), ("abeam", "abeam"), ("next_cutoff", "next_cutoff"),
+                     ("best", "best")):
+            assert np.array_equal(st[a].view(np.uint32), rst[b].view(np.uint32)), (tag, a)
+        assert np.array_equal(st["n_in"], rst["n_in"]), tag
+        assert np.array_equal(st["arcs_expanded"].astype(np.int64), rst["arcs_expanded"]), tag
+
+
+@pytest.mark.parametrize("sigma", [2.0, 3.0, 1.5])
+def test_config1_single_stream(oracle_mod, sigma):
+    """BASELINE.json configs[0]: 10k states / 50k arcs / 200 pdfs, 500 frames, beam 13, max-active 7000."""
+    O = oracle_mod
+    fst = synth.make_graph(10000, 5.0, 200, seed=12345)
+    ll = synth.make_loglikes(500, 200, sigma, seed=777)
+    cfg = _cfg()
+    g = CudaFst(fst)
+    dec = CudaDecoderBatch(g, cfg, 1, max_frames=512, collect_stats=True)
+    bp = dec.Decode([ll])[0]
+    assert dec.status(0) == 0
+    ref, rst = _oracle_decode(O, O.OracleGraph(fst), cfg, ll)
+    _compare(bp, dec.frame_stats(0), ref, rst, f"sigma={sigma}")
+
+
+def test_batch_of_streams_ragged(oracle_mod):
+    """Several streams of different lengths in one batch, each equal to its own oracle decode."""
+    O = oracle_mod
+    fst = synth.make_graph(5000, 5.0, 120, seed=99)
+    cfg = _cfg(max_active=3000)
+    og = O.OracleGraph(fst)
+    lens = [37, 120, 1, 64, 200, 90, 5, 150]
+    lls = [synth.make_loglikes(t, 120, 2.0 + 0.25 * (i % 3), seed=1000 + i) for i, t in enumerate(lens)]
+    g = CudaFst(fst)
+    dec = CudaDecoderBatch(g, cfg, len(lens), max_frames=256, collect_stats=True)
+    out = dec.Decode(lls)
+    for i, bp in enumerate(out):
+        assert dec.status(i) == 0
+        ref, rst = _oracle_decode(O, og, cfg, lls[i])
+        _compare(bp, dec.frame_stats(i), ref, rst, f"stream {i}")
+
+
+def test_chunked_advance_equals_one_shot(oracle_mod):
+    """Streaming: 30-frame chunks (config 5's call pattern) give the same result as one call,
+    and the decoder object is reusable across utterances (InitDecoding again)."""
+    O = oracle_mod
+    fst = synth.make_graph(8000, 5.0, 150, seed=5)
+    cfg = _cfg(max_active=4000)
+    ll = synth.make_loglikes(157, 150, 2.0, seed=31)
+    g = CudaFst(fst)
+    dec = CudaDecoderBatch(g, cfg, 1, max_frames=256, collect_stats=True)
+    ref, rst = _oracle_decode(O, O.OracleGraph(fst), cfg, ll)
+    for rep in range(2):
+        dec.InitDecoding()
+        for f0 in range(0, ll.shape[0], 30):
+            dec.AdvanceDecoding([ll[f0:f0 + 30]])
+        assert dec.NumFramesDecoded(0) == ll.shape[0]
+        dec.FinalizeDecoding()
+        bp = dec.GetBestPath()[0]
+        _compare(bp, dec.frame_stats(0), ref, rst, f"rep {rep}")
+
+
+@pytest.mark.parametrize("kw", [dict(max_active=500, min_active=50), dict(beam=6.0, min_active=2000, max_active=6000),
+                                dict(beam=20.0, max_active=2 ** 31 - 1, min_active=0)])
+def test_cutoff_branches(oracle_mod, kw):
+    """max-active binding, min-active widening and beam-only GetCutoff branches (inl.h:188-232)."""
+    O = oracle_mod
+    fst = synth.make_graph(6000, 5.0, 100, seed=21)
+    cfg = _cfg(**kw)
+    ll = synth.make_loglikes(120, 100, 2.0, seed=8)
+    g = CudaFst(fst)
+    dec = CudaDecoderBatch(g, cfg, 1, max_frames=128, collect_stats=True, hash_capacity=1 << 16)
+    bp = dec.Decode([ll])[0]
+    assert dec.status(0) == 0
+    oc = O.make_config(cfg.beam, min(cfg.max_active, 2 ** 31 - 1), cfg.min_active, cfg.lattice_beam)
+    d = O.OracleDecoder(O.OracleGraph(fst), oc, O.MODE_CANONICAL)
+    ref = d.decode(ll)
+    _compare(bp, dec.frame_stats(0), ref, d.frame_stats(), str(kw))
