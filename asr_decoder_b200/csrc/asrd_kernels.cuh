@@ -625,7 +625,12 @@ k_boundary(StreamState *const *streams, GraphView g, DecoderConfigDev cfg, int m
         cur_cut = block_kth_smallest<NT>(toks, n, (uint32_t)cfg.max_active, best_ord,
                                          f2ord(beam_cut), s_hist, s_misc);
         abeam = cur_cut - bc + cfg.beam_delta;
-      } else if (cfg.min_active > 0 && n > (uint32_t)cfg.min_active && le <= (uint32_t)cfg.min_active) {
+      } else if (n <= (uint32_t)cfg.min_active) {
+        // fewer tokens than min_active: min_active_cutoff stays +inf > beam_cutoff, so nothing is
+        // pruned and the adaptive beam is infinite (inl.h:183,205,220-226)
+        cur_cut = CUDART_INF_F;
+        abeam = CUDART_INF_F;
+      } else if (cfg.min_active > 0 && le <= (uint32_t)cfg.min_active) {
         // sorted[min_active] > beam_cutoff  <=>  at most min_active costs <= it (inl.h:205-226)
         cur_cut = block_kth_smallest<NT>(toks, n, (uint32_t)cfg.min_active, best_ord, 0xFFFFFFFFu,
                                          s_hist, s_misc);
