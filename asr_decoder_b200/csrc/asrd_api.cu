@@ -29,6 +29,77 @@ thread_local std::string g_last_error;
     }                                                                                    \
   } while (0)
 
+
+constexpr int kHostChunkFrames = 16;
+
+// per-device side stream + events for overlapping host->device staging with the search
+struct DeviceCtx {
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_ready = nullptr, ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+};
+std::mutex g_ctx_mu;
+DeviceCtx g_ctx[16];
+
+int GetCtx(int device, DeviceCtx **out) {
+  if (device < 0 || device >= 16) return ASRD_ERR_BAD_ARG;
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  DeviceCtx &c = g_ctx[device];
+  if (!c.copy_stream) {
+    CU_CHECK(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+    CU_CHECK(cudaEventCreateWithFlags(&c.ev_ready, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) {
+      CU_CHECK(cudaEventCreateWithFlags(&c.ev_copied[i], cudaEventDisableTiming));
+      CU_CHECK(cudaEventCreateWithFlags(&c.ev_done[i], cudaEventDisableTiming));
+    }
+  }
+  *out = &c;
+  return ASRD_OK;
+}
+
+// Optional per-kernel timing with CUDA events on the launching stream (asrd_profile_*):
+// class 0 = k_expand, class 1 = k_boundary.  Off by default: events between launches add gaps.
+std::atomic<int> g_profile{0};
+std::mutex g_prof_mu;
+double g_prof_ms[2] = {0, 0};
+long long g_prof_n[2] = {0, 0};
+
+struct Profiler {
+  bool on;
+  std::vector<cudaEvent_t> ev;  // begin/end pairs
+  std::vector<int> cls;
+  explicit Profiler(int enabled) : on(enabled != 0) {}
+  ~Profiler() {
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+  }
+  void Begin(int c, cudaStream_t s) {
+    if (!on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+    ev.push_back(e);
+    cls.push_back(c);
+  }
+  void End(cudaStream_t s) {
+    if (!on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+    ev.push_back(e);
+  }
+  int Finish(cudaStream_t s) {
+    if (!on) return ASRD_OK;
+    CU_CHECK(cudaStreamSynchronize(s));
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (size_t i = 0; i < cls.size(); ++i) {
+      float ms = 0.f;
+      CU_CHECK(cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]));
+      g_prof_ms[cls[i]] += ms;
+      g_prof_n[cls[i]] += 1;
+    }
+    return ASRD_OK;
+  }
+};
+
 int g_num_sms = 0;
 
 int EnsureDevice(int device) {
@@ -395,15 +466,35 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
   CU_CHECK(sc.Alloc(&d_params, (size_t)n));
   const int grid = ExpandGrid();
   const size_t dyn = sizeof(uint32_t) * ((size_t)n + 1);
-
-  // Host log-likelihoods are staged chunk by chunk so the staging buffer stays small.
-  const int32_t chunk = on_device ? max_nf : std::min<int32_t>(max_nf, 64);
-  float *d_stage = nullptr;
   const size_t row = (size_t)num_indices;
-  if (!on_device) CU_CHECK(sc.Alloc(&d_stage, (size_t)n * chunk * row));
+
+  // Host log-likelihoods: staged chunk by chunk through two device buffers, copied on a
+  // side stream so the H2D of chunk k+1 overlaps the search of chunk k.
+  const int32_t chunk = on_device ? max_nf : std::min<int32_t>(max_nf, kHostChunkFrames);
+  float *d_stage[2] = {nullptr, nullptr};
+  DeviceCtx *ctx = nullptr;
+  bool contiguous = false;
+  if (!on_device) {
+    if ((rc = GetCtx(decs[0]->graph->device, &ctx))) return rc;
+    const int nbuf = max_nf > chunk ? 2 : 1;
+    for (int b = 0; b < nbuf; ++b) CU_CHECK(sc.Alloc(&d_stage[b], (size_t)n * chunk * row));
+    if (nbuf == 1) d_stage[1] = d_stage[0];
+    CU_CHECK(cudaEventRecord(ctx->ev_ready, s));  // staging buffers exist from here on
+    CU_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_ready, 0));
+    // one [n, T, P] block with equal lengths -> a single pitched copy per chunk
+    contiguous = n > 1;
+    for (int i = 0; i < n && contiguous; ++i)
+      contiguous = nf[i] == nf[0] && stride[i] == num_indices &&
+                   (i == 0 || loglikes[i] - loglikes[i - 1] == loglikes[1] - loglikes[0]);
+    if (contiguous && (loglikes[1] - loglikes[0]) < (ptrdiff_t)((size_t)nf[0] * row)) contiguous = false;
+  }
   std::vector<AdvanceParams> hp(n);
-  for (int32_t f0 = 0; f0 < max_nf; f0 += chunk) {
+  Profiler prof(g_profile.load());
+  int k = 0;
+  for (int32_t f0 = 0; f0 < max_nf; f0 += chunk, ++k) {
     int32_t steps = 0;
+    float *stage = d_stage[k & 1];
+    if (!on_device && k >= 2) CU_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[k & 1], 0));
     for (int i = 0; i < n; ++i) {
       const int32_t c = std::max(0, std::min(chunk, nf[i] - f0));
       steps = std::max(steps, c);
@@ -412,26 +503,46 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
         hp[i].ll = loglikes[i] + (size_t)f0 * stride[i];
         hp[i].stride = stride[i];
       } else {
-        hp[i].ll = d_stage + (size_t)i * chunk * row;
+        hp[i].ll = stage + (size_t)i * chunk * row;
         hp[i].stride = num_indices;
-        if (c > 0)
-          CU_CHECK(cudaMemcpy2DAsync(d_stage + (size_t)i * chunk * row, row * 4,
+        if (c > 0 && !contiguous)
+          CU_CHECK(cudaMemcpy2DAsync(stage + (size_t)i * chunk * row, row * 4,
                                      loglikes[i] + (size_t)f0 * stride[i], (size_t)stride[i] * 4, row * 4,
-                                     (size_t)c, cudaMemcpyHostToDevice, s));
+                                     (size_t)c, cudaMemcpyHostToDevice, ctx->copy_stream));
       }
+    }
+    if (!on_device) {
+      if (contiguous)
+        CU_CHECK(cudaMemcpy2DAsync(stage, (size_t)chunk * row * 4, loglikes[0] + (size_t)f0 * row,
+                                   (size_t)(loglikes[1] - loglikes[0]) * 4, (size_t)steps * row * 4, (size_t)n,
+                                   cudaMemcpyHostToDevice, ctx->copy_stream));
+      CU_CHECK(cudaEventRecord(ctx->ev_copied[k & 1], ctx->copy_stream));
+      CU_CHECK(cudaStreamWaitEvent(s, ctx->ev_copied[k & 1], 0));
     }
     CU_CHECK(cudaMemcpyAsync(d_params, hp.data(), sizeof(AdvanceParams) * n, cudaMemcpyHostToDevice, s));
     k_begin_advance<<<(n + 127) / 128, 128, 0, s>>>(d_streams, d_params, n);
+    prof.Begin(1, s);
     k_boundary<<<n, kBoundaryThreads, 0, s>>>(d_streams, gv, cfg, kModePro);
+    prof.End(s);
     g_launches += 2;
     for (int32_t f = 0; f < steps; ++f) {
+      prof.Begin(0, s);
       k_expand<<<grid, kExpandThreads, dyn, s>>>(d_streams, n, gv);
+      prof.End(s);
+      prof.Begin(1, s);
       k_boundary<<<n, kBoundaryThreads, 0, s>>>(d_streams, gv, cfg, kModeEpi | (f + 1 < steps ? kModePro : 0));
+      prof.End(s);
       g_launches += 2;
     }
     CU_CHECK(cudaGetLastError());
+    if (!on_device) CU_CHECK(cudaEventRecord(ctx->ev_done[k & 1], s));
+  }
+  if (!on_device) {
+    // the copy stream must not run ahead into a later call's (recycled) staging memory
+    CU_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[(k - 1) & 1], 0));
   }
   for (int i = 0; i < n; ++i) decs[i]->frames_decoded += nf[i];
+  if ((rc = prof.Finish(s))) return rc;
   return ASRD_OK;
 }
 
@@ -547,6 +658,51 @@ int asrd_decoder_status(asrd_decoder *d, void *stream) {
   CU_CHECK(cudaMemcpyAsync(&st, &d->d_state->status, 4, cudaMemcpyDeviceToHost, s));
   CU_CHECK(cudaStreamSynchronize(s));
   return st;
+}
+
+int asrd_profile_enable(int on) {
+  g_profile.store(on ? 1 : 0);
+  return ASRD_OK;
+}
+
+int asrd_profile_reset(void) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_ms[0] = g_prof_ms[1] = 0;
+  g_prof_n[0] = g_prof_n[1] = 0;
+  return ASRD_OK;
+}
+
+int asrd_profile_get(double *expand_ms, int64_t *expand_launches, double *boundary_ms,
+                     int64_t *boundary_launches) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (expand_ms) *expand_ms = g_prof_ms[0];
+  if (expand_launches) *expand_launches = g_prof_n[0];
+  if (boundary_ms) *boundary_ms = g_prof_ms[1];
+  if (boundary_launches) *boundary_launches = g_prof_n[1];
+  return ASRD_OK;
+}
+
+int asrd_get_counters(asrd_decoder *const *decs, int32_t n, int64_t *arcs_expanded, int64_t *arcs_admitted,
+                      int64_t *tokens, void *stream) {
+  int rc = CheckBatch(decs, n);
+  if (rc) return rc;
+  if ((rc = EnsureDevice(decs[0]->graph->device))) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  Scratch sc(s);
+  StreamState **d_streams;
+  if ((rc = UploadStreams(decs, n, s, sc, &d_streams))) return rc;
+  unsigned long long *d_out;
+  CU_CHECK(sc.Alloc(&d_out, 3));
+  CU_CHECK(cudaMemsetAsync(d_out, 0, 24, s));
+  k_counters<<<(n + 127) / 128, 128, 0, s>>>(d_streams, n, d_out);
+  ++g_launches;
+  unsigned long long h[3];
+  CU_CHECK(cudaMemcpyAsync(h, d_out, 24, cudaMemcpyDeviceToHost, s));
+  CU_CHECK(cudaStreamSynchronize(s));
+  if (arcs_expanded) *arcs_expanded = (int64_t)h[0];
+  if (arcs_admitted) *arcs_admitted = (int64_t)h[1];
+  if (tokens) *tokens = (int64_t)h[2];
+  return ASRD_OK;
 }
 
 int asrd_synchronize(void *stream) {

@@ -71,6 +71,9 @@ struct StreamState {
   int32_t ll_frame0;
   int32_t target_frame; // decode while frame < target_frame
   int32_t pad0;
+  // ---- utterance totals
+  unsigned long long tot_arcs_expanded;
+  unsigned long long tot_arcs_admitted;
 };
 
 struct AdvanceParams {

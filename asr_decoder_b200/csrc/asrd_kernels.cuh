@@ -576,6 +576,13 @@ k_boundary(StreamState *const *streams, GraphView g, DecoderConfigDev cfg, int m
         s.arcs_admitted = is_init ? 0 : st->arcs_admitted;
         st->stats[t + 1] = s;
       }
+      if (is_init) {
+        st->tot_arcs_expanded = 0;
+        st->tot_arcs_admitted = 0;
+      } else {
+        st->tot_arcs_expanded += st->arcs_expanded;
+        st->tot_arcs_admitted += st->arcs_admitted;
+      }
       st->frame_off[t + 2] = out_base + n_alive;
       st->n_slots[next] = ntot;
       if (!is_init) st->n_slots[cur] = 0;
@@ -658,6 +665,17 @@ k_boundary(StreamState *const *streams, GraphView g, DecoderConfigDev cfg, int m
       st->tiles = (n + kTileTokens - 1) / kTileTokens;
     }
   }
+}
+
+// ------------------------------------------------------------------ counters
+
+__global__ void k_counters(StreamState *const *streams, int n, unsigned long long *out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const StreamState *st = streams[i];
+  atomicAdd(&out[0], st->tot_arcs_expanded);
+  atomicAdd(&out[1], st->tot_arcs_admitted);
+  atomicAdd(&out[2], (unsigned long long)st->frame_off[st->frame + 1]);
 }
 
 // ------------------------------------------------------------------ best path

@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py — batched WFST beam-search decode on B200 (BASELINE.json metric).
+
+A "step" is one pass of the hot path over one batch of synthetic utterances:
+InitDecoding -> AdvanceDecoding(all frames) -> FinalizeDecoding -> GetBestPath for every
+stream, i.e. the call sequence of the reference's offline bin
+(src/kaldi-nnet3bin/kaldi-hclg-my-decoder.cc:97-122).
+
+Workload at N=1 = BASELINE.json configs[1]: synthetic 1M-state / 5M-arc HCLG, 3000 pdfs,
+256 utterances x 333 frames (chain, 30 ms per frame), beam 13, max-active 7000, one-best.
+With N GPUs every rank holds a graph replica and its own 256-utterance batch (weak
+scaling, no collective on the data path).
+
+  value : RTFx with the log-likelihoods already resident in HBM
+  e2e   : RTFx through the C ABI with HOST (pinned) log-likelihoods, H2D + D2H inside
+  --impl reference : the reference's own CPU decoder (oracle/_ref/ref_decode, compiled from
+          /root/reference) on all host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FRAME_SECONDS = 0.03  # chain model, frame subsampling 3
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--states", type=int, default=1_000_000)
+    ap.add_argument("--pdfs", type=int, default=3000)
+    ap.add_argument("--utts", type=int, default=256)
+    ap.add_argument("--frames", type=int, default=333)
+    ap.add_argument("--sigma", type=float, default=2.0)
+    ap.add_argument("--beam", type=float, default=13.0)
+    ap.add_argument("--max-active", type=int, default=7000)
+    ap.add_argument("--min-active", type=int, default=200)
+    ap.add_argument("--lattice-beam", type=float, default=8.0)
+    ap.add_argument("--cpu-sample-utts", type=int, default=0, help="0 = 2 x host cores")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"synthetic HCLG {a.states} states avg-degree 5, {a.pdfs} pdfs; {a.utts} utts x {a.frames} frames "
+            f"(30 ms/frame), sigma={a.sigma}; beam={a.beam} max-active={a.max_active} "
+            f"min-active={a.min_active}; one-best")
+
+
+def make_inputs(a, rank):
+    from asr_decoder_b200 import synth
+    fst = synth.make_graph(a.states, 5.0, a.pdfs, seed=12345)
+    return fst, (lambda i: synth.make_loglikes(a.frames, a.pdfs, a.sigma, seed=100000 * rank + 1000 + i))
+
+
+# --------------------------------------------------------------------------- reference arm
+
+def cpu_reference_run(a, fst, gen, n_utts, repeats=1, threads=None):
+    """Time the reference's CPU decoder on `n_utts` utterances of the workload.
+    Returns dict(value=RTFx, seconds, kind, cores, sample)."""
+    from asr_decoder_b200 import fstio
+    from oracle import oracle as O
+    cores = threads or os.cpu_count() or 1
+    lls = [gen(i) for i in range(n_utts)]
+    audio = n_utts * a.frames * FRAME_SECONDS
+    if O.have_ref():
+        tmp = tempfile.mkdtemp(prefix="asrd_ref_")
+        try:
+            gp, lp = os.path.join(tmp, "g.fst"), os.path.join(tmp, "ll.bin")
+            fstio.write_fst(gp, fst)
+            fstio.write_loglikes(lp, lls)
+            secs = []
+            for _ in range(repeats):
+                _, summ = O.run_ref(gp, lp, stats=False, threads=cores, beam=a.beam, max_active=a.max_active,
+                                    min_active=a.min_active, lattice_beam=a.lattice_beam)
+                secs.append(summ["wall_s"])
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+        kind = "reference"
+    else:
+        # the C port in reference token order, one decoder object per thread
+        from concurrent.futures import ThreadPoolExecutor
+        og = O.OracleGraph(fst)
+        cfg = O.make_config(a.beam, a.max_active, a.min_active, a.lattice_beam)
+        decs = [O.OracleDecoder(og, cfg, O.MODE_REFERENCE) for _ in range(cores)]
+
+        def work(t):
+            for i in range(t, n_utts, cores):
+                decs[t].decode(lls[i])
+        secs = []
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            with ThreadPoolExecutor(cores) as ex:
+                list(ex.map(work, range(cores)))
+            secs.append(time.perf_counter() - t0)
+        kind = "port"
+    return dict(seconds=secs, value=audio / float(np.mean(secs)), kind=kind, cores=cores,
+                sample=f"{n_utts} of the workload's utterances x {a.frames} frames, {cores} threads "
+                       f"(one decoder object per thread, shared graph)")
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    fst, gen = make_inputs(a, 0)
+    cores = os.cpu_count() or 1
+    n_utts = a.cpu_sample_utts or max(2 * cores, 8)
+    n_utts = min(n_utts, a.utts)
+    res = cpu_reference_run(a, fst, gen, n_utts, repeats=a.warmup + a.steps)
+    timed = res["seconds"][a.warmup:]
+    audio = n_utts * a.frames * FRAME_SECONDS
+    value = audio / float(np.mean(timed))
+    line = {
+        "impl": "reference", "metric": "batched decode RTFx", "value": value, "unit": "x realtime",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * float(np.mean(timed)),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a)},
+        "cpu_baseline": {"value": value, "unit": "x realtime", "cores": res["cores"], "kind": res["kind"],
+                         "sample": res["sample"]},
+        "e2e": {"value": value, "unit": "x realtime", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- B200 arm
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+def run_b200_arm(a):
+    import torch
+    import torch.distributed as dist
+    from asr_decoder_b200 import _lib
+    from asr_decoder_b200.decoder import CudaDecoderBatch, CudaFst, LatticeFasterDecoderConfig
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L = _lib.lib()
+
+    fst, gen = make_inputs(a, rank)
+    n, T, P = a.utts, a.frames, a.pdfs
+    # host inputs in pinned memory (e2e source), device copy for the resident-input number
+    host = torch.empty((n, T, P), dtype=torch.float32).pin_memory()
+    hv = host.numpy()
+    for i in range(n):
+        hv[i] = gen(i)
+    dev = host.to(f"cuda:{local}", non_blocking=False)
+
+    cfg = LatticeFasterDecoderConfig(beam=a.beam, max_active=a.max_active, min_active=a.min_active,
+                                     lattice_beam=a.lattice_beam)
+    graph = CudaFst(fst, device=local)
+    tok_cap = int(min(max(a.frames + 2, 64) * 12000, 1 << 23))
+    batch = CudaDecoderBatch(graph, cfg, n, max_frames=T + 8, token_capacity=tok_cap)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def ptr_arrays(base_ptr, row_stride_elems):
+        ptrs = (C.c_void_p * n)(*[base_ptr + 4 * i * T * row_stride_elems for i in range(n)])
+        nfr = (C.c_int32 * n)(*([T] * n))
+        strides = (C.c_int32 * n)(*([P] * n))
+        return ptrs, nfr, strides
+
+    dev_args = ptr_arrays(dev.data_ptr(), P)
+    host_args = ptr_arrays(host.data_ptr(), P)
+
+    def step(args, on_device):
+        batch.InitDecoding(stream)
+        batch.AdvanceDecodingRaw(args[0], args[1], args[2], P, on_device, -1, stream)
+        batch.FinalizeDecoding(stream)
+        return batch.GetBestPath(True, stream, vectors=False)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- resident-input number (value)
+    for _ in range(a.warmup):
+        res_dev = step(dev_args, True)
+    bad = [r.status for r in res_dev if not r.ok]
+    if bad:
+        raise SystemExit(f"decode failed: statuses {sorted(set(bad))}")
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = L.asrd_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        res_dev = step(dev_args, True)
+    e1.record()
+    barrier()
+    launches = L.asrd_launch_count() - l0
+    ms_value = max_over_ranks(e0.elapsed_time(e1) / a.steps)
+    clocks = sampler.stop() if sampler else None
+
+    # ---- counters + per-kernel device time of one extra (untimed) step
+    ae, aa, tk = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+    L.asrd_get_counters(batch.handles, n, C.byref(ae), C.byref(aa), C.byref(tk), stream)
+    L.asrd_profile_reset()
+    L.asrd_profile_enable(1)
+    step(dev_args, True)
+    L.asrd_profile_enable(0)
+    xm, xn, bm, bn = C.c_double(0), C.c_int64(0), C.c_double(0), C.c_int64(0)
+    L.asrd_profile_get(C.byref(xm), C.byref(xn), C.byref(bm), C.byref(bn))
+
+    # ---- end-to-end number: host (pinned) log-likelihoods through the C ABI
+    e2e = None
+    if not a.no_e2e:
+        for _ in range(max(1, min(a.warmup, 2))):
+            res_host = step(host_args, False)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            res_host = step(host_args, False)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        ms_e2e = max_over_ranks(1e3 * (t1 - t0) / a.steps)
+        same = all(np.array_equal(x.ilabel, y.ilabel) and np.array_equal(x.olabel, y.olabel) and
+                   np.array_equal(x.acoustic.view(np.uint32), y.acoustic.view(np.uint32))
+                   for x, y in zip(res_dev, res_host))
+        d2h = int(sum(16 * len(r.ilabel) for r in res_host) + 8 * n)
+        e2e = (ms_e2e, same, d2h)
+
+    audio_all = sum_over_ranks(n * T * FRAME_SECONDS)
+    arcs_all = sum_over_ranks(float(ae.value))
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = float(json.load(open(peaks_path))["hbm_gbs"])
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    expand_s = xm.value / 1e3
+    achieved = 16.0 * ae.value / expand_s / 1e9 if expand_s > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "expand_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    line = {
+        "metric": "batched decode RTFx", "value": audio_all / (ms_value / 1e3), "unit": "x realtime",
+        "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_value,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "parallelism": f"replica-per-gpu x{world}, streams sharded",
+                   "l2": "inputs (1.02 GB of log-likelihoods + per-stream maps) exceed the 126 MB L2; no flush needed",
+                   "arena_tokens_per_stream": tok_cap},
+        "arcs_expanded_per_s": arcs_all / (ms_value / 1e3),
+        "arcs_expanded_per_step": arcs_all,
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "k_expand", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_arc": 16, "arcs_per_launch": ae.value / max(1, xn.value),
+                     "launch_ms": xm.value / max(1, xn.value), "launches_per_step": int(xn.value),
+                     "k_boundary_ms_per_launch": bm.value / max(1, bn.value),
+                     "kernel_share_of_step": {"k_expand": xm.value / (xm.value + bm.value + 1e-12),
+                                              "k_boundary": bm.value / (xm.value + bm.value + 1e-12)}},
+    }
+    if e2e is not None:
+        line["e2e"] = {"value": audio_all / (e2e[0] / 1e3), "unit": "x realtime", "ms_per_step": e2e[0],
+                       "h2d_bytes_per_step": int(n * T * P * 4), "d2h_bytes_per_step": e2e[2],
+                       "matches_resident_run": bool(e2e[1])}
+    if not a.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        k = min(a.cpu_sample_utts or max(2 * cores, 8), n)
+        res = cpu_reference_run(a, fst, gen, k, repeats=1)
+        line["cpu_baseline"] = {"value": res["value"], "unit": "x realtime", "cores": res["cores"],
+                                "kind": res["kind"], "sample": res["sample"]}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_b200_arm(a)
+
+
+if __name__ == "__main__":
+    main()

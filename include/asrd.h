@@ -169,6 +169,18 @@ int asrd_synchronize(void *stream);
 int asrd_host_alloc(void **ptr, int64_t bytes);
 int asrd_host_free(void *ptr);
 
+/* utterance totals summed over the n streams since their InitDecoding: emitting arcs fetched,
+ * arcs admitted, token records kept.  Synchronises `stream`. */
+int asrd_get_counters(asrd_decoder *const *decs, int32_t n, int64_t *arcs_expanded,
+                      int64_t *arcs_admitted, int64_t *tokens, void *stream);
+
+/* Per-kernel device timing with CUDA events on the launching stream (measurement aid for
+ * bench.py's roofline; adds gaps between launches, so keep it off in timed regions). */
+int asrd_profile_enable(int on);
+int asrd_profile_reset(void);
+int asrd_profile_get(double *expand_ms, int64_t *expand_launches, double *boundary_ms,
+                     int64_t *boundary_launches);
+
 /* number of kernels launched by this library since load (bench.py "gpu_launches") */
 int64_t asrd_launch_count(void);
 
