@@ -101,8 +101,7 @@ def lib():
     L.asrd_launch_count.restype = i64
     L.asrd_get_counters.argtypes = [vp, i32, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), vp]
     L.asrd_profile_enable.argtypes = [C.c_int]
-    L.asrd_profile_get.argtypes = [C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(C.c_double),
-                                   C.POINTER(i64)]
+    L.asrd_profile_get.argtypes = [C.POINTER(C.c_double), C.POINTER(i64)]
     _lib = L
     return L
 

@@ -57,11 +57,12 @@ int GetCtx(int device, DeviceCtx **out) {
 }
 
 // Optional per-kernel timing with CUDA events on the launching stream (asrd_profile_*):
-// class 0 = k_expand, class 1 = k_boundary.  Off by default: events between launches add gaps.
+// class 0 = k_expand, 1 = k_closure, 2 = k_finalize, 3 = k_cutoff.  Off by default: events
+// between launches add gaps.
 std::atomic<int> g_profile{0};
 std::mutex g_prof_mu;
-double g_prof_ms[2] = {0, 0};
-long long g_prof_n[2] = {0, 0};
+double g_prof_ms[4] = {0, 0, 0, 0};
+long long g_prof_n[4] = {0, 0, 0, 0};
 
 struct Profiler {
   bool on;
@@ -169,11 +170,51 @@ int CheckBatch(asrd_decoder *const *decs, int n) {
     if (!decs[i]) return ASRD_ERR_BAD_ARG;
     if (decs[i]->graph != decs[0]->graph) return ASRD_ERR_BAD_ARG;  // one graph per launch
     if (memcmp(&decs[i]->cfg, &decs[0]->cfg, sizeof(asrd_config)) != 0) return ASRD_ERR_BAD_ARG;
+    if (decs[i]->opts.hash_capacity != decs[0]->opts.hash_capacity) return ASRD_ERR_BAD_ARG;
+    if (decs[i]->opts.collect_stats != decs[0]->opts.collect_stats) return ASRD_ERR_BAD_ARG;
   }
   return ASRD_OK;
 }
 
-int ExpandGrid() { return g_num_sms * 8; }
+// ---- kernel launch plumbing -------------------------------------------------------------
+
+typedef void (*ExpandFn)(FrameDesc *, GraphView, int);
+
+struct ExpandPlan {
+  ExpandFn fn;
+  dim3 grid;
+  size_t dyn;
+};
+
+int EnvInt(const char *name, int dflt) {
+  const char *v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
+// Picks the k_expand instantiation (arcs in flight per lane; log-likelihood row staged in
+// shared memory when it fits) and sizes the grid to about one resident wave: blockIdx.y is
+// the stream, gridDim.x CTAs share one stream's token groups.
+int PlanExpand(int n_streams, int num_indices, ExpandPlan *plan) {
+  const int u = EnvInt("ASRD_EXPAND_U", 2);
+  const bool smem_ll = EnvInt("ASRD_SMEM_LL", 1) != 0 && (size_t)num_indices * 4 <= 96 * 1024;
+  ExpandFn fn;
+  if (smem_ll) fn = u >= 4 ? k_expand<4, true> : (u == 2 ? k_expand<2, true> : k_expand<1, true>);
+  else fn = u >= 4 ? k_expand<4, false> : (u == 2 ? k_expand<2, false> : k_expand<1, false>);
+  const size_t dyn = smem_ll ? (size_t)num_indices * 4 : 0;
+  if (dyn > 48 * 1024)
+    CU_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  int per_sm = 0;
+  CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kExpandThreads, dyn));
+  const int resident = g_num_sms * std::max(per_sm, 1);
+  int gx = EnvInt("ASRD_EXPAND_G", 0);
+  if (gx <= 0) gx = (resident + n_streams - 1) / n_streams;
+  plan->fn = fn;
+  plan->grid = dim3((unsigned)std::max(gx, 1), (unsigned)n_streams, 1);
+  plan->dyn = dyn;
+  return ASRD_OK;
+}
+
+int FinalizeGrid() { return g_num_sms * EnvInt("ASRD_FIN_CTAS_PER_SM", 6); }
 
 }  // namespace
 
@@ -227,6 +268,7 @@ int asrd_graph_create(const asrd_arc *arcs, const uint32_t *num_arcs, const uint
   std::vector<asrd_arc> parc((size_t)std::max<int64_t>(A, 1));
   std::vector<uint32_t> src((size_t)std::max<int64_t>(A, 1));
   std::vector<uint32_t> par((size_t)(A + 31) / 32 + 1, 0u);
+  std::vector<uint32_t> epsb((size_t)(S + 31) / 32 + 1, 0u);
   std::vector<std::pair<int32_t, uint32_t>> tmp;
   int64_t off = 0;
   for (int32_t s = 0; s < S; ++s) {
@@ -241,6 +283,7 @@ int asrd_graph_create(const asrd_arc *arcs, const uint32_t *num_arcs, const uint
     for (uint32_t k = 0; k < n; ++k)
       if (arcs[off + k].ilabel != 0) parc[off + w++] = arcs[off + k];
     rows[s] = make_uint2((uint32_t)off, (uint32_t)(off + ne));
+    if (ne) epsb[(size_t)s >> 5] |= 1u << (s & 31);
     for (uint32_t k = 0; k < n; ++k) {
       src[off + k] = (uint32_t)s;
       const asrd_arc &a = parc[off + k];
@@ -269,9 +312,11 @@ int asrd_graph_create(const asrd_arc *arcs, const uint32_t *num_arcs, const uint
   g->device = device;
   g->total_arcs = A;
   const size_t b_arcs = sizeof(asrd_arc) * parc.size(), b_rows = sizeof(uint2) * rows.size(),
-               b_src = sizeof(uint32_t) * src.size(), b_par = sizeof(uint32_t) * par.size();
+               b_src = sizeof(uint32_t) * src.size(), b_par = sizeof(uint32_t) * par.size(),
+               b_eps = sizeof(uint32_t) * epsb.size();
   if (cudaMalloc(&g->d_arcs, b_arcs) != cudaSuccess || cudaMalloc(&g->d_rows, b_rows) != cudaSuccess ||
-      cudaMalloc(&g->d_arc_src, b_src) != cudaSuccess || cudaMalloc(&g->d_par, b_par) != cudaSuccess) {
+      cudaMalloc(&g->d_arc_src, b_src) != cudaSuccess || cudaMalloc(&g->d_par, b_par) != cudaSuccess ||
+      cudaMalloc(&g->d_eps, b_eps) != cudaSuccess) {
     asrd_graph_destroy(g);
     return ASRD_ERR_NOMEM;
   }
@@ -279,11 +324,13 @@ int asrd_graph_create(const asrd_arc *arcs, const uint32_t *num_arcs, const uint
   CU_CHECK(cudaMemcpy(g->d_rows, rows.data(), b_rows, cudaMemcpyHostToDevice));
   CU_CHECK(cudaMemcpy(g->d_arc_src, src.data(), b_src, cudaMemcpyHostToDevice));
   CU_CHECK(cudaMemcpy(g->d_par, par.data(), b_par, cudaMemcpyHostToDevice));
-  g->device_bytes = (int64_t)(b_arcs + b_rows + b_src + b_par);
+  CU_CHECK(cudaMemcpy(g->d_eps, epsb.data(), b_eps, cudaMemcpyHostToDevice));
+  g->device_bytes = (int64_t)(b_arcs + b_rows + b_src + b_par + b_eps);
   g->view.arcs = (const int4 *)g->d_arcs;
   g->view.rows = (const uint2 *)g->d_rows;
   g->view.arc_src = (const uint32_t *)g->d_arc_src;
   g->view.par_bits = (const uint32_t *)g->d_par;
+  g->view.eps_bits = (const uint32_t *)g->d_eps;
   g->view.n_states = S;
   g->view.n_arcs = (uint32_t)A;
   g->view.start = start;
@@ -325,6 +372,7 @@ int asrd_graph_destroy(asrd_graph *g) {
   cudaFree(g->d_rows);
   cudaFree(g->d_arc_src);
   cudaFree(g->d_par);
+  cudaFree(g->d_eps);
   delete g;
   return ASRD_OK;
 }
@@ -362,7 +410,7 @@ int asrd_decoder_create(asrd_graph *g, const asrd_config *cfg, const asrd_device
     uint64_t want = (uint64_t)std::min<int64_t>((int64_t)cfg->max_active, 1 << 20) * 8;
     o.hash_capacity = (int32_t)std::min<uint64_t>(std::max<uint64_t>(NextPow2(want), 4096), 1u << 24);
   } else {
-    o.hash_capacity = (int32_t)NextPow2((uint64_t)o.hash_capacity);
+    o.hash_capacity = (int32_t)std::max<uint32_t>(NextPow2((uint64_t)o.hash_capacity), kMinHashCapacity);
   }
   if (o.max_frames <= 0) o.max_frames = 2048;
   if (o.token_capacity <= 0)  // 16 bytes per token record; ~1.5 x max_active survivors per frame
@@ -371,11 +419,11 @@ int asrd_decoder_create(asrd_graph *g, const asrd_config *cfg, const asrd_device
   if (o.token_capacity >= 0xFFFFFFF0ll) return ASRD_ERR_BAD_ARG;
   const size_t H = (size_t)o.hash_capacity;
   auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
-  const size_t b_hash = align(H * sizeof(HashEntry)), b_list = align(H * 4),
+  const size_t b_hash = align(H * sizeof(HashEntry)), b_list = align(H * 4), b_bm = align(H / 8),
                b_tok = align((size_t)o.token_capacity * 8), b_off = align(((size_t)o.max_frames + 2) * 4),
                b_stats = o.collect_stats ? align(((size_t)o.max_frames + 1) * sizeof(asrd_frame_stat)) : 0,
                b_state = align(sizeof(StreamState));
-  const size_t total = b_state + 2 * b_hash + 4 * b_list + 2 * b_tok + b_off + b_stats;
+  const size_t total = b_state + 2 * b_hash + 4 * b_bm + 2 * b_list + 2 * b_tok + b_off + b_stats;
   if (cudaMalloc(&d->slab, total) != cudaSuccess) {
     cudaGetLastError();
     delete d;
@@ -388,7 +436,8 @@ int asrd_decoder_create(asrd_graph *g, const asrd_config *cfg, const asrd_device
   d->d_state = (StreamState *)p; p += b_state;
   h.hash[0] = (HashEntry *)p; p += b_hash;
   h.hash[1] = (HashEntry *)p; p += b_hash;
-  for (int i = 0; i < 2; ++i) { h.slots[i] = (uint32_t *)p; p += b_list; }
+  for (int i = 0; i < 2; ++i) { h.bm[i] = (uint32_t *)p; p += b_bm; }
+  for (int i = 0; i < 2; ++i) { h.ebm[i] = (uint32_t *)p; p += b_bm; }
   for (int i = 0; i < 2; ++i) { h.queue[i] = (uint32_t *)p; p += b_list; }
   h.tok_sc = (uint2 *)p; p += b_tok;
   h.tok_aa = (uint2 *)p; p += b_tok;
@@ -400,8 +449,9 @@ int asrd_decoder_create(asrd_graph *g, const asrd_config *cfg, const asrd_device
   h.hash_shift = 32 - lg;
   h.token_capacity = (uint32_t)o.token_capacity;
   h.max_frames = o.max_frames;
-  // empty maps: key = 0xFFFFFFFF, val = +inf
+  // empty maps: key = 0xFFFFFFFF, val = +inf; empty bitmaps
   if (cudaMemset(h.hash[0], 0xFF, 2 * b_hash) != cudaSuccess ||
+      cudaMemset(h.bm[0], 0, 4 * b_bm) != cudaSuccess ||
       cudaMemcpy(d->d_state, &h, sizeof(h), cudaMemcpyHostToDevice) != cudaSuccess) {
     cudaFree(d->slab);
     delete d;
@@ -427,8 +477,16 @@ int asrd_init_decoding(asrd_decoder *const *decs, int32_t n, void *stream) {
   Scratch sc(s);
   StreamState **d_streams;
   if ((rc = UploadStreams(decs, n, s, sc, &d_streams))) return rc;
-  k_boundary<<<n, kBoundaryThreads, 0, s>>>(d_streams, decs[0]->graph->view, DevCfg(decs[0]), kModeInit);
-  ++g_launches;
+  const GraphView gv = decs[0]->graph->view;
+  const DecoderConfigDev cfg = DevCfg(decs[0]);
+  FrameDesc *d_desc;
+  CU_CHECK(sc.Alloc(&d_desc, (size_t)n));
+  const uint32_t gps = (uint32_t)decs[0]->opts.hash_capacity / 1024;
+  k_init<<<n, kStreamThreads, 0, s>>>(d_streams, d_desc, gv, cfg);
+  k_closure<<<n, kStreamThreads, 0, s>>>(d_desc, gv);
+  k_finalize<<<FinalizeGrid(), kFinThreads, 0, s>>>(d_desc, n, gps, gv, cfg);
+  k_cutoff<<<n, kStreamThreads, 0, s>>>(d_streams, d_desc, gv, cfg, kModeEpi);
+  g_launches += 4;
   CU_CHECK(cudaGetLastError());
   for (int i = 0; i < n; ++i) {
     decs[i]->frames_decoded = 0;
@@ -464,8 +522,12 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
   if ((rc = UploadStreams(decs, n, s, sc, &d_streams))) return rc;
   AdvanceParams *d_params;
   CU_CHECK(sc.Alloc(&d_params, (size_t)n));
-  const int grid = ExpandGrid();
-  const size_t dyn = sizeof(uint32_t) * ((size_t)n + 1);
+  FrameDesc *d_desc;
+  CU_CHECK(sc.Alloc(&d_desc, (size_t)n));
+  ExpandPlan plan;
+  if ((rc = PlanExpand(n, num_indices, &plan))) return rc;
+  const int fin_grid = FinalizeGrid();
+  const uint32_t gps = (uint32_t)decs[0]->opts.hash_capacity / 1024;
   const size_t row = (size_t)num_indices;
 
   // Host log-likelihoods: staged chunk by chunk through two device buffers, copied on a
@@ -521,18 +583,24 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
     }
     CU_CHECK(cudaMemcpyAsync(d_params, hp.data(), sizeof(AdvanceParams) * n, cudaMemcpyHostToDevice, s));
     k_begin_advance<<<(n + 127) / 128, 128, 0, s>>>(d_streams, d_params, n);
-    prof.Begin(1, s);
-    k_boundary<<<n, kBoundaryThreads, 0, s>>>(d_streams, gv, cfg, kModePro);
+    prof.Begin(3, s);
+    k_cutoff<<<n, kStreamThreads, 0, s>>>(d_streams, d_desc, gv, cfg, kModePro);
     prof.End(s);
     g_launches += 2;
     for (int32_t f = 0; f < steps; ++f) {
       prof.Begin(0, s);
-      k_expand<<<grid, kExpandThreads, dyn, s>>>(d_streams, n, gv);
+      plan.fn<<<plan.grid, kExpandThreads, plan.dyn, s>>>(d_desc, gv, num_indices);
       prof.End(s);
       prof.Begin(1, s);
-      k_boundary<<<n, kBoundaryThreads, 0, s>>>(d_streams, gv, cfg, kModeEpi | (f + 1 < steps ? kModePro : 0));
+      k_closure<<<n, kStreamThreads, 0, s>>>(d_desc, gv);
       prof.End(s);
-      g_launches += 2;
+      prof.Begin(2, s);
+      k_finalize<<<fin_grid, kFinThreads, 0, s>>>(d_desc, n, gps, gv, cfg);
+      prof.End(s);
+      prof.Begin(3, s);
+      k_cutoff<<<n, kStreamThreads, 0, s>>>(d_streams, d_desc, gv, cfg, kModeEpi | (f + 1 < steps ? kModePro : 0));
+      prof.End(s);
+      g_launches += 4;
     }
     CU_CHECK(cudaGetLastError());
     if (!on_device) CU_CHECK(cudaEventRecord(ctx->ev_done[k & 1], s));
@@ -667,18 +735,19 @@ int asrd_profile_enable(int on) {
 
 int asrd_profile_reset(void) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
-  g_prof_ms[0] = g_prof_ms[1] = 0;
-  g_prof_n[0] = g_prof_n[1] = 0;
+  for (int i = 0; i < 4; ++i) {
+    g_prof_ms[i] = 0;
+    g_prof_n[i] = 0;
+  }
   return ASRD_OK;
 }
 
-int asrd_profile_get(double *expand_ms, int64_t *expand_launches, double *boundary_ms,
-                     int64_t *boundary_launches) {
+int asrd_profile_get(double *kernel_ms, int64_t *kernel_launches) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
-  if (expand_ms) *expand_ms = g_prof_ms[0];
-  if (expand_launches) *expand_launches = g_prof_n[0];
-  if (boundary_ms) *boundary_ms = g_prof_ms[1];
-  if (boundary_launches) *boundary_launches = g_prof_n[1];
+  for (int i = 0; i < 4; ++i) {
+    if (kernel_ms) kernel_ms[i] = g_prof_ms[i];
+    if (kernel_launches) kernel_launches[i] = g_prof_n[i];
+  }
   return ASRD_OK;
 }
 

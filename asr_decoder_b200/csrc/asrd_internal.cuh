@@ -13,10 +13,11 @@ constexpr uint32_t kNoArc = 0xFFFFFFFFu;
 constexpr unsigned long long kInfVal = 0xFFFFFFFFFFFFFFFFull;
 constexpr uint32_t kOrdInf = 0xFF800000u;  // f2ord(+inf)
 
-constexpr int kExpandThreads = 256;   // CTA size of the expand kernel
-constexpr int kTileTokens = 256;      // tokens staged per CTA tile
-constexpr int kBoundaryThreads = 512; // CTA size of the per-stream frame-boundary kernel
-constexpr int kMaxBatch = 8192;       // streams per launch (tile prefix lives in shared memory)
+constexpr int kExpandThreads = 256;   // CTA size of the expand kernel (8 warps, one token group each)
+constexpr int kFinThreads = 256;      // CTA size of the finalize kernel
+constexpr int kStreamThreads = 1024;  // CTA size of the per-stream kernels (closure, cutoff)
+constexpr int kMaxBatch = 65535;      // streams per launch (gridDim.y of k_expand)
+constexpr int kMinHashCapacity = 4096;
 
 // One slot of the per-frame state->token map.  val = (ordered cost << 32) | global arc id,
 // recombined with a single 64-bit atomicMin: lowest cost wins, equal cost -> lowest arc id.
@@ -33,6 +34,7 @@ struct GraphView {
   const uint2 *rows;       // [S+1] {row_off, emit_off}: eps span [x, y), emitting span [y, rows[s+1].x)
   const uint32_t *arc_src; // [A] source state of every arc
   const uint32_t *par_bits;// [ceil(A/32)] arc has a same-class sibling with the same (src, dst)
+  const uint32_t *eps_bits;// [ceil(S/32)] state has at least one input-epsilon arc
   int32_t n_states;
   uint32_t n_arcs;
   int32_t start;
@@ -43,7 +45,8 @@ struct GraphView {
 struct StreamState {
   // ---- buffers
   HashEntry *hash[2];   // state->token maps; frame f lives in hash[f & 1]
-  uint32_t *slots[2];   // claimed-slot lists of the two maps
+  uint32_t *bm[2];      // claimed-slot bitmaps of the two maps (capacity / 32 words)
+  uint32_t *ebm[2];     // ... of which the state has eps arcs (seeds of the eps closure)
   uint32_t *queue[2];   // eps-closure frontier queues
   uint2 *tok_sc;        // token arena: {state, cost bits}
   uint2 *tok_aa;        // token arena: {reported arc id, acoustic cost bits}
@@ -53,28 +56,52 @@ struct StreamState {
   uint32_t hash_shift;  // 32 - log2(capacity)
   uint32_t token_capacity;
   int32_t max_frames;
-  // ---- search state
+  // ---- search state that survives between AdvanceDecoding calls
   int32_t frame;        // frames decoded so far == index of the current token span
   int32_t status;       // sticky ASRD_ERR_* raised by kernels
-  uint32_t n_slots[2];
   uint32_t n_cur;       // tokens in the current frame
-  float cur_cut;        // GetCutoff result for the current frame
-  float abeam;          // adaptive beam for the current frame
-  uint32_t next_cut_bits;  // running next_cutoff (ordered uint, atomicMin)
-  uint32_t arcs_expanded;
-  uint32_t arcs_admitted;
-  uint32_t tiles;       // expand tiles of the current frame (0 when the stream is idle)
   int32_t finalized;
+  unsigned long long best64;  // (ordered cost << 32 | state) of the best token of the current frame
   // ---- this AdvanceDecoding call
   const float *ll_base; // row of frame ll_frame0
   int32_t ll_stride;
   int32_t ll_frame0;
   int32_t target_frame; // decode while frame < target_frame
-  int32_t pad0;
+  int32_t pad1;
   // ---- utterance totals
   unsigned long long tot_arcs_expanded;
   unsigned long long tot_arcs_admitted;
 };
+
+// Per-stream descriptor of the frame step in flight: everything the grid-wide kernels need, in
+// one contiguous 128-byte record per stream (one L2 round trip instead of a pointer chase
+// through StreamState).  Rebuilt by k_cutoff(PRO) / k_init for every step; the running cutoff,
+// survivor counter and best token are accumulated here with atomics.
+struct __align__(16) FrameDesc {
+  StreamState *st;
+  const uint2 *toks;    // tokens of frame t (being expanded)
+  const float *ll;      // log-likelihood row of frame t
+  HashEntry *hn;        // map of frame t+1
+  HashEntry *hc;        // map of frame t
+  uint32_t *bm;         // claimed-slot bitmap of hn
+  uint32_t *ebm;        // eps-seed bitmap of hn
+  uint2 *out_sc;        // arena write window of frame t+1
+  uint2 *out_aa;
+  unsigned long long best64;
+  uint32_t n_cur;
+  float cur_cut;
+  float abeam;
+  uint32_t next_cut_bits;  // running next_cutoff (ordered uint, atomicMin)
+  uint32_t mask;
+  uint32_t shift;
+  uint32_t out_cap;
+  uint32_t n_alive;
+  uint32_t arcs_expanded;
+  uint32_t arcs_admitted;
+  int32_t stepping;
+  int32_t t;            // frame being expanded; -1 while InitDecoding completes frame 0
+};
+static_assert(sizeof(FrameDesc) == 128, "FrameDesc is one 128-byte line");
 
 struct AdvanceParams {
   const float *ll;
@@ -117,7 +144,7 @@ __host__ __device__ inline float ord2f(uint32_t o) {
 struct asrd_graph {
   int device;
   asrd::GraphView view;
-  void *d_arcs, *d_rows, *d_arc_src, *d_par;
+  void *d_arcs, *d_rows, *d_arc_src, *d_par, *d_eps;
   int64_t device_bytes;
   int64_t total_arcs;
 };

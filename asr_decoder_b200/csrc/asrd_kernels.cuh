@@ -1,13 +1,17 @@
 // Hand-written sm_100a kernels of the WFST token-passing beam search.
 //
-// Per decoded frame two launches serve ALL streams of a batch:
-//   k_expand    — load-balanced emitting-arc expansion (ProcessEmitting's hot loop,
+// Per decoded frame four launches serve ALL streams of a batch; all of them are warp-centric
+// (one warp per group of 32 tokens / 1024 map slots, work split by warp-shuffle prefix sums,
+// no block barriers on the hot paths):
+//   k_expand    — emitting-arc expansion (ProcessEmitting's hot loop,
 //                 reference src/my-decoder/online-decoder-base-inl.h:311-347)
-//   k_boundary  — one CTA per stream: eps closure (ProcessNonemitting, inl.h:353-431),
-//                 survivor compaction into the token arena, sibling-link resolution for the
-//                 trace-back (inl.h:1169-1186 + the lattice-beam link pruning of
-//                 inl.h:524-542), GetCutoff for the next frame (inl.h:138-234) and the
-//                 best-token pre-pass (inl.h:282-300).
+//   k_closure   — one CTA per stream: eps closure (ProcessNonemitting, inl.h:353-431) as
+//                 frontier rounds seeded from a bitmap of newly claimed eps states
+//   k_finalize  — over the claimed-slot bitmaps: survivors (cost < final cutoff) are appended to
+//                 the token arena with the arc the reference's trace-back would report
+//                 (inl.h:1169-1186 + the lattice-beam link pruning of inl.h:524-542)
+//   k_cutoff    — one CTA per stream: recycle the previous map, GetCutoff for the next frame
+//                 (inl.h:138-234, exact radix select) and the best-token pre-pass (inl.h:282-300)
 // k_best_path walks the back-trace (BestPathEnd / TraceBackBestPath, inl.h:1096-1200).
 #pragma once
 
@@ -20,9 +24,11 @@ namespace asrd {
 // ------------------------------------------------------------------ small helpers
 
 __device__ __forceinline__ uint32_t hash_state(uint32_t s, uint32_t mask, uint32_t shift) {
-  // Locality preserving: neighbouring states (the common case in HCLG rows) land in
-  // neighbouring slots, i.e. the same 32-byte sectors; the high bits decorrelate aliases.
-  return (s + (s >> (32u - shift)) * 0x9E3779B1u) & mask;
+  // Fibonacci hashing: the active states of a frame come in dense runs of neighbouring ids;
+  // the multiplicative scramble spreads them uniformly over the map, which keeps linear-probe
+  // chains short AND balances the per-1024-slot work groups of k_closure / k_finalize.
+  (void)mask;
+  return (s * 0x9E3779B1u) >> shift;
 }
 
 __device__ __forceinline__ unsigned long long pack_val(float cost, uint32_t arc) {
@@ -33,29 +39,24 @@ __device__ __forceinline__ bool par_bit(const uint32_t *bits, uint32_t arc) {
   return (__ldg(&bits[arc >> 5]) >> (arc & 31u)) & 1u;
 }
 
-// Find-or-claim `state` and recombine with atomicMin (FindOrAddToken, inl.h:88-136).
-__device__ __forceinline__ bool hash_insert(HashEntry *tab, uint32_t mask, uint32_t shift,
-                                            uint32_t state, unsigned long long packed,
-                                            uint32_t &slot, bool &is_new, unsigned long long &old) {
-  uint32_t h = hash_state(state, mask, shift);
-  is_new = false;
+// Find-or-claim the slot of `state` (FindOrAddToken, inl.h:88-136): CAS first, so a new
+// state costs one L2 round trip and an existing one as well.
+__device__ __forceinline__ bool hash_claim(HashEntry *tab, uint32_t mask, uint32_t h, uint32_t state,
+                                           uint32_t &slot, bool &is_new) {
   for (uint32_t probe = 0; probe <= mask; ++probe) {
-    uint32_t k = __ldcg(&tab[h].key);
-    if (k == kEmptyKey) {
-      k = atomicCAS(&tab[h].key, kEmptyKey, state);
-      if (k == kEmptyKey) {
-        is_new = true;
-        k = state;
-      }
-    }
-    if (k == state) {
-      old = atomicMin(&tab[h].val, packed);
+    const uint32_t k = atomicCAS(&tab[h].key, kEmptyKey, state);
+    if (k == kEmptyKey || k == state) {
+      is_new = (k == kEmptyKey);
       slot = h;
       return true;
     }
     h = (h + 1) & mask;
   }
   return false;
+}
+
+__device__ __forceinline__ bool eps_bit(const uint32_t *bits, uint32_t state) {
+  return (__ldg(&bits[state >> 5]) >> (state & 31u)) & 1u;
 }
 
 __device__ __forceinline__ bool hash_find(const HashEntry *tab, uint32_t mask, uint32_t shift,
@@ -147,7 +148,106 @@ __device__ __forceinline__ uint32_t block_sum_u32(uint32_t v, uint32_t *s_red) {
   return v;
 }
 
-// ------------------------------------------------------------------ begin-advance
+// ------------------------------------------------------------------ warp work splitting
+
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t n = __shfl_up_sync(kFull, v, d);
+    if (lane >= d) v += n;
+  }
+  return v;
+}
+
+// Lane that owns flattened item j, given each lane's exclusive prefix `off`: the last lane l
+// with off_l <= j (lanes with zero items never win because their successor shares the offset).
+// Must be called by the full warp.
+__device__ __forceinline__ int warp_owner(uint32_t off, uint32_t j) {
+  int l = 0;
+#pragma unroll
+  for (int step = 16; step > 0; step >>= 1) {
+    const uint32_t v = __shfl_sync(kFull, off, l + step);
+    if (v <= j) l += step;
+  }
+  return l;
+}
+
+// ------------------------------------------------------------------ init / begin-advance
+
+__device__ __forceinline__ void clear_map_by_bitmap(HashEntry *h, uint32_t *bm, uint32_t words, int warp,
+                                                    int lane, int n_warps) {
+  // lane b of a warp recycles slot b of the warp's current word: 512 contiguous bytes per word
+  for (uint32_t w = warp; w < words; w += n_warps) {
+    const uint32_t bits = bm[w];
+    if (bits) {
+      if ((bits >> lane) & 1u) {
+        HashEntry e;
+        e.key = kEmptyKey; e.aux = 0; e.val = kInfVal;
+        h[w * 32 + lane] = e;
+      }
+      __syncwarp();
+      if (lane == 0) bm[w] = 0;
+    }
+  }
+}
+
+// InitDecoding (inl.h:41-67): forget the previous utterance and seed the start token; the
+// closure / finalize / cutoff kernels that follow complete frame 0 with cutoff = beam.
+__global__ void __launch_bounds__(kStreamThreads)
+k_init(StreamState *const *streams, FrameDesc *desc, GraphView g, DecoderConfigDev cfg) {
+  StreamState *st = streams[blockIdx.x];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t mask = st->hash_mask;
+  const uint32_t words = (mask + 1) >> 5;
+  for (int w = 0; w < 2; ++w) {
+    clear_map_by_bitmap(st->hash[w], st->bm[w], words, warp, lane, kStreamThreads / 32);
+    uint32_t *ebm = st->ebm[w];
+    for (uint32_t i = tid; i < words; i += kStreamThreads) ebm[i] = 0;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    st->status = 0;
+    st->finalized = 0;
+    st->frame = -1;
+    st->target_frame = 0;
+    st->frame_off[0] = 0;
+    st->n_cur = 0;
+    st->best64 = kInfVal;
+    st->tot_arcs_expanded = st->tot_arcs_admitted = 0;
+    uint32_t slot;
+    bool is_new;
+    HashEntry *hn = st->hash[0];
+    hash_claim(hn, mask, hash_state((uint32_t)g.start, mask, st->hash_shift), (uint32_t)g.start, slot, is_new);
+    atomicMin(&hn[slot].val, pack_val(0.0f, kNoArc));
+    st->bm[0][slot >> 5] = 1u << (slot & 31u);
+    if (eps_bit(g.eps_bits, (uint32_t)g.start)) st->ebm[0][slot >> 5] = 1u << (slot & 31u);
+    FrameDesc d;
+    d.st = st;
+    d.toks = nullptr;
+    d.ll = nullptr;
+    d.hn = hn;
+    d.hc = st->hash[1];
+    d.bm = st->bm[0];
+    d.ebm = st->ebm[0];
+    d.out_sc = st->tok_sc;
+    d.out_aa = st->tok_aa;
+    d.best64 = kInfVal;
+    d.n_cur = 0;
+    d.cur_cut = 0.f;
+    d.abeam = 0.f;
+    d.next_cut_bits = f2ord(cfg.beam);
+    d.mask = mask;
+    d.shift = st->hash_shift;
+    d.out_cap = st->token_capacity;
+    d.n_alive = 0;
+    d.arcs_expanded = d.arcs_admitted = 0;
+    d.stepping = 1;
+    d.t = -1;
+    desc[blockIdx.x] = d;
+  }
+}
 
 __global__ void k_begin_advance(StreamState *const *streams, const AdvanceParams *params, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -167,187 +267,375 @@ __global__ void k_begin_advance(StreamState *const *streams, const AdvanceParams
 
 // ------------------------------------------------------------------ expand
 
-// Grid: persistent, a multiple of the SM count.  Every CTA scans the per-stream tile
-// counts into shared memory, then takes tiles round-robin.  A tile = kTileTokens tokens of
-// one stream; their emitting-arc spans are flattened through a shared-memory prefix so
-// that consecutive threads fetch consecutive 16-byte arc records (LDG.128).
-__global__ void __launch_bounds__(kExpandThreads)
-k_expand(StreamState *const *streams, int n_streams, GraphView g) {
-  extern __shared__ uint32_t s_dyn[];        // [n_streams + 1] tile prefix
-  __shared__ uint32_t s_warp[kExpandThreads / 32 + 1];
-  __shared__ uint32_t s_off[kTileTokens + 1];
-  __shared__ uint32_t s_base[kTileTokens];
-  __shared__ float s_cost[kTileTokens];
-  __shared__ uint32_t s_cnt[2];
-
-  const int tid = threadIdx.x;
-  const int lane = tid & 31;
-
-  // ---- tile prefix over streams
-  {
-    const int per = (n_streams + kExpandThreads - 1) / kExpandThreads;
-    const int b = tid * per;
-    uint32_t sum = 0;
-    for (int s = b; s < b + per && s < n_streams; ++s) sum += streams[s]->tiles;
-    uint32_t total;
-    uint32_t excl = block_exclusive_scan<kExpandThreads>(sum, s_warp, total);
-    for (int s = b; s < b + per && s < n_streams; ++s) {
-      s_dyn[s] = excl;
-      excl += streams[s]->tiles;
-    }
-    if (tid == 0) s_dyn[n_streams] = total;
+// Grid (G, n_streams): blockIdx.y is the stream, its CTAs share the stream's token groups.
+// One warp owns a group of 32 tokens: lane i loads token i and its emitting-arc span, a
+// shuffle prefix sum flattens the spans, and the lanes then walk the flattened arc list so
+// consecutive lanes fetch consecutive 16-byte arc records (LDG.128).  U x 32 arcs per warp are
+// in flight per iteration.  The stream's log-likelihood row is staged in shared memory once
+// per CTA (the only block barrier).  Token recombination: one 64-bit atomicMin per admitted
+// arc on (ordered cost << 32 | arc id) in the per-frame state->token map.
+template <int U, bool SMEM_LL>
+__global__ void __launch_bounds__(kExpandThreads, U == 1 ? 8 : 5)
+k_expand(FrameDesc *desc, GraphView g, int num_indices) {
+  extern __shared__ float s_ll[];
+  FrameDesc *d = &desc[blockIdx.y];
+  if (!d->stepping) return;
+  const uint32_t n_cur = d->n_cur;
+  const uint32_t n_groups = (n_cur + 31) >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const uint32_t warp_global = blockIdx.x * (kExpandThreads / 32) + (tid >> 5);
+  const uint32_t n_warps = gridDim.x * (kExpandThreads / 32);
+  if (blockIdx.x * (kExpandThreads / 32) >= n_groups) return;  // whole CTA idle
+  const float *__restrict__ ll = d->ll;
+  if (SMEM_LL) {
+    for (int c = tid; c < num_indices; c += kExpandThreads) s_ll[c] = __ldg(&ll[c]);
     __syncthreads();
   }
-  const uint32_t total_tiles = s_dyn[n_streams];
+  const uint2 *__restrict__ toks = d->toks;
+  const float cur_cut = d->cur_cut, abeam = d->abeam;
+  HashEntry *hn = d->hn;
+  uint32_t *bm = d->bm, *ebm = d->ebm;
+  const uint32_t mask = d->mask, shift = d->shift;
+  uint32_t *next_cut = &d->next_cut_bits;
 
-  for (uint32_t gt = blockIdx.x; gt < total_tiles; gt += gridDim.x) {
-    // stream of this tile: last s with prefix[s] <= gt
-    int lo = 0, hi = n_streams;  // invariant: prefix[lo] <= gt < prefix[hi]
-    while (hi - lo > 1) {
-      int mid = (lo + hi) >> 1;
-      if (s_dyn[mid] <= gt) lo = mid; else hi = mid;
-    }
-    StreamState *st = streams[lo];
-    const uint32_t tile = gt - s_dyn[lo];
-    const int frame = st->frame;
-    const uint32_t n_cur = st->n_cur;
-    const float cur_cut = st->cur_cut;
-    const float abeam = st->abeam;
-    const uint32_t tok_base = st->frame_off[frame];
-    const float *__restrict__ ll = st->ll_base + (size_t)(frame - st->ll_frame0) * st->ll_stride;
-    HashEntry *hn = st->hash[(frame + 1) & 1];
-    uint32_t *slots = st->slots[(frame + 1) & 1];
-    uint32_t *n_slots = &st->n_slots[(frame + 1) & 1];
-    const uint32_t mask = st->hash_mask, shift = st->hash_shift;
-    uint32_t *next_cut = &st->next_cut_bits;
-
-    // ---- stage the tile: per-token emitting span
-    const uint32_t i = tile * kTileTokens + tid;
-    uint32_t deg = 0, base = 0;
-    float cost = 0.f;
+  uint32_t expanded = 0, admitted = 0;
+  for (uint32_t grp = warp_global; grp < n_groups; grp += n_warps) {
+    // ---- lane i: token i of the group and its emitting span
+    const uint32_t i = grp * 32 + lane;
+    uint32_t deg = 0, base = 0, cost_bits = 0;
     if (i < n_cur) {
-      uint2 sc = st->tok_sc[tok_base + i];
-      cost = __uint_as_float(sc.y);
-      if (cost <= cur_cut) {  // inclusive, inl.h:315
-        uint2 r0 = __ldg(&g.rows[sc.x]);
-        uint32_t end = __ldg(&g.rows[sc.x + 1]).x;
+      const uint2 sc = __ldg(&toks[i]);
+      cost_bits = sc.y;
+      if (__uint_as_float(sc.y) <= cur_cut) {  // inclusive, inl.h:315
+        const uint2 r0 = __ldg(&g.rows[sc.x]);
+        const uint32_t end = __ldg(&g.rows[sc.x + 1]).x;
         base = r0.y;
         deg = end - r0.y;
       }
     }
-    uint32_t total;
-    uint32_t off = block_exclusive_scan<kExpandThreads>(deg, s_warp, total);
-    s_off[tid] = off;
-    s_base[tid] = base;
-    s_cost[tid] = cost;
-    if (tid == 0) {
-      s_off[kTileTokens] = total;
-      s_cnt[0] = 0;
-    }
-    __syncthreads();
+    const uint32_t incl = warp_incl_scan(deg, lane);
+    const uint32_t off = incl - deg;
+    const uint32_t total = __shfl_sync(kFull, incl, 31);
+    expanded += total;
 
-    uint32_t admitted = 0;
-    for (uint32_t jb = 0; jb < total; jb += kExpandThreads) {
-      const uint32_t j = jb + tid;
-      const bool in = j < total;
-      bool need_cut = false, is_new = false;
-      uint32_t cand_bits = 0xFFFFFFFFu, slot = 0;
-      if (in) {
-        // owner token: last t with s_off[t] <= j
-        int l = 0, h = kTileTokens;
-        while (h - l > 1) {
-          int m = (l + h) >> 1;
-          if (s_off[m] <= j) l = m; else h = m;
-        }
-        const uint32_t a = s_base[l] + (j - s_off[l]);
-        const int4 arc = __ldg(&g.arcs[a]);
-        const float ac = -__ldg(&ll[arc.x - 1]);
-        const float tot = (s_cost[l] + ac) + __int_as_float(arc.z);  // inl.h:326-329
-        const float nc = ord2f(*(volatile uint32_t *)next_cut);
-        if (tot < nc) {  // inl.h:330 (running cutoff; the boundary kernel applies the final one)
-          const float cand = tot + abeam;
-          if (cand < nc) {
-            need_cut = true;
-            cand_bits = f2ord(cand);
+    for (uint32_t jb = 0; jb < total; jb += 32 * U) {
+      const float nc = ord2f(*(volatile uint32_t *)next_cut);  // running cutoff, inl.h:330
+      bool in[U];
+      uint32_t a[U];
+      float tcost[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t j = jb + u * 32 + lane;
+        in[u] = j < total;
+        const int l = warp_owner(off, j);
+        const uint32_t off_l = __shfl_sync(kFull, off, l);
+        const uint32_t base_l = __shfl_sync(kFull, base, l);
+        tcost[u] = __uint_as_float(__shfl_sync(kFull, cost_bits, l));
+        a[u] = base_l + (j - off_l);
+      }
+      int4 arc[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (in[u]) arc[u] = __ldg(&g.arcs[a[u]]);
+      float tot[U];
+      bool adm[U];
+      uint32_t h0[U], k0[U];
+      bool epsb[U];
+      uint32_t cand_bits = 0xFFFFFFFFu;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        adm[u] = false;
+        tot[u] = 0.f;
+        h0[u] = 0;
+        k0[u] = 0;
+        epsb[u] = false;
+        if (in[u]) {
+          const float ac = -(SMEM_LL ? s_ll[arc[u].x - 1] : __ldg(&ll[arc[u].x - 1]));
+          tot[u] = (tcost[u] + ac) + __int_as_float(arc[u].z);  // inl.h:326-329
+          adm[u] = tot[u] < nc;
+          if (adm[u]) {
+            const float cand = tot[u] + abeam;  // inl.h:332-333
+            if (cand < nc) cand_bits = min(cand_bits, f2ord(cand));
+            h0[u] = hash_state((uint32_t)arc[u].w, mask, shift);
+            k0[u] = __ldcg(&hn[h0[u]].key);  // first probe of every admitted arc in flight together
+            epsb[u] = eps_bit(g.eps_bits, (uint32_t)arc[u].w);
           }
-          unsigned long long old;
-          if (!hash_insert(hn, mask, shift, (uint32_t)arc.w, pack_val(tot, a), slot, is_new, old))
-            atomicMin(&st->status, ASRD_ERR_HASH_OVERFLOW);
-          ++admitted;
         }
       }
       // warp-aggregated cutoff tightening (inl.h:332-333)
-      if (__any_sync(0xFFFFFFFFu, need_cut)) {
-        uint32_t wmin = __reduce_min_sync(0xFFFFFFFFu, cand_bits);
+      if (__any_sync(kFull, cand_bits != 0xFFFFFFFFu)) {
+        const uint32_t wmin = __reduce_min_sync(kFull, cand_bits);
         if (lane == 0) atomicMin(next_cut, wmin);
       }
-      // warp-aggregated append of newly claimed slots
-      const unsigned newm = __ballot_sync(0xFFFFFFFFu, is_new);
-      if (newm) {
-        uint32_t pos0 = 0;
-        if (lane == 0) pos0 = atomicAdd(n_slots, __popc(newm));
-        pos0 = __shfl_sync(0xFFFFFFFFu, pos0, 0);
-        if (is_new) slots[pos0 + __popc(newm & ((1u << lane) - 1u))] = slot;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (adm[u]) {
+          const uint32_t state = (uint32_t)arc[u].w;
+          uint32_t slot = h0[u];
+          bool is_new = false, ok = k0[u] == state;
+          if (!ok) {
+            ok = hash_claim(hn, mask, h0[u], state, slot, is_new);
+          }
+          if (ok) {
+            atomicMin(&hn[slot].val, pack_val(tot[u], a[u]));
+            if (is_new) {
+              atomicOr(&bm[slot >> 5], 1u << (slot & 31u));
+              if (epsb[u]) atomicOr(&ebm[slot >> 5], 1u << (slot & 31u));
+            }
+          } else {
+            atomicMin(&d->st->status, ASRD_ERR_HASH_OVERFLOW);
+          }
+          ++admitted;
+        }
       }
     }
-    admitted = __reduce_add_sync(0xFFFFFFFFu, admitted);
-    if (lane == 0 && admitted) atomicAdd(&s_cnt[0], admitted);
-    __syncthreads();
-    if (tid == 0) {
-      atomicAdd(&st->arcs_expanded, total);
-      atomicAdd(&st->arcs_admitted, s_cnt[0]);
-    }
-    __syncthreads();
+  }
+  admitted = __reduce_add_sync(kFull, admitted);
+  if (lane == 0 && expanded) {
+    atomicAdd(&d->arcs_expanded, expanded);
+    atomicAdd(&d->arcs_admitted, admitted);
   }
 }
 
-// ------------------------------------------------------------------ frame boundary
+// ------------------------------------------------------------------ eps closure
 
-enum { kModeInit = 1, kModeEpi = 2, kModePro = 4 };
+// ProcessNonemitting (inl.h:353-431) for the frame being completed, one CTA per stream.
+// Round 1 takes the newly claimed states that have eps arcs (bitmap filled by k_expand);
+// later rounds take the states whose cost dropped (inl.h:425-426), de-duplicated by a round
+// stamp.  min-plus relaxation with a static cutoff has a unique fixed point, so the parallel
+// rounds end with exactly the reference's token costs.
+__global__ void __launch_bounds__(kStreamThreads, 2)
+k_closure(FrameDesc *desc, GraphView g) {
+  constexpr int NT = kStreamThreads;
+  __shared__ uint32_t s_qn[2];
+  FrameDesc *d = &desc[blockIdx.x];
+  if (!d->stepping) return;
+  StreamState *st = d->st;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t mask = d->mask, shift = d->shift;
+  const uint32_t groups = (mask + 1) >> 10;  // 32 bitmap words (1024 slots) per group
+  HashEntry *hn = d->hn;
+  uint32_t *bm = d->bm;
+  uint32_t *ebm = d->ebm;
+  const float nc = ord2f(d->next_cut_bits);  // the FINAL next_cutoff of this frame
+  uint32_t *q0 = st->queue[0], *q1 = st->queue[1];
+  if (tid == 0) s_qn[0] = s_qn[1] = 0;
+  __syncthreads();
 
-// exact k-th smallest (0-based) cost among the tokens [base, base+n) restricted to keys
-// below `limit_ord` (exclusive; 0xFFFFFFFF = no limit): what std::nth_element yields in
-// GetCutoff (inl.h:190-193, 211-216).  MSB-first radix select over (ordered key - min key).
+  auto relax_from = [&](uint32_t slot, uint32_t round) {
+    const uint4 e = __ldcg(reinterpret_cast<const uint4 *>(&hn[slot]));
+    const uint32_t state = e.x;
+    const float cost = ord2f(e.w);
+    if (!(cost < nc)) return;  // inl.h:391
+    const uint2 r = __ldg(&g.rows[state]);
+    uint32_t *qout = ((round + 1) & 1) ? q1 : q0;
+    for (uint32_t a = r.x; a < r.y; ++a) {
+      const int4 arc = __ldg(&g.arcs[a]);
+      const float tot = cost + __int_as_float(arc.z);  // inl.h:413-414
+      if (tot < nc) {                                   // inl.h:415
+        uint32_t slot2;
+        bool is_new;
+        if (!hash_claim(hn, mask, hash_state((uint32_t)arc.w, mask, shift), (uint32_t)arc.w, slot2, is_new)) {
+          atomicMin(&st->status, ASRD_ERR_HASH_OVERFLOW);
+          continue;
+        }
+        const unsigned long long pk = pack_val(tot, a);
+        const unsigned long long old = atomicMin(&hn[slot2].val, pk);
+        if (is_new) atomicOr(&bm[slot2 >> 5], 1u << (slot2 & 31u));
+        const bool changed = (uint32_t)(pk >> 32) < (uint32_t)(old >> 32);  // inl.h:115-127
+        if (changed && eps_bit(g.eps_bits, (uint32_t)arc.w) &&
+            atomicExch(&hn[slot2].aux, round + 1) != round + 1)
+          qout[atomicAdd(&s_qn[(round + 1) & 1], 1u)] = slot2;  // inl.h:425-426
+      }
+    }
+  };
+
+  // round 1 (inl.h:376-381): gather the seeds into the queue first so that the relaxation work
+  // is spread evenly over the CTA no matter how the set bits cluster
+  for (uint32_t w = tid; w < (groups << 5); w += NT) {
+    uint32_t bits = ebm[w];
+    if (bits) {
+      ebm[w] = 0;
+      uint32_t pos = atomicAdd(&s_qn[1], (uint32_t)__popc(bits));
+      while (bits) {
+        const uint32_t b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        q1[pos++] = (w << 5) + b;
+      }
+    }
+  }
+  for (uint32_t round = 1;; ++round) {
+    __syncthreads();
+    const uint32_t nq = s_qn[round & 1];
+    if (nq == 0) break;
+    __syncthreads();
+    if (tid == 0) s_qn[(round + 1) & 1] = 0;
+    __syncthreads();
+    const uint32_t *qin = (round & 1) ? q1 : q0;
+    for (uint32_t i = tid; i < nq; i += NT) relax_from(qin[i], round);
+  }
+}
+
+// ------------------------------------------------------------------ finalize
+
+// One warp per 1024 map slots (32 bitmap words) of a stepping stream: the set bits are spread
+// over the lanes by rank; survivors (cost < final next_cutoff) get a token record at a
+// warp-aggregated arena position.
+__global__ void __launch_bounds__(kFinThreads)
+k_finalize(FrameDesc *desc, int n_streams, uint32_t groups_per_stream, GraphView g, DecoderConfigDev cfg) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  const uint32_t warp_global = blockIdx.x * (kFinThreads / 32) + (tid >> 5);
+  const uint32_t n_warps = gridDim.x * (kFinThreads / 32);
+  const uint32_t total_groups = groups_per_stream * (uint32_t)n_streams;
+
+  for (uint32_t c = warp_global; c < total_groups; c += n_warps) {
+    const uint32_t s = c / groups_per_stream, grp = c % groups_per_stream;
+    FrameDesc *d = &desc[s];
+    if (!d->stepping) continue;
+    const uint32_t word = __ldcg(&d->bm[grp * 32 + lane]);
+    if (!__any_sync(kFull, word != 0)) continue;
+    const uint32_t cnt = __popc(word);
+    const uint32_t incl = warp_incl_scan(cnt, lane);
+    const uint32_t off = incl - cnt;
+    const uint32_t total = __shfl_sync(kFull, incl, 31);
+    HashEntry *hn = d->hn;
+    HashEntry *hc = d->hc;
+    const uint32_t mask = d->mask, shift = d->shift;
+    const float nc = ord2f(d->next_cut_bits);
+    const float *__restrict__ ll = d->ll;
+    const uint32_t cap = d->out_cap;
+    unsigned long long best64 = kInfVal;
+
+    for (uint32_t ib = 0; ib < total; ib += 32) {
+      const uint32_t it = ib + lane;
+      const int l = warp_owner(off, it);
+      const uint32_t wl = __shfl_sync(kFull, word, l);
+      const uint32_t offl = __shfl_sync(kFull, off, l);
+      bool alive = false;
+      uint32_t key = 0, rep = kNoArc;
+      float cost = 0.f, ac = 0.f;
+      if (it < total) {
+        const uint32_t b = __fns(wl, 0, (int)(it - offl) + 1);
+        const uint32_t slot = ((grp * 32 + l) << 5) + b;
+        const uint4 e = __ldcg(reinterpret_cast<const uint4 *>(&hn[slot]));
+        key = e.x;
+        rep = e.z;  // low word of val = winning arc
+        cost = ord2f(e.w);
+        alive = cost < nc;
+      }
+      const unsigned am = __ballot_sync(kFull, alive);
+      if (am == 0) continue;
+      uint32_t pos0 = 0;
+      if (lane == 0) pos0 = atomicAdd(&d->n_alive, (uint32_t)__popc(am));
+      if (alive && rep != kNoArc) {
+        const int4 arc = __ldg(&g.arcs[rep]);
+        const bool emitting = arc.x != 0;
+        if (emitting) ac = -__ldg(&ll[arc.x - 1]);
+        if (par_bit(g.par_bits, rep)) {
+          // The reference reports, for the step pred -> tok, the most recently added
+          // surviving forward link (inl.h:1169-1186); links are prepended in arc order
+          // (inl.h:340-341) and excised when link_extra_cost > lattice_beam (inl.h:524-542),
+          // which for a best-path token is (tot' - tok.cost) > lattice_beam.
+          const uint32_t src = __ldg(&g.arc_src[rep]);
+          const uint2 r = __ldg(&g.rows[src]);
+          unsigned long long pv;
+          if (emitting) {
+            const uint32_t end = __ldg(&g.rows[src + 1]).x;
+            if (hash_find(hc, mask, shift, src, pv)) {
+              const float pc = ord2f((uint32_t)(pv >> 32));
+              for (uint32_t a2 = end; a2-- > rep + 1;) {
+                const int4 arc2 = __ldg(&g.arcs[a2]);
+                if ((uint32_t)arc2.w != key) continue;
+                const float ac2 = -__ldg(&ll[arc2.x - 1]);
+                const float tot2 = (pc + ac2) + __int_as_float(arc2.z);
+                if (tot2 < nc && !((tot2 - cost) > cfg.lattice_beam)) {
+                  rep = a2;
+                  ac = ac2;
+                  break;
+                }
+              }
+            }
+          } else {
+            if (hash_find(hn, mask, shift, src, pv)) {
+              const float pc = ord2f((uint32_t)(pv >> 32));
+              for (uint32_t a2 = r.y; a2-- > rep + 1;) {
+                const int4 arc2 = __ldg(&g.arcs[a2]);
+                if ((uint32_t)arc2.w != key) continue;
+                const float tot2 = pc + __int_as_float(arc2.z);
+                if (pc < nc && tot2 < nc && !((tot2 - cost) > cfg.lattice_beam)) {
+                  rep = a2;
+                  break;
+                }
+              }
+            }
+          }
+        }
+      }
+      pos0 = __shfl_sync(kFull, pos0, 0);
+      if (alive) {
+        const uint32_t idx = pos0 + __popc(am & ((1u << lane) - 1u));
+        if (idx < cap) {
+          d->out_sc[idx] = make_uint2(key, __float_as_uint(cost));
+          d->out_aa[idx] = make_uint2(rep, __float_as_uint(ac));
+        }
+        const unsigned long long b64 = ((unsigned long long)f2ord(cost) << 32) | key;
+        best64 = b64 < best64 ? b64 : best64;
+      }
+    }
+#pragma unroll
+    for (int dlt = 16; dlt > 0; dlt >>= 1) {
+      const unsigned long long o = __shfl_xor_sync(kFull, best64, dlt);
+      best64 = o < best64 ? o : best64;
+    }
+    if (lane == 0 && best64 != kInfVal) atomicMin(&d->best64, best64);
+  }
+}
+
+// ------------------------------------------------------------------ cutoff
+
+enum { kModeEpi = 2, kModePro = 4 };
+
+// exact k-th smallest (0-based) cost among the tokens with ordered key < limit_ord: what
+// std::nth_element yields in GetCutoff (inl.h:190-193, 211-216).  MSB-first radix select over
+// (ordered key - min key), starting at the top byte of `range` (an upper bound of that span).
 template <int NT>
 __device__ float block_kth_smallest(const uint2 *tok_sc, uint32_t n, uint32_t k, uint32_t min_ord,
-                                    uint32_t limit_ord, uint32_t *s_hist, uint32_t *s_misc) {
+                                    uint32_t limit_ord, uint32_t range, uint32_t *s_hist, uint32_t *s_misc) {
   const int tid = threadIdx.x;
-  // highest relative key
-  uint32_t kmax = 0;
-  for (uint32_t i = tid; i < n; i += NT) {
-    uint32_t key = f2ord(__uint_as_float(tok_sc[i].y));
-    if (key < limit_ord) kmax = max(kmax, key - min_ord);
-  }
-  kmax = __reduce_max_sync(0xFFFFFFFFu, kmax);
-  if (tid == 0) s_misc[0] = 0;
-  __syncthreads();
-  if ((tid & 31) == 0) atomicMax(&s_misc[0], kmax);
-  __syncthreads();
-  kmax = s_misc[0];
-  __syncthreads();
   int top = 24;
-  while (top > 0 && (kmax >> top) == 0) top -= 8;
+  while (top > 0 && (range >> top) == 0) top -= 8;
   uint32_t prefix = 0, pmask = 0, kk = k;
   for (int sh = top; sh >= 0; sh -= 8) {
     for (int b = tid; b < 256; b += NT) s_hist[b] = 0;
     __syncthreads();
     for (uint32_t i = tid; i < n; i += NT) {
-      uint32_t key = f2ord(__uint_as_float(tok_sc[i].y));
+      const uint32_t key = f2ord(__uint_as_float(tok_sc[i].y));
       if (key < limit_ord) {
-        uint32_t rk = key - min_ord;
+        const uint32_t rk = key - min_ord;
         if ((rk & pmask) == prefix) atomicAdd(&s_hist[(rk >> sh) & 255u], 1u);
       }
     }
     __syncthreads();
-    if (tid == 0) {
-      uint32_t acc = 0;
-      int b = 0;
-      for (; b < 255; ++b) {
-        if (acc + s_hist[b] > kk) break;
-        acc += s_hist[b];
+    if (tid < 32) {  // warp 0: locate the bin holding rank kk
+      uint32_t c[8], sum = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        c[q] = s_hist[tid * 8 + q];
+        sum += c[q];
       }
-      s_misc[0] = (uint32_t)b;
-      s_misc[1] = kk - acc;
+      const uint32_t incl = warp_incl_scan(sum, tid);
+      uint32_t acc = incl - sum;
+      if (kk >= acc && kk < incl) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (kk < acc + c[q]) {
+            s_misc[0] = (uint32_t)(tid * 8 + q);
+            s_misc[1] = kk - acc;
+            break;
+          }
+          acc += c[q];
+        }
+      }
     }
     __syncthreads();
     prefix |= s_misc[0] << sh;
@@ -358,290 +646,104 @@ __device__ float block_kth_smallest(const uint2 *tok_sc, uint32_t n, uint32_t k,
   return ord2f(prefix + min_ord);
 }
 
-__global__ void __launch_bounds__(kBoundaryThreads)
-k_boundary(StreamState *const *streams, GraphView g, DecoderConfigDev cfg, int mode) {
-  constexpr int NT = kBoundaryThreads;
-  __shared__ uint32_t s_warp[NT / 32 + 1];
+// One CTA per stream.  EPI: close the frame step (arena offsets, statistics, recycle the map of
+// the previous frame).  PRO: GetCutoff (inl.h:138-234) over the new frame's tokens, best-token
+// pre-pass (inl.h:282-300), and the descriptor of the next step.
+__global__ void __launch_bounds__(kStreamThreads, 2)
+k_cutoff(StreamState *const *streams, FrameDesc *desc, GraphView g, DecoderConfigDev cfg, int mode) {
+  constexpr int NT = kStreamThreads;
   __shared__ unsigned long long s_red64[NT / 32];
   __shared__ uint32_t s_red32[NT / 32];
   __shared__ uint32_t s_hist[256];
   __shared__ uint32_t s_misc[4];
-  __shared__ uint32_t s_nslots;
-  __shared__ uint32_t s_qn[2];
-
   StreamState *st = streams[blockIdx.x];
-  const int tid = threadIdx.x;
-  const bool is_init = (mode & kModeInit) != 0;
-  const uint32_t mask = st->hash_mask, shift = st->hash_shift;
+  FrameDesc *d = &desc[blockIdx.x];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  // =============================== epilogue of the frame just expanded (or InitDecoding)
-  const bool stepping = is_init || ((mode & kModeEpi) && st->frame < st->target_frame);
-  if (stepping) {
-    const int t = is_init ? -1 : st->frame;  // tokens of frame t+1 are being completed
-    const int next = (t + 1) & 1, cur = t & 1;
-    HashEntry *hn = st->hash[next];
-    HashEntry *hc = st->hash[cur];
-    uint32_t *slots = st->slots[next];
-    const float *__restrict__ ll =
-        is_init ? nullptr : st->ll_base + (size_t)(t - st->ll_frame0) * st->ll_stride;
-    float nc;
-    if (is_init) {
-      // InitDecoding (inl.h:41-67): forget the previous utterance, seed the start token,
-      // closure with cutoff = beam.
-      for (int w = 0; w < 2; ++w) {
-        HashEntry *h = st->hash[w];
-        const uint32_t *sl = st->slots[w];
-        const uint32_t ns = st->n_slots[w];
-        for (uint32_t i = tid; i < ns; i += NT) {
-          HashEntry e;
-          e.key = kEmptyKey; e.aux = 0; e.val = kInfVal;
-          h[sl[i]] = e;
-        }
-      }
-      __syncthreads();
-      nc = cfg.beam;
-      if (tid == 0) {
-        st->n_slots[0] = st->n_slots[1] = 0;
-        st->status = 0;
-        st->finalized = 0;
-        st->target_frame = 0;
-        st->frame_off[0] = 0;
-        uint32_t slot; bool is_new; unsigned long long old;
-        hash_insert(hn, mask, shift, (uint32_t)g.start, pack_val(0.0f, kNoArc), slot, is_new, old);
-        slots[0] = slot;
-        s_nslots = 1;
-      }
-    } else {
-      nc = ord2f(st->next_cut_bits);  // the FINAL next_cutoff of this frame
-      if (tid == 0) s_nslots = st->n_slots[next];
-    }
-    if (tid == 0) s_qn[0] = s_qn[1] = 0;
-    __syncthreads();
-
-    // ---- eps closure (ProcessNonemitting, inl.h:353-431) as frontier rounds
-    {
-      const uint32_t n0 = s_nslots;
-      for (uint32_t i = tid; i < n0; i += NT) {  // inl.h:376-381
-        const uint32_t slot = slots[i];
-        const uint32_t key = __ldcg(&hn[slot].key);
-        const float cost = ord2f((uint32_t)(__ldcg(&hn[slot].val) >> 32));
-        const uint2 r = __ldg(&g.rows[key]);
-        if (cost < nc && r.y > r.x) {
-          hn[slot].aux = 1;
-          st->queue[1][atomicAdd(&s_qn[1], 1u)] = slot;
-        }
-      }
-      for (uint32_t round = 1;; ++round) {
-        __syncthreads();
-        const uint32_t nq = s_qn[round & 1];
-        if (nq == 0) break;
-        __syncthreads();
-        if (tid == 0) s_qn[(round + 1) & 1] = 0;
-        __syncthreads();
-        const uint32_t *qin = st->queue[round & 1];
-        uint32_t *qout = st->queue[(round + 1) & 1];
-        for (uint32_t i = tid; i < nq; i += NT) {
-          const uint32_t slot = qin[i];
-          const uint32_t state = __ldcg(&hn[slot].key);
-          const float cost = ord2f((uint32_t)(__ldcg(&hn[slot].val) >> 32));
-          if (!(cost < nc)) continue;  // inl.h:391
-          const uint2 r = __ldg(&g.rows[state]);
-          for (uint32_t a = r.x; a < r.y; ++a) {
-            const int4 arc = __ldg(&g.arcs[a]);
-            const float tot = cost + __int_as_float(arc.z);  // inl.h:413-414
-            if (tot < nc) {                                   // inl.h:415
-              uint32_t slot2; bool is_new; unsigned long long old;
-              const unsigned long long pk = pack_val(tot, a);
-              if (!hash_insert(hn, mask, shift, (uint32_t)arc.w, pk, slot2, is_new, old)) {
-                atomicMin(&st->status, ASRD_ERR_HASH_OVERFLOW);
-                continue;
-              }
-              if (is_new) slots[atomicAdd(&s_nslots, 1u)] = slot2;
-              const bool changed = (uint32_t)(pk >> 32) < (uint32_t)(old >> 32);  // inl.h:115-127
-              if (changed) {
-                const uint2 r2 = __ldg(&g.rows[arc.w]);
-                if (r2.y > r2.x && atomicExch(&hn[slot2].aux, round + 1) != round + 1)
-                  qout[atomicAdd(&s_qn[(round + 1) & 1], 1u)] = slot2;  // inl.h:425-426
-              }
-            }
-          }
-        }
-      }
-    }
-    __syncthreads();
-
-    // ---- survivors (cost < final cutoff) -> token arena, in slot-list order
-    const uint32_t ntot = s_nslots;
+  if ((mode & kModeEpi) && d->stepping) {
+    const int t = d->t;
     const uint32_t out_base = st->frame_off[t + 1];
-    const uint32_t cap = st->token_capacity;
-    uint32_t running = 0;
-    unsigned long long best64 = kInfVal;
-    for (uint32_t c = 0; c < ntot; c += NT) {
-      const uint32_t i = c + tid;
-      bool alive = false;
-      uint32_t key = 0;
-      unsigned long long val = kInfVal;
-      float cost = 0.f;
-      if (i < ntot) {
-        const uint32_t slot = slots[i];
-        key = __ldcg(&hn[slot].key);
-        val = __ldcg(&hn[slot].val);
-        cost = ord2f((uint32_t)(val >> 32));
-        alive = cost < nc;
-      }
-      uint32_t tot_c;
-      const uint32_t pos = block_exclusive_scan<NT>(alive ? 1u : 0u, s_warp, tot_c);
-      const uint32_t idx = out_base + running + pos;
-      if (alive && idx < cap) {
-        uint32_t rep = (uint32_t)val;
-        float ac = 0.f;
-        if (rep != kNoArc) {
-          const int4 arc = __ldg(&g.arcs[rep]);
-          const bool emitting = arc.x != 0;
-          if (emitting) ac = -__ldg(&ll[arc.x - 1]);
-          if (par_bit(g.par_bits, rep)) {
-            // The reference reports, for the step pred -> tok, the most recently added
-            // surviving forward link (inl.h:1169-1186); links are prepended in arc order
-            // (inl.h:340-341) and excised when link_extra_cost > lattice_beam (inl.h:524-542),
-            // which for a best-path token is (tot' - tok.cost) > lattice_beam.
-            const uint32_t src = __ldg(&g.arc_src[rep]);
-            const uint2 r = __ldg(&g.rows[src]);
-            unsigned long long pv;
-            if (emitting) {
-              const uint32_t end = __ldg(&g.rows[src + 1]).x;
-              if (hash_find(hc, mask, shift, src, pv)) {
-                const float pc = ord2f((uint32_t)(pv >> 32));
-                for (uint32_t a2 = end; a2-- > rep + 1;) {
-                  const int4 arc2 = __ldg(&g.arcs[a2]);
-                  if ((uint32_t)arc2.w != key) continue;
-                  const float ac2 = -__ldg(&ll[arc2.x - 1]);
-                  const float tot2 = (pc + ac2) + __int_as_float(arc2.z);
-                  if (tot2 < nc && !((tot2 - cost) > cfg.lattice_beam)) {
-                    rep = a2;
-                    ac = ac2;
-                    break;
-                  }
-                }
-              }
-            } else {
-              if (hash_find(hn, mask, shift, src, pv)) {
-                const float pc = ord2f((uint32_t)(pv >> 32));
-                for (uint32_t a2 = r.y; a2-- > rep + 1;) {
-                  const int4 arc2 = __ldg(&g.arcs[a2]);
-                  if ((uint32_t)arc2.w != key) continue;
-                  const float tot2 = pc + __int_as_float(arc2.z);
-                  if (pc < nc && tot2 < nc && !((tot2 - cost) > cfg.lattice_beam)) {
-                    rep = a2;
-                    break;
-                  }
-                }
-              }
-            }
-          }
-        }
-        st->tok_sc[idx] = make_uint2(key, __float_as_uint(cost));
-        st->tok_aa[idx] = make_uint2(rep, __float_as_uint(ac));
-        const unsigned long long b = ((unsigned long long)f2ord(cost) << 32) | key;
-        best64 = b < best64 ? b : best64;
-      }
-      running += tot_c;
-    }
-    uint32_t n_alive = running;
-    if (out_base + n_alive > cap) {
-      n_alive = cap > out_base ? cap - out_base : 0;
+    uint32_t n_alive = d->n_alive;
+    if (n_alive > d->out_cap) {
+      n_alive = d->out_cap;
       if (tid == 0) atomicMin(&st->status, ASRD_ERR_ARENA_OVERFLOW);
     }
-    // ---- recycle the map of the previous frame (after every sibling look-up is done)
+    // recycle the map of the previous frame (its last reader was k_finalize)
+    clear_map_by_bitmap(st->hash[t & 1], st->bm[t & 1], (st->hash_mask + 1) >> 5, warp, lane, NT / 32);
     __syncthreads();
-    if (!is_init) {
-      const uint32_t *sl = st->slots[cur];
-      const uint32_t ns = st->n_slots[cur];
-      for (uint32_t i = tid; i < ns; i += NT) {
-        HashEntry e;
-        e.key = kEmptyKey; e.aux = 0; e.val = kInfVal;
-        hc[sl[i]] = e;
-      }
-    }
-    best64 = block_min_u64<NT>(best64, s_red64);
     if (tid == 0) {
+      const unsigned long long b64 = d->best64;
       if (cfg.collect_stats && st->stats) {
         asrd_frame_stat s;
-        s.n_in = is_init ? 0 : st->n_cur;
-        s.cur_cutoff = is_init ? 0.f : st->cur_cut;
-        s.abeam = is_init ? 0.f : st->abeam;
-        s.next_cutoff = nc;
+        s.n_in = d->n_cur;
+        s.cur_cutoff = d->cur_cut;
+        s.abeam = d->abeam;
+        s.next_cutoff = ord2f(d->next_cut_bits);
         s.n_tokens = n_alive;
-        s.best = ord2f((uint32_t)(best64 >> 32));
-        s.arcs_expanded = is_init ? 0 : st->arcs_expanded;
-        s.arcs_admitted = is_init ? 0 : st->arcs_admitted;
+        s.best = b64 == kInfVal ? CUDART_INF_F : ord2f((uint32_t)(b64 >> 32));
+        s.arcs_expanded = d->arcs_expanded;
+        s.arcs_admitted = d->arcs_admitted;
         st->stats[t + 1] = s;
       }
-      if (is_init) {
-        st->tot_arcs_expanded = 0;
-        st->tot_arcs_admitted = 0;
-      } else {
-        st->tot_arcs_expanded += st->arcs_expanded;
-        st->tot_arcs_admitted += st->arcs_admitted;
-      }
+      st->tot_arcs_expanded += d->arcs_expanded;
+      st->tot_arcs_admitted += d->arcs_admitted;
       st->frame_off[t + 2] = out_base + n_alive;
-      st->n_slots[next] = ntot;
-      if (!is_init) st->n_slots[cur] = 0;
       st->frame = t + 1;
       st->n_cur = n_alive;
-      st->tiles = 0;
+      st->best64 = b64;
+      d->stepping = 0;
     }
     __syncthreads();
   }
 
-  // =============================== prologue of the next frame: GetCutoff + pre-pass
   if (mode & kModePro) {
-    __syncthreads();
     const int t = st->frame;
     if (t >= st->target_frame) {
-      if (tid == 0) st->tiles = 0;
+      if (tid == 0) d->stepping = 0;
       return;
     }
     const uint32_t n = st->n_cur;
-    const uint2 *toks = st->tok_sc + st->frame_off[t];
+    const uint32_t tok_off = st->frame_off[t];
+    const uint2 *toks = st->tok_sc + tok_off;
     const float *__restrict__ ll = st->ll_base + (size_t)(t - st->ll_frame0) * st->ll_stride;
-    // best token: lowest cost, ties -> lowest state id (inl.h:169-179)
-    unsigned long long best64 = kInfVal;
-    for (uint32_t i = tid; i < n; i += NT) {
-      const uint2 sc = toks[i];
-      const unsigned long long b = ((unsigned long long)f2ord(__uint_as_float(sc.y)) << 32) | sc.x;
-      best64 = b < best64 ? b : best64;
-    }
-    best64 = block_min_u64<NT>(best64, s_red64);
+    // best token: lowest cost, ties -> lowest state id (inl.h:169-179); accumulated by k_finalize
+    const unsigned long long best64 = st->best64;
     float cur_cut = CUDART_INF_F, abeam = cfg.beam;
     uint32_t next_bits = kOrdInf;
     if (n > 0) {
       const uint32_t best_ord = (uint32_t)(best64 >> 32);
       const float bc = ord2f(best_ord);
       const float beam_cut = bc + cfg.beam;  // inl.h:182
-      uint32_t lt = 0, le = 0;
-      for (uint32_t i = tid; i < n; i += NT) {
-        const float c = __uint_as_float(toks[i].y);
-        lt += c < beam_cut;
-        le += c <= beam_cut;
-      }
-      lt = block_sum_u32<NT>(lt, s_red32);
-      le = block_sum_u32<NT>(le, s_red32);
+      const uint32_t beam_ord = f2ord(beam_cut);
       cur_cut = beam_cut;
-      if (lt > (uint32_t)cfg.max_active) {
-        // sorted[max_active] < beam_cutoff  <=>  more than max_active costs below it (inl.h:188-203)
-        cur_cut = block_kth_smallest<NT>(toks, n, (uint32_t)cfg.max_active, best_ord,
-                                         f2ord(beam_cut), s_hist, s_misc);
-        abeam = cur_cut - bc + cfg.beam_delta;
-      } else if (n <= (uint32_t)cfg.min_active) {
-        // fewer tokens than min_active: min_active_cutoff stays +inf > beam_cutoff, so nothing is
+      if (n <= (uint32_t)cfg.min_active && n <= (uint32_t)cfg.max_active) {
+        // fewer tokens than min_active: min_active_cutoff stays +inf > beam_cutoff, nothing is
         // pruned and the adaptive beam is infinite (inl.h:183,205,220-226)
         cur_cut = CUDART_INF_F;
         abeam = CUDART_INF_F;
-      } else if (cfg.min_active > 0 && le <= (uint32_t)cfg.min_active) {
-        // sorted[min_active] > beam_cutoff  <=>  at most min_active costs <= it (inl.h:205-226)
-        cur_cut = block_kth_smallest<NT>(toks, n, (uint32_t)cfg.min_active, best_ord, 0xFFFFFFFFu,
-                                         s_hist, s_misc);
-        abeam = cur_cut - bc + cfg.beam_delta;
+      } else {
+        uint32_t lt = 0, le = 0;
+        for (uint32_t i = tid; i < n; i += NT) {
+          const float c = __uint_as_float(toks[i].y);
+          lt += c < beam_cut;
+          le += c <= beam_cut;
+        }
+        lt = block_sum_u32<NT>(lt, s_red32);
+        le = block_sum_u32<NT>(le, s_red32);
+        if (lt > (uint32_t)cfg.max_active) {
+          // sorted[max_active] < beam_cutoff  <=>  more than max_active costs below it (inl.h:188-203)
+          cur_cut = block_kth_smallest<NT>(toks, n, (uint32_t)cfg.max_active, best_ord, beam_ord,
+                                           beam_ord - best_ord, s_hist, s_misc);
+          abeam = cur_cut - bc + cfg.beam_delta;
+        } else if (n <= (uint32_t)cfg.min_active) {
+          cur_cut = CUDART_INF_F;
+          abeam = CUDART_INF_F;
+        } else if (cfg.min_active > 0 && le <= (uint32_t)cfg.min_active) {
+          // sorted[min_active] > beam_cutoff  <=>  at most min_active costs <= it (inl.h:205-226)
+          cur_cut = block_kth_smallest<NT>(toks, n, (uint32_t)cfg.min_active, best_ord, 0xFFFFFFFFu,
+                                           0xFFFFFFFFu, s_hist, s_misc);
+          abeam = cur_cut - bc + cfg.beam_delta;
+        }
       }
       // best-token pre-pass (inl.h:282-300): association (cost + w) - loglike
       const uint32_t sb = (uint32_t)best64;
@@ -653,16 +755,35 @@ k_boundary(StreamState *const *streams, GraphView g, DecoderConfigDev cfg, int m
         const float tot = bc + __int_as_float(arc.z) - __ldg(&ll[arc.x - 1]);
         mn = min(mn, f2ord(tot + abeam));
       }
-      unsigned long long m64 = block_min_u64<NT>((unsigned long long)mn, s_red64);
+      const unsigned long long m64 = block_min_u64<NT>((unsigned long long)mn, s_red64);
       next_bits = (uint32_t)m64;
     }
     if (tid == 0) {
-      st->cur_cut = cur_cut;
-      st->abeam = abeam;
-      st->next_cut_bits = next_bits;
-      st->arcs_expanded = 0;
-      st->arcs_admitted = 0;
-      st->tiles = (n + kTileTokens - 1) / kTileTokens;
+      const uint32_t out_base = st->frame_off[t + 1];
+      FrameDesc nd;
+      nd.st = st;
+      nd.toks = toks;
+      nd.ll = ll;
+      nd.hn = st->hash[(t + 1) & 1];
+      nd.hc = st->hash[t & 1];
+      nd.bm = st->bm[(t + 1) & 1];
+      nd.ebm = st->ebm[(t + 1) & 1];
+      nd.out_sc = st->tok_sc + out_base;
+      nd.out_aa = st->tok_aa + out_base;
+      nd.best64 = kInfVal;
+      nd.n_cur = n;
+      nd.cur_cut = cur_cut;
+      nd.abeam = abeam;
+      nd.next_cut_bits = next_bits;
+      nd.mask = st->hash_mask;
+      nd.shift = st->hash_shift;
+      nd.out_cap = st->token_capacity > out_base ? st->token_capacity - out_base : 0;
+      nd.n_alive = 0;
+      nd.arcs_expanded = 0;
+      nd.arcs_admitted = 0;
+      nd.stepping = 1;
+      nd.t = t;
+      *d = nd;
     }
   }
 }

@@ -283,8 +283,11 @@ def run_b200_arm(a):
     L.asrd_profile_enable(1)
     step(dev_args, True)
     L.asrd_profile_enable(0)
-    xm, xn, bm, bn = C.c_double(0), C.c_int64(0), C.c_double(0), C.c_int64(0)
-    L.asrd_profile_get(C.byref(xm), C.byref(xn), C.byref(bm), C.byref(bn))
+    kms, kn = (C.c_double * 4)(), (C.c_int64 * 4)()
+    L.asrd_profile_get(kms, kn)
+    xm, xn = C.c_double(kms[0]), C.c_int64(kn[0])
+    knames = ["k_expand", "k_closure", "k_finalize", "k_cutoff"]
+    ktot = sum(kms) + 1e-12
 
     # ---- end-to-end number: host (pinned) log-likelihoods through the C ABI
     e2e = None
@@ -341,9 +344,8 @@ def run_b200_arm(a):
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_arc": 16, "arcs_per_launch": ae.value / max(1, xn.value),
                      "launch_ms": xm.value / max(1, xn.value), "launches_per_step": int(xn.value),
-                     "k_boundary_ms_per_launch": bm.value / max(1, bn.value),
-                     "kernel_share_of_step": {"k_expand": xm.value / (xm.value + bm.value + 1e-12),
-                                              "k_boundary": bm.value / (xm.value + bm.value + 1e-12)}},
+                     "kernel_ms_per_launch": {k: kms[i] / max(1, kn[i]) for i, k in enumerate(knames)},
+                     "kernel_share_of_step": {k: kms[i] / ktot for i, k in enumerate(knames)}},
     }
     if e2e is not None:
         line["e2e"] = {"value": audio_all / (e2e[0] / 1e3), "unit": "x realtime", "ms_per_step": e2e[0],

@@ -178,8 +178,9 @@ int asrd_get_counters(asrd_decoder *const *decs, int32_t n, int64_t *arcs_expand
  * bench.py's roofline; adds gaps between launches, so keep it off in timed regions). */
 int asrd_profile_enable(int on);
 int asrd_profile_reset(void);
-int asrd_profile_get(double *expand_ms, int64_t *expand_launches, double *boundary_ms,
-                     int64_t *boundary_launches);
+/* kernel_ms[4], kernel_launches[4]: accumulated device time and launch counts of
+ * {k_expand, k_closure, k_finalize, k_cutoff} since the last reset */
+int asrd_profile_get(double *kernel_ms, int64_t *kernel_launches);
 
 /* number of kernels launched by this library since load (bench.py "gpu_launches") */
 int64_t asrd_launch_count(void);
