@@ -420,10 +420,11 @@ int asrd_decoder_create(asrd_graph *g, const asrd_config *cfg, const asrd_device
   const size_t H = (size_t)o.hash_capacity;
   auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
   const size_t b_hash = align(H * sizeof(HashEntry)), b_list = align(H * 4), b_bm = align(H / 8),
-               b_tok = align((size_t)o.token_capacity * 8), b_off = align(((size_t)o.max_frames + 2) * 4),
+               b_tok = align((size_t)o.token_capacity * 8), b_arc = align((size_t)o.token_capacity * 4),
+               b_off = align(((size_t)o.max_frames + 2) * 4),
                b_stats = o.collect_stats ? align(((size_t)o.max_frames + 1) * sizeof(asrd_frame_stat)) : 0,
                b_state = align(sizeof(StreamState));
-  const size_t total = b_state + 2 * b_hash + 4 * b_bm + 2 * b_list + 2 * b_tok + b_off + b_stats;
+  const size_t total = b_state + 2 * b_hash + 4 * b_bm + 2 * b_list + b_tok + b_arc + 2 * b_off + b_stats;
   if (cudaMalloc(&d->slab, total) != cudaSuccess) {
     cudaGetLastError();
     delete d;
@@ -440,8 +441,9 @@ int asrd_decoder_create(asrd_graph *g, const asrd_config *cfg, const asrd_device
   for (int i = 0; i < 2; ++i) { h.ebm[i] = (uint32_t *)p; p += b_bm; }
   for (int i = 0; i < 2; ++i) { h.queue[i] = (uint32_t *)p; p += b_list; }
   h.tok_sc = (uint2 *)p; p += b_tok;
-  h.tok_aa = (uint2 *)p; p += b_tok;
+  h.tok_arc = (uint32_t *)p; p += b_arc;
   h.frame_off = (uint32_t *)p; p += b_off;
+  h.frame_nc = (float *)p; p += b_off;
   h.stats = o.collect_stats ? (asrd_frame_stat *)p : nullptr;
   h.hash_mask = (uint32_t)H - 1;
   uint32_t lg = 0;
@@ -465,6 +467,7 @@ int asrd_decoder_destroy(asrd_decoder *d) {
   if (!d) return ASRD_OK;
   cudaSetDevice(d->graph->device);
   cudaFree(d->slab);
+  cudaFree(d->d_ll_hist);
   delete d;
   return ASRD_OK;
 }
@@ -484,7 +487,7 @@ int asrd_init_decoding(asrd_decoder *const *decs, int32_t n, void *stream) {
   const uint32_t gps = (uint32_t)decs[0]->opts.hash_capacity / 1024;
   k_init<<<n, kStreamThreads, 0, s>>>(d_streams, d_desc, gv, cfg);
   k_closure<<<n, kStreamThreads, 0, s>>>(d_desc, gv);
-  k_finalize<<<FinalizeGrid(), kFinThreads, 0, s>>>(d_desc, n, gps, gv, cfg);
+  k_finalize<<<FinalizeGrid(), kFinThreads, 0, s>>>(d_desc, n, gps);
   k_cutoff<<<n, kStreamThreads, 0, s>>>(d_streams, d_desc, gv, cfg, kModeEpi);
   g_launches += 4;
   CU_CHECK(cudaGetLastError());
@@ -515,6 +518,23 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
     max_nf = std::max(max_nf, nf[i]);
   }
   if (max_nf == 0) return ASRD_OK;
+  // log-likelihood history (read by the search and by the trace-back); sized on first use
+  for (int i = 0; i < n; ++i) {
+    asrd_decoder *d = decs[i];
+    if (d->d_ll_hist && d->ll_cols != num_indices) return ASRD_ERR_BAD_ARG;  // columns must not change
+    if (!d->d_ll_hist) {
+      const int32_t hs = (num_indices + 3) & ~3;
+      if (cudaMalloc((void **)&d->d_ll_hist, (size_t)d->opts.max_frames * hs * sizeof(float)) != cudaSuccess) {
+        cudaGetLastError();
+        return ASRD_ERR_NOMEM;
+      }
+      d->ll_cols = num_indices;
+      d->h_state.ll_hist = d->d_ll_hist;
+      d->h_state.ll_stride = hs;
+      CU_CHECK(cudaMemcpyAsync(&d->d_state->ll_hist, &d->h_state.ll_hist, sizeof(float *), cudaMemcpyHostToDevice, s));
+      CU_CHECK(cudaMemcpyAsync(&d->d_state->ll_stride, &d->h_state.ll_stride, sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    }
+  }
   const GraphView gv = decs[0]->graph->view;
   const DecoderConfigDev cfg = DevCfg(decs[0]);
   Scratch sc(s);
@@ -582,7 +602,9 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
       CU_CHECK(cudaStreamWaitEvent(s, ctx->ev_copied[k & 1], 0));
     }
     CU_CHECK(cudaMemcpyAsync(d_params, hp.data(), sizeof(AdvanceParams) * n, cudaMemcpyHostToDevice, s));
-    k_begin_advance<<<(n + 127) / 128, 128, 0, s>>>(d_streams, d_params, n);
+    k_begin_advance<<<dim3((unsigned)std::min(steps, 8), (unsigned)n), 256, 0, s>>>(d_streams, d_params, num_indices);
+    // the rows now live in the per-stream history: the staging buffer may be refilled
+    if (!on_device) CU_CHECK(cudaEventRecord(ctx->ev_done[k & 1], s));
     prof.Begin(3, s);
     k_cutoff<<<n, kStreamThreads, 0, s>>>(d_streams, d_desc, gv, cfg, kModePro);
     prof.End(s);
@@ -595,7 +617,7 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
       k_closure<<<n, kStreamThreads, 0, s>>>(d_desc, gv);
       prof.End(s);
       prof.Begin(2, s);
-      k_finalize<<<fin_grid, kFinThreads, 0, s>>>(d_desc, n, gps, gv, cfg);
+      k_finalize<<<fin_grid, kFinThreads, 0, s>>>(d_desc, n, gps);
       prof.End(s);
       prof.Begin(3, s);
       k_cutoff<<<n, kStreamThreads, 0, s>>>(d_streams, d_desc, gv, cfg, kModeEpi | (f + 1 < steps ? kModePro : 0));
@@ -603,7 +625,6 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
       g_launches += 4;
     }
     CU_CHECK(cudaGetLastError());
-    if (!on_device) CU_CHECK(cudaEventRecord(ctx->ev_done[k & 1], s));
   }
   if (!on_device) {
     // the copy stream must not run ahead into a later call's (recycled) staging memory
@@ -651,8 +672,8 @@ int asrd_get_best_path(asrd_decoder *const *decs, int32_t n, int32_t use_final_p
   CU_CHECK(sc.Alloc(&d_ac, tot));
   CU_CHECK(sc.Alloc(&d_n, (size_t)n));
   CU_CHECK(sc.Alloc(&d_st, (size_t)n));
-  k_best_path<<<n, 256, 0, s>>>(d_streams, decs[0]->graph->view, use_final_probs, cap, d_il, d_ol, d_gr,
-                                d_ac, d_n, d_st);
+  k_best_path<<<n, 256, 0, s>>>(d_streams, decs[0]->graph->view, DevCfg(decs[0]), use_final_probs, cap, d_il,
+                                d_ol, d_gr, d_ac, d_n, d_st);
   ++g_launches;
   CU_CHECK(cudaGetLastError());
   CU_CHECK(cudaMemcpyAsync(n_arcs, d_n, 4 * (size_t)n, cudaMemcpyDeviceToHost, s));

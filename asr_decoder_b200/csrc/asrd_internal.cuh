@@ -49,8 +49,10 @@ struct StreamState {
   uint32_t *ebm[2];     // ... of which the state has eps arcs (seeds of the eps closure)
   uint32_t *queue[2];   // eps-closure frontier queues
   uint2 *tok_sc;        // token arena: {state, cost bits}
-  uint2 *tok_aa;        // token arena: {reported arc id, acoustic cost bits}
+  uint32_t *tok_arc;    // token arena: arc that set the token's cost (kNoArc for the start token)
   uint32_t *frame_off;  // [max_frames + 2] arena offset of every frame's token span
+  float *frame_nc;      // [max_frames + 2] final next_cutoff of the step that produced each frame
+  float *ll_hist;       // [max_frames x ll_stride] log-likelihood rows seen so far (trace-back needs them)
   asrd_frame_stat *stats;  // [max_frames + 1] or null
   uint32_t hash_mask;
   uint32_t hash_shift;  // 32 - log2(capacity)
@@ -62,12 +64,8 @@ struct StreamState {
   uint32_t n_cur;       // tokens in the current frame
   int32_t finalized;
   unsigned long long best64;  // (ordered cost << 32 | state) of the best token of the current frame
-  // ---- this AdvanceDecoding call
-  const float *ll_base; // row of frame ll_frame0
-  int32_t ll_stride;
-  int32_t ll_frame0;
-  int32_t target_frame; // decode while frame < target_frame
-  int32_t pad1;
+  int32_t ll_stride;    // floats per history row
+  int32_t target_frame; // this AdvanceDecoding call decodes while frame < target_frame
   // ---- utterance totals
   unsigned long long tot_arcs_expanded;
   unsigned long long tot_arcs_admitted;
@@ -86,7 +84,7 @@ struct __align__(16) FrameDesc {
   uint32_t *bm;         // claimed-slot bitmap of hn
   uint32_t *ebm;        // eps-seed bitmap of hn
   uint2 *out_sc;        // arena write window of frame t+1
-  uint2 *out_aa;
+  uint32_t *out_arc;
   unsigned long long best64;
   uint32_t n_cur;
   float cur_cut;
@@ -104,9 +102,9 @@ struct __align__(16) FrameDesc {
 static_assert(sizeof(FrameDesc) == 128, "FrameDesc is one 128-byte line");
 
 struct AdvanceParams {
-  const float *ll;
-  int32_t stride;
-  int32_t n_frames;
+  const float *ll;   // device pointer to the first new row of this chunk
+  int32_t stride;    // floats between rows
+  int32_t n_frames;  // rows in this chunk
 };
 
 struct DecoderConfigDev {
@@ -157,6 +155,8 @@ struct asrd_decoder {
   asrd::StreamState h_state;   // host mirror of the static fields
   void *slab;                  // one allocation carved into the buffers above
   int64_t slab_bytes;
+  float *d_ll_hist;            // allocated at the first AdvanceDecoding (needs num_indices)
+  int32_t ll_cols;
   int32_t frames_decoded;      // host-side mirror of StreamState::frame
   int32_t finalized;
   int32_t initialized;

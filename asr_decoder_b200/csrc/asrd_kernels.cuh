@@ -178,17 +178,21 @@ __device__ __forceinline__ int warp_owner(uint32_t off, uint32_t j) {
 
 __device__ __forceinline__ void clear_map_by_bitmap(HashEntry *h, uint32_t *bm, uint32_t words, int warp,
                                                     int lane, int n_warps) {
-  // lane b of a warp recycles slot b of the warp's current word: 512 contiguous bytes per word
-  for (uint32_t w = warp; w < words; w += n_warps) {
-    const uint32_t bits = bm[w];
-    if (bits) {
+  // Each warp takes 32 bitmap words at a time (one coalesced load), then lane b recycles slot b
+  // of every non-empty word: 512 contiguous bytes per word, no dependent global loads.
+  for (uint32_t w0 = warp * 32; w0 < words; w0 += n_warps * 32) {
+    const uint32_t mine = (w0 + lane < words) ? bm[w0 + lane] : 0u;
+    if (mine) bm[w0 + lane] = 0;
+    unsigned nz = __ballot_sync(kFull, mine != 0);
+    while (nz) {
+      const int k = __ffs(nz) - 1;
+      nz &= nz - 1;
+      const uint32_t bits = __shfl_sync(kFull, mine, k);
       if ((bits >> lane) & 1u) {
         HashEntry e;
         e.key = kEmptyKey; e.aux = 0; e.val = kInfVal;
-        h[w * 32 + lane] = e;
+        h[(w0 + k) * 32 + lane] = e;
       }
-      __syncwarp();
-      if (lane == 0) bm[w] = 0;
     }
   }
 }
@@ -232,7 +236,7 @@ k_init(StreamState *const *streams, FrameDesc *desc, GraphView g, DecoderConfigD
     d.bm = st->bm[0];
     d.ebm = st->ebm[0];
     d.out_sc = st->tok_sc;
-    d.out_aa = st->tok_aa;
+    d.out_arc = st->tok_arc;
     d.best64 = kInfVal;
     d.n_cur = 0;
     d.cur_cut = 0.f;
@@ -249,20 +253,35 @@ k_init(StreamState *const *streams, FrameDesc *desc, GraphView g, DecoderConfigD
   }
 }
 
-__global__ void k_begin_advance(StreamState *const *streams, const AdvanceParams *params, int n) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  StreamState *st = streams[i];
-  AdvanceParams p = params[i];
-  st->ll_base = p.ll;
-  st->ll_stride = p.stride;
-  st->ll_frame0 = st->frame;
-  int target = st->frame + p.n_frames;
-  if (target > st->max_frames) {
-    target = st->max_frames;
-    atomicMin(&st->status, ASRD_ERR_FRAMES_OVERFLOW);
+// Start of an AdvanceDecoding chunk: append the chunk's log-likelihood rows to every stream's
+// history (the search reads them from there, and so does the trace-back) and set the frame
+// target.  One CTA per (row block, stream).
+__global__ void __launch_bounds__(256)
+k_begin_advance(StreamState *const *streams, const AdvanceParams *params, int num_indices) {
+  StreamState *st = streams[blockIdx.y];
+  const AdvanceParams p = params[blockIdx.y];
+  const int frame0 = st->frame;
+  int nf = p.n_frames;
+  if (frame0 + nf > st->max_frames) {
+    nf = st->max_frames - frame0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicMin(&st->status, ASRD_ERR_FRAMES_OVERFLOW);
   }
-  st->target_frame = target;
+  if (blockIdx.x == 0 && threadIdx.x == 0) st->target_frame = frame0 + (nf > 0 ? nf : 0);
+  const int hs = st->ll_stride;
+  float *dst = st->ll_hist + (size_t)frame0 * hs;
+  const bool vec = ((num_indices & 3) == 0) && ((p.stride & 3) == 0) && ((hs & 3) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(p.ll) & 15) == 0);
+  for (int r = blockIdx.x; r < nf; r += gridDim.x) {
+    const float *src = p.ll + (size_t)r * p.stride;
+    float *drow = dst + (size_t)r * hs;
+    if (vec) {
+      const float4 *s4 = reinterpret_cast<const float4 *>(src);
+      float4 *d4 = reinterpret_cast<float4 *>(drow);
+      for (int c = threadIdx.x; c < (num_indices >> 2); c += blockDim.x) d4[c] = __ldg(&s4[c]);
+    } else {
+      for (int c = threadIdx.x; c < num_indices; c += blockDim.x) drow[c] = __ldg(&src[c]);
+    }
+  }
 }
 
 // ------------------------------------------------------------------ expand
@@ -300,6 +319,9 @@ k_expand(FrameDesc *desc, GraphView g, int num_indices) {
 
   uint32_t expanded = 0, admitted = 0;
   for (uint32_t grp = warp_global; grp < n_groups; grp += n_warps) {
+    // running cutoff (inl.h:330), refreshed once per group; our own tightenings are applied
+    // locally below, other warps' arrive with the next group
+    float nc = ord2f(__ldcg(next_cut));
     // ---- lane i: token i of the group and its emitting span
     const uint32_t i = grp * 32 + lane;
     uint32_t deg = 0, base = 0, cost_bits = 0;
@@ -319,7 +341,6 @@ k_expand(FrameDesc *desc, GraphView g, int num_indices) {
     expanded += total;
 
     for (uint32_t jb = 0; jb < total; jb += 32 * U) {
-      const float nc = ord2f(*(volatile uint32_t *)next_cut);  // running cutoff, inl.h:330
       bool in[U];
       uint32_t a[U];
       float tcost[U];
@@ -366,6 +387,7 @@ k_expand(FrameDesc *desc, GraphView g, int num_indices) {
       if (__any_sync(kFull, cand_bits != 0xFFFFFFFFu)) {
         const uint32_t wmin = __reduce_min_sync(kFull, cand_bits);
         if (lane == 0) atomicMin(next_cut, wmin);
+        nc = fminf(nc, ord2f(wmin));
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -411,7 +433,7 @@ k_closure(FrameDesc *desc, GraphView g) {
   FrameDesc *d = &desc[blockIdx.x];
   if (!d->stepping) return;
   StreamState *st = d->st;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   const uint32_t mask = d->mask, shift = d->shift;
   const uint32_t groups = (mask + 1) >> 10;  // 32 bitmap words (1024 slots) per group
   HashEntry *hn = d->hn;
@@ -479,10 +501,10 @@ k_closure(FrameDesc *desc, GraphView g) {
 // ------------------------------------------------------------------ finalize
 
 // One warp per 1024 map slots (32 bitmap words) of a stepping stream: the set bits are spread
-// over the lanes by rank; survivors (cost < final next_cutoff) get a token record at a
-// warp-aggregated arena position.
+// over the lanes by rank; survivors (cost < final next_cutoff) get a token record
+// {state, cost, winning arc} at a warp-aggregated arena position.
 __global__ void __launch_bounds__(kFinThreads)
-k_finalize(FrameDesc *desc, int n_streams, uint32_t groups_per_stream, GraphView g, DecoderConfigDev cfg) {
+k_finalize(FrameDesc *desc, int n_streams, uint32_t groups_per_stream) {
   const int tid = threadIdx.x, lane = tid & 31;
   const uint32_t warp_global = blockIdx.x * (kFinThreads / 32) + (tid >> 5);
   const uint32_t n_warps = gridDim.x * (kFinThreads / 32);
@@ -498,12 +520,11 @@ k_finalize(FrameDesc *desc, int n_streams, uint32_t groups_per_stream, GraphView
     const uint32_t incl = warp_incl_scan(cnt, lane);
     const uint32_t off = incl - cnt;
     const uint32_t total = __shfl_sync(kFull, incl, 31);
-    HashEntry *hn = d->hn;
-    HashEntry *hc = d->hc;
-    const uint32_t mask = d->mask, shift = d->shift;
+    const HashEntry *hn = d->hn;
     const float nc = ord2f(d->next_cut_bits);
-    const float *__restrict__ ll = d->ll;
     const uint32_t cap = d->out_cap;
+    uint2 *out_sc = d->out_sc;
+    uint32_t *out_arc = d->out_arc;
     unsigned long long best64 = kInfVal;
 
     for (uint32_t ib = 0; ib < total; ib += 32) {
@@ -513,7 +534,7 @@ k_finalize(FrameDesc *desc, int n_streams, uint32_t groups_per_stream, GraphView
       const uint32_t offl = __shfl_sync(kFull, off, l);
       bool alive = false;
       uint32_t key = 0, rep = kNoArc;
-      float cost = 0.f, ac = 0.f;
+      float cost = 0.f;
       if (it < total) {
         const uint32_t b = __fns(wl, 0, (int)(it - offl) + 1);
         const uint32_t slot = ((grp * 32 + l) << 5) + b;
@@ -527,56 +548,12 @@ k_finalize(FrameDesc *desc, int n_streams, uint32_t groups_per_stream, GraphView
       if (am == 0) continue;
       uint32_t pos0 = 0;
       if (lane == 0) pos0 = atomicAdd(&d->n_alive, (uint32_t)__popc(am));
-      if (alive && rep != kNoArc) {
-        const int4 arc = __ldg(&g.arcs[rep]);
-        const bool emitting = arc.x != 0;
-        if (emitting) ac = -__ldg(&ll[arc.x - 1]);
-        if (par_bit(g.par_bits, rep)) {
-          // The reference reports, for the step pred -> tok, the most recently added
-          // surviving forward link (inl.h:1169-1186); links are prepended in arc order
-          // (inl.h:340-341) and excised when link_extra_cost > lattice_beam (inl.h:524-542),
-          // which for a best-path token is (tot' - tok.cost) > lattice_beam.
-          const uint32_t src = __ldg(&g.arc_src[rep]);
-          const uint2 r = __ldg(&g.rows[src]);
-          unsigned long long pv;
-          if (emitting) {
-            const uint32_t end = __ldg(&g.rows[src + 1]).x;
-            if (hash_find(hc, mask, shift, src, pv)) {
-              const float pc = ord2f((uint32_t)(pv >> 32));
-              for (uint32_t a2 = end; a2-- > rep + 1;) {
-                const int4 arc2 = __ldg(&g.arcs[a2]);
-                if ((uint32_t)arc2.w != key) continue;
-                const float ac2 = -__ldg(&ll[arc2.x - 1]);
-                const float tot2 = (pc + ac2) + __int_as_float(arc2.z);
-                if (tot2 < nc && !((tot2 - cost) > cfg.lattice_beam)) {
-                  rep = a2;
-                  ac = ac2;
-                  break;
-                }
-              }
-            }
-          } else {
-            if (hash_find(hn, mask, shift, src, pv)) {
-              const float pc = ord2f((uint32_t)(pv >> 32));
-              for (uint32_t a2 = r.y; a2-- > rep + 1;) {
-                const int4 arc2 = __ldg(&g.arcs[a2]);
-                if ((uint32_t)arc2.w != key) continue;
-                const float tot2 = pc + __int_as_float(arc2.z);
-                if (pc < nc && tot2 < nc && !((tot2 - cost) > cfg.lattice_beam)) {
-                  rep = a2;
-                  break;
-                }
-              }
-            }
-          }
-        }
-      }
       pos0 = __shfl_sync(kFull, pos0, 0);
       if (alive) {
         const uint32_t idx = pos0 + __popc(am & ((1u << lane) - 1u));
         if (idx < cap) {
-          d->out_sc[idx] = make_uint2(key, __float_as_uint(cost));
-          d->out_aa[idx] = make_uint2(rep, __float_as_uint(ac));
+          out_sc[idx] = make_uint2(key, __float_as_uint(cost));
+          out_arc[idx] = rep;
         }
         const unsigned long long b64 = ((unsigned long long)f2ord(cost) << 32) | key;
         best64 = b64 < best64 ? b64 : best64;
@@ -688,6 +665,7 @@ k_cutoff(StreamState *const *streams, FrameDesc *desc, GraphView g, DecoderConfi
       st->tot_arcs_expanded += d->arcs_expanded;
       st->tot_arcs_admitted += d->arcs_admitted;
       st->frame_off[t + 2] = out_base + n_alive;
+      st->frame_nc[t + 1] = ord2f(d->next_cut_bits);
       st->frame = t + 1;
       st->n_cur = n_alive;
       st->best64 = b64;
@@ -705,7 +683,7 @@ k_cutoff(StreamState *const *streams, FrameDesc *desc, GraphView g, DecoderConfi
     const uint32_t n = st->n_cur;
     const uint32_t tok_off = st->frame_off[t];
     const uint2 *toks = st->tok_sc + tok_off;
-    const float *__restrict__ ll = st->ll_base + (size_t)(t - st->ll_frame0) * st->ll_stride;
+    const float *__restrict__ ll = st->ll_hist + (size_t)t * st->ll_stride;
     // best token: lowest cost, ties -> lowest state id (inl.h:169-179); accumulated by k_finalize
     const unsigned long long best64 = st->best64;
     float cur_cut = CUDART_INF_F, abeam = cfg.beam;
@@ -769,7 +747,7 @@ k_cutoff(StreamState *const *streams, FrameDesc *desc, GraphView g, DecoderConfi
       nd.bm = st->bm[(t + 1) & 1];
       nd.ebm = st->ebm[(t + 1) & 1];
       nd.out_sc = st->tok_sc + out_base;
-      nd.out_aa = st->tok_aa + out_base;
+      nd.out_arc = st->tok_arc + out_base;
       nd.best64 = kInfVal;
       nd.n_cur = n;
       nd.cur_cut = cur_cut;
@@ -805,9 +783,15 @@ __global__ void k_counters(StreamState *const *streams, int n, unsigned long lon
 // super-final state when use_final_probs and one is alive, else the cheapest token; ties ->
 // lowest state id) and follows the winning arcs back to the start token
 // (TraceBackBestPath, inl.h:1160-1200).  Arcs are emitted end -> start.
+//
+// For every step pred -> tok the reference reports the most recently added surviving forward
+// link (inl.h:1169-1186); links are prepended in arc order (inl.h:340-341, 421-422) and excised
+// when link_extra_cost > lattice_beam (inl.h:524-542), which on the best path is
+// (tot' - tok.cost) > lattice_beam.  With parallel arcs pred.state -> tok.state that is the
+// highest-index admitted sibling within lattice_beam, not necessarily the cheapest one.
 __global__ void __launch_bounds__(256)
-k_best_path(StreamState *const *streams, GraphView g, int use_final, int cap, int32_t *o_il,
-            int32_t *o_ol, float *o_gr, float *o_ac, int32_t *o_n, int32_t *o_status) {
+k_best_path(StreamState *const *streams, GraphView g, DecoderConfigDev cfg, int use_final, int cap,
+            int32_t *o_il, int32_t *o_ol, float *o_gr, float *o_ac, int32_t *o_n, int32_t *o_status) {
   constexpr int NT = 256;
   __shared__ unsigned long long s_red64[NT / 32];
   __shared__ uint32_t s_found;
@@ -822,19 +806,29 @@ k_best_path(StreamState *const *streams, GraphView g, int use_final, int cap, in
     }
     return;
   }
+  auto find_token = [&](int frame, uint32_t state) -> uint32_t {
+    if (tid == 0) s_found = 0xFFFFFFFFu;
+    __syncthreads();
+    const uint32_t b = st->frame_off[frame], n = st->frame_off[frame + 1] - b;
+    for (uint32_t i = tid; i < n; i += NT)
+      if (st->tok_sc[b + i].x == state) s_found = b + i;
+    __syncthreads();
+    const uint32_t idx = s_found;
+    __syncthreads();
+    return idx;
+  };
   // end token
   const uint32_t b0 = st->frame_off[f], n0 = st->frame_off[f + 1] - b0;
   unsigned long long best_all = kInfVal, best_fin = kInfVal;
   for (uint32_t i = tid; i < n0; i += NT) {
     const uint2 sc = st->tok_sc[b0 + i];
-    // key: (cost, state) for the argmin; the index is recovered by a second scan
     const unsigned long long b = ((unsigned long long)f2ord(__uint_as_float(sc.y)) << 32) | sc.x;
     best_all = b < best_all ? b : best_all;
     if ((int32_t)sc.x == g.final_state) best_fin = b < best_fin ? b : best_fin;
   }
   best_all = block_min_u64<NT>(best_all, s_red64);
   best_fin = block_min_u64<NT>(best_fin, s_red64);
-  unsigned long long pick = (use_final && best_fin != kInfVal) ? best_fin : best_all;
+  const unsigned long long pick = (use_final && best_fin != kInfVal) ? best_fin : best_all;
   if (pick == kInfVal) {
     if (tid == 0) {
       o_n[blockIdx.x] = 0;
@@ -842,51 +836,75 @@ k_best_path(StreamState *const *streams, GraphView g, int use_final, int cap, in
     }
     return;
   }
-  uint32_t want = (uint32_t)pick;  // state of the token to locate in frame f
+  uint32_t idx = find_token(f, (uint32_t)pick);
   int n_out = 0;
-  int status = ASRD_OK;
-  while (true) {
-    // locate the token of `want` in frame f
-    if (tid == 0) s_found = 0xFFFFFFFFu;
-    __syncthreads();
-    const uint32_t b = st->frame_off[f], n = st->frame_off[f + 1] - b;
-    for (uint32_t i = tid; i < n; i += NT)
-      if (st->tok_sc[b + i].x == want) s_found = b + i;
-    __syncthreads();
-    const uint32_t idx = s_found;
-    __syncthreads();
-    if (idx == 0xFFFFFFFFu) {
-      status = ASRD_ERR_STATE;  // broken back-trace: cannot happen unless the arena overflowed
-      break;
-    }
-    const uint2 aa = st->tok_aa[idx];
-    int32_t il = 0, ol = 0;
-    float gr = 0.f;
-    const float ac = __uint_as_float(aa.y);
-    if (aa.x != kNoArc) {
-      const int4 arc = __ldg(&g.arcs[aa.x]);
-      il = arc.x;
-      ol = arc.y;
-      gr = __int_as_float(arc.z);
-    }
+  int status = idx == 0xFFFFFFFFu ? ASRD_ERR_STATE : ASRD_OK;
+  while (status == ASRD_OK) {
+    const uint2 sc = st->tok_sc[idx];
+    const uint32_t state = sc.x;
+    const float cost = __uint_as_float(sc.y);
+    uint32_t rep = st->tok_arc[idx];
     if (n_out >= cap) {
       status = ASRD_ERR_PATH_OVERFLOW;
       break;
     }
-    if (tid == 0) {
-      o_il[ob + n_out] = il;
-      o_ol[ob + n_out] = ol;
-      o_gr[ob + n_out] = gr;
-      o_ac[ob + n_out] = ac;
+    if (rep == kNoArc) {  // start token: label-free arc with unit weight (inl.h:1193-1198)
+      if (tid == 0) {
+        o_il[ob + n_out] = 0;
+        o_ol[ob + n_out] = 0;
+        o_gr[ob + n_out] = 0.f;
+        o_ac[ob + n_out] = 0.f;
+      }
+      ++n_out;
+      break;
     }
-    ++n_out;
-    if (aa.x == kNoArc) break;  // start token (inl.h:1193-1198)
-    want = __ldg(&g.arc_src[aa.x]);
-    if (il != 0) --f;
-    if (f < 0) {
+    int4 arc = __ldg(&g.arcs[rep]);
+    const bool emitting = arc.x != 0;
+    const uint32_t src = __ldg(&g.arc_src[rep]);
+    const int fp = emitting ? f - 1 : f;
+    if (fp < 0) {
       status = ASRD_ERR_STATE;
       break;
     }
+    const uint32_t pidx = find_token(fp, src);
+    if (pidx == 0xFFFFFFFFu) {
+      status = ASRD_ERR_STATE;  // broken back-trace: cannot happen unless the arena overflowed
+      break;
+    }
+    const float *__restrict__ ll = emitting ? st->ll_hist + (size_t)fp * st->ll_stride : nullptr;
+    if (par_bit(g.par_bits, rep)) {
+      const float pc = __uint_as_float(st->tok_sc[pidx].y);
+      const float nc = st->frame_nc[f];
+      const uint2 r = __ldg(&g.rows[src]);
+      const uint32_t hi = emitting ? __ldg(&g.rows[src + 1]).x : r.y;
+      for (uint32_t a2 = hi; a2-- > rep + 1;) {
+        const int4 arc2 = __ldg(&g.arcs[a2]);
+        if ((uint32_t)arc2.w != state) continue;
+        float tot2;
+        bool admitted;
+        if (emitting) {
+          tot2 = (pc + (-ll[arc2.x - 1])) + __int_as_float(arc2.z);  // inl.h:326-329
+          admitted = tot2 < nc;                                      // inl.h:330
+        } else {
+          tot2 = pc + __int_as_float(arc2.z);                        // inl.h:413-414
+          admitted = pc < nc && tot2 < nc;                           // inl.h:391,415
+        }
+        if (admitted && !((tot2 - cost) > cfg.lattice_beam)) {       // inl.h:524-532
+          rep = a2;
+          arc = arc2;
+          break;
+        }
+      }
+    }
+    if (tid == 0) {
+      o_il[ob + n_out] = arc.x;
+      o_ol[ob + n_out] = arc.y;
+      o_gr[ob + n_out] = __int_as_float(arc.z);
+      o_ac[ob + n_out] = emitting ? -ll[arc.x - 1] : 0.f;
+    }
+    ++n_out;
+    f = fp;
+    idx = pidx;
   }
   if (tid == 0) {
     o_n[blockIdx.x] = n_out;
