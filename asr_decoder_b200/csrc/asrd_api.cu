@@ -195,7 +195,7 @@ int EnvInt(const char *name, int dflt) {
 // shared memory when it fits) and sizes the grid to about one resident wave: blockIdx.y is
 // the stream, gridDim.x CTAs share one stream's token groups.
 int PlanExpand(int n_streams, int num_indices, ExpandPlan *plan) {
-  const int u = EnvInt("ASRD_EXPAND_U", 2);
+  const int u = EnvInt("ASRD_EXPAND_U", 1);
   const bool smem_ll = EnvInt("ASRD_SMEM_LL", 1) != 0 && (size_t)num_indices * 4 <= 96 * 1024;
   ExpandFn fn;
   if (smem_ll) fn = u >= 4 ? k_expand<4, true> : (u == 2 ? k_expand<2, true> : k_expand<1, true>);
@@ -207,7 +207,7 @@ int PlanExpand(int n_streams, int num_indices, ExpandPlan *plan) {
   CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kExpandThreads, dyn));
   const int resident = g_num_sms * std::max(per_sm, 1);
   int gx = EnvInt("ASRD_EXPAND_G", 0);
-  if (gx <= 0) gx = (resident + n_streams - 1) / n_streams;
+  if (gx <= 0) gx = (4 * resident + n_streams - 1) / n_streams;  // ~4 waves of small CTAs balance best
   plan->fn = fn;
   plan->grid = dim3((unsigned)std::max(gx, 1), (unsigned)n_streams, 1);
   plan->dyn = dyn;
@@ -486,10 +486,15 @@ int asrd_init_decoding(asrd_decoder *const *decs, int32_t n, void *stream) {
   CU_CHECK(sc.Alloc(&d_desc, (size_t)n));
   const uint32_t gps = (uint32_t)decs[0]->opts.hash_capacity / 1024;
   k_init<<<n, kStreamThreads, 0, s>>>(d_streams, d_desc, gv, cfg);
-  k_closure<<<n, kStreamThreads, 0, s>>>(d_desc, gv);
-  k_finalize<<<FinalizeGrid(), kFinThreads, 0, s>>>(d_desc, n, gps);
-  k_cutoff<<<n, kStreamThreads, 0, s>>>(d_streams, d_desc, gv, cfg, kModeEpi);
-  g_launches += 4;
+  if (EnvInt("ASRD_FUSED_POST", 1)) {
+    k_post<<<n, kStreamThreads, 0, s>>>(d_streams, d_desc, gv, cfg, kModeEpi);
+    g_launches += 2;
+  } else {
+    k_closure<<<n, kStreamThreads, 0, s>>>(d_desc, gv);
+    k_finalize<<<FinalizeGrid(), kFinThreads, 0, s>>>(d_desc, n, gps);
+    k_cutoff<<<n, kStreamThreads, 0, s>>>(d_streams, d_desc, gv, cfg, kModeEpi);
+    g_launches += 4;
+  }
   CU_CHECK(cudaGetLastError());
   for (int i = 0; i < n; ++i) {
     decs[i]->frames_decoded = 0;
@@ -547,6 +552,7 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
   ExpandPlan plan;
   if ((rc = PlanExpand(n, num_indices, &plan))) return rc;
   const int fin_grid = FinalizeGrid();
+  const bool fused_post = EnvInt("ASRD_FUSED_POST", 1) != 0;
   const uint32_t gps = (uint32_t)decs[0]->opts.hash_capacity / 1024;
   const size_t row = (size_t)num_indices;
 
@@ -613,16 +619,24 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
       prof.Begin(0, s);
       plan.fn<<<plan.grid, kExpandThreads, plan.dyn, s>>>(d_desc, gv, num_indices);
       prof.End(s);
-      prof.Begin(1, s);
-      k_closure<<<n, kStreamThreads, 0, s>>>(d_desc, gv);
-      prof.End(s);
-      prof.Begin(2, s);
-      k_finalize<<<fin_grid, kFinThreads, 0, s>>>(d_desc, n, gps);
-      prof.End(s);
-      prof.Begin(3, s);
-      k_cutoff<<<n, kStreamThreads, 0, s>>>(d_streams, d_desc, gv, cfg, kModeEpi | (f + 1 < steps ? kModePro : 0));
-      prof.End(s);
-      g_launches += 4;
+      const int post_mode = kModeEpi | (f + 1 < steps ? kModePro : 0);
+      if (fused_post) {
+        prof.Begin(1, s);
+        k_post<<<n, kStreamThreads, 0, s>>>(d_streams, d_desc, gv, cfg, post_mode);
+        prof.End(s);
+        g_launches += 2;
+      } else {
+        prof.Begin(1, s);
+        k_closure<<<n, kStreamThreads, 0, s>>>(d_desc, gv);
+        prof.End(s);
+        prof.Begin(2, s);
+        k_finalize<<<fin_grid, kFinThreads, 0, s>>>(d_desc, n, gps);
+        prof.End(s);
+        prof.Begin(3, s);
+        k_cutoff<<<n, kStreamThreads, 0, s>>>(d_streams, d_desc, gv, cfg, post_mode);
+        prof.End(s);
+        g_launches += 4;
+      }
     }
     CU_CHECK(cudaGetLastError());
   }
@@ -672,23 +686,18 @@ int asrd_get_best_path(asrd_decoder *const *decs, int32_t n, int32_t use_final_p
   CU_CHECK(sc.Alloc(&d_ac, tot));
   CU_CHECK(sc.Alloc(&d_n, (size_t)n));
   CU_CHECK(sc.Alloc(&d_st, (size_t)n));
-  k_best_path<<<n, 256, 0, s>>>(d_streams, decs[0]->graph->view, DevCfg(decs[0]), use_final_probs, cap, d_il,
+  k_best_path<<<n, kBestPathThreads, 0, s>>>(d_streams, decs[0]->graph->view, DevCfg(decs[0]), use_final_probs, cap, d_il,
                                 d_ol, d_gr, d_ac, d_n, d_st);
   ++g_launches;
   CU_CHECK(cudaGetLastError());
   CU_CHECK(cudaMemcpyAsync(n_arcs, d_n, 4 * (size_t)n, cudaMemcpyDeviceToHost, s));
   CU_CHECK(cudaMemcpyAsync(status, d_st, 4 * (size_t)n, cudaMemcpyDeviceToHost, s));
   CU_CHECK(cudaStreamSynchronize(s));
-  // arcs come back end -> start; copy only what each stream produced and flip to path order
-  for (int i = 0; i < n; ++i) {
-    const int32_t m = std::max(0, std::min(n_arcs[i], cap));
-    const size_t b = (size_t)i * cap;
-    if (m == 0) continue;
-    CU_CHECK(cudaMemcpyAsync(ilabel + b, d_il + b, 4 * (size_t)m, cudaMemcpyDeviceToHost, s));
-    CU_CHECK(cudaMemcpyAsync(olabel + b, d_ol + b, 4 * (size_t)m, cudaMemcpyDeviceToHost, s));
-    CU_CHECK(cudaMemcpyAsync(graph + b, d_gr + b, 4 * (size_t)m, cudaMemcpyDeviceToHost, s));
-    CU_CHECK(cudaMemcpyAsync(acoustic + b, d_ac + b, 4 * (size_t)m, cudaMemcpyDeviceToHost, s));
-  }
+  // arcs come back end -> start; one copy per array, then flip each stream to path order
+  CU_CHECK(cudaMemcpyAsync(ilabel, d_il, 4 * tot, cudaMemcpyDeviceToHost, s));
+  CU_CHECK(cudaMemcpyAsync(olabel, d_ol, 4 * tot, cudaMemcpyDeviceToHost, s));
+  CU_CHECK(cudaMemcpyAsync(graph, d_gr, 4 * tot, cudaMemcpyDeviceToHost, s));
+  CU_CHECK(cudaMemcpyAsync(acoustic, d_ac, 4 * tot, cudaMemcpyDeviceToHost, s));
   CU_CHECK(cudaStreamSynchronize(s));
   for (int i = 0; i < n; ++i) {
     const int32_t m = std::max(0, std::min(n_arcs[i], cap));

@@ -16,6 +16,7 @@ constexpr uint32_t kOrdInf = 0xFF800000u;  // f2ord(+inf)
 constexpr int kExpandThreads = 256;   // CTA size of the expand kernel (8 warps, one token group each)
 constexpr int kFinThreads = 256;      // CTA size of the finalize kernel
 constexpr int kStreamThreads = 1024;  // CTA size of the per-stream kernels (closure, cutoff)
+constexpr int kBestPathThreads = 512; // CTA size of the back-trace kernel
 constexpr int kMaxBatch = 65535;      // streams per launch (gridDim.y of k_expand)
 constexpr int kMinHashCapacity = 4096;
 

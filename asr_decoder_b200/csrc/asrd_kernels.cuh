@@ -623,6 +623,103 @@ __device__ float block_kth_smallest(const uint2 *tok_sc, uint32_t n, uint32_t k,
   return ord2f(prefix + min_ord);
 }
 
+// GetCutoff (inl.h:138-234) over the current frame's tokens, best-token pre-pass
+// (inl.h:282-300), and the descriptor of the next expansion.  Whole-CTA device function.
+template <int NT>
+__device__ __forceinline__ void cutoff_prologue(StreamState *st, FrameDesc *d, const GraphView &g,
+                                                const DecoderConfigDev &cfg, unsigned long long *s_red64,
+                                                uint32_t *s_red32, uint32_t *s_hist, uint32_t *s_misc) {
+  const int tid = threadIdx.x;
+  const int t = st->frame;
+  if (t >= st->target_frame) {
+    if (tid == 0) d->stepping = 0;
+    return;
+  }
+  const uint32_t n = st->n_cur;
+  const uint32_t tok_off = st->frame_off[t];
+  const uint2 *toks = st->tok_sc + tok_off;
+  const float *__restrict__ ll = st->ll_hist + (size_t)t * st->ll_stride;
+  // best token: lowest cost, ties -> lowest state id (inl.h:169-179); accumulated by k_finalize
+  const unsigned long long best64 = st->best64;
+  float cur_cut = CUDART_INF_F, abeam = cfg.beam;
+  uint32_t next_bits = kOrdInf;
+  if (n > 0) {
+    const uint32_t best_ord = (uint32_t)(best64 >> 32);
+    const float bc = ord2f(best_ord);
+    const float beam_cut = bc + cfg.beam;  // inl.h:182
+    const uint32_t beam_ord = f2ord(beam_cut);
+    cur_cut = beam_cut;
+    if (n <= (uint32_t)cfg.min_active && n <= (uint32_t)cfg.max_active) {
+      // fewer tokens than min_active: min_active_cutoff stays +inf > beam_cutoff, nothing is
+      // pruned and the adaptive beam is infinite (inl.h:183,205,220-226)
+      cur_cut = CUDART_INF_F;
+      abeam = CUDART_INF_F;
+    } else {
+      uint32_t lt = 0, le = 0;
+      for (uint32_t i = tid; i < n; i += NT) {
+        const float c = __uint_as_float(toks[i].y);
+        lt += c < beam_cut;
+        le += c <= beam_cut;
+      }
+      lt = block_sum_u32<NT>(lt, s_red32);
+      le = block_sum_u32<NT>(le, s_red32);
+      if (lt > (uint32_t)cfg.max_active) {
+        // sorted[max_active] < beam_cutoff  <=>  more than max_active costs below it (inl.h:188-203)
+        cur_cut = block_kth_smallest<NT>(toks, n, (uint32_t)cfg.max_active, best_ord, beam_ord,
+                                         beam_ord - best_ord, s_hist, s_misc);
+        abeam = cur_cut - bc + cfg.beam_delta;
+      } else if (n <= (uint32_t)cfg.min_active) {
+        cur_cut = CUDART_INF_F;
+        abeam = CUDART_INF_F;
+      } else if (cfg.min_active > 0 && le <= (uint32_t)cfg.min_active) {
+        // sorted[min_active] > beam_cutoff  <=>  at most min_active costs <= it (inl.h:205-226)
+        cur_cut = block_kth_smallest<NT>(toks, n, (uint32_t)cfg.min_active, best_ord, 0xFFFFFFFFu,
+                                         0xFFFFFFFFu, s_hist, s_misc);
+        abeam = cur_cut - bc + cfg.beam_delta;
+      }
+    }
+    // best-token pre-pass (inl.h:282-300): association (cost + w) - loglike
+    const uint32_t sb = (uint32_t)best64;
+    const uint2 r = __ldg(&g.rows[sb]);
+    const uint32_t end = __ldg(&g.rows[sb + 1]).x;
+    uint32_t mn = kOrdInf;
+    for (uint32_t a = r.y + tid; a < end; a += NT) {
+      const int4 arc = __ldg(&g.arcs[a]);
+      const float tot = bc + __int_as_float(arc.z) - __ldg(&ll[arc.x - 1]);
+      mn = min(mn, f2ord(tot + abeam));
+    }
+    const unsigned long long m64 = block_min_u64<NT>((unsigned long long)mn, s_red64);
+    next_bits = (uint32_t)m64;
+  }
+  if (tid == 0) {
+    const uint32_t out_base = st->frame_off[t + 1];
+    FrameDesc nd;
+    nd.st = st;
+    nd.toks = toks;
+    nd.ll = ll;
+    nd.hn = st->hash[(t + 1) & 1];
+    nd.hc = st->hash[t & 1];
+    nd.bm = st->bm[(t + 1) & 1];
+    nd.ebm = st->ebm[(t + 1) & 1];
+    nd.out_sc = st->tok_sc + out_base;
+    nd.out_arc = st->tok_arc + out_base;
+    nd.best64 = kInfVal;
+    nd.n_cur = n;
+    nd.cur_cut = cur_cut;
+    nd.abeam = abeam;
+    nd.next_cut_bits = next_bits;
+    nd.mask = st->hash_mask;
+    nd.shift = st->hash_shift;
+    nd.out_cap = st->token_capacity > out_base ? st->token_capacity - out_base : 0;
+    nd.n_alive = 0;
+    nd.arcs_expanded = 0;
+    nd.arcs_admitted = 0;
+    nd.stepping = 1;
+    nd.t = t;
+    *d = nd;
+  }
+}
+
 // One CTA per stream.  EPI: close the frame step (arena offsets, statistics, recycle the map of
 // the previous frame).  PRO: GetCutoff (inl.h:138-234) over the new frame's tokens, best-token
 // pre-pass (inl.h:282-300), and the descriptor of the next step.
@@ -674,96 +771,187 @@ k_cutoff(StreamState *const *streams, FrameDesc *desc, GraphView g, DecoderConfi
     __syncthreads();
   }
 
-  if (mode & kModePro) {
-    const int t = st->frame;
-    if (t >= st->target_frame) {
-      if (tid == 0) d->stepping = 0;
-      return;
-    }
-    const uint32_t n = st->n_cur;
-    const uint32_t tok_off = st->frame_off[t];
-    const uint2 *toks = st->tok_sc + tok_off;
-    const float *__restrict__ ll = st->ll_hist + (size_t)t * st->ll_stride;
-    // best token: lowest cost, ties -> lowest state id (inl.h:169-179); accumulated by k_finalize
-    const unsigned long long best64 = st->best64;
-    float cur_cut = CUDART_INF_F, abeam = cfg.beam;
-    uint32_t next_bits = kOrdInf;
-    if (n > 0) {
-      const uint32_t best_ord = (uint32_t)(best64 >> 32);
-      const float bc = ord2f(best_ord);
-      const float beam_cut = bc + cfg.beam;  // inl.h:182
-      const uint32_t beam_ord = f2ord(beam_cut);
-      cur_cut = beam_cut;
-      if (n <= (uint32_t)cfg.min_active && n <= (uint32_t)cfg.max_active) {
-        // fewer tokens than min_active: min_active_cutoff stays +inf > beam_cutoff, nothing is
-        // pruned and the adaptive beam is infinite (inl.h:183,205,220-226)
-        cur_cut = CUDART_INF_F;
-        abeam = CUDART_INF_F;
-      } else {
-        uint32_t lt = 0, le = 0;
-        for (uint32_t i = tid; i < n; i += NT) {
-          const float c = __uint_as_float(toks[i].y);
-          lt += c < beam_cut;
-          le += c <= beam_cut;
-        }
-        lt = block_sum_u32<NT>(lt, s_red32);
-        le = block_sum_u32<NT>(le, s_red32);
-        if (lt > (uint32_t)cfg.max_active) {
-          // sorted[max_active] < beam_cutoff  <=>  more than max_active costs below it (inl.h:188-203)
-          cur_cut = block_kth_smallest<NT>(toks, n, (uint32_t)cfg.max_active, best_ord, beam_ord,
-                                           beam_ord - best_ord, s_hist, s_misc);
-          abeam = cur_cut - bc + cfg.beam_delta;
-        } else if (n <= (uint32_t)cfg.min_active) {
-          cur_cut = CUDART_INF_F;
-          abeam = CUDART_INF_F;
-        } else if (cfg.min_active > 0 && le <= (uint32_t)cfg.min_active) {
-          // sorted[min_active] > beam_cutoff  <=>  at most min_active costs <= it (inl.h:205-226)
-          cur_cut = block_kth_smallest<NT>(toks, n, (uint32_t)cfg.min_active, best_ord, 0xFFFFFFFFu,
-                                           0xFFFFFFFFu, s_hist, s_misc);
-          abeam = cur_cut - bc + cfg.beam_delta;
-        }
-      }
-      // best-token pre-pass (inl.h:282-300): association (cost + w) - loglike
-      const uint32_t sb = (uint32_t)best64;
-      const uint2 r = __ldg(&g.rows[sb]);
-      const uint32_t end = __ldg(&g.rows[sb + 1]).x;
-      uint32_t mn = kOrdInf;
-      for (uint32_t a = r.y + tid; a < end; a += NT) {
-        const int4 arc = __ldg(&g.arcs[a]);
-        const float tot = bc + __int_as_float(arc.z) - __ldg(&ll[arc.x - 1]);
-        mn = min(mn, f2ord(tot + abeam));
-      }
-      const unsigned long long m64 = block_min_u64<NT>((unsigned long long)mn, s_red64);
-      next_bits = (uint32_t)m64;
-    }
+  if (mode & kModePro) cutoff_prologue<NT>(st, d, g, cfg, s_red64, s_red32, s_hist, s_misc);
+}
+
+// ------------------------------------------------------------------ fused per-stream post phase
+
+// k_closure + k_finalize + k_cutoff for one stream in ONE CTA: everything that follows the
+// emitting expansion of a frame only touches the stream's own state, so a single resident CTA
+// carries it from the eps closure to the descriptor of the next expansion without going back
+// to the host-visible launch queue (three launches and their descriptor round trips saved).
+// The survivor counter and the best token live in shared memory instead of global atomics.
+__global__ void __launch_bounds__(kStreamThreads, 2)
+k_post(StreamState *const *streams, FrameDesc *desc, GraphView g, DecoderConfigDev cfg, int mode) {
+  constexpr int NT = kStreamThreads;
+  __shared__ unsigned long long s_red64[NT / 32];
+  __shared__ uint32_t s_red32[NT / 32];
+  __shared__ uint32_t s_hist[256];
+  __shared__ uint32_t s_misc[4];
+  __shared__ uint32_t s_qn[2];
+  __shared__ uint32_t s_alive;
+  __shared__ unsigned long long s_best;
+  StreamState *st = streams[blockIdx.x];
+  FrameDesc *d = &desc[blockIdx.x];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  if ((mode & kModeEpi) && d->stepping) {
+    const int t = d->t;
+    const uint32_t mask = d->mask, shift = d->shift;
+    const uint32_t groups = (mask + 1) >> 10;
+    HashEntry *hn = d->hn;
+    uint32_t *bm = d->bm;
+    uint32_t *ebm = d->ebm;
+    const float nc = ord2f(d->next_cut_bits);  // the FINAL next_cutoff of this frame
+    uint32_t *q0 = st->queue[0], *q1 = st->queue[1];
     if (tid == 0) {
-      const uint32_t out_base = st->frame_off[t + 1];
-      FrameDesc nd;
-      nd.st = st;
-      nd.toks = toks;
-      nd.ll = ll;
-      nd.hn = st->hash[(t + 1) & 1];
-      nd.hc = st->hash[t & 1];
-      nd.bm = st->bm[(t + 1) & 1];
-      nd.ebm = st->ebm[(t + 1) & 1];
-      nd.out_sc = st->tok_sc + out_base;
-      nd.out_arc = st->tok_arc + out_base;
-      nd.best64 = kInfVal;
-      nd.n_cur = n;
-      nd.cur_cut = cur_cut;
-      nd.abeam = abeam;
-      nd.next_cut_bits = next_bits;
-      nd.mask = st->hash_mask;
-      nd.shift = st->hash_shift;
-      nd.out_cap = st->token_capacity > out_base ? st->token_capacity - out_base : 0;
-      nd.n_alive = 0;
-      nd.arcs_expanded = 0;
-      nd.arcs_admitted = 0;
-      nd.stepping = 1;
-      nd.t = t;
-      *d = nd;
+      s_qn[0] = s_qn[1] = 0;
+      s_alive = 0;
+      s_best = kInfVal;
     }
+    __syncthreads();
+
+    // ---- eps closure (ProcessNonemitting, inl.h:353-431)
+    auto relax_from = [&](uint32_t slot, uint32_t round) {
+      const uint4 e = __ldcg(reinterpret_cast<const uint4 *>(&hn[slot]));
+      const uint32_t state = e.x;
+      const float cost = ord2f(e.w);
+      if (!(cost < nc)) return;  // inl.h:391
+      const uint2 r = __ldg(&g.rows[state]);
+      uint32_t *qout = ((round + 1) & 1) ? q1 : q0;
+      for (uint32_t a = r.x; a < r.y; ++a) {
+        const int4 arc = __ldg(&g.arcs[a]);
+        const float tot = cost + __int_as_float(arc.z);  // inl.h:413-414
+        if (tot < nc) {                                   // inl.h:415
+          uint32_t slot2;
+          bool is_new;
+          if (!hash_claim(hn, mask, hash_state((uint32_t)arc.w, mask, shift), (uint32_t)arc.w, slot2, is_new)) {
+            atomicMin(&st->status, ASRD_ERR_HASH_OVERFLOW);
+            continue;
+          }
+          const unsigned long long pk = pack_val(tot, a);
+          const unsigned long long old = atomicMin(&hn[slot2].val, pk);
+          if (is_new) atomicOr(&bm[slot2 >> 5], 1u << (slot2 & 31u));
+          const bool changed = (uint32_t)(pk >> 32) < (uint32_t)(old >> 32);  // inl.h:115-127
+          if (changed && eps_bit(g.eps_bits, (uint32_t)arc.w) &&
+              atomicExch(&hn[slot2].aux, round + 1) != round + 1)
+            qout[atomicAdd(&s_qn[(round + 1) & 1], 1u)] = slot2;  // inl.h:425-426
+        }
+      }
+    };
+    for (uint32_t w = tid; w < (groups << 5); w += NT) {  // round-1 seeds (inl.h:376-381)
+      uint32_t bits = ebm[w];
+      if (bits) {
+        ebm[w] = 0;
+        uint32_t pos = atomicAdd(&s_qn[1], (uint32_t)__popc(bits));
+        while (bits) {
+          const uint32_t b = __ffs(bits) - 1;
+          bits &= bits - 1;
+          q1[pos++] = (w << 5) + b;
+        }
+      }
+    }
+    for (uint32_t round = 1;; ++round) {
+      __syncthreads();
+      const uint32_t nq = s_qn[round & 1];
+      if (nq == 0) break;
+      __syncthreads();
+      if (tid == 0) s_qn[(round + 1) & 1] = 0;
+      __syncthreads();
+      const uint32_t *qin = (round & 1) ? q1 : q0;
+      for (uint32_t i = tid; i < nq; i += NT) relax_from(qin[i], round);
+    }
+    // (the loop exits right after a barrier: every relaxation is visible)
+
+    // ---- survivors -> token arena
+    {
+      const uint32_t cap = d->out_cap;
+      uint2 *out_sc = d->out_sc;
+      uint32_t *out_arc = d->out_arc;
+      unsigned long long best64 = kInfVal;
+      for (uint32_t grp = warp; grp < groups; grp += NT / 32) {
+        const uint32_t word = __ldcg(&bm[grp * 32 + lane]);
+        if (!__any_sync(kFull, word != 0)) continue;
+        const uint32_t cnt = __popc(word);
+        const uint32_t incl = warp_incl_scan(cnt, lane);
+        const uint32_t off = incl - cnt;
+        const uint32_t total = __shfl_sync(kFull, incl, 31);
+        for (uint32_t ib = 0; ib < total; ib += 32) {
+          const uint32_t it = ib + lane;
+          const int l = warp_owner(off, it);
+          const uint32_t wl = __shfl_sync(kFull, word, l);
+          const uint32_t offl = __shfl_sync(kFull, off, l);
+          bool alive = false;
+          uint32_t key = 0, rep = kNoArc;
+          float cost = 0.f;
+          if (it < total) {
+            const uint32_t b = __fns(wl, 0, (int)(it - offl) + 1);
+            const uint32_t slot = ((grp * 32 + l) << 5) + b;
+            const uint4 e = __ldcg(reinterpret_cast<const uint4 *>(&hn[slot]));
+            key = e.x;
+            rep = e.z;
+            cost = ord2f(e.w);
+            alive = cost < nc;
+          }
+          const unsigned am = __ballot_sync(kFull, alive);
+          if (am == 0) continue;
+          uint32_t pos0 = 0;
+          if (lane == 0) pos0 = atomicAdd(&s_alive, (uint32_t)__popc(am));
+          pos0 = __shfl_sync(kFull, pos0, 0);
+          if (alive) {
+            const uint32_t idx = pos0 + __popc(am & ((1u << lane) - 1u));
+            if (idx < cap) {
+              out_sc[idx] = make_uint2(key, __float_as_uint(cost));
+              out_arc[idx] = rep;
+            }
+            const unsigned long long b64 = ((unsigned long long)f2ord(cost) << 32) | key;
+            best64 = b64 < best64 ? b64 : best64;
+          }
+        }
+      }
+#pragma unroll
+      for (int dlt = 16; dlt > 0; dlt >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(kFull, best64, dlt);
+        best64 = o < best64 ? o : best64;
+      }
+      if (lane == 0 && best64 != kInfVal) atomicMin(&s_best, best64);
+    }
+    // ---- recycle the map of the previous frame
+    clear_map_by_bitmap(st->hash[t & 1], st->bm[t & 1], (mask + 1) >> 5, warp, lane, NT / 32);
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t n_alive = s_alive;
+      if (n_alive > d->out_cap) {
+        n_alive = d->out_cap;
+        atomicMin(&st->status, ASRD_ERR_ARENA_OVERFLOW);
+      }
+      const unsigned long long b64 = s_best;
+      const uint32_t out_base = st->frame_off[t + 1];
+      if (cfg.collect_stats && st->stats) {
+        asrd_frame_stat fs;
+        fs.n_in = d->n_cur;
+        fs.cur_cutoff = d->cur_cut;
+        fs.abeam = d->abeam;
+        fs.next_cutoff = nc;
+        fs.n_tokens = n_alive;
+        fs.best = b64 == kInfVal ? CUDART_INF_F : ord2f((uint32_t)(b64 >> 32));
+        fs.arcs_expanded = d->arcs_expanded;
+        fs.arcs_admitted = d->arcs_admitted;
+        st->stats[t + 1] = fs;
+      }
+      st->tot_arcs_expanded += d->arcs_expanded;
+      st->tot_arcs_admitted += d->arcs_admitted;
+      st->frame_off[t + 2] = out_base + n_alive;
+      st->frame_nc[t + 1] = nc;
+      st->frame = t + 1;
+      st->n_cur = n_alive;
+      st->best64 = b64;
+      d->stepping = 0;
+    }
+    __syncthreads();
   }
+
+  if (mode & kModePro) cutoff_prologue<NT>(st, d, g, cfg, s_red64, s_red32, s_hist, s_misc);
 }
 
 // ------------------------------------------------------------------ counters
@@ -789,10 +977,10 @@ __global__ void k_counters(StreamState *const *streams, int n, unsigned long lon
 // when link_extra_cost > lattice_beam (inl.h:524-542), which on the best path is
 // (tot' - tok.cost) > lattice_beam.  With parallel arcs pred.state -> tok.state that is the
 // highest-index admitted sibling within lattice_beam, not necessarily the cheapest one.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kBestPathThreads)
 k_best_path(StreamState *const *streams, GraphView g, DecoderConfigDev cfg, int use_final, int cap,
             int32_t *o_il, int32_t *o_ol, float *o_gr, float *o_ac, int32_t *o_n, int32_t *o_status) {
-  constexpr int NT = 256;
+  constexpr int NT = kBestPathThreads;
   __shared__ unsigned long long s_red64[NT / 32];
   __shared__ uint32_t s_found;
   StreamState *st = streams[blockIdx.x];
@@ -810,8 +998,18 @@ k_best_path(StreamState *const *streams, GraphView g, DecoderConfigDev cfg, int 
     if (tid == 0) s_found = 0xFFFFFFFFu;
     __syncthreads();
     const uint32_t b = st->frame_off[frame], n = st->frame_off[frame + 1] - b;
-    for (uint32_t i = tid; i < n; i += NT)
-      if (st->tok_sc[b + i].x == state) s_found = b + i;
+    const uint2 *__restrict__ toks = st->tok_sc + b;
+    for (uint32_t i0 = 0; i0 < n; i0 += NT * 4) {  // four independent loads in flight per thread
+      uint32_t k[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t i = i0 + u * NT + tid;
+        k[u] = i < n ? __ldg(&toks[i]).x : 0xFFFFFFFFu;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (k[u] == state) s_found = b + i0 + u * NT + tid;
+    }
     __syncthreads();
     const uint32_t idx = s_found;
     __syncthreads();

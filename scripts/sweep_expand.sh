@@ -1,8 +1,8 @@
 #!/bin/bash
-# quick A/B of k_expand variants (run under gpurun)
+# quick A/B of kernel variants (run under gpurun)
 run() {
   echo "== $*"
-  env "$@" python bench.py --steps 2 --warmup 2 --no-cpu-baseline 2>&1 | python -c "
+  env "$@" python bench.py --steps 2 --warmup 2 --no-cpu-baseline --no-e2e 2>&1 | python -c "
 import sys, json
 for l in sys.stdin:
     if l.startswith('{'):
@@ -11,6 +11,5 @@ for l in sys.stdin:
     else: print(l.rstrip()[:300])
 "
 }
-run ASRD_EXPAND_U=1 ASRD_EXPAND_G=16
-run ASRD_EXPAND_U=1 ASRD_EXPAND_G=32
-run ASRD_EXPAND_U=2 ASRD_EXPAND_G=16
+run ASRD_FUSED_POST=1
+run ASRD_FUSED_POST=0
