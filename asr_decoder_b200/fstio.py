@@ -90,12 +90,16 @@ def write_fst(path: str, fst: Fst) -> None:
 
 def read_fst(path: str) -> Fst:
     with open(path, "rb") as f:
-        hdr = np.frombuffer(f.read(24), dtype="<i4")
+        raw = f.read(24)
+        if len(raw) != 24:
+            raise IOError(f"{path}: truncated newfst header")
+        hdr = np.frombuffer(raw, dtype="<i4")
         start, final_state, n_states, n_arcs = (int(x) for x in hdr[:4])
-        info = np.frombuffer(f.read(12 * n_states), dtype=STATEINFO_DTYPE)
-        arcs = np.frombuffer(f.read(16 * n_arcs), dtype=ARC_DTYPE)
-    if info.shape[0] != n_states or arcs.shape[0] != n_arcs:
+        raw_info, raw_arcs = f.read(12 * n_states), f.read(16 * n_arcs)
+    if len(raw_info) != 12 * n_states or len(raw_arcs) != 16 * n_arcs:
         raise IOError(f"{path}: truncated newfst file")
+    info = np.frombuffer(raw_info, dtype=STATEINFO_DTYPE)
+    arcs = np.frombuffer(raw_arcs, dtype=ARC_DTYPE)
     if int(info["num_arcs"].sum()) != n_arcs:
         raise IOError(f"{path}: state arc counts do not sum to total_arcs")
     return Fst(start, final_state, arcs.copy(), info["num_arcs"].copy(),

@@ -75,6 +75,7 @@ class Probe : public OnlineLatticeDecoderMempool {
   typedef OnlineLatticeDecoderMempool Base;
   Probe(Fst *fst, const LatticeFasterDecoderConfig &c) : Base(fst, c), collect(false) {}
   bool collect;
+  int dump_frame = -1;           // debug: print the hash-list key order of this frame to stderr
   std::vector<FrameStat> stats;  // index 0 = after InitDecoding
   FrameStat pending;
 
@@ -106,6 +107,11 @@ class Probe : public OnlineLatticeDecoderMempool {
       if (e->val->_tot_cost < best) best = e->val->_tot_cost;
     }
     s.best = best;
+    if ((int)stats.size() == dump_frame) {
+      fprintf(stderr, "ORDER");
+      for (const Elem *e = _toks.GetList(); e != NULL; e = e->tail) fprintf(stderr, " %d", e->key);
+      fprintf(stderr, "\n");
+    }
     stats.push_back(s);
   }
   int NumToks() const { return _num_toks; }
@@ -137,11 +143,13 @@ struct Options {
   bool lattice = false;
   int chunk = 0;  // >0: feed AdvanceDecoding in chunks of this many frames
   int repeat = 1;
+  int dump_frame = -1;
 };
 
 void DecodeOne(Probe *dec, const Utt &u, const Options &o, Result *r) {
   auto t0 = std::chrono::steady_clock::now();
   dec->collect = o.stats;
+  dec->dump_frame = o.dump_frame;
   dec->stats.clear();
   dec->InitDecoding();
   MatrixDecodable decodable(&u, u.T);
@@ -274,6 +282,7 @@ int main(int argc, char **argv) {
     else if ((v = val("--threads"))) o.threads = atoi(v);
     else if ((v = val("--chunk"))) o.chunk = atoi(v);
     else if ((v = val("--repeat"))) o.repeat = atoi(v);
+    else if ((v = val("--dump-frame"))) o.dump_frame = atoi(v);
     else if (a == "--stats") o.stats = true;
     else if (a == "--lattice") o.lattice = true;
     else { fprintf(stderr, "unknown arg %s\n", a.c_str()); return 2; }

@@ -883,6 +883,16 @@ void orc_path_to_vector(const int32_t *ilabel, const int32_t *olabel, const floa
   *lm = best_lm;
 }
 
+/* debug: keys of the current frame in hash-list order */
+int32_t orc_current_order(const OrcDecoder *d, int32_t *keys, int32_t cap) {
+  int32_t n = 0;
+  for (Elem *e = d->list_head; e; e = e->tail) {
+    if (n < cap) keys[n] = e->key;
+    ++n;
+  }
+  return n;
+}
+
 int32_t orc_frame_stats(const OrcDecoder *d, OrcFrameStat *out, int32_t cap) {
   int32_t n = (int32_t)d->n_stats;
   for (int32_t i = 0; i < n && i < cap; ++i) out[i] = d->stats[i];

@@ -113,3 +113,62 @@ def test_cutoff_branches(oracle_mod, kw):
     d = O.OracleDecoder(O.OracleGraph(fst), oc, O.MODE_CANONICAL)
     ref = d.decode(ll)
     _compare(bp, dec.frame_stats(0), ref, d.frame_stats(), str(kw))
+
+
+@pytest.mark.parametrize("name", ["g1", "g2", "g3"])
+def test_golden_fixtures_from_the_compiled_reference(oracle_mod, name):
+    """CUDA path == the compiled reference's own one-best (committed golden vectors, all
+    self-stable) and == the canonical oracle per frame."""
+    import json
+    import os
+    from asr_decoder_b200 import fstio
+    O = oracle_mod
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    fst = fstio.read_fst(os.path.join(gold, name + ".fst"))
+    lls = fstio.read_loglikes(os.path.join(gold, name + ".llb"))
+    meta = json.load(open(os.path.join(gold, name + ".json")))
+    cfg = _cfg(**meta["config"])
+    g = CudaFst(fst)
+    dec = CudaDecoderBatch(g, cfg, len(lls), max_frames=128, collect_stats=True)
+    out = dec.Decode(lls)
+    og = O.OracleGraph(fst)
+    for i, (bp, ref) in enumerate(zip(out, meta["reference"])):
+        assert dec.status(i) == 0
+        assert meta["self_stable"][i]
+        assert bp.ok == ref["ok"]
+        assert bp.words == ref["words"] and bp.ali == ref["ali"], (name, i)
+        assert bp.tot_bits == ref["tot_bits"], (name, i, bp.tot, ref["tot"])
+        assert abs(bp.tot - ref["tot"]) <= 1e-4 * abs(ref["tot"])   # north_star tolerance (met exactly)
+        can, cst = _oracle_decode(O, og, cfg, lls[i])
+        _compare(bp, dec.frame_stats(i), can, cst, f"{name}/{i}")
+
+
+def test_no_frames_and_error_paths(oracle_mod):
+    from asr_decoder_b200 import _lib
+    fst = synth.make_graph(400, 4.0, 20, seed=2)
+    g = CudaFst(fst)
+    dec = CudaDecoderBatch(g, _cfg(), 2, max_frames=16)
+    dec.InitDecoding()
+    out = dec.GetBestPath()
+    assert [o.ok for o in out] == [False, False] and out[0].status == -7   # nothing decoded yet
+    ll = synth.make_loglikes(5, 20, 2.0, seed=1)
+    dec.AdvanceDecoding([ll, ll[:0]])                                       # ragged: second stream gets 0 frames
+    assert dec.NumFramesDecoded(0) == 5 and dec.NumFramesDecoded(1) == 0
+    dec.FinalizeDecoding()
+    with pytest.raises(_lib.AsrdError) as e:                                # Advance after Finalize (inl.h:634)
+        dec.AdvanceDecoding([ll, ll])
+    assert e.value.status == -9
+    out = dec.GetBestPath()
+    assert out[0].ok and not out[1].ok
+    with pytest.raises(_lib.AsrdError):                                     # fewer columns than ilabels
+        dec.InitDecoding()
+        dec.AdvanceDecoding([ll[:, :10], ll[:, :10]])
+
+
+def test_arena_overflow_is_reported_not_silent():
+    fst = synth.make_graph(3000, 5.0, 50, seed=4)
+    g = CudaFst(fst)
+    dec = CudaDecoderBatch(g, _cfg(), 1, max_frames=64, token_capacity=2000)
+    ll = synth.make_loglikes(40, 50, 2.0, seed=3)
+    out = dec.Decode([ll])
+    assert dec.status(0) == -5 and not out[0].ok and out[0].status == -5
