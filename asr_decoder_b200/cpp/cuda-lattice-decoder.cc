@@ -1,0 +1,134 @@
+#include "cuda-lattice-decoder.h"
+
+#include <algorithm>
+#include <cstdio>
+
+namespace asrd_host {
+
+CudaLatticeDecoder::CudaLatticeDecoder(CudaFst *graph, const LatticeFasterDecoderConfig &config, int max_frames,
+                                       void *cuda_stream)
+    : d_(NULL), stream_(cuda_stream), finalized_(false) {
+  config.Check();
+  asrd_config c;
+  c.beam = config._beam;
+  c.max_active = config._max_active;
+  c.min_active = config._min_active;
+  c.lattice_beam = config._lattice_beam;
+  c.prune_interval = config._prune_interval;
+  c.beam_delta = config._beam_delta;
+  c.hash_ratio = config._hash_ratio;
+  c.prune_scale = config._prune_scale;
+  asrd_device_options o = asrd_device_options();
+  o.max_frames = max_frames;
+  o.collect_stats = 1;
+  Check(asrd_decoder_create(graph ? graph->handle() : NULL, &c, &o, &d_), "asrd_decoder_create");
+}
+
+CudaLatticeDecoder::~CudaLatticeDecoder() { asrd_decoder_destroy(d_); }
+
+void CudaLatticeDecoder::Check(int status, const char *what) const {
+  if (status != ASRD_OK)  // the reference's LOG_ERR throws std::runtime_error (util/log-message.cc:122-144)
+    throw std::runtime_error(std::string(what) + ": " + asrd_strerror(status));
+}
+
+void CudaLatticeDecoder::InitDecoding() {
+  asrd_decoder *h[1] = {d_};
+  Check(asrd_init_decoding(h, 1, stream_), "asrd_init_decoding");
+  finalized_ = false;
+}
+
+int32 CudaLatticeDecoder::NumFramesDecoded() const { return asrd_num_frames_decoded(d_); }
+
+void CudaLatticeDecoder::Upload(AmInterface *decodable, int32 first, int32 count) {
+  asrd_decoder *h[1] = {d_};
+  const int32 P = decodable->NumIndices();
+  const float *rows;
+  int32 stride;
+  MatrixDecodableInterface *m = dynamic_cast<MatrixDecodableInterface *>(decodable);
+  if (m) {
+    rows = m->Data() + (size_t)first * m->Stride();
+    stride = m->Stride();
+  } else {
+    stage_.resize((size_t)count * P);  // pull model: T x P virtual calls (itf/decodable-itf.h:65-104)
+    for (int32 f = 0; f < count; ++f)
+      for (int32 i = 0; i < P; ++i) stage_[(size_t)f * P + i] = decodable->LogLikelihood(first + f, i + 1);
+    rows = stage_.data();
+    stride = P;
+  }
+  const float *ptrs[1] = {rows};
+  const int32_t nf[1] = {count}, st[1] = {stride};
+  Check(asrd_advance_decoding(h, 1, ptrs, nf, st, P, -1, 0, stream_), "asrd_advance_decoding");
+  Check(asrd_synchronize(stream_), "asrd_synchronize");  // rows may be reused by the caller
+}
+
+void CudaLatticeDecoder::AdvanceDecoding(AmInterface *decodable, int32 max_num_frames) {
+  // inl.h:630-668
+  if (finalized_) Check(ASRD_ERR_STATE, "AdvanceDecoding after FinalizeDecoding");
+  const int32 decoded = NumFramesDecoded();
+  int32 target = decodable->NumFramesReady();
+  if (target < decoded) Check(ASRD_ERR_BAD_ARG, "NumFramesReady() decreased");
+  if (max_num_frames >= 0) target = std::min(target, decoded + max_num_frames);
+  if (target > decoded) Upload(decodable, decoded, target - decoded);
+}
+
+BaseFloat CudaLatticeDecoder::ProcessEmitting(AmInterface *decodable) {
+  const int32 f = NumFramesDecoded();
+  Upload(decodable, f, 1);
+  std::vector<asrd_frame_stat> st((size_t)f + 2);
+  const int32 n = asrd_frame_stats(d_, st.data(), (int32)st.size(), stream_);
+  return n > f + 1 ? st[f + 1].next_cutoff : std::numeric_limits<BaseFloat>::infinity();
+}
+
+void CudaLatticeDecoder::ProcessNonemitting(BaseFloat) {}
+
+void CudaLatticeDecoder::FinalizeDecoding() {
+  asrd_decoder *h[1] = {d_};
+  Check(asrd_finalize_decoding(h, 1, stream_), "asrd_finalize_decoding");
+  finalized_ = true;
+}
+
+bool CudaLatticeDecoder::Decode(AmInterface *decodable) {
+  // Every reference caller uses Init/Advance/Finalize; the reference's own Decode() loop reads one
+  // frame past the end (inl.h:615) — not reproduced.
+  InitDecoding();
+  AdvanceDecoding(decodable);
+  FinalizeDecoding();
+  return NumFramesDecoded() > 0;
+}
+
+bool CudaLatticeDecoder::GetBestPath(Lattice *ofst, bool use_final_probs) {
+  // inl.h:1071-1094: a linear lattice, built from the end of the path towards the start
+  ofst->DeleteStates();
+  asrd_decoder *h[1] = {d_};
+  int32_t cap = 4 * std::max(NumFramesDecoded(), 0) + 64;
+  std::vector<int32_t> il, ol;
+  std::vector<float> gr, ac;
+  int32_t n = 0, status = 0;
+  for (;;) {
+    il.resize(cap); ol.resize(cap); gr.resize(cap); ac.resize(cap);
+    Check(asrd_get_best_path(h, 1, use_final_probs ? 1 : 0, cap, il.data(), ol.data(), gr.data(), ac.data(), &n,
+                             &status, stream_), "asrd_get_best_path");
+    if (status != ASRD_ERR_PATH_OVERFLOW) break;
+    cap *= 4;
+  }
+  if (status == ASRD_ERR_NO_TOKENS) return false;  // the reference warns and returns false (inl.h:1078-1079)
+  Check(status, "GetBestPath");
+  StateId state = ofst->AddState();
+  ofst->SetFinal(state);
+  for (int32_t k = n - 1; k >= 0; --k) {  // path order is start -> end; the reference adds end -> start
+    LatticeArc arc(il[k], ol[k], state, LatticeWeight(gr[k], ac[k]));
+    StateId ns = ofst->AddState();
+    ofst->AddArc(ns, arc);
+    state = ns;
+  }
+  ofst->SetStart(state);
+  return true;
+}
+
+bool CudaLatticeDecoder::GetRawLattice(Lattice *ofst, bool) {
+  ofst->DeleteStates();
+  fprintf(stderr, "WARNING CudaLatticeDecoder::GetRawLattice: lattice mode is not built yet (one-best only)\n");
+  return false;
+}
+
+}  // namespace asrd_host

@@ -1,0 +1,76 @@
+// CudaLatticeDecoder — the drop-in `DecoderItf` implementation backed by the B200 library
+// (include/asrd.h).  Same constructor shape as the reference decoders
+// (OnlineLatticeDecoderBase(FST*, const LatticeFasterDecoderConfig&),
+// my-decoder/online-decoder-base.h:95): the graph handle is shared and NOT owned
+// (online-decoder-base-inl.h:24, _delete_fst(false)).
+#ifndef ASRD_CPP_CUDA_LATTICE_DECODER_H_
+#define ASRD_CPP_CUDA_LATTICE_DECODER_H_
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "asrd.h"
+#include "decoder-itf.h"
+
+namespace asrd_host {
+
+// Device-resident HCLG: what replaces `Fst` (newfst/optimize-fst.h:53-307) for this decoder.
+class CudaFst {
+ public:
+  CudaFst() : g_(NULL) {}
+  ~CudaFst() { asrd_graph_destroy(g_); }
+  // Fst::ReadFst(const char*), optimize-fst.h:208-219 (same file format)
+  bool ReadFst(const char *file, int device = 0) {
+    asrd_graph_destroy(g_);
+    g_ = NULL;
+    return asrd_graph_read(file, device, &g_) == ASRD_OK;
+  }
+  // from the arrays an already loaded reference `Fst` holds
+  bool FromArrays(const asrd_arc *arcs, const uint32_t *num_arcs, const uint32_t *niepsilons, int32_t states,
+                  int64_t n_arcs, int32_t start, int32_t final_state, int device = 0) {
+    asrd_graph_destroy(g_);
+    g_ = NULL;
+    return asrd_graph_create(arcs, num_arcs, niepsilons, states, n_arcs, start, final_state, device, &g_) == ASRD_OK;
+  }
+  asrd_graph *handle() const { return g_; }
+
+ private:
+  CudaFst(const CudaFst &);
+  CudaFst &operator=(const CudaFst &);
+  asrd_graph *g_;
+};
+
+class CudaLatticeDecoder : public DecoderItf {
+ public:
+  CudaLatticeDecoder(CudaFst *graph, const LatticeFasterDecoderConfig &config, int max_frames = 0,
+                     void *cuda_stream = NULL);
+  virtual ~CudaLatticeDecoder();
+
+  virtual void InitDecoding();
+  virtual void AdvanceDecoding(AmInterface *decodable, int32 max_num_frames = -1);
+  virtual void FinalizeDecoding();
+  virtual int32 NumFramesDecoded() const;
+  // One frame step on the device (emitting expansion AND the eps closure, which is fused into
+  // the same step); returns the next cutoff like the reference (inl.h:349-350).
+  virtual BaseFloat ProcessEmitting(AmInterface *decodable);
+  // The closure already ran inside the step; kept for interface completeness (decoder-itf.h:20).
+  virtual void ProcessNonemitting(BaseFloat cost_cutoff);
+  virtual bool Decode(AmInterface *decodable);
+  virtual bool GetBestPath(Lattice *ofst, bool use_final_probs = true);
+  // Lattice generation is the next scope row; one-best mode keeps no links.
+  virtual bool GetRawLattice(Lattice *ofst, bool use_final_probs = true);
+
+  asrd_decoder *handle() const { return d_; }
+
+ private:
+  void Check(int status, const char *what) const;  // LOG_ERR -> throw std::runtime_error
+  void Upload(AmInterface *decodable, int32 first, int32 count);
+  asrd_decoder *d_;
+  void *stream_;
+  bool finalized_;
+  std::vector<float> stage_;
+};
+
+}  // namespace asrd_host
+#endif
