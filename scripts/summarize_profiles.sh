@@ -1,0 +1,42 @@
+#!/bin/bash
+# Turn the ncu artefacts of one tag in gpurun_out/ into committed text summaries under profiles/.
+# usage: scripts/summarize_profiles.sh <tag> [kernel ...]
+TAG=$1; shift
+OUT=profiles/${TAG}_summary.txt
+mkdir -p profiles
+{
+echo "# ncu summary, tag ${TAG} ($(date -u +%Y-%m-%dT%H:%MZ)); config 2 batch (256 streams), see scripts/profile_ncu.sh"
+echo
+echo "## launch list (gpu__time_duration.sum per launch, ns; cold-cache serialised replay: compare SHARES)"
+python - <<PY
+import csv, collections
+rows = list(csv.reader(l for l in open('gpurun_out/${TAG}_launches.csv') if l.startswith('"')))
+hdr = rows[0]; ki = hdr.index('Kernel Name'); vi = hdr.index('Metric Value')
+agg = collections.defaultdict(list)
+for r in rows[1:]:
+    agg[r[ki].split('(')[0]].append(float(r[vi].replace(',','')))
+tot = sum(sum(v) for v in agg.values())
+for k,v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+    print(f"{k:28s} launches {len(v):4d}  avg_us {sum(v)/len(v)/1e3:9.1f}  share {sum(v)/tot:.3f}")
+PY
+for K in "$@"; do
+  F=gpurun_out/${TAG}_$K.ncu-rep
+  [ -f $F ] || continue
+  echo
+  echo "## $K  (ncu --set full, one launch mid-utterance, --frames 100 run)"
+  ncu -i $F --page details 2>/dev/null | grep -E "Duration|Elapsed Cycles|Executed Instructions |Registers Per|Theoretical Occ|Achieved Occ|Issue Slots Busy|L2 Hit|L1/TEX Hit|DRAM Throughput|Warp Cycles Per Issued|Grid Size|Block Size|Memory Throughput|Eligible Warps|Active Warps Per"
+  ncu -i $F --page raw --csv 2>/dev/null | python -c "
+import csv,sys
+rows=list(csv.reader(sys.stdin)); hdr=rows[0]
+for w in ['dram__bytes_read.sum','dram__bytes_write.sum','lts__t_sector_hit_rate.pct','sm__warps_active.avg.pct_of_peak_sustained_active','launch__registers_per_thread']:
+    if w in hdr:
+        i=hdr.index(w); print('   ', w, rows[1][i], [r[i] for r in rows[2:]])
+"
+  ncu -i $F --page source --csv --print-source cuda,sass 2>/dev/null > /tmp/ncu_src_$$.csv
+  echo "   top stall lines (share of warp-stall samples, dominant reasons):"
+  python scripts/ncu_lines.py /tmp/ncu_src_$$.csv 14 | sed 's/^/    /'
+  rm -f /tmp/ncu_src_$$.csv
+done
+} > $OUT
+cp gpurun_out/${TAG}_launches.csv profiles/${TAG}_launches.csv
+echo wrote $OUT
