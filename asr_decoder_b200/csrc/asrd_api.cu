@@ -3,6 +3,7 @@
 // search step runs in the kernels of asrd_kernels.cuh.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -116,6 +117,17 @@ int EnsureDevice(int device) {
     cudaDeviceProp p;
     CU_CHECK(cudaGetDeviceProperties(&p, device));
     g_num_sms = p.multiProcessorCount;
+  }
+  static bool pool_tuned[64] = {false};
+  if (device < 64 && !pool_tuned[device]) {
+    // keep the stream-ordered scratch (staging buffers, descriptors) cached across the
+    // synchronising calls instead of returning it to the driver at every sync
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    pool_tuned[device] = true;
   }
   return ASRD_OK;
 }
@@ -558,7 +570,7 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
 
   // Host log-likelihoods: staged chunk by chunk through two device buffers, copied on a
   // side stream so the H2D of chunk k+1 overlaps the search of chunk k.
-  const int32_t chunk = on_device ? max_nf : std::min<int32_t>(max_nf, kHostChunkFrames);
+  const int32_t chunk = on_device ? max_nf : std::min<int32_t>(max_nf, std::max(1, EnvInt("ASRD_HOST_CHUNK", kHostChunkFrames)));
   float *d_stage[2] = {nullptr, nullptr};
   DeviceCtx *ctx = nullptr;
   bool contiguous = false;
@@ -578,6 +590,9 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
   }
   std::vector<AdvanceParams> hp(n);
   Profiler prof(g_profile.load());
+  const bool trace = EnvInt("ASRD_TRACE", 0) != 0;
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
   int k = 0;
   for (int32_t f0 = 0; f0 < max_nf; f0 += chunk, ++k) {
     int32_t steps = 0;
@@ -607,7 +622,9 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
       CU_CHECK(cudaEventRecord(ctx->ev_copied[k & 1], ctx->copy_stream));
       CU_CHECK(cudaStreamWaitEvent(s, ctx->ev_copied[k & 1], 0));
     }
+    if (trace) fprintf(stderr, "[asrd] chunk %d copies issued at %.2f ms\n", k, since());
     CU_CHECK(cudaMemcpyAsync(d_params, hp.data(), sizeof(AdvanceParams) * n, cudaMemcpyHostToDevice, s));
+    if (trace) fprintf(stderr, "[asrd] chunk %d params copied at %.2f ms\n", k, since());
     k_begin_advance<<<dim3((unsigned)std::min(steps, 8), (unsigned)n), 256, 0, s>>>(d_streams, d_params, num_indices);
     // the rows now live in the per-stream history: the staging buffer may be refilled
     if (!on_device) CU_CHECK(cudaEventRecord(ctx->ev_done[k & 1], s));
@@ -645,6 +662,11 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
     CU_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[(k - 1) & 1], 0));
   }
   for (int i = 0; i < n; ++i) decs[i]->frames_decoded += nf[i];
+  if (trace) {
+    fprintf(stderr, "[asrd] all issued at %.2f ms\n", since());
+    cudaStreamSynchronize(s);
+    fprintf(stderr, "[asrd] stream done at %.2f ms\n", since());
+  }
   if ((rc = prof.Finish(s))) return rc;
   return ASRD_OK;
 }
