@@ -102,6 +102,11 @@ struct Profiler {
   }
 };
 
+int EnvInt(const char *name, int dflt) {
+  const char *v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
 int g_num_sms = 0;
 
 int EnsureDevice(int device) {
@@ -122,6 +127,16 @@ int EnsureDevice(int device) {
   if (device < 64 && !pool_tuned[device]) {
     // keep the stream-ordered scratch (staging buffers, descriptors) cached across the
     // synchronising calls instead of returning it to the driver at every sync
+    // L2 set-aside for the evict_last (persisting) graph loads of k_expand / k_post
+    if (EnvInt("ASRD_L2_PERSIST", 1)) {
+      cudaDeviceProp p;
+      if (cudaGetDeviceProperties(&p, device) == cudaSuccess && p.persistingL2CacheMaxSize > 0) {
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)p.persistingL2CacheMaxSize);
+        if (EnvInt("ASRD_TRACE", 0))
+          fprintf(stderr, "[asrd] L2 %d MB, persisting set-aside %d MB\n", p.l2CacheSize >> 20,
+                  p.persistingL2CacheMaxSize >> 20);
+      }
+    }
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
       unsigned long long keep = ~0ull;
@@ -190,18 +205,14 @@ int CheckBatch(asrd_decoder *const *decs, int n) {
 
 // ---- kernel launch plumbing -------------------------------------------------------------
 
-typedef void (*ExpandFn)(FrameDesc *, GraphView, int);
+typedef void (*ExpandFn)(FrameDesc *, GraphView, int, int);
 
 struct ExpandPlan {
   ExpandFn fn;
   dim3 grid;
   size_t dyn;
+  int flags;
 };
-
-int EnvInt(const char *name, int dflt) {
-  const char *v = getenv(name);
-  return v && *v ? atoi(v) : dflt;
-}
 
 // Picks the k_expand instantiation (arcs in flight per lane; log-likelihood row staged in
 // shared memory when it fits) and sizes the grid to about one resident wave: blockIdx.y is
@@ -223,6 +234,7 @@ int PlanExpand(int n_streams, int num_indices, ExpandPlan *plan) {
   plan->fn = fn;
   plan->grid = dim3((unsigned)std::max(gx, 1), (unsigned)n_streams, 1);
   plan->dyn = dyn;
+  plan->flags = EnvInt("ASRD_EXPAND_FLAGS", 1);
   return ASRD_OK;
 }
 
@@ -318,6 +330,13 @@ int asrd_graph_create(const asrd_arc *arcs, const uint32_t *num_arcs, const uint
   }
   if (off != A) return ASRD_ERR_BAD_ARG;
   rows[S] = make_uint2((uint32_t)A, (uint32_t)A);
+  std::vector<uint2> erows((size_t)S);
+  for (int32_t s = 0; s < S; ++s) erows[s] = make_uint2(rows[s].y, rows[s + 1].x);
+  // device copy only: flag arcs whose destination has eps arcs (saves a bitmap probe per admitted arc)
+  for (int64_t a = 0; a < A; ++a) {
+    const uint32_t ns = (uint32_t)parc[a].nextstate;
+    if ((epsb[ns >> 5] >> (ns & 31)) & 1u) parc[a].nextstate = (int32_t)(ns | kDestEpsBit);
+  }
 
   asrd_graph *g = new asrd_graph();
   memset(g, 0, sizeof(*g));
@@ -325,8 +344,9 @@ int asrd_graph_create(const asrd_arc *arcs, const uint32_t *num_arcs, const uint
   g->total_arcs = A;
   const size_t b_arcs = sizeof(asrd_arc) * parc.size(), b_rows = sizeof(uint2) * rows.size(),
                b_src = sizeof(uint32_t) * src.size(), b_par = sizeof(uint32_t) * par.size(),
-               b_eps = sizeof(uint32_t) * epsb.size();
+               b_eps = sizeof(uint32_t) * epsb.size(), b_erows = sizeof(uint2) * std::max<size_t>(erows.size(), 1);
   if (cudaMalloc(&g->d_arcs, b_arcs) != cudaSuccess || cudaMalloc(&g->d_rows, b_rows) != cudaSuccess ||
+      cudaMalloc(&g->d_erows, b_erows) != cudaSuccess ||
       cudaMalloc(&g->d_arc_src, b_src) != cudaSuccess || cudaMalloc(&g->d_par, b_par) != cudaSuccess ||
       cudaMalloc(&g->d_eps, b_eps) != cudaSuccess) {
     asrd_graph_destroy(g);
@@ -337,9 +357,11 @@ int asrd_graph_create(const asrd_arc *arcs, const uint32_t *num_arcs, const uint
   CU_CHECK(cudaMemcpy(g->d_arc_src, src.data(), b_src, cudaMemcpyHostToDevice));
   CU_CHECK(cudaMemcpy(g->d_par, par.data(), b_par, cudaMemcpyHostToDevice));
   CU_CHECK(cudaMemcpy(g->d_eps, epsb.data(), b_eps, cudaMemcpyHostToDevice));
-  g->device_bytes = (int64_t)(b_arcs + b_rows + b_src + b_par + b_eps);
+  CU_CHECK(cudaMemcpy(g->d_erows, erows.data(), sizeof(uint2) * erows.size(), cudaMemcpyHostToDevice));
+  g->device_bytes = (int64_t)(b_arcs + b_rows + b_erows + b_src + b_par + b_eps);
   g->view.arcs = (const int4 *)g->d_arcs;
   g->view.rows = (const uint2 *)g->d_rows;
+  g->view.erows = (const uint2 *)g->d_erows;
   g->view.arc_src = (const uint32_t *)g->d_arc_src;
   g->view.par_bits = (const uint32_t *)g->d_par;
   g->view.eps_bits = (const uint32_t *)g->d_eps;
@@ -382,6 +404,7 @@ int asrd_graph_destroy(asrd_graph *g) {
   cudaSetDevice(g->device);
   cudaFree(g->d_arcs);
   cudaFree(g->d_rows);
+  cudaFree(g->d_erows);
   cudaFree(g->d_arc_src);
   cudaFree(g->d_par);
   cudaFree(g->d_eps);
@@ -634,7 +657,7 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
     g_launches += 2;
     for (int32_t f = 0; f < steps; ++f) {
       prof.Begin(0, s);
-      plan.fn<<<plan.grid, kExpandThreads, plan.dyn, s>>>(d_desc, gv, num_indices);
+      plan.fn<<<plan.grid, kExpandThreads, plan.dyn, s>>>(d_desc, gv, num_indices, plan.flags);
       prof.End(s);
       const int post_mode = kModeEpi | (f + 1 < steps ? kModePro : 0);
       if (fused_post) {

@@ -12,6 +12,8 @@ constexpr uint32_t kEmptyKey = 0xFFFFFFFFu;
 constexpr uint32_t kNoArc = 0xFFFFFFFFu;
 constexpr unsigned long long kInfVal = 0xFFFFFFFFFFFFFFFFull;
 constexpr uint32_t kOrdInf = 0xFF800000u;  // f2ord(+inf)
+constexpr uint32_t kDestEpsBit = 0x80000000u;  // device copy of StdArc::nextstate: top bit = dest has eps arcs
+constexpr uint32_t kStateMask = 0x7FFFFFFFu;
 
 constexpr int kExpandThreads = 256;   // CTA size of the expand kernel (8 warps, one token group each)
 constexpr int kFinThreads = 256;      // CTA size of the finalize kernel
@@ -31,8 +33,9 @@ struct __align__(16) HashEntry {
 // Device-resident graph: the reference's two flat arrays (src/newfst/optimize-fst.h:60-61)
 // as CSR.  arcs[] are the 16-byte StdArc records verbatim (eps arcs first in every row).
 struct GraphView {
-  const int4 *arcs;        // {ilabel, olabel, weight bits, nextstate}
-  const uint2 *rows;       // [S+1] {row_off, emit_off}: eps span [x, y), emitting span [y, rows[s+1].x)
+  const int4 *arcs;        // {ilabel, olabel, weight bits, nextstate | kDestEpsBit if the destination has eps arcs}
+  const uint2 *rows;       // [S+1] {row_off, emit_off}: eps span [x, y)
+  const uint2 *erows;      // [S]   {emit_off, row_end}: emitting span [x, y) — one 8-byte load per token
   const uint32_t *arc_src; // [A] source state of every arc
   const uint32_t *par_bits;// [ceil(A/32)] arc has a same-class sibling with the same (src, dst)
   const uint32_t *eps_bits;// [ceil(S/32)] state has at least one input-epsilon arc
@@ -143,7 +146,7 @@ __host__ __device__ inline float ord2f(uint32_t o) {
 struct asrd_graph {
   int device;
   asrd::GraphView view;
-  void *d_arcs, *d_rows, *d_arc_src, *d_par, *d_eps;
+  void *d_arcs, *d_rows, *d_erows, *d_arc_src, *d_par, *d_eps;
   int64_t device_bytes;
   int64_t total_arcs;
 };

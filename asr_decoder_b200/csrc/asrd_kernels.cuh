@@ -31,6 +31,33 @@ __device__ __forceinline__ uint32_t hash_state(uint32_t s, uint32_t mask, uint32
   return (s * 0x9E3779B1u) >> shift;
 }
 
+// L2 residency control.  The graph (arcs + rows, ~88 MB at config 2) is re-read every frame by
+// every stream at random and fits the 126 MB L2; the per-stream maps, token arena and
+// log-likelihood rows stream through.  Graph loads carry an evict_last policy, streaming
+// accesses evict_first, so the streaming traffic stops flushing the graph out of L2.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ int4 ldg_arc(const int4 *ptr, uint64_t pol) {
+  int4 r;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.s32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(ptr), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ uint2 ldg_u2(const uint2 *ptr, uint64_t pol) {
+  uint2 r;
+  asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(r.x), "=r"(r.y) : "l"(ptr), "l"(pol));
+  return r;
+}
+
 __device__ __forceinline__ unsigned long long pack_val(float cost, uint32_t arc) {
   return ((unsigned long long)f2ord(cost) << 32) | arc;
 }
@@ -295,7 +322,7 @@ k_begin_advance(StreamState *const *streams, const AdvanceParams *params, int nu
 // arc on (ordered cost << 32 | arc id) in the per-frame state->token map.
 template <int U, bool SMEM_LL>
 __global__ void __launch_bounds__(kExpandThreads, U == 1 ? 8 : 5)
-k_expand(FrameDesc *desc, GraphView g, int num_indices) {
+k_expand(FrameDesc *desc, GraphView g, int num_indices, int flags) {
   extern __shared__ float s_ll[];
   FrameDesc *d = &desc[blockIdx.y];
   if (!d->stepping) return;
@@ -316,6 +343,8 @@ k_expand(FrameDesc *desc, GraphView g, int num_indices) {
   uint32_t *bm = d->bm, *ebm = d->ebm;
   const uint32_t mask = d->mask, shift = d->shift;
   uint32_t *next_cut = &d->next_cut_bits;
+  const bool hints = (flags & 1) != 0;
+  const uint64_t pol_graph = hints ? l2_policy_evict_last() : 0, pol_stream = hints ? l2_policy_evict_first() : 0;
 
   uint32_t expanded = 0, admitted = 0;
   for (uint32_t grp = warp_global; grp < n_groups; grp += n_warps) {
@@ -326,13 +355,12 @@ k_expand(FrameDesc *desc, GraphView g, int num_indices) {
     const uint32_t i = grp * 32 + lane;
     uint32_t deg = 0, base = 0, cost_bits = 0;
     if (i < n_cur) {
-      const uint2 sc = __ldg(&toks[i]);
+      const uint2 sc = hints ? ldg_u2(&toks[i], pol_stream) : __ldg(&toks[i]);
       cost_bits = sc.y;
       if (__uint_as_float(sc.y) <= cur_cut) {  // inclusive, inl.h:315
-        const uint2 r0 = __ldg(&g.rows[sc.x]);
-        const uint32_t end = __ldg(&g.rows[sc.x + 1]).x;
-        base = r0.y;
-        deg = end - r0.y;
+        const uint2 er = hints ? ldg_u2(&g.erows[sc.x], pol_graph) : __ldg(&g.erows[sc.x]);
+        base = er.x;
+        deg = er.y - er.x;
       }
     }
     const uint32_t incl = warp_incl_scan(deg, lane);
@@ -357,52 +385,53 @@ k_expand(FrameDesc *desc, GraphView g, int num_indices) {
       int4 arc[U];
 #pragma unroll
       for (int u = 0; u < U; ++u)
-        if (in[u]) arc[u] = __ldg(&g.arcs[a[u]]);
+        if (in[u]) arc[u] = hints ? ldg_arc(&g.arcs[a[u]], pol_graph) : __ldg(&g.arcs[a[u]]);
       float tot[U];
       bool adm[U];
-      uint32_t h0[U], k0[U];
-      bool epsb[U];
+      uint32_t h0[U];
+      uint4 e0[U];
       uint32_t cand_bits = 0xFFFFFFFFu;
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         adm[u] = false;
         tot[u] = 0.f;
         h0[u] = 0;
-        k0[u] = 0;
-        epsb[u] = false;
+        e0[u] = make_uint4(0, 0, 0, 0);
         if (in[u]) {
           const float ac = -(SMEM_LL ? s_ll[arc[u].x - 1] : __ldg(&ll[arc[u].x - 1]));
           tot[u] = (tcost[u] + ac) + __int_as_float(arc[u].z);  // inl.h:326-329
-          adm[u] = tot[u] < nc;
+          adm[u] = tot[u] < nc && !(flags & 2);   // (flags & 2): measurement aid, no map traffic
           if (adm[u]) {
             const float cand = tot[u] + abeam;  // inl.h:332-333
             if (cand < nc) cand_bits = min(cand_bits, f2ord(cand));
-            h0[u] = hash_state((uint32_t)arc[u].w, mask, shift);
-            k0[u] = __ldcg(&hn[h0[u]].key);  // first probe of every admitted arc in flight together
-            epsb[u] = eps_bit(g.eps_bits, (uint32_t)arc[u].w);
+            h0[u] = hash_state((uint32_t)arc[u].w & kStateMask, mask, shift);
+            // first probe: the whole 16-byte entry {key, stamp, val} in one request
+            e0[u] = __ldcg(reinterpret_cast<const uint4 *>(&hn[h0[u]]));
           }
         }
       }
       // warp-aggregated cutoff tightening (inl.h:332-333)
       if (__any_sync(kFull, cand_bits != 0xFFFFFFFFu)) {
         const uint32_t wmin = __reduce_min_sync(kFull, cand_bits);
-        if (lane == 0) atomicMin(next_cut, wmin);
+        if (lane == 0 && !(flags & 4)) atomicMin(next_cut, wmin);
         nc = fminf(nc, ord2f(wmin));
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         if (adm[u]) {
-          const uint32_t state = (uint32_t)arc[u].w;
+          const uint32_t state = (uint32_t)arc[u].w & kStateMask;
+          const unsigned long long pk = pack_val(tot[u], a[u]);
           uint32_t slot = h0[u];
-          bool is_new = false, ok = k0[u] == state;
-          if (!ok) {
-            ok = hash_claim(hn, mask, h0[u], state, slot, is_new);
-          }
+          bool is_new = false, ok = e0[u].x == state;
+          // the map value only ever decreases: if what we saw already beats us, so does the
+          // current value — no atomic needed (most admitted arcs lose the recombination)
+          const bool lost = ok && (((unsigned long long)e0[u].w << 32) | e0[u].z) <= pk;
+          if (!ok) ok = hash_claim(hn, mask, h0[u], state, slot, is_new);
           if (ok) {
-            atomicMin(&hn[slot].val, pack_val(tot[u], a[u]));
+            if (!lost) atomicMin(&hn[slot].val, pk);
             if (is_new) {
               atomicOr(&bm[slot >> 5], 1u << (slot & 31u));
-              if (epsb[u]) atomicOr(&ebm[slot >> 5], 1u << (slot & 31u));
+              if ((uint32_t)arc[u].w & kDestEpsBit) atomicOr(&ebm[slot >> 5], 1u << (slot & 31u));
             }
           } else {
             atomicMin(&d->st->status, ASRD_ERR_HASH_OVERFLOW);
@@ -457,7 +486,8 @@ k_closure(FrameDesc *desc, GraphView g) {
       if (tot < nc) {                                   // inl.h:415
         uint32_t slot2;
         bool is_new;
-        if (!hash_claim(hn, mask, hash_state((uint32_t)arc.w, mask, shift), (uint32_t)arc.w, slot2, is_new)) {
+        const uint32_t dst = (uint32_t)arc.w & kStateMask;
+        if (!hash_claim(hn, mask, hash_state(dst, mask, shift), dst, slot2, is_new)) {
           atomicMin(&st->status, ASRD_ERR_HASH_OVERFLOW);
           continue;
         }
@@ -465,7 +495,7 @@ k_closure(FrameDesc *desc, GraphView g) {
         const unsigned long long old = atomicMin(&hn[slot2].val, pk);
         if (is_new) atomicOr(&bm[slot2 >> 5], 1u << (slot2 & 31u));
         const bool changed = (uint32_t)(pk >> 32) < (uint32_t)(old >> 32);  // inl.h:115-127
-        if (changed && eps_bit(g.eps_bits, (uint32_t)arc.w) &&
+        if (changed && ((uint32_t)arc.w & kDestEpsBit) &&
             atomicExch(&hn[slot2].aux, round + 1) != round + 1)
           qout[atomicAdd(&s_qn[(round + 1) & 1], 1u)] = slot2;  // inl.h:425-426
       }
@@ -680,10 +710,9 @@ __device__ __forceinline__ void cutoff_prologue(StreamState *st, FrameDesc *d, c
     }
     // best-token pre-pass (inl.h:282-300): association (cost + w) - loglike
     const uint32_t sb = (uint32_t)best64;
-    const uint2 r = __ldg(&g.rows[sb]);
-    const uint32_t end = __ldg(&g.rows[sb + 1]).x;
+    const uint2 er = __ldg(&g.erows[sb]);
     uint32_t mn = kOrdInf;
-    for (uint32_t a = r.y + tid; a < end; a += NT) {
+    for (uint32_t a = er.x + tid; a < er.y; a += NT) {
       const int4 arc = __ldg(&g.arcs[a]);
       const float tot = bc + __int_as_float(arc.z) - __ldg(&ll[arc.x - 1]);
       mn = min(mn, f2ord(tot + abeam));
@@ -825,7 +854,8 @@ k_post(StreamState *const *streams, FrameDesc *desc, GraphView g, DecoderConfigD
         if (tot < nc) {                                   // inl.h:415
           uint32_t slot2;
           bool is_new;
-          if (!hash_claim(hn, mask, hash_state((uint32_t)arc.w, mask, shift), (uint32_t)arc.w, slot2, is_new)) {
+          const uint32_t dst = (uint32_t)arc.w & kStateMask;
+          if (!hash_claim(hn, mask, hash_state(dst, mask, shift), dst, slot2, is_new)) {
             atomicMin(&st->status, ASRD_ERR_HASH_OVERFLOW);
             continue;
           }
@@ -833,7 +863,7 @@ k_post(StreamState *const *streams, FrameDesc *desc, GraphView g, DecoderConfigD
           const unsigned long long old = atomicMin(&hn[slot2].val, pk);
           if (is_new) atomicOr(&bm[slot2 >> 5], 1u << (slot2 & 31u));
           const bool changed = (uint32_t)(pk >> 32) < (uint32_t)(old >> 32);  // inl.h:115-127
-          if (changed && eps_bit(g.eps_bits, (uint32_t)arc.w) &&
+          if (changed && ((uint32_t)arc.w & kDestEpsBit) &&
               atomicExch(&hn[slot2].aux, round + 1) != round + 1)
             qout[atomicAdd(&s_qn[(round + 1) & 1], 1u)] = slot2;  // inl.h:425-426
         }
@@ -1073,11 +1103,10 @@ k_best_path(StreamState *const *streams, GraphView g, DecoderConfigDev cfg, int 
     if (par_bit(g.par_bits, rep)) {
       const float pc = __uint_as_float(st->tok_sc[pidx].y);
       const float nc = st->frame_nc[f];
-      const uint2 r = __ldg(&g.rows[src]);
-      const uint32_t hi = emitting ? __ldg(&g.rows[src + 1]).x : r.y;
+      const uint32_t hi = emitting ? __ldg(&g.erows[src]).y : __ldg(&g.rows[src]).y;
       for (uint32_t a2 = hi; a2-- > rep + 1;) {
         const int4 arc2 = __ldg(&g.arcs[a2]);
-        if ((uint32_t)arc2.w != state) continue;
+        if (((uint32_t)arc2.w & kStateMask) != state) continue;
         float tot2;
         bool admitted;
         if (emitting) {
