@@ -128,7 +128,7 @@ int EnsureDevice(int device) {
     // keep the stream-ordered scratch (staging buffers, descriptors) cached across the
     // synchronising calls instead of returning it to the driver at every sync
     // L2 set-aside for the evict_last (persisting) graph loads of k_expand / k_post
-    if (EnvInt("ASRD_L2_PERSIST", 1)) {
+    if (EnvInt("ASRD_L2_PERSIST", 0)) {
       cudaDeviceProp p;
       if (cudaGetDeviceProperties(&p, device) == cudaSuccess && p.persistingL2CacheMaxSize > 0) {
         cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)p.persistingL2CacheMaxSize);
@@ -188,6 +188,7 @@ DecoderConfigDev DevCfg(const asrd_decoder *d) {
   c.lattice_beam = d->cfg.lattice_beam;
   c.beam_delta = d->cfg.beam_delta;
   c.collect_stats = d->opts.collect_stats;
+  c.debug_flags = EnvInt("ASRD_DEBUG_FLAGS", 0);
   return c;
 }
 
@@ -234,11 +235,10 @@ int PlanExpand(int n_streams, int num_indices, ExpandPlan *plan) {
   plan->fn = fn;
   plan->grid = dim3((unsigned)std::max(gx, 1), (unsigned)n_streams, 1);
   plan->dyn = dyn;
-  plan->flags = EnvInt("ASRD_EXPAND_FLAGS", 1);
+  plan->flags = EnvInt("ASRD_EXPAND_FLAGS", 0);
   return ASRD_OK;
 }
 
-int FinalizeGrid() { return g_num_sms * EnvInt("ASRD_FIN_CTAS_PER_SM", 6); }
 
 }  // namespace
 
@@ -459,7 +459,7 @@ int asrd_decoder_create(asrd_graph *g, const asrd_config *cfg, const asrd_device
                b_off = align(((size_t)o.max_frames + 2) * 4),
                b_stats = o.collect_stats ? align(((size_t)o.max_frames + 1) * sizeof(asrd_frame_stat)) : 0,
                b_state = align(sizeof(StreamState));
-  const size_t total = b_state + 2 * b_hash + 4 * b_bm + 2 * b_list + b_tok + b_arc + 2 * b_off + b_stats;
+  const size_t total = b_state + b_hash + 2 * b_bm + 2 * b_list + b_tok + b_arc + 2 * b_off + b_stats;
   if (cudaMalloc(&d->slab, total) != cudaSuccess) {
     cudaGetLastError();
     delete d;
@@ -470,10 +470,9 @@ int asrd_decoder_create(asrd_graph *g, const asrd_config *cfg, const asrd_device
   StreamState &h = d->h_state;
   memset(&h, 0, sizeof(h));
   d->d_state = (StreamState *)p; p += b_state;
-  h.hash[0] = (HashEntry *)p; p += b_hash;
-  h.hash[1] = (HashEntry *)p; p += b_hash;
-  for (int i = 0; i < 2; ++i) { h.bm[i] = (uint32_t *)p; p += b_bm; }
-  for (int i = 0; i < 2; ++i) { h.ebm[i] = (uint32_t *)p; p += b_bm; }
+  h.hash = (HashEntry *)p; p += b_hash;
+  h.bm = (uint32_t *)p; p += b_bm;
+  h.ebm = (uint32_t *)p; p += b_bm;
   for (int i = 0; i < 2; ++i) { h.queue[i] = (uint32_t *)p; p += b_list; }
   h.tok_sc = (uint2 *)p; p += b_tok;
   h.tok_arc = (uint32_t *)p; p += b_arc;
@@ -487,8 +486,8 @@ int asrd_decoder_create(asrd_graph *g, const asrd_config *cfg, const asrd_device
   h.token_capacity = (uint32_t)o.token_capacity;
   h.max_frames = o.max_frames;
   // empty maps: key = 0xFFFFFFFF, val = +inf; empty bitmaps
-  if (cudaMemset(h.hash[0], 0xFF, 2 * b_hash) != cudaSuccess ||
-      cudaMemset(h.bm[0], 0, 4 * b_bm) != cudaSuccess ||
+  if (cudaMemset(h.hash, 0xFF, b_hash) != cudaSuccess ||
+      cudaMemset(h.bm, 0, 2 * b_bm) != cudaSuccess ||
       cudaMemcpy(d->d_state, &h, sizeof(h), cudaMemcpyHostToDevice) != cudaSuccess) {
     cudaFree(d->slab);
     delete d;
@@ -519,17 +518,9 @@ int asrd_init_decoding(asrd_decoder *const *decs, int32_t n, void *stream) {
   const DecoderConfigDev cfg = DevCfg(decs[0]);
   FrameDesc *d_desc;
   CU_CHECK(sc.Alloc(&d_desc, (size_t)n));
-  const uint32_t gps = (uint32_t)decs[0]->opts.hash_capacity / 1024;
   k_init<<<n, kStreamThreads, 0, s>>>(d_streams, d_desc, gv, cfg);
-  if (EnvInt("ASRD_FUSED_POST", 1)) {
-    k_post<<<n, kStreamThreads, 0, s>>>(d_streams, d_desc, gv, cfg, kModeEpi);
-    g_launches += 2;
-  } else {
-    k_closure<<<n, kStreamThreads, 0, s>>>(d_desc, gv);
-    k_finalize<<<FinalizeGrid(), kFinThreads, 0, s>>>(d_desc, n, gps);
-    k_cutoff<<<n, kStreamThreads, 0, s>>>(d_streams, d_desc, gv, cfg, kModeEpi);
-    g_launches += 4;
-  }
+  k_post<<<n, kStreamThreads, 0, s>>>(d_streams, d_desc, gv, cfg, kModeEpi);
+  g_launches += 2;
   CU_CHECK(cudaGetLastError());
   for (int i = 0; i < n; ++i) {
     decs[i]->frames_decoded = 0;
@@ -586,9 +577,7 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
   CU_CHECK(sc.Alloc(&d_desc, (size_t)n));
   ExpandPlan plan;
   if ((rc = PlanExpand(n, num_indices, &plan))) return rc;
-  const int fin_grid = FinalizeGrid();
-  const bool fused_post = EnvInt("ASRD_FUSED_POST", 1) != 0;
-  const uint32_t gps = (uint32_t)decs[0]->opts.hash_capacity / 1024;
+
   const size_t row = (size_t)num_indices;
 
   // Host log-likelihoods: staged chunk by chunk through two device buffers, copied on a
@@ -651,8 +640,8 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
     k_begin_advance<<<dim3((unsigned)std::min(steps, 8), (unsigned)n), 256, 0, s>>>(d_streams, d_params, num_indices);
     // the rows now live in the per-stream history: the staging buffer may be refilled
     if (!on_device) CU_CHECK(cudaEventRecord(ctx->ev_done[k & 1], s));
-    prof.Begin(3, s);
-    k_cutoff<<<n, kStreamThreads, 0, s>>>(d_streams, d_desc, gv, cfg, kModePro);
+    prof.Begin(1, s);
+    k_post<<<n, kStreamThreads, 0, s>>>(d_streams, d_desc, gv, cfg, kModePro);
     prof.End(s);
     g_launches += 2;
     for (int32_t f = 0; f < steps; ++f) {
@@ -660,23 +649,10 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
       plan.fn<<<plan.grid, kExpandThreads, plan.dyn, s>>>(d_desc, gv, num_indices, plan.flags);
       prof.End(s);
       const int post_mode = kModeEpi | (f + 1 < steps ? kModePro : 0);
-      if (fused_post) {
-        prof.Begin(1, s);
-        k_post<<<n, kStreamThreads, 0, s>>>(d_streams, d_desc, gv, cfg, post_mode);
-        prof.End(s);
-        g_launches += 2;
-      } else {
-        prof.Begin(1, s);
-        k_closure<<<n, kStreamThreads, 0, s>>>(d_desc, gv);
-        prof.End(s);
-        prof.Begin(2, s);
-        k_finalize<<<fin_grid, kFinThreads, 0, s>>>(d_desc, n, gps);
-        prof.End(s);
-        prof.Begin(3, s);
-        k_cutoff<<<n, kStreamThreads, 0, s>>>(d_streams, d_desc, gv, cfg, post_mode);
-        prof.End(s);
-        g_launches += 4;
-      }
+      prof.Begin(1, s);
+      k_post<<<n, kStreamThreads, 0, s>>>(d_streams, d_desc, gv, cfg, post_mode);
+      prof.End(s);
+      g_launches += 2;
     }
     CU_CHECK(cudaGetLastError());
   }

@@ -48,9 +48,9 @@ struct GraphView {
 // Per-stream (per decoder object) state, resident in HBM.
 struct StreamState {
   // ---- buffers
-  HashEntry *hash[2];   // state->token maps; frame f lives in hash[f & 1]
-  uint32_t *bm[2];      // claimed-slot bitmaps of the two maps (capacity / 32 words)
-  uint32_t *ebm[2];     // ... of which the state has eps arcs (seeds of the eps closure)
+  HashEntry *hash;      // state->token map of the frame being built (recycled by the finalize phase)
+  uint32_t *bm;         // claimed-slot bitmap of the map (capacity / 32 words)
+  uint32_t *ebm;        // ... of which the state has eps arcs (seeds of the eps closure)
   uint32_t *queue[2];   // eps-closure frontier queues
   uint2 *tok_sc;        // token arena: {state, cost bits}
   uint32_t *tok_arc;    // token arena: arc that set the token's cost (kNoArc for the start token)
@@ -84,7 +84,7 @@ struct __align__(16) FrameDesc {
   const uint2 *toks;    // tokens of frame t (being expanded)
   const float *ll;      // log-likelihood row of frame t
   HashEntry *hn;        // map of frame t+1
-  HashEntry *hc;        // map of frame t
+  void *reserved0;
   uint32_t *bm;         // claimed-slot bitmap of hn
   uint32_t *ebm;        // eps-seed bitmap of hn
   uint2 *out_sc;        // arena write window of frame t+1
@@ -118,6 +118,7 @@ struct DecoderConfigDev {
   float lattice_beam;
   float beam_delta;
   int32_t collect_stats;
+  int32_t debug_flags;   // measurement aids (ASRD_DEBUG_FLAGS)
 };
 
 // order-preserving float <-> uint32 map (handles negative costs)

@@ -232,11 +232,9 @@ k_init(StreamState *const *streams, FrameDesc *desc, GraphView g, DecoderConfigD
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t mask = st->hash_mask;
   const uint32_t words = (mask + 1) >> 5;
-  for (int w = 0; w < 2; ++w) {
-    clear_map_by_bitmap(st->hash[w], st->bm[w], words, warp, lane, kStreamThreads / 32);
-    uint32_t *ebm = st->ebm[w];
-    for (uint32_t i = tid; i < words; i += kStreamThreads) ebm[i] = 0;
-  }
+  // the map is normally left clean by the last finalize phase; an aborted utterance may not have
+  clear_map_by_bitmap(st->hash, st->bm, words, warp, lane, kStreamThreads / 32);
+  for (uint32_t i = tid; i < words; i += kStreamThreads) st->ebm[i] = 0;
   __syncthreads();
   if (tid == 0) {
     st->status = 0;
@@ -249,19 +247,18 @@ k_init(StreamState *const *streams, FrameDesc *desc, GraphView g, DecoderConfigD
     st->tot_arcs_expanded = st->tot_arcs_admitted = 0;
     uint32_t slot;
     bool is_new;
-    HashEntry *hn = st->hash[0];
+    HashEntry *hn = st->hash;
     hash_claim(hn, mask, hash_state((uint32_t)g.start, mask, st->hash_shift), (uint32_t)g.start, slot, is_new);
     atomicMin(&hn[slot].val, pack_val(0.0f, kNoArc));
-    st->bm[0][slot >> 5] = 1u << (slot & 31u);
-    if (eps_bit(g.eps_bits, (uint32_t)g.start)) st->ebm[0][slot >> 5] = 1u << (slot & 31u);
+    st->bm[slot >> 5] = 1u << (slot & 31u);
+    if (eps_bit(g.eps_bits, (uint32_t)g.start)) st->ebm[slot >> 5] = 1u << (slot & 31u);
     FrameDesc d;
     d.st = st;
     d.toks = nullptr;
     d.ll = nullptr;
     d.hn = hn;
-    d.hc = st->hash[1];
-    d.bm = st->bm[0];
-    d.ebm = st->ebm[0];
+    d.bm = st->bm;
+    d.ebm = st->ebm;
     d.out_sc = st->tok_sc;
     d.out_arc = st->tok_arc;
     d.best64 = kInfVal;
@@ -448,156 +445,6 @@ k_expand(FrameDesc *desc, GraphView g, int num_indices, int flags) {
   }
 }
 
-// ------------------------------------------------------------------ eps closure
-
-// ProcessNonemitting (inl.h:353-431) for the frame being completed, one CTA per stream.
-// Round 1 takes the newly claimed states that have eps arcs (bitmap filled by k_expand);
-// later rounds take the states whose cost dropped (inl.h:425-426), de-duplicated by a round
-// stamp.  min-plus relaxation with a static cutoff has a unique fixed point, so the parallel
-// rounds end with exactly the reference's token costs.
-__global__ void __launch_bounds__(kStreamThreads, 2)
-k_closure(FrameDesc *desc, GraphView g) {
-  constexpr int NT = kStreamThreads;
-  __shared__ uint32_t s_qn[2];
-  FrameDesc *d = &desc[blockIdx.x];
-  if (!d->stepping) return;
-  StreamState *st = d->st;
-  const int tid = threadIdx.x;
-  const uint32_t mask = d->mask, shift = d->shift;
-  const uint32_t groups = (mask + 1) >> 10;  // 32 bitmap words (1024 slots) per group
-  HashEntry *hn = d->hn;
-  uint32_t *bm = d->bm;
-  uint32_t *ebm = d->ebm;
-  const float nc = ord2f(d->next_cut_bits);  // the FINAL next_cutoff of this frame
-  uint32_t *q0 = st->queue[0], *q1 = st->queue[1];
-  if (tid == 0) s_qn[0] = s_qn[1] = 0;
-  __syncthreads();
-
-  auto relax_from = [&](uint32_t slot, uint32_t round) {
-    const uint4 e = __ldcg(reinterpret_cast<const uint4 *>(&hn[slot]));
-    const uint32_t state = e.x;
-    const float cost = ord2f(e.w);
-    if (!(cost < nc)) return;  // inl.h:391
-    const uint2 r = __ldg(&g.rows[state]);
-    uint32_t *qout = ((round + 1) & 1) ? q1 : q0;
-    for (uint32_t a = r.x; a < r.y; ++a) {
-      const int4 arc = __ldg(&g.arcs[a]);
-      const float tot = cost + __int_as_float(arc.z);  // inl.h:413-414
-      if (tot < nc) {                                   // inl.h:415
-        uint32_t slot2;
-        bool is_new;
-        const uint32_t dst = (uint32_t)arc.w & kStateMask;
-        if (!hash_claim(hn, mask, hash_state(dst, mask, shift), dst, slot2, is_new)) {
-          atomicMin(&st->status, ASRD_ERR_HASH_OVERFLOW);
-          continue;
-        }
-        const unsigned long long pk = pack_val(tot, a);
-        const unsigned long long old = atomicMin(&hn[slot2].val, pk);
-        if (is_new) atomicOr(&bm[slot2 >> 5], 1u << (slot2 & 31u));
-        const bool changed = (uint32_t)(pk >> 32) < (uint32_t)(old >> 32);  // inl.h:115-127
-        if (changed && ((uint32_t)arc.w & kDestEpsBit) &&
-            atomicExch(&hn[slot2].aux, round + 1) != round + 1)
-          qout[atomicAdd(&s_qn[(round + 1) & 1], 1u)] = slot2;  // inl.h:425-426
-      }
-    }
-  };
-
-  // round 1 (inl.h:376-381): gather the seeds into the queue first so that the relaxation work
-  // is spread evenly over the CTA no matter how the set bits cluster
-  for (uint32_t w = tid; w < (groups << 5); w += NT) {
-    uint32_t bits = ebm[w];
-    if (bits) {
-      ebm[w] = 0;
-      uint32_t pos = atomicAdd(&s_qn[1], (uint32_t)__popc(bits));
-      while (bits) {
-        const uint32_t b = __ffs(bits) - 1;
-        bits &= bits - 1;
-        q1[pos++] = (w << 5) + b;
-      }
-    }
-  }
-  for (uint32_t round = 1;; ++round) {
-    __syncthreads();
-    const uint32_t nq = s_qn[round & 1];
-    if (nq == 0) break;
-    __syncthreads();
-    if (tid == 0) s_qn[(round + 1) & 1] = 0;
-    __syncthreads();
-    const uint32_t *qin = (round & 1) ? q1 : q0;
-    for (uint32_t i = tid; i < nq; i += NT) relax_from(qin[i], round);
-  }
-}
-
-// ------------------------------------------------------------------ finalize
-
-// One warp per 1024 map slots (32 bitmap words) of a stepping stream: the set bits are spread
-// over the lanes by rank; survivors (cost < final next_cutoff) get a token record
-// {state, cost, winning arc} at a warp-aggregated arena position.
-__global__ void __launch_bounds__(kFinThreads)
-k_finalize(FrameDesc *desc, int n_streams, uint32_t groups_per_stream) {
-  const int tid = threadIdx.x, lane = tid & 31;
-  const uint32_t warp_global = blockIdx.x * (kFinThreads / 32) + (tid >> 5);
-  const uint32_t n_warps = gridDim.x * (kFinThreads / 32);
-  const uint32_t total_groups = groups_per_stream * (uint32_t)n_streams;
-
-  for (uint32_t c = warp_global; c < total_groups; c += n_warps) {
-    const uint32_t s = c / groups_per_stream, grp = c % groups_per_stream;
-    FrameDesc *d = &desc[s];
-    if (!d->stepping) continue;
-    const uint32_t word = __ldcg(&d->bm[grp * 32 + lane]);
-    if (!__any_sync(kFull, word != 0)) continue;
-    const uint32_t cnt = __popc(word);
-    const uint32_t incl = warp_incl_scan(cnt, lane);
-    const uint32_t off = incl - cnt;
-    const uint32_t total = __shfl_sync(kFull, incl, 31);
-    const HashEntry *hn = d->hn;
-    const float nc = ord2f(d->next_cut_bits);
-    const uint32_t cap = d->out_cap;
-    uint2 *out_sc = d->out_sc;
-    uint32_t *out_arc = d->out_arc;
-    unsigned long long best64 = kInfVal;
-
-    for (uint32_t ib = 0; ib < total; ib += 32) {
-      const uint32_t it = ib + lane;
-      const int l = warp_owner(off, it);
-      const uint32_t wl = __shfl_sync(kFull, word, l);
-      const uint32_t offl = __shfl_sync(kFull, off, l);
-      bool alive = false;
-      uint32_t key = 0, rep = kNoArc;
-      float cost = 0.f;
-      if (it < total) {
-        const uint32_t b = __fns(wl, 0, (int)(it - offl) + 1);
-        const uint32_t slot = ((grp * 32 + l) << 5) + b;
-        const uint4 e = __ldcg(reinterpret_cast<const uint4 *>(&hn[slot]));
-        key = e.x;
-        rep = e.z;  // low word of val = winning arc
-        cost = ord2f(e.w);
-        alive = cost < nc;
-      }
-      const unsigned am = __ballot_sync(kFull, alive);
-      if (am == 0) continue;
-      uint32_t pos0 = 0;
-      if (lane == 0) pos0 = atomicAdd(&d->n_alive, (uint32_t)__popc(am));
-      pos0 = __shfl_sync(kFull, pos0, 0);
-      if (alive) {
-        const uint32_t idx = pos0 + __popc(am & ((1u << lane) - 1u));
-        if (idx < cap) {
-          out_sc[idx] = make_uint2(key, __float_as_uint(cost));
-          out_arc[idx] = rep;
-        }
-        const unsigned long long b64 = ((unsigned long long)f2ord(cost) << 32) | key;
-        best64 = b64 < best64 ? b64 : best64;
-      }
-    }
-#pragma unroll
-    for (int dlt = 16; dlt > 0; dlt >>= 1) {
-      const unsigned long long o = __shfl_xor_sync(kFull, best64, dlt);
-      best64 = o < best64 ? o : best64;
-    }
-    if (lane == 0 && best64 != kInfVal) atomicMin(&d->best64, best64);
-  }
-}
-
 // ------------------------------------------------------------------ cutoff
 
 enum { kModeEpi = 2, kModePro = 4 };
@@ -726,10 +573,9 @@ __device__ __forceinline__ void cutoff_prologue(StreamState *st, FrameDesc *d, c
     nd.st = st;
     nd.toks = toks;
     nd.ll = ll;
-    nd.hn = st->hash[(t + 1) & 1];
-    nd.hc = st->hash[t & 1];
-    nd.bm = st->bm[(t + 1) & 1];
-    nd.ebm = st->ebm[(t + 1) & 1];
+    nd.hn = st->hash;
+    nd.bm = st->bm;
+    nd.ebm = st->ebm;
     nd.out_sc = st->tok_sc + out_base;
     nd.out_arc = st->tok_arc + out_base;
     nd.best64 = kInfVal;
@@ -747,60 +593,6 @@ __device__ __forceinline__ void cutoff_prologue(StreamState *st, FrameDesc *d, c
     nd.t = t;
     *d = nd;
   }
-}
-
-// One CTA per stream.  EPI: close the frame step (arena offsets, statistics, recycle the map of
-// the previous frame).  PRO: GetCutoff (inl.h:138-234) over the new frame's tokens, best-token
-// pre-pass (inl.h:282-300), and the descriptor of the next step.
-__global__ void __launch_bounds__(kStreamThreads, 2)
-k_cutoff(StreamState *const *streams, FrameDesc *desc, GraphView g, DecoderConfigDev cfg, int mode) {
-  constexpr int NT = kStreamThreads;
-  __shared__ unsigned long long s_red64[NT / 32];
-  __shared__ uint32_t s_red32[NT / 32];
-  __shared__ uint32_t s_hist[256];
-  __shared__ uint32_t s_misc[4];
-  StreamState *st = streams[blockIdx.x];
-  FrameDesc *d = &desc[blockIdx.x];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-  if ((mode & kModeEpi) && d->stepping) {
-    const int t = d->t;
-    const uint32_t out_base = st->frame_off[t + 1];
-    uint32_t n_alive = d->n_alive;
-    if (n_alive > d->out_cap) {
-      n_alive = d->out_cap;
-      if (tid == 0) atomicMin(&st->status, ASRD_ERR_ARENA_OVERFLOW);
-    }
-    // recycle the map of the previous frame (its last reader was k_finalize)
-    clear_map_by_bitmap(st->hash[t & 1], st->bm[t & 1], (st->hash_mask + 1) >> 5, warp, lane, NT / 32);
-    __syncthreads();
-    if (tid == 0) {
-      const unsigned long long b64 = d->best64;
-      if (cfg.collect_stats && st->stats) {
-        asrd_frame_stat s;
-        s.n_in = d->n_cur;
-        s.cur_cutoff = d->cur_cut;
-        s.abeam = d->abeam;
-        s.next_cutoff = ord2f(d->next_cut_bits);
-        s.n_tokens = n_alive;
-        s.best = b64 == kInfVal ? CUDART_INF_F : ord2f((uint32_t)(b64 >> 32));
-        s.arcs_expanded = d->arcs_expanded;
-        s.arcs_admitted = d->arcs_admitted;
-        st->stats[t + 1] = s;
-      }
-      st->tot_arcs_expanded += d->arcs_expanded;
-      st->tot_arcs_admitted += d->arcs_admitted;
-      st->frame_off[t + 2] = out_base + n_alive;
-      st->frame_nc[t + 1] = ord2f(d->next_cut_bits);
-      st->frame = t + 1;
-      st->n_cur = n_alive;
-      st->best64 = b64;
-      d->stepping = 0;
-    }
-    __syncthreads();
-  }
-
-  if (mode & kModePro) cutoff_prologue<NT>(st, d, g, cfg, s_red64, s_red32, s_hist, s_misc);
 }
 
 // ------------------------------------------------------------------ fused per-stream post phase
@@ -902,6 +694,7 @@ k_post(StreamState *const *streams, FrameDesc *desc, GraphView g, DecoderConfigD
       for (uint32_t grp = warp; grp < groups; grp += NT / 32) {
         const uint32_t word = __ldcg(&bm[grp * 32 + lane]);
         if (!__any_sync(kFull, word != 0)) continue;
+        if (word) bm[grp * 32 + lane] = 0;
         const uint32_t cnt = __popc(word);
         const uint32_t incl = warp_incl_scan(cnt, lane);
         const uint32_t off = incl - cnt;
@@ -938,6 +731,20 @@ k_post(StreamState *const *streams, FrameDesc *desc, GraphView g, DecoderConfigD
             best64 = b64 < best64 ? b64 : best64;
           }
         }
+        // The map of this frame dies here (the next expansion reads the arena, and so does the
+        // trace-back): recycle the group's slots while their sectors are still in L2.  Lane b
+        // takes slot b of every non-empty word — 512 contiguous bytes per word, issued by other
+        // lanes than the ones that loaded the entries (a same-thread load->store on one address
+        // serialises the LSU; measured 5x slower).
+        unsigned nz = __ballot_sync(kFull, word != 0);
+        while (nz) {
+          const int k = __ffs(nz) - 1;
+          nz &= nz - 1;
+          const uint32_t bits = __shfl_sync(kFull, word, k);
+          if ((bits >> lane) & 1u)
+            __stcg(reinterpret_cast<uint4 *>(&hn[((grp * 32 + k) << 5) + lane]),
+                   make_uint4(kEmptyKey, 0u, 0xFFFFFFFFu, 0xFFFFFFFFu));
+        }
       }
 #pragma unroll
       for (int dlt = 16; dlt > 0; dlt >>= 1) {
@@ -946,8 +753,6 @@ k_post(StreamState *const *streams, FrameDesc *desc, GraphView g, DecoderConfigD
       }
       if (lane == 0 && best64 != kInfVal) atomicMin(&s_best, best64);
     }
-    // ---- recycle the map of the previous frame
-    clear_map_by_bitmap(st->hash[t & 1], st->bm[t & 1], (mask + 1) >> 5, warp, lane, NT / 32);
     __syncthreads();
     if (tid == 0) {
       uint32_t n_alive = s_alive;

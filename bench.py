@@ -286,8 +286,8 @@ def run_b200_arm(a):
     kms, kn = (C.c_double * 4)(), (C.c_int64 * 4)()
     L.asrd_profile_get(kms, kn)
     xm, xn = C.c_double(kms[0]), C.c_int64(kn[0])
-    knames = ["k_expand", "k_closure", "k_finalize", "k_cutoff"]
-    ktot = sum(kms) + 1e-12
+    knames = ["k_expand", "k_post"]
+    ktot = kms[0] + kms[1] + 1e-12
 
     # ---- end-to-end number: host (pinned) log-likelihoods through the C ABI
     e2e = None

@@ -179,7 +179,7 @@ int asrd_get_counters(asrd_decoder *const *decs, int32_t n, int64_t *arcs_expand
 int asrd_profile_enable(int on);
 int asrd_profile_reset(void);
 /* kernel_ms[4], kernel_launches[4]: accumulated device time and launch counts of
- * {k_expand, k_closure, k_finalize, k_cutoff} since the last reset */
+ * {k_expand, k_post, unused, unused} since the last reset */
 int asrd_profile_get(double *kernel_ms, int64_t *kernel_launches);
 
 /* number of kernels launched by this library since load (bench.py "gpu_launches") */

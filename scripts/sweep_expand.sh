@@ -10,5 +10,4 @@ for l in sys.stdin:
     else: print(l.rstrip()[:300])
 "
 }
-run ASRD_L2_PERSIST=1 ASRD_TRACE=1 ASRD_HOST_CHUNK=16
-run ASRD_L2_PERSIST=0
+run ASRD_DEBUG_FLAGS=0
