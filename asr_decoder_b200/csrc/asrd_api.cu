@@ -34,9 +34,12 @@ thread_local std::string g_last_error;
 constexpr int kHostChunkFrames = 16;
 
 // per-device side stream + events for overlapping host->device staging with the search
+constexpr int kMaxWorkers = 8;
 struct DeviceCtx {
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t worker[kMaxWorkers] = {nullptr};
   cudaEvent_t ev_ready = nullptr, ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[kMaxWorkers] = {nullptr};
 };
 std::mutex g_ctx_mu;
 DeviceCtx g_ctx[16];
@@ -51,6 +54,11 @@ int GetCtx(int device, DeviceCtx **out) {
     for (int i = 0; i < 2; ++i) {
       CU_CHECK(cudaEventCreateWithFlags(&c.ev_copied[i], cudaEventDisableTiming));
       CU_CHECK(cudaEventCreateWithFlags(&c.ev_done[i], cudaEventDisableTiming));
+    }
+    CU_CHECK(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
+    for (int i = 0; i < kMaxWorkers; ++i) {
+      CU_CHECK(cudaStreamCreateWithFlags(&c.worker[i], cudaStreamNonBlocking));
+      CU_CHECK(cudaEventCreateWithFlags(&c.ev_join[i], cudaEventDisableTiming));
     }
   }
   *out = &c;
@@ -568,26 +576,38 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
   }
   const GraphView gv = decs[0]->graph->view;
   const DecoderConfigDev cfg = DevCfg(decs[0]);
+  DeviceCtx *ctx = nullptr;
+  if ((rc = GetCtx(decs[0]->graph->device, &ctx))) return rc;
   Scratch sc(s);
   StreamState **d_streams;
   if ((rc = UploadStreams(decs, n, s, sc, &d_streams))) return rc;
   AdvanceParams *d_params;
-  CU_CHECK(sc.Alloc(&d_params, (size_t)n));
   FrameDesc *d_desc;
-  CU_CHECK(sc.Alloc(&d_desc, (size_t)n));
-  ExpandPlan plan;
-  if ((rc = PlanExpand(n, num_indices, &plan))) return rc;
-
   const size_t row = (size_t)num_indices;
+  const int32_t chunk = on_device ? max_nf : std::min<int32_t>(max_nf, std::max(1, EnvInt("ASRD_HOST_CHUNK", kHostChunkFrames)));
+  const int n_chunks = (max_nf + chunk - 1) / chunk;
+  CU_CHECK(sc.Alloc(&d_params, (size_t)n * n_chunks));
+  CU_CHECK(sc.Alloc(&d_desc, (size_t)n));
+
+  // Sub-batch pipelining: the batch is cut into sub-batches that run their frame loops on
+  // separate worker streams.  The per-stream post phase (k_post) is a latency-bound chain;
+  // the expansion (k_expand) is throughput-bound and fills the machine, so expansions of
+  // different sub-batches serialise by themselves while each k_post overlaps the expansion of
+  // the other sub-batches.
+  int sub = EnvInt("ASRD_SUBBATCH", 32);
+  if (sub <= 0 || sub > n) sub = n;
+  const int n_sub = (n + sub - 1) / sub;
+  const int n_workers = std::max(1, std::min({n_sub, EnvInt("ASRD_WORKERS", 8), kMaxWorkers}));
+  const bool single = n_sub == 1;
+  std::vector<ExpandPlan> plans(n_sub);
+  for (int b = 0; b < n_sub; ++b)
+    if ((rc = PlanExpand(std::min(sub, n - b * sub), num_indices, &plans[b]))) return rc;
 
   // Host log-likelihoods: staged chunk by chunk through two device buffers, copied on a
   // side stream so the H2D of chunk k+1 overlaps the search of chunk k.
-  const int32_t chunk = on_device ? max_nf : std::min<int32_t>(max_nf, std::max(1, EnvInt("ASRD_HOST_CHUNK", kHostChunkFrames)));
   float *d_stage[2] = {nullptr, nullptr};
-  DeviceCtx *ctx = nullptr;
   bool contiguous = false;
   if (!on_device) {
-    if ((rc = GetCtx(decs[0]->graph->device, &ctx))) return rc;
     const int nbuf = max_nf > chunk ? 2 : 1;
     for (int b = 0; b < nbuf; ++b) CU_CHECK(sc.Alloc(&d_stage[b], (size_t)n * chunk * row));
     if (nbuf == 1) d_stage[1] = d_stage[0];
@@ -600,66 +620,111 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
                    (i == 0 || loglikes[i] - loglikes[i - 1] == loglikes[1] - loglikes[0]);
     if (contiguous && (loglikes[1] - loglikes[0]) < (ptrdiff_t)((size_t)nf[0] * row)) contiguous = false;
   }
-  std::vector<AdvanceParams> hp(n);
+  std::vector<AdvanceParams> hp((size_t)n * n_chunks);
+  std::vector<int32_t> steps_of((size_t)n_chunks * n_sub, 0);
+  for (int k = 0; k < n_chunks; ++k) {
+    const int32_t f0 = k * chunk;
+    for (int i = 0; i < n; ++i) {
+      AdvanceParams &p = hp[(size_t)k * n + i];
+      const int32_t c = std::max(0, std::min(chunk, nf[i] - f0));
+      p.n_frames = c;
+      p.frame0 = decs[i]->frames_decoded + std::min(f0, nf[i]);
+      if (on_device) {
+        p.ll = loglikes[i] + (size_t)f0 * stride[i];
+        p.stride = stride[i];
+      } else {
+        p.ll = d_stage[k & 1] + (size_t)i * chunk * row;
+        p.stride = num_indices;
+      }
+      int32_t &st = steps_of[(size_t)k * n_sub + i / sub];
+      st = std::max(st, c);
+    }
+  }
+  CU_CHECK(cudaMemcpyAsync(d_params, hp.data(), sizeof(AdvanceParams) * hp.size(), cudaMemcpyHostToDevice, s));
+
   Profiler prof(g_profile.load());
   const bool trace = EnvInt("ASRD_TRACE", 0) != 0;
   const auto t_begin = std::chrono::steady_clock::now();
   auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
-  int k = 0;
-  for (int32_t f0 = 0; f0 < max_nf; f0 += chunk, ++k) {
-    int32_t steps = 0;
+  std::vector<cudaEvent_t> ev_rows;  // rows of chunk k are in the histories
+  auto cleanup = [&]() { for (cudaEvent_t e : ev_rows) cudaEventDestroy(e); };
+  for (int k = 0; k < n_chunks; ++k) {
+    const int32_t f0 = k * chunk;
     float *stage = d_stage[k & 1];
-    if (!on_device && k >= 2) CU_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[k & 1], 0));
-    for (int i = 0; i < n; ++i) {
-      const int32_t c = std::max(0, std::min(chunk, nf[i] - f0));
-      steps = std::max(steps, c);
-      hp[i].n_frames = c;
-      if (on_device) {
-        hp[i].ll = loglikes[i] + (size_t)f0 * stride[i];
-        hp[i].stride = stride[i];
-      } else {
-        hp[i].ll = stage + (size_t)i * chunk * row;
-        hp[i].stride = num_indices;
+    // ---- rows of this chunk -> device (copy stream) -> per-stream histories (stream s)
+    if (!on_device) {
+      if (k >= 2) CU_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[k & 1], 0));
+      int32_t widest = 0;
+      for (int i = 0; i < n; ++i) {
+        const int32_t c = hp[(size_t)k * n + i].n_frames;
+        widest = std::max(widest, c);
         if (c > 0 && !contiguous)
           CU_CHECK(cudaMemcpy2DAsync(stage + (size_t)i * chunk * row, row * 4,
                                      loglikes[i] + (size_t)f0 * stride[i], (size_t)stride[i] * 4, row * 4,
                                      (size_t)c, cudaMemcpyHostToDevice, ctx->copy_stream));
       }
-    }
-    if (!on_device) {
       if (contiguous)
         CU_CHECK(cudaMemcpy2DAsync(stage, (size_t)chunk * row * 4, loglikes[0] + (size_t)f0 * row,
-                                   (size_t)(loglikes[1] - loglikes[0]) * 4, (size_t)steps * row * 4, (size_t)n,
+                                   (size_t)(loglikes[1] - loglikes[0]) * 4, (size_t)widest * row * 4, (size_t)n,
                                    cudaMemcpyHostToDevice, ctx->copy_stream));
       CU_CHECK(cudaEventRecord(ctx->ev_copied[k & 1], ctx->copy_stream));
       CU_CHECK(cudaStreamWaitEvent(s, ctx->ev_copied[k & 1], 0));
     }
     if (trace) fprintf(stderr, "[asrd] chunk %d copies issued at %.2f ms\n", k, since());
-    CU_CHECK(cudaMemcpyAsync(d_params, hp.data(), sizeof(AdvanceParams) * n, cudaMemcpyHostToDevice, s));
-    if (trace) fprintf(stderr, "[asrd] chunk %d params copied at %.2f ms\n", k, since());
-    k_begin_advance<<<dim3((unsigned)std::min(steps, 8), (unsigned)n), 256, 0, s>>>(d_streams, d_params, num_indices);
-    // the rows now live in the per-stream history: the staging buffer may be refilled
+    k_begin_advance<<<dim3(8, (unsigned)n), 256, 0, s>>>(d_streams, d_params + (size_t)k * n, num_indices);
+    ++g_launches;
+    // the rows now live in the per-stream histories: the staging buffer may be refilled
     if (!on_device) CU_CHECK(cudaEventRecord(ctx->ev_done[k & 1], s));
-    prof.Begin(1, s);
-    k_post<<<n, kStreamThreads, 0, s>>>(d_streams, d_desc, gv, cfg, kModePro);
-    prof.End(s);
-    g_launches += 2;
-    for (int32_t f = 0; f < steps; ++f) {
-      prof.Begin(0, s);
-      plan.fn<<<plan.grid, kExpandThreads, plan.dyn, s>>>(d_desc, gv, num_indices, plan.flags);
-      prof.End(s);
-      const int post_mode = kModeEpi | (f + 1 < steps ? kModePro : 0);
-      prof.Begin(1, s);
-      k_post<<<n, kStreamThreads, 0, s>>>(d_streams, d_desc, gv, cfg, post_mode);
-      prof.End(s);
-      g_launches += 2;
+    cudaEvent_t ev;
+    CU_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    ev_rows.push_back(ev);
+    CU_CHECK(cudaEventRecord(ev, s));
+  }
+  // ---- frame loops: one per sub-batch, on the worker streams (or on s when there is one)
+  for (int k = 0; k < n_chunks; ++k) {
+    for (int w = 0; w < (single ? 0 : n_workers); ++w) CU_CHECK(cudaStreamWaitEvent(ctx->worker[w], ev_rows[k], 0));
+    int32_t max_steps = 0;
+    for (int b = 0; b < n_sub; ++b) max_steps = std::max(max_steps, steps_of[(size_t)k * n_sub + b]);
+    for (int32_t f = -1; f < max_steps; ++f) {
+      for (int b = 0; b < n_sub; ++b) {
+        const int32_t steps = steps_of[(size_t)k * n_sub + b];
+        if (steps == 0 || f >= steps) continue;
+        cudaStream_t ws = single ? s : ctx->worker[b % n_workers];
+        const int nb = std::min(sub, n - b * sub);
+        StreamState **bs = d_streams + (size_t)b * sub;
+        FrameDesc *bd = d_desc + (size_t)b * sub;
+        if (f < 0) {  // GetCutoff + pre-pass of the chunk's first frame
+          prof.Begin(1, ws);
+          k_post<<<nb, kStreamThreads, 0, ws>>>(bs, bd, gv, cfg, kModePro);
+          prof.End(ws);
+          ++g_launches;
+          continue;
+        }
+        prof.Begin(0, ws);
+        plans[b].fn<<<plans[b].grid, kExpandThreads, plans[b].dyn, ws>>>(bd, gv, num_indices, plans[b].flags);
+        prof.End(ws);
+        prof.Begin(1, ws);
+        k_post<<<nb, kStreamThreads, 0, ws>>>(bs, bd, gv, cfg, kModeEpi | (f + 1 < steps ? kModePro : 0));
+        prof.End(ws);
+        g_launches += 2;
+      }
     }
-    CU_CHECK(cudaGetLastError());
+    if (cudaGetLastError() != cudaSuccess) {
+      cleanup();
+      return ASRD_ERR_CUDA;
+    }
+  }
+  if (!single) {  // join the workers back into the caller's stream
+    for (int w = 0; w < n_workers; ++w) {
+      CU_CHECK(cudaEventRecord(ctx->ev_join[w], ctx->worker[w]));
+      CU_CHECK(cudaStreamWaitEvent(s, ctx->ev_join[w], 0));
+    }
   }
   if (!on_device) {
     // the copy stream must not run ahead into a later call's (recycled) staging memory
-    CU_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[(k - 1) & 1], 0));
+    CU_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[(n_chunks - 1) & 1], 0));
   }
+  cleanup();
   for (int i = 0; i < n; ++i) decs[i]->frames_decoded += nf[i];
   if (trace) {
     fprintf(stderr, "[asrd] all issued at %.2f ms\n", since());

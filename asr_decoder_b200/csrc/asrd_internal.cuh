@@ -109,6 +109,8 @@ struct AdvanceParams {
   const float *ll;   // device pointer to the first new row of this chunk
   int32_t stride;    // floats between rows
   int32_t n_frames;  // rows in this chunk
+  int32_t frame0;    // frame index of the first row (host-tracked, so chunks can be staged ahead)
+  int32_t pad;
 };
 
 struct DecoderConfigDev {

@@ -284,13 +284,14 @@ __global__ void __launch_bounds__(256)
 k_begin_advance(StreamState *const *streams, const AdvanceParams *params, int num_indices) {
   StreamState *st = streams[blockIdx.y];
   const AdvanceParams p = params[blockIdx.y];
-  const int frame0 = st->frame;
+  const int frame0 = p.frame0;
   int nf = p.n_frames;
   if (frame0 + nf > st->max_frames) {
     nf = st->max_frames - frame0;
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicMin(&st->status, ASRD_ERR_FRAMES_OVERFLOW);
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) st->target_frame = frame0 + (nf > 0 ? nf : 0);
+  // chunks are staged ahead of the frame loops: the target only ever grows
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(&st->target_frame, frame0 + (nf > 0 ? nf : 0));
   const int hs = st->ll_stride;
   float *dst = st->ll_hist + (size_t)frame0 * hs;
   const bool vec = ((num_indices & 3) == 0) && ((p.stride & 3) == 0) && ((hs & 3) == 0) &&

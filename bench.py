@@ -279,9 +279,17 @@ def run_b200_arm(a):
     # ---- counters + per-kernel device time of one extra (untimed) step
     ae, aa, tk = C.c_int64(0), C.c_int64(0), C.c_int64(0)
     L.asrd_get_counters(batch.handles, n, C.byref(ae), C.byref(aa), C.byref(tk), stream)
+    # per-kernel device time: one extra untimed step with the sub-batch pipelining switched off,
+    # so that every launch runs alone on the stream its events are recorded on
     L.asrd_profile_reset()
     L.asrd_profile_enable(1)
+    saved = os.environ.get("ASRD_SUBBATCH")
+    os.environ["ASRD_SUBBATCH"] = "0"
     step(dev_args, True)
+    if saved is None:
+        del os.environ["ASRD_SUBBATCH"]
+    else:
+        os.environ["ASRD_SUBBATCH"] = saved
     L.asrd_profile_enable(0)
     kms, kn = (C.c_double * 4)(), (C.c_int64 * 4)()
     L.asrd_profile_get(kms, kn)
@@ -344,6 +352,7 @@ def run_b200_arm(a):
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_arc": 16, "arcs_per_launch": ae.value / max(1, xn.value),
                      "launch_ms": xm.value / max(1, xn.value), "launches_per_step": int(xn.value),
+                     "timing": "CUDA events around every launch of one extra step run without sub-batch overlap",
                      "kernel_ms_per_launch": {k: kms[i] / max(1, kn[i]) for i, k in enumerate(knames)},
                      "kernel_share_of_step": {k: kms[i] / ktot for i, k in enumerate(knames)}},
     }
