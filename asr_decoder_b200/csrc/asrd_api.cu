@@ -464,10 +464,10 @@ int asrd_decoder_create(asrd_graph *g, const asrd_config *cfg, const asrd_device
   auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
   const size_t b_hash = align(H * sizeof(HashEntry)), b_list = align(H * 4), b_bm = align(H / 8),
                b_tok = align((size_t)o.token_capacity * 8), b_arc = align((size_t)o.token_capacity * 4),
-               b_off = align(((size_t)o.max_frames + 2) * 4),
+               b_off = align(((size_t)o.max_frames + 4) * 4),
                b_stats = o.collect_stats ? align(((size_t)o.max_frames + 1) * sizeof(asrd_frame_stat)) : 0,
                b_state = align(sizeof(StreamState));
-  const size_t total = b_state + b_hash + 2 * b_bm + 2 * b_list + b_tok + b_arc + 2 * b_off + b_stats;
+  const size_t total = b_state + b_hash + 2 * b_bm + 2 * b_list + b_tok + b_arc + 3 * b_off + b_stats;
   if (cudaMalloc(&d->slab, total) != cudaSuccess) {
     cudaGetLastError();
     delete d;
@@ -486,6 +486,7 @@ int asrd_decoder_create(asrd_graph *g, const asrd_config *cfg, const asrd_device
   h.tok_arc = (uint32_t *)p; p += b_arc;
   h.frame_off = (uint32_t *)p; p += b_off;
   h.frame_nc = (float *)p; p += b_off;
+  h.frame_cur = (float *)p; p += b_off;
   h.stats = o.collect_stats ? (asrd_frame_stat *)p : nullptr;
   h.hash_mask = (uint32_t)H - 1;
   uint32_t lg = 0;
@@ -793,6 +794,92 @@ int asrd_get_best_path(asrd_decoder *const *decs, int32_t n, int32_t use_final_p
     std::reverse(graph + b, graph + b + m);
     std::reverse(acoustic + b, acoustic + b + m);
   }
+  return ASRD_OK;
+}
+
+int asrd_get_raw_lattice(asrd_decoder *d, int32_t use_final_probs, asrd_lat_token *toks, int64_t tok_cap,
+                         asrd_lat_link *links, int64_t link_cap, int64_t *n_toks, int64_t *n_links,
+                         void *stream) {
+  if (!d || !n_toks || !n_links || tok_cap < 0 || link_cap < 0 || tok_cap > 0x7FFFFFFF || link_cap > 0x7FFFFFFF)
+    return ASRD_ERR_BAD_ARG;
+  if (!d->initialized) return ASRD_ERR_STATE;
+  if (d->finalized && !use_final_probs) return ASRD_ERR_STATE;  // inl.h:879-884
+  if (d->frames_decoded <= 0 || !d->d_ll_hist) {
+    *n_toks = *n_links = 0;
+    return ASRD_ERR_NO_TOKENS;
+  }
+  int rc = EnsureDevice(d->graph->device);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  Scratch sc(s);
+  asrd_decoder *one[1] = {d};
+  StreamState **d_streams;
+  if ((rc = UploadStreams(one, 1, s, sc, &d_streams))) return rc;
+  const size_t H = (size_t)d->opts.hash_capacity;
+  LatticeOut h;
+  memset(&h, 0, sizeof(h));
+  LatticeOut *d_out;
+  LatEntry *maps;
+  CU_CHECK(sc.Alloc(&d_out, 1));
+  CU_CHECK(sc.Alloc(&maps, 2 * H));
+  CU_CHECK(sc.Alloc(&h.toks, (size_t)std::max<int64_t>(tok_cap, 1)));
+  CU_CHECK(sc.Alloc(&h.tok_arena_idx, (size_t)std::max<int64_t>(tok_cap, 1)));
+  CU_CHECK(sc.Alloc(&h.links, (size_t)std::max<int64_t>(link_cap, 1)));
+  h.map[0] = maps;
+  h.map[1] = maps + H;
+  h.tok_cap = (uint32_t)tok_cap;
+  h.link_cap = (uint32_t)link_cap;
+  CU_CHECK(cudaMemsetAsync(maps, 0xFF, 2 * H * sizeof(LatEntry), s));
+  CU_CHECK(cudaMemcpyAsync(d_out, &h, sizeof(h), cudaMemcpyHostToDevice, s));
+  k_lattice<<<1, kStreamThreads, 0, s>>>(d_streams, d_out, d->graph->view, DevCfg(d), use_final_probs ? 1 : 0);
+  ++g_launches;
+  CU_CHECK(cudaGetLastError());
+  LatticeOut r;
+  CU_CHECK(cudaMemcpyAsync(&r, d_out, sizeof(r), cudaMemcpyDeviceToHost, s));
+  CU_CHECK(cudaStreamSynchronize(s));
+  *n_toks = r.n_toks;
+  *n_links = r.n_links;
+  if (r.n_toks > h.tok_cap || r.n_links > h.link_cap) return ASRD_ERR_PATH_OVERFLOW;
+  if (r.n_toks == 0) return ASRD_ERR_NO_TOKENS;
+  if (!toks || !links) return ASRD_ERR_BAD_ARG;
+  std::vector<uint32_t> arena(r.n_toks);
+  CU_CHECK(cudaMemcpyAsync(toks, h.toks, sizeof(asrd_lat_token) * r.n_toks, cudaMemcpyDeviceToHost, s));
+  CU_CHECK(cudaMemcpyAsync(arena.data(), h.tok_arena_idx, 4 * (size_t)r.n_toks, cudaMemcpyDeviceToHost, s));
+  if (r.n_links)
+    CU_CHECK(cudaMemcpyAsync(links, h.links, sizeof(asrd_lat_link) * r.n_links, cudaMemcpyDeviceToHost, s));
+  CU_CHECK(cudaStreamSynchronize(s));
+  // Canonical order: tokens by (frame, state), links by (src, dst, arc labels) — the kernel emits
+  // them in scheduling order.  Links carry arena indices; map them to token indices.
+  std::vector<uint32_t> order(r.n_toks);
+  for (uint32_t i = 0; i < r.n_toks; ++i) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+    if (toks[a].frame != toks[b].frame) return toks[a].frame < toks[b].frame;
+    return toks[a].state < toks[b].state;
+  });
+  std::vector<asrd_lat_token> sorted(r.n_toks);
+  std::vector<std::pair<uint32_t, uint32_t>> a2i(r.n_toks);
+  for (uint32_t i = 0; i < r.n_toks; ++i) {
+    sorted[i] = toks[order[i]];
+    a2i[i] = std::make_pair(arena[order[i]], i);
+  }
+  std::copy(sorted.begin(), sorted.end(), toks);
+  std::sort(a2i.begin(), a2i.end());
+  auto lookup = [&](uint32_t arena_idx) -> int32_t {
+    auto it = std::lower_bound(a2i.begin(), a2i.end(), std::make_pair(arena_idx, 0u));
+    return (it != a2i.end() && it->first == arena_idx) ? (int32_t)it->second : -1;
+  };
+  for (uint32_t i = 0; i < r.n_links; ++i) {
+    links[i].src = lookup((uint32_t)links[i].src);
+    links[i].dst = lookup((uint32_t)links[i].dst);
+    if (links[i].src < 0 || links[i].dst < 0) return ASRD_ERR_STATE;
+  }
+  std::sort(links, links + r.n_links, [](const asrd_lat_link &a, const asrd_lat_link &b) {
+    if (a.src != b.src) return a.src < b.src;
+    if (a.dst != b.dst) return a.dst < b.dst;
+    if (a.ilabel != b.ilabel) return a.ilabel < b.ilabel;
+    if (a.olabel != b.olabel) return a.olabel < b.olabel;
+    return a.graph < b.graph;
+  });
   return ASRD_OK;
 }
 

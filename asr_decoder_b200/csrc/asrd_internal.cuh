@@ -56,6 +56,7 @@ struct StreamState {
   uint32_t *tok_arc;    // token arena: arc that set the token's cost (kNoArc for the start token)
   uint32_t *frame_off;  // [max_frames + 2] arena offset of every frame's token span
   float *frame_nc;      // [max_frames + 2] final next_cutoff of the step that produced each frame
+  float *frame_cur;     // [max_frames + 2] GetCutoff result of each frame (which tokens were expanded)
   float *ll_hist;       // [max_frames x ll_stride] log-likelihood rows seen so far (trace-back needs them)
   asrd_frame_stat *stats;  // [max_frames + 1] or null
   uint32_t hash_mask;
@@ -104,6 +105,23 @@ struct __align__(16) FrameDesc {
   int32_t t;            // frame being expanded; -1 while InitDecoding completes frame 0
 };
 static_assert(sizeof(FrameDesc) == 128, "FrameDesc is one 128-byte line");
+
+// One slot of the per-frame lookup maps of the lattice back-sweep.
+struct __align__(16) LatEntry {
+  uint32_t key;        // state, kEmptyKey when free
+  uint32_t cost_bits;  // token cost
+  uint32_t extra_ord;  // ordered extra_cost (atomicMin), kOrdInf = token not (yet) reachable
+  uint32_t idx;        // arena index of the token
+};
+
+struct LatticeOut {    // per-stream output window of k_lattice
+  asrd_lat_token *toks;
+  uint32_t *tok_arena_idx;   // arena index of every emitted token (links refer to arena indices)
+  asrd_lat_link *links;
+  LatEntry *map[2];
+  uint32_t tok_cap, link_cap;
+  uint32_t n_toks, n_links;   // produced (may exceed the caps: then nothing beyond the cap was written)
+};
 
 struct AdvanceParams {
   const float *ll;   // device pointer to the first new row of this chunk

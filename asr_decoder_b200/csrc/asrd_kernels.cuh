@@ -580,6 +580,7 @@ __device__ __forceinline__ void cutoff_prologue(StreamState *st, FrameDesc *d, c
     nd.out_sc = st->tok_sc + out_base;
     nd.out_arc = st->tok_arc + out_base;
     nd.best64 = kInfVal;
+    st->frame_cur[t] = cur_cut;
     nd.n_cur = n;
     nd.cur_cut = cur_cut;
     nd.abeam = abeam;
@@ -788,6 +789,211 @@ k_post(StreamState *const *streams, FrameDesc *desc, GraphView g, DecoderConfigD
   }
 
   if (mode & kModePro) cutoff_prologue<NT>(st, d, g, cfg, s_red64, s_red32, s_hist, s_misc);
+}
+
+// ------------------------------------------------------------------ raw lattice
+
+// GetRawLattice (inl.h:868-975) with the pruning of FinalizeDecoding (inl.h:725-847), one CTA
+// per stream.  The device keeps tokens only.  Forward links are REGENERATED here: a link
+// tok -> dst exists iff tok was expanded (cost <= cur_cutoff of its frame, inl.h:315; for eps
+// arcs cost < the frame's closure cutoff, inl.h:391) and the arc's cost is below the final
+// cutoff of the destination frame (inl.h:330, 415) — exactly the links the canonical search
+// admits.  One backward sweep over the frames computes the extra costs (inl.h:524-562; eps links
+// inside a frame iterate to the exact fixed point), drops links with
+// link_extra_cost > lattice_beam and tokens without surviving links, and emits the survivors.
+// Two small per-frame maps (state -> cost, extra, arena index) replace the reference's pointers.
+__device__ __forceinline__ bool lat_find(const LatEntry *m, uint32_t mask, uint32_t shift, uint32_t state,
+                                         uint32_t &slot) {
+  uint32_t h = hash_state(state, mask, shift);
+  for (uint32_t probe = 0; probe <= mask; ++probe) {
+    const uint32_t k = __ldcg(&m[h].key);
+    if (k == state) {
+      slot = h;
+      return true;
+    }
+    if (k == kEmptyKey) return false;
+    h = (h + 1) & mask;
+  }
+  return false;
+}
+
+__global__ void __launch_bounds__(kStreamThreads, 2)
+k_lattice(StreamState *const *streams, LatticeOut *outs, GraphView g, DecoderConfigDev cfg, int use_final) {
+  constexpr int NT = kStreamThreads;
+  __shared__ unsigned long long s_red64[NT / 32];
+  __shared__ uint32_t s_changed;
+  StreamState *st = streams[blockIdx.x];
+  LatticeOut *out = &outs[blockIdx.x];
+  const int tid = threadIdx.x;
+  const int F = st->frame;
+  if (tid == 0) {
+    out->n_toks = 0;
+    out->n_links = 0;
+  }
+  if (F < 0) return;
+  const uint32_t mask = st->hash_mask, shift = st->hash_shift;
+  const float beam = cfg.lattice_beam;
+  uint32_t *slots[2] = {st->queue[0], st->queue[1]};  // slot of token i of the frame in map[f & 1]
+
+  // ---- final costs (ComputeFinalCosts, inl.h:670-720): the token on the super-final state, if any
+  float final_best = 0.f;
+  bool any_final = false;
+  {
+    const uint32_t b0 = st->frame_off[F], n0 = st->frame_off[F + 1] - b0;
+    unsigned long long best_all = kInfVal, best_fin = kInfVal;
+    for (uint32_t i = tid; i < n0; i += NT) {
+      const uint2 sc = st->tok_sc[b0 + i];
+      const unsigned long long b = ((unsigned long long)f2ord(__uint_as_float(sc.y)) << 32) | sc.x;
+      best_all = b < best_all ? b : best_all;
+      if ((int32_t)sc.x == g.final_state) best_fin = b < best_fin ? b : best_fin;
+    }
+    best_all = block_min_u64<NT>(best_all, s_red64);
+    best_fin = block_min_u64<NT>(best_fin, s_red64);
+    any_final = use_final && best_fin != kInfVal;
+    final_best = ord2f((uint32_t)((any_final ? best_fin : best_all) >> 32));  // inl.h:709-719
+  }
+
+  auto emit_link = [&](uint32_t src_idx, uint32_t dst_idx, const int4 &arc, float ac) {
+    const uint32_t p = atomicAdd(&out->n_links, 1u);
+    if (p < out->link_cap) {
+      asrd_lat_link l;
+      l.src = (int32_t)src_idx;
+      l.dst = (int32_t)dst_idx;
+      l.ilabel = arc.x;
+      l.olabel = arc.y;
+      l.graph = __int_as_float(arc.z);
+      l.acoustic = ac;
+      out->links[p] = l;
+    }
+  };
+
+  for (int f = F; f >= 0; --f) {
+    LatEntry *mc = out->map[f & 1];        // this frame
+    LatEntry *mn = out->map[(f + 1) & 1];  // frame f + 1 (complete)
+    uint32_t *sl = slots[f & 1];
+    const uint32_t b0 = st->frame_off[f], n = st->frame_off[f + 1] - b0;
+    const float nc_f = st->frame_nc[f];
+    // ---- recycle the map this frame reuses (it held frame f + 2)
+    if (f + 2 <= F) {
+      const uint32_t n2 = st->frame_off[f + 3] - st->frame_off[f + 2];
+      for (uint32_t i = tid; i < n2; i += NT) {
+        LatEntry e;
+        e.key = kEmptyKey; e.cost_bits = 0; e.extra_ord = kOrdInf; e.idx = 0;
+        mc[sl[i]] = e;
+      }
+    }
+    __syncthreads();
+    // ---- insert the frame's tokens
+    for (uint32_t i = tid; i < n; i += NT) {
+      const uint2 sc = st->tok_sc[b0 + i];
+      float init = CUDART_INF_F;
+      if (f == F) {  // PruneForwardLinksFinal, inl.h:758-775, 815-816
+        const float fc = (!any_final || (int32_t)sc.x == g.final_state) ? 0.f : CUDART_INF_F;
+        init = __uint_as_float(sc.y) + fc - final_best;
+        if (init > beam) init = CUDART_INF_F;
+      }
+      uint32_t h = hash_state(sc.x, mask, shift);
+      for (;;) {
+        if (atomicCAS(&mc[h].key, kEmptyKey, sc.x) == kEmptyKey) break;
+        h = (h + 1) & mask;
+      }
+      mc[h].cost_bits = sc.y;
+      mc[h].extra_ord = f2ord(init);
+      mc[h].idx = b0 + i;
+      sl[i] = h;
+    }
+    __syncthreads();
+    // ---- emitting links into frame f + 1 (its extra costs are final)
+    if (f < F) {
+      const float cur_cut = st->frame_cur[f];
+      const float nc_next = st->frame_nc[f + 1];
+      const float *__restrict__ ll = st->ll_hist + (size_t)f * st->ll_stride;
+      for (uint32_t i = tid; i < n; i += NT) {
+        const uint2 sc = st->tok_sc[b0 + i];
+        const float cost = __uint_as_float(sc.y);
+        if (!(cost <= cur_cut)) continue;  // inl.h:315
+        const uint2 er = __ldg(&g.erows[sc.x]);
+        float best = CUDART_INF_F;
+        for (uint32_t a = er.x; a < er.y; ++a) {
+          const int4 arc = __ldg(&g.arcs[a]);
+          const float ac = -__ldg(&ll[arc.x - 1]);
+          const float tot = (cost + ac) + __int_as_float(arc.z);  // inl.h:326-329
+          if (!(tot < nc_next)) continue;                           // inl.h:330, final cutoff
+          uint32_t ds;
+          if (!lat_find(mn, mask, shift, (uint32_t)arc.w & kStateMask, ds)) continue;
+          const float dextra = ord2f(__ldcg(&mn[ds].extra_ord));
+          float le = dextra + (tot - __uint_as_float(__ldcg(&mn[ds].cost_bits)));  // inl.h:524-526
+          if (le > beam) continue;                                                  // inl.h:532
+          if (le < 0.f) le = 0.f;                                                   // inl.h:545-551
+          best = fminf(best, le);
+          emit_link(b0 + i, __ldcg(&mn[ds].idx), arc, ac);
+        }
+        if (best < CUDART_INF_F) atomicMin(&mc[sl[i]].extra_ord, f2ord(best));
+      }
+    }
+    // ---- eps links inside the frame: exact fixed point of the extra costs
+    for (;;) {
+      __syncthreads();
+      if (tid == 0) s_changed = 0;
+      __syncthreads();
+      for (uint32_t i = tid; i < n; i += NT) {
+        const uint2 sc = st->tok_sc[b0 + i];
+        const float cost = __uint_as_float(sc.y);
+        if (!(cost < nc_f)) continue;  // inl.h:391
+        const uint2 r = __ldg(&g.rows[sc.x]);
+        if (r.y == r.x) continue;
+        float mine = ord2f(__ldcg(&mc[sl[i]].extra_ord));
+        for (uint32_t a = r.x; a < r.y; ++a) {
+          const int4 arc = __ldg(&g.arcs[a]);
+          const float tot = cost + __int_as_float(arc.z);  // inl.h:413-414
+          if (!(tot < nc_f)) continue;                      // inl.h:415
+          uint32_t ds;
+          if (!lat_find(mc, mask, shift, (uint32_t)arc.w & kStateMask, ds)) continue;
+          float le = ord2f(__ldcg(&mc[ds].extra_ord)) + (tot - __uint_as_float(__ldcg(&mc[ds].cost_bits)));
+          if (le > beam) continue;
+          if (le < 0.f) le = 0.f;
+          if (le < mine) {
+            mine = le;
+            atomicMin(&mc[sl[i]].extra_ord, f2ord(le));
+            s_changed = 1;
+          }
+        }
+      }
+      __syncthreads();
+      if (!s_changed) break;
+    }
+    // ---- emit the frame's surviving eps links and tokens
+    for (uint32_t i = tid; i < n; i += NT) {
+      const uint2 sc = st->tok_sc[b0 + i];
+      const float cost = __uint_as_float(sc.y);
+      const float extra = ord2f(__ldcg(&mc[sl[i]].extra_ord));
+      if (!(extra < CUDART_INF_F)) continue;  // PruneTokensForFrame, inl.h:591
+      const uint32_t p = atomicAdd(&out->n_toks, 1u);
+      if (p < out->tok_cap) {
+        asrd_lat_token t;
+        t.frame = f;
+        t.state = (int32_t)sc.x;
+        t.cost = cost;
+        t.extra = extra;
+        t.is_final = (f == F && (!any_final || (int32_t)sc.x == g.final_state)) ? 1 : 0;  // inl.h:935-951
+        out->toks[p] = t;
+        out->tok_arena_idx[p] = b0 + i;  // links carry arena indices; the host maps them through this
+      }
+      if (!(cost < nc_f)) continue;
+      const uint2 r = __ldg(&g.rows[sc.x]);
+      for (uint32_t a = r.x; a < r.y; ++a) {
+        const int4 arc = __ldg(&g.arcs[a]);
+        const float tot = cost + __int_as_float(arc.z);
+        if (!(tot < nc_f)) continue;
+        uint32_t ds;
+        if (!lat_find(mc, mask, shift, (uint32_t)arc.w & kStateMask, ds)) continue;
+        const float le = ord2f(__ldcg(&mc[ds].extra_ord)) + (tot - __uint_as_float(__ldcg(&mc[ds].cost_bits)));
+        if (le > beam) continue;
+        emit_link(b0 + i, __ldcg(&mc[ds].idx), arc, 0.f);
+      }
+    }
+    __syncthreads();
+  }
 }
 
 // ------------------------------------------------------------------ counters

@@ -27,6 +27,10 @@ from . import _lib
 from ._lib import asrd_config, asrd_device_options, asrd_frame_stat, check
 from .fstio import Fst, read_fst
 
+LAT_TOKEN_DTYPE = np.dtype([("frame", "<i4"), ("state", "<i4"), ("cost", "<f4"), ("extra", "<f4"),
+                            ("is_final", "<i4")])
+LAT_LINK_DTYPE = np.dtype([("src", "<i4"), ("dst", "<i4"), ("ilabel", "<i4"), ("olabel", "<i4"),
+                           ("graph", "<f4"), ("acoustic", "<f4")])
 FRAME_STAT_DTYPE = np.dtype([("n_in", "<u4"), ("cur_cutoff", "<f4"), ("abeam", "<f4"),
                              ("next_cutoff", "<f4"), ("n_tokens", "<u4"), ("best", "<f4"),
                              ("arcs_expanded", "<u4"), ("arcs_admitted", "<u4")])
@@ -258,6 +262,28 @@ class CudaDecoderBatch:
             out.append(BestPath(bool(ok), int(st[i]), il[i, :m].copy(), ol[i, :m].copy(), gr[i, :m].copy(),
                                 ac[i, :m].copy(), words, ali, tot, lm))
         return out
+
+    def GetRawLattice(self, i: int = 0, use_final_probs: bool = True, stream: int = 0):
+        """``DecoderItf::GetRawLattice`` for stream ``i`` (inl.h:868-975), after the lattice-beam
+        pruning of ``FinalizeDecoding``: (tokens, links) as structured arrays, tokens sorted by
+        (frame, state), ``links['src'/'dst']`` index into tokens.  ``None`` when the reference
+        would return false."""
+        L = _lib.lib()
+        tok_cap, link_cap = 1 << 16, 1 << 17
+        while True:
+            toks = np.zeros(tok_cap, LAT_TOKEN_DTYPE)
+            links = np.zeros(link_cap, LAT_LINK_DTYPE)
+            nt, nl = C.c_int64(0), C.c_int64(0)
+            rc = L.asrd_get_raw_lattice(self.handles[i], int(use_final_probs), toks.ctypes.data, tok_cap,
+                                        links.ctypes.data, link_cap, C.byref(nt), C.byref(nl), stream)
+            if rc == -8:  # ASRD_ERR_PATH_OVERFLOW: retry with what the kernel asked for
+                tok_cap = max(tok_cap, int(nt.value) + 16)
+                link_cap = max(link_cap, int(nl.value) + 16)
+                continue
+            if rc == -7:
+                return None
+            check(rc, "asrd_get_raw_lattice")
+            return toks[:nt.value].copy(), links[:nl.value].copy()
 
     def frame_stats(self, i: int = 0, stream: int = 0) -> np.ndarray:
         L = _lib.lib()

@@ -88,6 +88,23 @@ typedef struct {
   uint32_t arcs_admitted;/* ... whose cost was below the running cutoff when scored */
 } asrd_frame_stat;
 
+/* Raw lattice (DecoderItf::GetRawLattice, inl.h:868-975): one state per surviving token, one
+ * arc per surviving forward link, after the lattice-beam pruning of FinalizeDecoding
+ * (inl.h:725-847).  Links refer to tokens by index into the token array. */
+typedef struct {
+  int32_t frame;     /* 0 = before the first frame */
+  int32_t state;     /* HCLG state */
+  float cost;        /* forward cost (StdToken::_tot_cost) */
+  float extra;       /* extra_cost after pruning (StdToken::_extra_cost) */
+  int32_t is_final;  /* lattice state is final (inl.h:935-951) */
+} asrd_lat_token;
+
+typedef struct {
+  int32_t src, dst;  /* token indices */
+  int32_t ilabel, olabel;
+  float graph, acoustic;
+} asrd_lat_link;
+
 typedef struct asrd_graph asrd_graph;
 typedef struct asrd_decoder asrd_decoder;
 
@@ -142,6 +159,18 @@ int asrd_finalize_decoding(asrd_decoder *const *decs, int32_t n, void *stream);
 
 /* DecoderItf::NumFramesDecoded (decoder-itf.h:18) */
 int32_t asrd_num_frames_decoded(const asrd_decoder *d);
+
+/* DecoderItf::GetRawLattice (decoder-itf.h:23; inl.h:868-975) for one stream, including the
+ * final lattice-beam pruning (PruneForwardLinksFinal / PruneForwardLinks / PruneTokensForFrame,
+ * inl.h:482-607,725-847).  The device keeps tokens only; the forward links are regenerated from
+ * the tokens, the graph, the log-likelihood history and the per-frame cutoffs in one backward
+ * sweep, pruned there, and only the survivors are copied out.  Tokens come frame by frame with
+ * eps links pointing forward inside a frame's block is NOT guaranteed: sort topologically if
+ * needed.  n_toks / n_links receive the produced counts; ASRD_ERR_PATH_OVERFLOW when a cap was
+ * too small (call again with larger buffers).  Requires FinalizeDecoding when use_final_probs. */
+int asrd_get_raw_lattice(asrd_decoder *d, int32_t use_final_probs, asrd_lat_token *toks, int64_t tok_cap,
+                         asrd_lat_link *links, int64_t link_cap, int64_t *n_toks, int64_t *n_links,
+                         void *stream);
 
 /* DecoderItf::GetBestPath (decoder-itf.h:22; inl.h:1071-1200), batched.  For stream i the
  * arcs of the linear best-path lattice are written in path order (start -> end) to

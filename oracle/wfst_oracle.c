@@ -713,7 +713,10 @@ void orc_advance_decoding(OrcDecoder *d, const float *loglikes, int32_t stride,
     target = d->num_frames_decoded + max_num_frames;
   while (d->num_frames_decoded < target) {
     int nfd = (int)d->n_active - 1; /* NumFramesDecoded(), online-decoder-base.h:133 */
-    if (nfd % d->cfg.prune_interval == 0)
+    /* Canonical mode prunes once, at FinalizeDecoding, with exact extra costs: the periodic
+     * prune works on lower bounds of the final extra costs (every path to the end passes the
+     * current frame), so it only ever removes a subset of what the final prune removes. */
+    if (d->mode == ORC_MODE_REFERENCE && nfd % d->cfg.prune_interval == 0)
       prune_active_tokens(d, d->cfg.lattice_beam * d->cfg.prune_scale);
     float cutoff = process_emitting(d, loglikes + (size_t)d->num_frames_decoded * stride);
     process_nonemitting(d, cutoff);
@@ -752,7 +755,7 @@ static void prune_forward_links_final(OrcDecoder *d) {
   d->finalized = 1;
   hl_delete_elems(d);
   int changed = 1;
-  const float delta = 1.0e-5f;
+  const float delta = d->mode == ORC_MODE_CANONICAL ? 0.0f : 1.0e-5f; /* canonical: exact fixed point */
   while (changed) {
     changed = 0;
     for (Tok *tok = d->active[frame_plus_one].toks; tok; tok = tok->next) {
