@@ -54,7 +54,7 @@ int main(int argc, char **argv) {
   LatticeFasterDecoderConfig cfg;
   cfg._beam = 13.0f; cfg._max_active = 7000; cfg._min_active = 200; cfg._lattice_beam = 8.0f;
   int chunk = 0;
-  bool pull = false;
+  bool pull = false, lattice = false;
   for (int i = 1; i < argc; ++i) {
     std::string a = argv[i];
     size_t eq = a.find('=');
@@ -67,6 +67,7 @@ int main(int argc, char **argv) {
     else if (k == "--lattice-beam") cfg._lattice_beam = atof(v.c_str());
     else if (k == "--chunk") chunk = atoi(v.c_str());
     else if (k == "--pull") pull = true;
+    else if (k == "--lattice") lattice = true;
     else { fprintf(stderr, "unknown arg %s\n", a.c_str()); return 2; }
   }
   FILE *fp = fopen(loglikes.c_str(), "rb");
@@ -108,8 +109,24 @@ int main(int argc, char **argv) {
       float tot = 0, lm = 0;
       bool ok = decode->GetBestPath(&best_path);
       if (ok) ok = LatticeToVector(best_path, words, ali, tot, lm);
-      printf("{\"utt\": %d, \"ok\": %s, \"frames\": %d, \"tot\": %.9g, \"tot_bits\": %u, \"lm_bits\": %u, \"words\": [",
-             i, ok ? "true" : "false", decode->NumFramesDecoded(), tot, Bits(tot), Bits(lm));
+      int raw_states = -1, raw_arcs = -1, raw_finals = 0;
+      if (lattice) {  // kaldi-hclg-my-decoder.cc:134: decode.GetRawLattice(&lat1, true)
+        Lattice lat1;
+        if (decode->GetRawLattice(&lat1, true)) {
+          raw_states = lat1.NumStates();
+          raw_arcs = 0;
+          for (int st = 0; st < lat1.NumStates(); ++st) {
+            raw_arcs += (int)lat1.GetState(st)->GetArcSize();
+            raw_finals += lat1.Final(st) ? 1 : 0;
+            for (size_t a = 0; a < lat1.GetState(st)->GetArcSize(); ++a)
+              if (lat1.GetState(st)->GetArc(a)->_to <= st && lat1.GetState(st)->GetArc(a)->_to != st) raw_arcs = -1000000;  // must be topologically sorted
+          }
+        }
+      }
+      printf("{\"utt\": %d, \"ok\": %s, \"frames\": %d, \"tot\": %.9g, \"tot_bits\": %u, \"lm_bits\": %u, "
+             "\"raw_states\": %d, \"raw_arcs\": %d, \"raw_finals\": %d, \"words\": [",
+             i, ok ? "true" : "false", decode->NumFramesDecoded(), tot, Bits(tot), Bits(lm), raw_states, raw_arcs,
+             raw_finals);
       for (size_t k = 0; k < words.size(); ++k) printf("%s%d", k ? "," : "", words[k]);
       printf("], \"ali\": [");
       for (size_t k = 0; k < ali.size(); ++k) printf("%s%d", k ? "," : "", ali[k]);

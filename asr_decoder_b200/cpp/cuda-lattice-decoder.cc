@@ -125,10 +125,67 @@ bool CudaLatticeDecoder::GetBestPath(Lattice *ofst, bool use_final_probs) {
   return true;
 }
 
-bool CudaLatticeDecoder::GetRawLattice(Lattice *ofst, bool) {
+bool CudaLatticeDecoder::GetRawLattice(Lattice *ofst, bool use_final_probs) {
+  // inl.h:868-975: one lattice state per surviving token (frame by frame, topologically sorted
+  // inside a frame, so state 0 is the start state), one arc per surviving forward link.
   ofst->DeleteStates();
-  fprintf(stderr, "WARNING CudaLatticeDecoder::GetRawLattice: lattice mode is not built yet (one-best only)\n");
-  return false;
+  if (finalized_ && !use_final_probs) {
+    fprintf(stderr, "WARNING You cannot call FinalizeDecoding() and then call GetRawLattice() with "
+                    "use_final_probs == false\n");  // inl.h:879-884
+    return false;
+  }
+  int64_t tok_cap = 1 << 15, link_cap = 1 << 16, nt = 0, nl = 0;
+  std::vector<asrd_lat_token> toks;
+  std::vector<asrd_lat_link> links;
+  for (;;) {
+    toks.resize(tok_cap);
+    links.resize(link_cap);
+    int rc = asrd_get_raw_lattice(d_, use_final_probs ? 1 : 0, toks.data(), tok_cap, links.data(), link_cap, &nt,
+                                  &nl, stream_);
+    if (rc == ASRD_ERR_PATH_OVERFLOW) {
+      tok_cap = std::max(tok_cap, nt + 16);
+      link_cap = std::max(link_cap, nl + 16);
+      continue;
+    }
+    if (rc == ASRD_ERR_NO_TOKENS) return false;  // inl.h:906-911
+    Check(rc, "asrd_get_raw_lattice");
+    break;
+  }
+  // Topological order inside every frame (eps links stay inside a frame): Kahn's algorithm over
+  // the frame's eps links; tokens arrive sorted by (frame, state).
+  std::vector<int32_t> indeg(nt, 0), order;
+  std::vector<std::vector<int32_t> > eps_out(nt);
+  for (int64_t i = 0; i < nl; ++i)
+    if (links[i].ilabel == 0) {
+      eps_out[links[i].src].push_back(links[i].dst);
+      ++indeg[links[i].dst];
+    }
+  order.reserve(nt);
+  for (int64_t b = 0; b < nt;) {
+    int64_t e = b;
+    while (e < nt && toks[e].frame == toks[b].frame) ++e;
+    std::vector<int32_t> ready;
+    for (int64_t i = e; i-- > b;)
+      if (indeg[i] == 0) ready.push_back((int32_t)i);
+    while (!ready.empty()) {
+      const int32_t t = ready.back();
+      ready.pop_back();
+      order.push_back(t);
+      for (size_t k = 0; k < eps_out[t].size(); ++k)
+        if (--indeg[eps_out[t][k]] == 0) ready.push_back(eps_out[t][k]);
+    }
+    b = e;
+  }
+  if ((int64_t)order.size() != nt) Check(ASRD_ERR_STATE, "epsilon loop in the lattice");  // inl.h:1061-1062
+  std::vector<StateId> state_of(nt);
+  for (int64_t k = 0; k < nt; ++k) state_of[order[k]] = ofst->AddState();
+  ofst->SetStart(0);
+  for (int64_t i = 0; i < nt; ++i)
+    if (toks[i].is_final) ofst->SetFinal(state_of[i]);
+  for (int64_t i = 0; i < nl; ++i)  // final costs are 0 on the single super-final state (inl.h:695)
+    ofst->AddArc(state_of[links[i].src], LatticeArc(links[i].ilabel, links[i].olabel, state_of[links[i].dst],
+                                                    LatticeWeight(links[i].graph, links[i].acoustic)));
+  return ofst->NumStates() > 0;
 }
 
 }  // namespace asrd_host

@@ -58,7 +58,8 @@ class CudaLatticeDecoder : public DecoderItf {
   virtual void ProcessNonemitting(BaseFloat cost_cutoff);
   virtual bool Decode(AmInterface *decodable);
   virtual bool GetBestPath(Lattice *ofst, bool use_final_probs = true);
-  // Lattice generation is the next scope row; one-best mode keeps no links.
+  // Raw lattice after the lattice-beam pruning of FinalizeDecoding; the forward links are
+  // regenerated and pruned on the device (asrd_get_raw_lattice), the Lattice is built here.
   virtual bool GetRawLattice(Lattice *ofst, bool use_final_probs = true);
 
   asrd_decoder *handle() const { return d_; }

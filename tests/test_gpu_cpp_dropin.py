@@ -30,3 +30,28 @@ def test_decoder_itf_drop_in_matches_reference_golden(name, extra):
         assert r["ok"] == ref["ok"] and r["frames"] == ref["frames"]
         assert r["words"] == ref["words"] and r["ali"] == ref["ali"]
         assert r["tot_bits"] == ref["tot_bits"] and r["lm_bits"] == ref["lm_bits"]
+
+
+def test_get_raw_lattice_through_decoder_itf(oracle_mod):
+    """DecoderItf::GetRawLattice of the C++ class: topologically sorted Lattice whose state / arc
+    counts equal the canonical oracle's surviving tokens / links."""
+    import numpy as np
+    from asr_decoder_b200 import fstio
+    O = oracle_mod
+    name = "g3"
+    meta = json.load(open(os.path.join(GOLD, name + ".json")))
+    cfg = meta["config"]
+    cmd = [BIN, f"--graph={GOLD}/{name}.fst", f"--loglikes={GOLD}/{name}.llb", f"--beam={cfg['beam']}",
+           f"--max-active={cfg['max_active']}", f"--min-active={cfg['min_active']}",
+           f"--lattice-beam={cfg['lattice_beam']}", "--lattice"]
+    out = subprocess.run(cmd, check=True, stdout=subprocess.PIPE).stdout.decode()
+    res = [json.loads(l) for l in out.splitlines() if l.startswith("{")]
+    fst = fstio.read_fst(os.path.join(GOLD, name + ".fst"))
+    lls = fstio.read_loglikes(os.path.join(GOLD, name + ".llb"))
+    og = O.OracleGraph(fst)
+    for r, ll in zip(res, lls):
+        d = O.OracleDecoder(og, O.make_config(**cfg), O.MODE_CANONICAL)
+        d.decode(ll)
+        nt, nl = d.counts()
+        assert (r["raw_states"], r["raw_arcs"]) == (nt, nl)
+        assert r["raw_finals"] >= 1
