@@ -66,6 +66,12 @@ def lib():
         L.orc_decoder_create.restype = C.c_void_p
         L.orc_decoder_create.argtypes = [C.c_void_p, C.POINTER(OrcConfig), C.c_int]
         L.orc_decoder_destroy.argtypes = [C.c_void_p]
+        L.orc_lm_create.restype = C.c_void_p
+        L.orc_lm_create.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_int64]
+        L.orc_lm_destroy.argtypes = [C.c_void_p]
+        L.orc_decoder_create_biglm.restype = C.c_void_p
+        L.orc_decoder_create_biglm.argtypes = [C.c_void_p, C.POINTER(OrcConfig), C.c_int, C.c_void_p, C.c_void_p]
         L.orc_init_decoding.argtypes = [C.c_void_p]
         L.orc_advance_decoding.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
         L.orc_finalize_decoding.argtypes = [C.c_void_p]
@@ -143,13 +149,36 @@ class OracleGraph:
             self.h = None
 
 
-class OracleDecoder:
-    """Mirrors the reference's DecoderItf call sequence (src/my-decoder/decoder-itf.h:10-25)."""
+class OracleLm:
+    """LM FSA for the biglm oracle (asr_decoder_b200.lm.LmFsa; pass the OLD LM already rescaled by -1)."""
 
-    def __init__(self, graph: OracleGraph, cfg: OrcConfig = None, mode: int = MODE_CANONICAL):
+    def __init__(self, lm):
+        self._an = np.ascontiguousarray(lm.states["arc_num"], np.int32)
+        self._bp = np.ascontiguousarray(lm.states["backoff_prob"], np.float32)
+        self._bi = np.ascontiguousarray(lm.states["backoff_id"], np.int32)
+        self._arcs = np.ascontiguousarray(lm.arcs)
+        self.h = lib().orc_lm_create(lm.bos, lm.eos, len(lm.states), self._an.ctypes.data, self._bp.ctypes.data,
+                                     self._bi.ctypes.data, self._arcs.ctypes.data, len(lm.arcs))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_lm_destroy(self.h)
+            self.h = None
+
+
+class OracleDecoder:
+    """Mirrors the reference's DecoderItf call sequence (src/my-decoder/decoder-itf.h:10-25).
+    With lm1/lm2 it restates OnlineLatticeDecoderMempoolBiglm (…-biglm.h)."""
+
+    def __init__(self, graph: OracleGraph, cfg: OrcConfig = None, mode: int = MODE_CANONICAL,
+                 lm1: "OracleLm" = None, lm2: "OracleLm" = None):
         self.graph = graph
         self.cfg = cfg or make_config()
-        self.h = lib().orc_decoder_create(graph.h, C.byref(self.cfg), mode)
+        self._lms = (lm1, lm2)
+        if lm1 is not None:
+            self.h = lib().orc_decoder_create_biglm(graph.h, C.byref(self.cfg), mode, lm1.h, lm2.h)
+        else:
+            self.h = lib().orc_decoder_create(graph.h, C.byref(self.cfg), mode)
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -217,6 +246,22 @@ class OracleDecoder:
         if finalize:
             self.FinalizeDecoding()
         return self.GetBestPath(True)
+
+
+def run_ref_biglm(graph_path: str, loglikes_path: str, lm1_path: str, lm2_path: str, **cfg):
+    """Run the compiled reference biglm decoder (lm1 is scaled by -1 inside, like the reference bin)."""
+    if not (os.path.exists(REF_BIN_BIGLM) and os.access(REF_BIN_BIGLM, os.X_OK)):
+        raise RuntimeError("oracle/_ref/ref_decode_biglm is not built")
+    cmd = [REF_BIN_BIGLM, f"--graph={graph_path}", f"--loglikes={loglikes_path}", f"--lm1={lm1_path}",
+           f"--lm2={lm2_path}"]
+    for k, v in cfg.items():
+        cmd.append(f"--{k.replace('_', '-')}={v}")
+    out = subprocess.run(cmd, check=True, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout
+    return [json.loads(l) for l in out.decode().splitlines() if l.startswith("{")]
+
+
+def have_ref_biglm() -> bool:
+    return os.path.exists(REF_BIN_BIGLM) and os.access(REF_BIN_BIGLM, os.X_OK)
 
 
 def have_ref() -> bool:

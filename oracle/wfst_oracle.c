@@ -61,6 +61,111 @@ void orc_graph_destroy(OrcGraph *g) {
   free(g);
 }
 
+/* ------------------------------------------------------------------ LM FSAs (biglm) */
+
+typedef struct OrcLm {
+  int32_t bos, eos;
+  int32_t n_states;
+  int32_t *arc_num;
+  float *backoff_prob;
+  int32_t *backoff_id;
+  int64_t *arc_off;
+  OrcLmArc *arcs;
+} OrcLm;
+
+OrcLm *orc_lm_create(int32_t bos, int32_t eos, int32_t n_states, const int32_t *arc_num,
+                     const float *backoff_prob, const int32_t *backoff_id, const OrcLmArc *arcs,
+                     int64_t n_arcs) {
+  OrcLm *lm = (OrcLm *)calloc(1, sizeof(OrcLm));
+  lm->bos = bos;
+  lm->eos = eos;
+  lm->n_states = n_states;
+  lm->arc_num = (int32_t *)malloc(sizeof(int32_t) * (size_t)n_states);
+  lm->backoff_prob = (float *)malloc(sizeof(float) * (size_t)n_states);
+  lm->backoff_id = (int32_t *)malloc(sizeof(int32_t) * (size_t)n_states);
+  lm->arc_off = (int64_t *)malloc(sizeof(int64_t) * ((size_t)n_states + 1));
+  lm->arcs = (OrcLmArc *)malloc(sizeof(OrcLmArc) * (size_t)(n_arcs ? n_arcs : 1));
+  memcpy(lm->arc_num, arc_num, sizeof(int32_t) * (size_t)n_states);
+  memcpy(lm->backoff_prob, backoff_prob, sizeof(float) * (size_t)n_states);
+  memcpy(lm->backoff_id, backoff_id, sizeof(int32_t) * (size_t)n_states);
+  memcpy(lm->arcs, arcs, sizeof(OrcLmArc) * (size_t)n_arcs);
+  lm->arc_off[0] = 0;
+  for (int32_t i = 0; i < n_states; ++i) lm->arc_off[i + 1] = lm->arc_off[i] + arc_num[i];
+  return lm;
+}
+
+void orc_lm_destroy(OrcLm *lm) {
+  if (!lm) return;
+  free(lm->arc_num);
+  free(lm->backoff_prob);
+  free(lm->backoff_id);
+  free(lm->arc_off);
+  free(lm->arcs);
+  free(lm);
+}
+
+/* Fsa::GetArc, src/newlm/arpa2fsa.cc:244-262 (start state 0 is direct-indexed by word id,
+ * FsaState::SearchStartArc arpa2fsa.h:211-214; other states binary search, arpa2fsa.h:194-210) */
+static int fsa_get_arc(const OrcLm *lm, int32_t id, int32_t word, float *weight, int32_t *to) {
+  if (word == 0) {
+    *weight = lm->backoff_prob[id];
+    *to = lm->backoff_id[id];
+    return 1;
+  }
+  const OrcLmArc *arc = lm->arcs + lm->arc_off[id];
+  const OrcLmArc *hit = NULL;
+  if (id == 0) {
+    hit = &arc[word];
+  } else {
+    int start = 0, end = lm->arc_num[id] - 1, mid = (start + end) / 2;
+    while (start <= end) {
+      if (arc[mid].wordid > word) end = mid - 1;
+      else if (arc[mid].wordid < word) start = mid + 1;
+      else { hit = &arc[mid]; break; }
+      mid = (start + end) / 2;
+    }
+  }
+  if (!hit) return 0;
+  *weight = hit->weight;
+  *to = hit->tostateid;
+  return 1;
+}
+
+/* ComposeArpaLm::Start, src/newlm/compose-arpalm.cc:5-13 */
+static int32_t clm_start(const OrcLm *lm) {
+  float w = 0.0f;
+  int32_t to = 0;
+  fsa_get_arc(lm, 0, lm->bos, &w, &to);
+  return to;
+}
+
+/* ComposeArpaLm::GetArc, compose-arpalm.cc:52-70: walk the back-off chain; Value1 = -(sum) */
+static void clm_get_arc(const OrcLm *lm, int32_t s, int32_t word, int32_t *next, float *value1) {
+  float weight = 0.0f, w_arc = 0.0f;
+  int32_t to = 0;
+  while (!fsa_get_arc(lm, s, word, &w_arc, &to)) {
+    fsa_get_arc(lm, s, 0, &w_arc, &to);
+    s = to;
+    weight += w_arc;
+  }
+  weight += w_arc;
+  *value1 = -1 * weight;
+  *next = to;
+}
+
+/* ComposeArpaLm::Final, compose-arpalm.cc:15-29 */
+static float clm_final(const OrcLm *lm, int32_t s) {
+  float weight = 0.0f, w_arc = 0.0f;
+  int32_t to = 0;
+  while (!fsa_get_arc(lm, s, lm->eos, &w_arc, &to)) {
+    fsa_get_arc(lm, s, 0, &w_arc, &to);
+    s = to;
+    weight += w_arc;
+  }
+  weight += w_arc;
+  return (-1.0 * weight);
+}
+
 /* -------------------------------------------------------- tokens and links */
 
 typedef struct Lnk {
@@ -78,10 +183,13 @@ typedef struct Tok {
   int32_t state; /* convenience only (the reference keeps it in the hash Elem) */
   int32_t frame;
   uint32_t arc;  /* global index of the arc that set `tot` (canonical tie-break) */
+  int32_t lm_state; /* biglm: DiffArpaLm pair-state id */
+  int has_final;    /* member of the reference's _final_costs map */
+  float final_cost;
 } Tok; /* StdToken, src/my-decoder/online-decoder-base.h:54-84 */
 
 typedef struct Elem {
-  int32_t key;
+  uint64_t key; /* StateId, or for biglm PairId = fst_state + (lm_state << 32) (…-biglm.h:77-80) */
   Tok *val;
   struct Elem *tail;
 } Elem; /* HashList::Elem, src/util/hash-list.h:16-21 */
@@ -124,8 +232,13 @@ struct OrcDecoder {
   int warned, finalized;
   /* final costs: there is a single super-final state, so the reference's
      unordered_map<Token*,BaseFloat> (inl.h:691-697) has at most one entry */
-  Tok *final_tok;
   int final_costs_nonempty;
+  /* biglm (…-biglm.h): LM-difference composition */
+  const struct OrcLm *lm1, *lm2;
+  int32_t (*pairs)[2];   /* DiffArpaLm::_state_vec */
+  int32_t n_pairs, cap_pairs;
+  int32_t *pair_map;     /* open-addressing map pair -> id (DiffArpaLm::_state_map) */
+  int32_t pair_map_size;
   float final_relative_cost, final_best_cost;
   /* stats */
   OrcFrameStat *stats;
@@ -161,6 +274,9 @@ static Tok *new_token(OrcDecoder *d, float tot, float extra, Lnk *links, Tok *ne
   t->state = -1;
   t->frame = -1;
   t->arc = NO_ARC;
+  t->lm_state = 0;
+  t->has_final = 0;
+  t->final_cost = 0.0f;
   d->num_toks++;
   return t;
 }
@@ -267,7 +383,7 @@ static Elem *hl_new(OrcDecoder *d) {
 /* HashList::Insert, hash-list-inl.h:127-173: returns the existing element when the key
  * is present; otherwise appends to the key's bucket, buckets being chained in creation
  * order — this defines the reference's token visiting order. */
-static Elem *hl_insert(OrcDecoder *d, int32_t key, Tok *val) {
+static Elem *hl_insert(OrcDecoder *d, uint64_t key, Tok *val) {
   size_t index = (size_t)key % d->hash_size;
   Bucket *bk = &d->buckets[index];
   if (bk->last_elem) {
@@ -299,6 +415,69 @@ static Elem *hl_insert(OrcDecoder *d, int32_t key, Tok *val) {
   return el;
 }
 
+/* ------------------------------------------------------------------ DiffArpaLm */
+
+#define KEY_STATE(k) ((int32_t)(uint32_t)(k))
+#define KEY_LM(k) ((int32_t)(uint32_t)((k) >> 32))
+#define MAKE_KEY(st, lm) ((uint64_t)(uint32_t)(st) + ((uint64_t)(uint32_t)(lm) << 32)) /* …-biglm.h:77-80 */
+
+/* DiffArpaLm::Reset, src/newlm/diff-lm.h:39-46 */
+static void difflm_reset(OrcDecoder *d) {
+  if (!d->pair_map) {
+    d->pair_map_size = 1 << 16;
+    d->pair_map = (int32_t *)malloc(sizeof(int32_t) * (size_t)d->pair_map_size);
+    d->cap_pairs = 1 << 15;
+    d->pairs = (int32_t(*)[2])malloc(sizeof(int32_t[2]) * (size_t)d->cap_pairs);
+  }
+  for (int32_t i = 0; i < d->pair_map_size; ++i) d->pair_map[i] = -1;
+  d->n_pairs = 0;
+}
+
+static int32_t difflm_intern(OrcDecoder *d, int32_t a, int32_t b) {
+  uint32_t h = ((uint32_t)a * 7853u + (uint32_t)b) & (uint32_t)(d->pair_map_size - 1);
+  for (;;) {
+    int32_t id = d->pair_map[h];
+    if (id < 0) break;
+    if (d->pairs[id][0] == a && d->pairs[id][1] == b) return id;
+    h = (h + 1) & (uint32_t)(d->pair_map_size - 1);
+  }
+  if (d->n_pairs + 1 >= d->cap_pairs) {
+    fprintf(stderr, "[oracle] too many LM pair states\n");
+    abort();
+  }
+  d->pairs[d->n_pairs][0] = a;
+  d->pairs[d->n_pairs][1] = b;
+  d->pair_map[h] = d->n_pairs;
+  return d->n_pairs++;
+}
+
+/* NextLmState (…-biglm.h:54-70) over DiffArpaLm::GetArc (diff-lm.h:63-111).  Reference mode
+ * reproduces the reference's argument quirk: both LMs are queried from FSA state number `s`
+ * (the pair-state id), not from the members of the pair (diff-lm.h:75,80,86; SURVEY.md
+ * Appendix B-6).  Canonical mode implements the intended semantics. */
+static int32_t next_lm_state(OrcDecoder *d, int32_t lm_state, int32_t olabel, float *lm_score) {
+  if (olabel == 0) {
+    *lm_score = 0;
+    return lm_state;
+  }
+  int32_t s1 = lm_state, s2 = lm_state;
+  if (d->mode == ORC_MODE_CANONICAL) {
+    s1 = d->pairs[lm_state][0];
+    s2 = d->pairs[lm_state][1];
+  }
+  int32_t n1, n2;
+  float v1, v2;
+  clm_get_arc(d->lm1, s1, olabel, &n1, &v1);
+  clm_get_arc(d->lm2, s2, olabel, &n2, &v2);
+  *lm_score = v1 + v2; /* Times(w1, w2).Value1(), weigth.h:318-323 */
+  return difflm_intern(d, n1, n2);
+}
+
+/* DiffArpaLm::Final, diff-lm.h:48-55 (this one does use the pair) */
+static float difflm_final(OrcDecoder *d, int32_t lm_state) {
+  return clm_final(d->lm1, d->pairs[lm_state][0]) + clm_final(d->lm2, d->pairs[lm_state][1]);
+}
+
 /* ------------------------------------------------------------------ decoder */
 
 OrcDecoder *orc_decoder_create(const OrcGraph *g, const OrcConfig *cfg, int mode) {
@@ -317,6 +496,16 @@ OrcDecoder *orc_decoder_create(const OrcGraph *g, const OrcConfig *cfg, int mode
 
 static void clear_active_tokens(OrcDecoder *d);
 
+/* OnlineLatticeDecoderMempoolBaseBiglm(fst, config, oldlm, newlm), …-biglm.h:21-30; the caller has
+ * already scaled the old LM by -1 (kaldi-hclg-my-decoder-biglm.cc:55-60) */
+OrcDecoder *orc_decoder_create_biglm(const OrcGraph *g, const OrcConfig *cfg, int mode, const OrcLm *lm1,
+                                     const OrcLm *lm2) {
+  OrcDecoder *d = orc_decoder_create(g, cfg, mode);
+  d->lm1 = lm1;
+  d->lm2 = lm2;
+  return d;
+}
+
 void orc_decoder_destroy(OrcDecoder *d) {
   if (!d) return;
   for (size_t i = 0; i < d->n_blocks; ++i) free(d->blocks[i]);
@@ -326,6 +515,8 @@ void orc_decoder_destroy(OrcDecoder *d) {
   free(d->queue);
   free(d->tmp);
   free(d->stats);
+  free(d->pairs);
+  free(d->pair_map);
   free(d);
 }
 
@@ -376,14 +567,15 @@ static inline int better(const OrcDecoder *d, float tot, uint32_t arc, const Tok
 }
 
 /* FindOrAddToken, inl.h:88-136 */
-static Elem *find_or_add_token(OrcDecoder *d, int32_t state, int32_t frame_plus_one, float tot,
+static Elem *find_or_add_token(OrcDecoder *d, uint64_t key, int32_t frame_plus_one, float tot,
                                Tok *back, uint32_t arc, int *changed) {
   assert((size_t)frame_plus_one < d->n_active);
   Tok **toks = &d->active[frame_plus_one].toks;
-  Elem *e = hl_insert(d, state, NULL);
+  Elem *e = hl_insert(d, key, NULL);
   if (e->val == NULL) {
     Tok *t = new_token(d, tot, 0.0f, NULL, *toks, back);
-    t->state = state;
+    t->state = KEY_STATE(key);
+    t->lm_state = KEY_LM(key);
     t->frame = frame_plus_one;
     t->arc = arc;
     *toks = t;
@@ -475,10 +667,12 @@ static void possibly_resize_hash(OrcDecoder *d, size_t num_toks) {
   if (new_sz > d->hash_size) hl_set_size(d, new_sz);
 }
 
-/* ProcessEmitting, inl.h:246-351.  `ll` is the log-likelihood row of this frame,
- * column = ilabel - 1. */
+/* ProcessEmitting, inl.h:246-351; biglm variant …-biglm.h:318-400 (graph cost += LM-difference
+ * score of the arc's word, token key = (fst state, lm state)).  `ll` is the log-likelihood row
+ * of this frame, column = ilabel - 1. */
 static float process_emitting(OrcDecoder *d, const float *ll) {
   const OrcGraph *g = d->g;
+  const int biglm = d->lm1 != NULL;
   int frame = (int)d->n_active - 1;
   active_resize(d, d->n_active + 1);
   Elem *final_toks = hl_clear(d);
@@ -486,21 +680,33 @@ static float process_emitting(OrcDecoder *d, const float *ll) {
   float adaptive_beam = 0;
   size_t tok_cnt = 0;
   float cur_cutoff = get_cutoff(d, final_toks, &tok_cnt, &adaptive_beam, &best_elem);
-  possibly_resize_hash(d, tok_cnt);
+  /* The biglm class shadows _toks (…-biglm.h:73) but calls the BASE PossiblyResizeHash
+   * (…-biglm.h:335), which resizes the base class's unused hash: the biglm hash keeps its
+   * constructor size (…-biglm.h:27). */
+  if (!biglm) possibly_resize_hash(d, tok_cnt);
   memset(&d->pending, 0, sizeof(d->pending));
   d->pending.n_in = (uint32_t)tok_cnt;
   d->pending.cur_cutoff = cur_cutoff;
   d->pending.abeam = adaptive_beam;
 
   float next_cutoff = ORC_INF;
-  /* best-token pre-pass, inl.h:282-300; note the association (cost + w) - loglike */
+  /* best-token pre-pass, inl.h:282-300: (cost + w) - loglike;
+   * biglm …-biglm.h:339-357: ((lm_score + cost) + w) - loglike */
   if (best_elem) {
     Tok *tok = best_elem->val;
-    for (int64_t a = g->row_off[best_elem->key]; a < g->row_off[best_elem->key + 1]; ++a) {
+    const int32_t bs = KEY_STATE(best_elem->key), blm = KEY_LM(best_elem->key);
+    for (int64_t a = g->row_off[bs]; a < g->row_off[bs + 1]; ++a) {
       const OrcArc *arc = &g->arcs[a];
       if (arc->ilabel != 0) {
         d->pending.ll_calls++;
-        float tot_score = tok->tot + arc->weight - ll[arc->ilabel - 1];
+        float tot_score;
+        if (biglm) {
+          float lm_score;
+          next_lm_state(d, blm, arc->olabel, &lm_score);
+          tot_score = lm_score + tok->tot + arc->weight - ll[arc->ilabel - 1];
+        } else {
+          tot_score = tok->tot + arc->weight - ll[arc->ilabel - 1];
+        }
         if (tot_score + adaptive_beam < next_cutoff) next_cutoff = tot_score + adaptive_beam;
       }
     }
@@ -512,20 +718,27 @@ static float process_emitting(OrcDecoder *d, const float *ll) {
     for (Elem *e = final_toks; e; e = e->tail) {
       Tok *tok = e->val;
       if (tok->tot <= cur_cutoff) {
-        for (int64_t a = g->row_off[e->key]; a < g->row_off[e->key + 1]; ++a) {
+        const int32_t st = KEY_STATE(e->key), lms = KEY_LM(e->key);
+        for (int64_t a = g->row_off[st]; a < g->row_off[st + 1]; ++a) {
           const OrcArc *arc = &g->arcs[a];
           if (arc->ilabel != 0) {
             float ac = -ll[arc->ilabel - 1];
-            float tot = tok->tot + ac + arc->weight;
+            float graph_cost = arc->weight;
+            if (biglm) {
+              float lm_score;
+              next_lm_state(d, lms, arc->olabel, &lm_score);
+              graph_cost = arc->weight + lm_score;
+            }
+            float tot = tok->tot + ac + graph_cost;
             if (tot + adaptive_beam < next_cutoff) next_cutoff = tot + adaptive_beam;
           }
         }
       }
     }
   }
-  /* main pass, inl.h:311-347 */
+  /* main pass, inl.h:311-347 / …-biglm.h:363-396 */
   for (Elem *e = final_toks, *e_tail; e; e = e_tail) {
-    int32_t state = e->key;
+    const int32_t state = KEY_STATE(e->key), lm_state = KEY_LM(e->key);
     Tok *tok = e->val;
     if (tok->tot <= cur_cutoff) {
       for (int64_t a = g->row_off[state]; a < g->row_off[state + 1]; ++a) {
@@ -533,14 +746,21 @@ static float process_emitting(OrcDecoder *d, const float *ll) {
         if (arc->ilabel != 0) {
           d->pending.ll_calls++;
           d->pending.arcs_expanded++;
-          float ac_cost = -ll[arc->ilabel - 1];
+          int32_t next_lm = 0;
           float graph_cost = arc->weight;
+          if (biglm) {
+            float lm_score;
+            next_lm = next_lm_state(d, lm_state, arc->olabel, &lm_score);
+            graph_cost = arc->weight + lm_score; /* …-biglm.h:379 */
+          }
+          float ac_cost = -ll[arc->ilabel - 1];
           float cur_cost = tok->tot;
           float tot_cost = cur_cost + ac_cost + graph_cost;
           if (tot_cost >= next_cutoff) continue;
           else if (tot_cost + adaptive_beam < next_cutoff)
             next_cutoff = tot_cost + adaptive_beam; /* never fires in canonical mode */
-          Elem *nt = find_or_add_token(d, arc->nextstate, frame + 1, tot_cost, tok, (uint32_t)a, NULL);
+          Elem *nt = find_or_add_token(d, MAKE_KEY(arc->nextstate, next_lm), frame + 1, tot_cost, tok,
+                                       (uint32_t)a, NULL);
           tok->links = new_link(d, nt->val, arc->ilabel, arc->olabel, graph_cost, ac_cost, tok->links);
           d->pending.arcs_admitted++;
         }
@@ -553,14 +773,15 @@ static float process_emitting(OrcDecoder *d, const float *ll) {
   return next_cutoff;
 }
 
-/* ProcessNonemitting, inl.h:353-431 */
+/* ProcessNonemitting, inl.h:353-431 / …-biglm.h:402-466 */
 static void process_nonemitting(OrcDecoder *d, float cutoff) {
   const OrcGraph *g = d->g;
+  const int biglm = d->lm1 != NULL;
   int frame = (int)d->n_active - 1;
   assert(d->n_queue == 0);
   if (d->list_head == NULL && !d->warned) d->warned = 1; /* "no surviving tokens" */
   for (Elem *e = d->list_head; e; e = e->tail) {
-    if (has_eps(g, e->key)) {
+    if (has_eps(g, KEY_STATE(e->key))) {
       if (d->n_queue == d->cap_queue) {
         d->cap_queue = d->cap_queue ? d->cap_queue * 2 : 4096;
         d->queue = (Elem **)realloc(d->queue, d->cap_queue * sizeof(Elem *));
@@ -570,7 +791,7 @@ static void process_nonemitting(OrcDecoder *d, float cutoff) {
   }
   while (d->n_queue) {
     Elem *elem = d->queue[--d->n_queue];
-    int32_t state = elem->key;
+    const int32_t state = KEY_STATE(elem->key), lm_state = KEY_LM(elem->key);
     Tok *tok = elem->val;
     float cur_cost = tok->tot;
     if (cur_cost >= cutoff) continue; /* inl.h:391 */
@@ -579,11 +800,18 @@ static void process_nonemitting(OrcDecoder *d, float cutoff) {
       const OrcArc *arc = &g->arcs[a];
       if (arc->ilabel == 0) {
         d->pending.eps_arcs++;
+        int32_t next_lm = 0;
         float graph_cost = arc->weight;
+        if (biglm) {
+          float lm_score;
+          next_lm = next_lm_state(d, lm_state, arc->olabel, &lm_score);
+          graph_cost = arc->weight + lm_score; /* …-biglm.h:446-448 */
+        }
         float tot_cost = cur_cost + graph_cost;
         if (tot_cost < cutoff) { /* inl.h:415 */
           int changed = 0;
-          Elem *nt = find_or_add_token(d, arc->nextstate, frame, tot_cost, tok, (uint32_t)a, &changed);
+          Elem *nt = find_or_add_token(d, MAKE_KEY(arc->nextstate, next_lm), frame, tot_cost, tok,
+                                       (uint32_t)a, &changed);
           tok->links = new_link(d, nt->val, 0, arc->olabel, graph_cost, 0.0f, tok->links);
           if (changed && has_eps(g, arc->nextstate)) {
             if (d->n_queue == d->cap_queue) {
@@ -617,7 +845,6 @@ void orc_init_decoding(OrcDecoder *d) {
   d->n_tmp = 0;
   d->warned = 0;
   d->finalized = 0;
-  d->final_tok = NULL;
   d->final_costs_nonempty = 0;
   d->n_stats = 0;
   memset(&d->pending, 0, sizeof(d->pending));
@@ -626,7 +853,13 @@ void orc_init_decoding(OrcDecoder *d) {
   start_tok->state = d->g->start;
   start_tok->frame = 0;
   d->active[0].toks = start_tok;
-  hl_insert(d, d->g->start, start_tok);
+  int32_t start_lm = 0;
+  if (d->lm1) { /* …-biglm.h:98-120: _diff_lm.Reset(); start pair = (graph start, difflm start) */
+    difflm_reset(d);
+    start_lm = difflm_intern(d, clm_start(d->lm1), clm_start(d->lm2));
+    start_tok->lm_state = start_lm;
+  }
+  hl_insert(d, MAKE_KEY(d->g->start, start_lm), start_tok);
   process_nonemitting(d, d->cfg.beam);
   d->num_frames_decoded = 0;
 }
@@ -725,17 +958,30 @@ void orc_advance_decoding(OrcDecoder *d, const float *loglikes, int32_t stride,
 
 int32_t orc_num_frames_decoded(const OrcDecoder *d) { return (int32_t)d->n_active - 1; }
 
-/* ComputeFinalCosts, inl.h:670-720 (iterates the current-frame hash list) */
-static void compute_final_costs(OrcDecoder *d, Tok **final_tok, int *nonempty, float *rel,
-                                float *best_out) {
+/* ComputeFinalCosts, inl.h:670-720 (iterates the current-frame hash list); biglm variant
+ * …-biglm.h:157-215: every final-state token gets final cost = DiffArpaLm::Final(lm state), and
+ * best_cost_with_final is taken over ALL tokens.  Marks tokens instead
+ * of filling the reference's unordered_map<Token*, BaseFloat>. */
+static void compute_final_costs(OrcDecoder *d, int *nonempty, float *rel, float *best_out) {
   float best_cost = ORC_INF, best_with_final = ORC_INF;
-  *final_tok = NULL;
   *nonempty = 0;
   for (Elem *e = d->list_head; e; e = e->tail) {
     Tok *tok = e->val;
+    tok->has_final = 0;
+    tok->final_cost = 0.0f;
+    const int fst_final = KEY_STATE(e->key) == d->g->final_state; /* Fst::IsFinal, optimize-fst.h:189-192 */
     if (tok->tot < best_cost) best_cost = tok->tot;
-    if (e->key == d->g->final_state) { /* Fst::IsFinal, optimize-fst.h:189-192; final cost 0 */
-      *final_tok = tok;
+    if (d->lm1) {
+      float lm_final = difflm_final(d, KEY_LM(e->key));
+      float cost_with_final = tok->tot + lm_final;
+      if (cost_with_final < best_with_final) best_with_final = cost_with_final;
+      if (fst_final) {
+        tok->has_final = 1;
+        tok->final_cost = lm_final;
+        *nonempty = 1;
+      }
+    } else if (fst_final) {
+      tok->has_final = 1; /* final cost 0: the weights live on the eps arcs into the super-final state */
       *nonempty = 1;
       if (tok->tot < best_with_final) best_with_final = tok->tot;
     }
@@ -747,11 +993,10 @@ static void compute_final_costs(OrcDecoder *d, Tok **final_tok, int *nonempty, f
   if (best_out) *best_out = best_with_final != ORC_INF ? best_with_final : best_cost;
 }
 
-/* PruneForwardLinksFinal, inl.h:725-824 */
+/* PruneForwardLinksFinal, inl.h:725-824 (biglm: …-biglm.h:468-566, same arithmetic) */
 static void prune_forward_links_final(OrcDecoder *d) {
   int frame_plus_one = (int)d->n_active - 1;
-  compute_final_costs(d, &d->final_tok, &d->final_costs_nonempty, &d->final_relative_cost,
-                      &d->final_best_cost);
+  compute_final_costs(d, &d->final_costs_nonempty, &d->final_relative_cost, &d->final_best_cost);
   d->finalized = 1;
   hl_delete_elems(d);
   int changed = 1;
@@ -762,7 +1007,7 @@ static void prune_forward_links_final(OrcDecoder *d) {
       Lnk *link, *prev_link = NULL;
       float final_cost;
       if (!d->final_costs_nonempty) final_cost = 0.0f;
-      else final_cost = (tok == d->final_tok) ? 0.0f : ORC_INF;
+      else final_cost = tok->has_final ? tok->final_cost : ORC_INF;
       float tok_extra_cost = tok->tot + final_cost - d->final_best_cost;
       for (link = tok->links; link;) {
         Tok *next_tok = link->next_tok;
@@ -806,26 +1051,26 @@ void orc_finalize_decoding(OrcDecoder *d) {
 int32_t orc_get_best_path(OrcDecoder *d, int use_final_probs, int32_t *ilabel, int32_t *olabel,
                           float *graph, float *acoustic, int32_t cap) {
   if ((int)d->n_active - 1 <= 0) return -1;
-  Tok *ftok = NULL;
   int nonempty = 0;
   if (d->finalized) {
-    ftok = d->final_tok;
     nonempty = d->final_costs_nonempty;
   } else if (use_final_probs) {
-    compute_final_costs(d, &ftok, &nonempty, NULL, NULL);
+    compute_final_costs(d, &nonempty, NULL, NULL);
   }
   float best_cost = ORC_INF;
   Tok *best_tok = NULL;
   for (Tok *tok = d->active[d->n_active - 1].toks; tok; tok = tok->next) {
     float cost = tok->tot;
-    if (use_final_probs && nonempty) {
-      if (tok != ftok) cost = ORC_INF;
+    if (use_final_probs && nonempty) { /* inl.h:1126-1139 */
+      if (tok->has_final) cost += tok->final_cost;
+      else cost = ORC_INF;
     }
     if (cost < best_cost) {
       best_cost = cost;
       best_tok = tok;
     } else if (d->mode == ORC_MODE_CANONICAL && best_tok && cost == best_cost && cost != ORC_INF &&
-               tok->state < best_tok->state) {
+               (tok->state < best_tok->state ||
+                (tok->state == best_tok->state && tok->lm_state < best_tok->lm_state))) {
       best_tok = tok;
     }
   }

@@ -70,6 +70,13 @@ typedef struct {
 
 enum { ORC_MODE_REFERENCE = 0, ORC_MODE_CANONICAL = 1 };
 
+typedef struct {
+  int32_t wordid;
+  float weight;
+  int32_t tostateid;
+} OrcLmArc; /* reference FsaArc, src/newlm/arpa2fsa.h:23-30 */
+
+typedef struct OrcLm OrcLm;
 typedef struct OrcGraph OrcGraph;
 typedef struct OrcDecoder OrcDecoder;
 
@@ -78,6 +85,14 @@ OrcGraph *orc_graph_create(const OrcArc *arcs, const int64_t *row_off, const uin
 void orc_graph_destroy(OrcGraph *g);
 
 OrcDecoder *orc_decoder_create(const OrcGraph *g, const OrcConfig *cfg, int mode);
+/* LM FSA (state 0 = unigram state, direct-indexed by word id); weights as stored by the reference
+ * (natural-log probabilities, the old LM already scaled by -1 by the caller) */
+OrcLm *orc_lm_create(int32_t bos, int32_t eos, int32_t n_states, const int32_t *arc_num,
+                     const float *backoff_prob, const int32_t *backoff_id, const OrcLmArc *arcs,
+                     int64_t n_arcs);
+void orc_lm_destroy(OrcLm *lm);
+OrcDecoder *orc_decoder_create_biglm(const OrcGraph *g, const OrcConfig *cfg, int mode, const OrcLm *lm1,
+                                     const OrcLm *lm2);
 void orc_decoder_destroy(OrcDecoder *d);
 
 void orc_init_decoding(OrcDecoder *d);
