@@ -16,7 +16,8 @@ LIB_PATH = os.path.join(HERE, "libasrd_b200.so")
 SYMBOLS = [
     "asrd_strerror", "asrd_abi_version", "asrd_device_count",
     "asrd_graph_create", "asrd_graph_read", "asrd_graph_destroy", "asrd_graph_info",
-    "asrd_decoder_create", "asrd_decoder_destroy",
+    "asrd_lm_create", "asrd_lm_destroy",
+    "asrd_decoder_create", "asrd_decoder_create_biglm", "asrd_decoder_destroy",
     "asrd_init_decoding", "asrd_advance_decoding", "asrd_finalize_decoding",
     "asrd_num_frames_decoded", "asrd_get_best_path", "asrd_path_to_vector",
     "asrd_frame_stats", "asrd_decoder_status", "asrd_synchronize",
@@ -84,6 +85,10 @@ def lib():
     L.asrd_decoder_create.argtypes = [vp, C.POINTER(asrd_config), C.POINTER(asrd_device_options),
                                       C.POINTER(vp)]
     L.asrd_decoder_destroy.argtypes = [vp]
+    L.asrd_lm_create.argtypes = [i32, i32, i32, vp, vp, vp, vp, i64, C.c_int, C.POINTER(vp)]
+    L.asrd_lm_destroy.argtypes = [vp]
+    L.asrd_decoder_create_biglm.argtypes = [vp, C.POINTER(asrd_config), C.POINTER(asrd_device_options), vp, vp,
+                                            C.POINTER(vp)]
     L.asrd_init_decoding.argtypes = [vp, i32, vp]
     L.asrd_advance_decoding.argtypes = [vp, i32, vp, vp, vp, i32, i32, i32, vp]
     L.asrd_finalize_decoding.argtypes = [vp, i32, vp]

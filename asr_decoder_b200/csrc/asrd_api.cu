@@ -200,6 +200,16 @@ DecoderConfigDev DevCfg(const asrd_decoder *d) {
   return c;
 }
 
+LmPair Lms(const asrd_decoder *d) {
+  LmPair p;
+  memset(&p, 0, sizeof(p));
+  if (d->lm1) {
+    p.lm1 = d->lm1->view;
+    p.lm2 = d->lm2->view;
+  }
+  return p;
+}
+
 int CheckBatch(asrd_decoder *const *decs, int n) {
   if (!decs || n <= 0 || n > kMaxBatch) return ASRD_ERR_BAD_ARG;
   for (int i = 0; i < n; ++i) {
@@ -208,13 +218,14 @@ int CheckBatch(asrd_decoder *const *decs, int n) {
     if (memcmp(&decs[i]->cfg, &decs[0]->cfg, sizeof(asrd_config)) != 0) return ASRD_ERR_BAD_ARG;
     if (decs[i]->opts.hash_capacity != decs[0]->opts.hash_capacity) return ASRD_ERR_BAD_ARG;
     if (decs[i]->opts.collect_stats != decs[0]->opts.collect_stats) return ASRD_ERR_BAD_ARG;
+    if (decs[i]->lm1 != decs[0]->lm1 || decs[i]->lm2 != decs[0]->lm2) return ASRD_ERR_BAD_ARG;
   }
   return ASRD_OK;
 }
 
 // ---- kernel launch plumbing -------------------------------------------------------------
 
-typedef void (*ExpandFn)(FrameDesc *, GraphView, int, int);
+typedef void (*ExpandFn)(FrameDesc *, GraphView, int, int, LmPair);
 
 struct ExpandPlan {
   ExpandFn fn;
@@ -226,12 +237,13 @@ struct ExpandPlan {
 // Picks the k_expand instantiation (arcs in flight per lane; log-likelihood row staged in
 // shared memory when it fits) and sizes the grid to about one resident wave: blockIdx.y is
 // the stream, gridDim.x CTAs share one stream's token groups.
-int PlanExpand(int n_streams, int num_indices, ExpandPlan *plan) {
+int PlanExpand(int n_streams, int num_indices, bool biglm, ExpandPlan *plan) {
   const int u = EnvInt("ASRD_EXPAND_U", 1);
   const bool smem_ll = EnvInt("ASRD_SMEM_LL", 1) != 0 && (size_t)num_indices * 4 <= 96 * 1024;
   ExpandFn fn;
-  if (smem_ll) fn = u >= 4 ? k_expand<4, true> : (u == 2 ? k_expand<2, true> : k_expand<1, true>);
-  else fn = u >= 4 ? k_expand<4, false> : (u == 2 ? k_expand<2, false> : k_expand<1, false>);
+  if (biglm) fn = smem_ll ? k_expand<1, true, true> : k_expand<1, false, true>;
+  else if (smem_ll) fn = u >= 4 ? k_expand<4, true, false> : (u == 2 ? k_expand<2, true, false> : k_expand<1, true, false>);
+  else fn = u >= 4 ? k_expand<4, false, false> : (u == 2 ? k_expand<2, false, false> : k_expand<1, false, false>);
   const size_t dyn = smem_ll ? (size_t)num_indices * 4 : 0;
   if (dyn > 48 * 1024)
     CU_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
@@ -433,9 +445,11 @@ int asrd_graph_info(const asrd_graph *g, int32_t *total_states, int64_t *total_a
 
 // ------------------------------------------------------------------------- decoder
 
-int asrd_decoder_create(asrd_graph *g, const asrd_config *cfg, const asrd_device_options *opts,
-                        asrd_decoder **out) {
+static int DecoderCreate(asrd_graph *g, const asrd_config *cfg, const asrd_device_options *opts, asrd_lm *lm1,
+                         asrd_lm *lm2, asrd_decoder **out) {
   if (!g || !cfg || !out) return ASRD_ERR_BAD_ARG;
+  if ((lm1 == nullptr) != (lm2 == nullptr)) return ASRD_ERR_BAD_ARG;
+  if (lm1 && (lm1->device != g->device || lm2->device != g->device)) return ASRD_ERR_BAD_ARG;
   // LatticeFasterDecoderConfig::Check, src/my-decoder/lattice-faster-decoder-conf.h:62-67
   if (!(cfg->beam > 0.0f && cfg->max_active > 1 && cfg->lattice_beam > 0.0f && cfg->beam_delta > 0.0f) ||
       cfg->min_active < 0)
@@ -445,6 +459,8 @@ int asrd_decoder_create(asrd_graph *g, const asrd_config *cfg, const asrd_device
   asrd_decoder *d = new asrd_decoder();
   memset((void *)d, 0, sizeof(*d));
   d->graph = g;
+  d->lm1 = lm1;
+  d->lm2 = lm2;
   d->cfg = *cfg;
   if (opts) d->opts = *opts;
   asrd_device_options &o = d->opts;
@@ -467,7 +483,9 @@ int asrd_decoder_create(asrd_graph *g, const asrd_config *cfg, const asrd_device
                b_off = align(((size_t)o.max_frames + 4) * 4),
                b_stats = o.collect_stats ? align(((size_t)o.max_frames + 1) * sizeof(asrd_frame_stat)) : 0,
                b_state = align(sizeof(StreamState));
-  const size_t total = b_state + b_hash + 2 * b_bm + 2 * b_list + b_tok + b_arc + 3 * b_off + b_stats;
+  const size_t pair_cap = lm1 ? (size_t)1 << 16 : 0;
+  const size_t b_lm = lm1 ? b_arc : 0, b_pair = align(pair_cap * 8);
+  const size_t total = b_state + b_hash + 2 * b_bm + 3 * b_list + b_tok + b_arc + 3 * b_off + b_stats + b_lm + b_pair;
   if (cudaMalloc(&d->slab, total) != cudaSuccess) {
     cudaGetLastError();
     delete d;
@@ -482,6 +500,12 @@ int asrd_decoder_create(asrd_graph *g, const asrd_config *cfg, const asrd_device
   h.bm = (uint32_t *)p; p += b_bm;
   h.ebm = (uint32_t *)p; p += b_bm;
   for (int i = 0; i < 2; ++i) { h.queue[i] = (uint32_t *)p; p += b_list; }
+  h.stamp = (uint32_t *)p; p += b_list;
+  if (lm1) {
+    h.tok_lm = (uint32_t *)p; p += b_lm;
+    h.pair_map = (unsigned long long *)p; p += b_pair;
+    h.pair_mask = (uint32_t)pair_cap - 1;
+  }
   h.tok_sc = (uint2 *)p; p += b_tok;
   h.tok_arc = (uint32_t *)p; p += b_arc;
   h.frame_off = (uint32_t *)p; p += b_off;
@@ -506,6 +530,73 @@ int asrd_decoder_create(asrd_graph *g, const asrd_config *cfg, const asrd_device
   return ASRD_OK;
 }
 
+int asrd_decoder_create(asrd_graph *g, const asrd_config *cfg, const asrd_device_options *opts,
+                        asrd_decoder **out) {
+  return DecoderCreate(g, cfg, opts, nullptr, nullptr, out);
+}
+
+int asrd_decoder_create_biglm(asrd_graph *g, const asrd_config *cfg, const asrd_device_options *opts,
+                              asrd_lm *old_lm, asrd_lm *new_lm, asrd_decoder **out) {
+  if (!old_lm || !new_lm) return ASRD_ERR_BAD_ARG;
+  return DecoderCreate(g, cfg, opts, old_lm, new_lm, out);
+}
+
+int asrd_lm_create(int32_t bos, int32_t eos, int32_t n_states, const int32_t *arc_num,
+                   const float *backoff_prob, const int32_t *backoff_id, const asrd_lm_arc *arcs,
+                   int64_t n_arcs, int device, asrd_lm **out) {
+  if (!arc_num || !backoff_prob || !backoff_id || !arcs || !out || n_states <= 0 || n_arcs <= 0 ||
+      n_arcs >= 0x7FFFFFFFll || bos <= 0 || eos <= 0)
+    return ASRD_ERR_BAD_ARG;
+  int rc = EnsureDevice(device);
+  if (rc) return rc;
+  std::vector<uint32_t> off((size_t)n_states + 1, 0);
+  for (int32_t i = 0; i < n_states; ++i) {
+    if (arc_num[i] < 0 || backoff_id[i] < 0 || backoff_id[i] >= n_states) return ASRD_ERR_BAD_ARG;
+    off[i + 1] = off[i] + (uint32_t)arc_num[i];
+  }
+  if ((int64_t)off[n_states] != n_arcs || bos >= arc_num[0] || eos >= arc_num[0]) return ASRD_ERR_BAD_ARG;
+  std::vector<int32_t> word((size_t)n_arcs), to((size_t)n_arcs);
+  std::vector<float> weight((size_t)n_arcs);
+  for (int64_t a = 0; a < n_arcs; ++a) {
+    word[a] = arcs[a].wordid;
+    weight[a] = arcs[a].weight;
+    to[a] = arcs[a].tostateid;
+    if (to[a] < 0 || to[a] >= n_states) return ASRD_ERR_BAD_ARG;
+  }
+  for (int32_t w = 0; w < arc_num[0]; ++w)
+    if (word[w] != w) return ASRD_ERR_BAD_ARG;  // the unigram state is direct-indexed by word id
+  auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  const size_t b_off = align(off.size() * 4), b_a = align((size_t)n_arcs * 4), b_s = align((size_t)n_states * 4);
+  asrd_lm *lm = new asrd_lm();
+  memset(lm, 0, sizeof(*lm));
+  lm->device = device;
+  if (cudaMalloc(&lm->slab, b_off + 3 * b_a + 2 * b_s) != cudaSuccess) {
+    cudaGetLastError();
+    delete lm;
+    return ASRD_ERR_NOMEM;
+  }
+  char *p = (char *)lm->slab;
+  lm->view.arc_off = (const uint32_t *)p; CU_CHECK(cudaMemcpy(p, off.data(), off.size() * 4, cudaMemcpyHostToDevice)); p += b_off;
+  lm->view.arc_word = (const int32_t *)p; CU_CHECK(cudaMemcpy(p, word.data(), (size_t)n_arcs * 4, cudaMemcpyHostToDevice)); p += b_a;
+  lm->view.arc_weight = (const float *)p; CU_CHECK(cudaMemcpy(p, weight.data(), (size_t)n_arcs * 4, cudaMemcpyHostToDevice)); p += b_a;
+  lm->view.arc_to = (const int32_t *)p; CU_CHECK(cudaMemcpy(p, to.data(), (size_t)n_arcs * 4, cudaMemcpyHostToDevice)); p += b_a;
+  lm->view.backoff_prob = (const float *)p; CU_CHECK(cudaMemcpy(p, backoff_prob, (size_t)n_states * 4, cudaMemcpyHostToDevice)); p += b_s;
+  lm->view.backoff_id = (const int32_t *)p; CU_CHECK(cudaMemcpy(p, backoff_id, (size_t)n_states * 4, cudaMemcpyHostToDevice)); p += b_s;
+  lm->view.bos = bos;
+  lm->view.eos = eos;
+  lm->view.n_states = n_states;
+  *out = lm;
+  return ASRD_OK;
+}
+
+int asrd_lm_destroy(asrd_lm *lm) {
+  if (!lm) return ASRD_OK;
+  cudaSetDevice(lm->device);
+  cudaFree(lm->slab);
+  delete lm;
+  return ASRD_OK;
+}
+
 int asrd_decoder_destroy(asrd_decoder *d) {
   if (!d) return ASRD_OK;
   cudaSetDevice(d->graph->device);
@@ -527,8 +618,14 @@ int asrd_init_decoding(asrd_decoder *const *decs, int32_t n, void *stream) {
   const DecoderConfigDev cfg = DevCfg(decs[0]);
   FrameDesc *d_desc;
   CU_CHECK(sc.Alloc(&d_desc, (size_t)n));
-  k_init<<<n, kStreamThreads, 0, s>>>(d_streams, d_desc, gv, cfg);
-  k_post<<<n, kStreamThreads, 0, s>>>(d_streams, d_desc, gv, cfg, kModeEpi);
+  const LmPair lms = Lms(decs[0]);
+  if (decs[0]->lm1) {
+    k_init<true><<<n, kStreamThreads, 0, s>>>(d_streams, d_desc, gv, cfg, lms);
+    k_post<true><<<n, kStreamThreads, 0, s>>>(d_streams, d_desc, gv, cfg, kModeEpi, lms);
+  } else {
+    k_init<false><<<n, kStreamThreads, 0, s>>>(d_streams, d_desc, gv, cfg, lms);
+    k_post<false><<<n, kStreamThreads, 0, s>>>(d_streams, d_desc, gv, cfg, kModeEpi, lms);
+  }
   g_launches += 2;
   CU_CHECK(cudaGetLastError());
   for (int i = 0; i < n; ++i) {
@@ -577,6 +674,8 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
   }
   const GraphView gv = decs[0]->graph->view;
   const DecoderConfigDev cfg = DevCfg(decs[0]);
+  const bool biglm = decs[0]->lm1 != nullptr;
+  const LmPair lms = Lms(decs[0]);
   DeviceCtx *ctx = nullptr;
   if ((rc = GetCtx(decs[0]->graph->device, &ctx))) return rc;
   Scratch sc(s);
@@ -602,7 +701,7 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
   const bool single = n_sub == 1;
   std::vector<ExpandPlan> plans(n_sub);
   for (int b = 0; b < n_sub; ++b)
-    if ((rc = PlanExpand(std::min(sub, n - b * sub), num_indices, &plans[b]))) return rc;
+    if ((rc = PlanExpand(std::min(sub, n - b * sub), num_indices, biglm, &plans[b]))) return rc;
 
   // Host log-likelihoods: staged chunk by chunk through two device buffers, copied on a
   // side stream so the H2D of chunk k+1 overlaps the search of chunk k.
@@ -696,16 +795,19 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
         FrameDesc *bd = d_desc + (size_t)b * sub;
         if (f < 0) {  // GetCutoff + pre-pass of the chunk's first frame
           prof.Begin(1, ws);
-          k_post<<<nb, kStreamThreads, 0, ws>>>(bs, bd, gv, cfg, kModePro);
+          if (biglm) k_post<true><<<nb, kStreamThreads, 0, ws>>>(bs, bd, gv, cfg, kModePro, lms);
+          else k_post<false><<<nb, kStreamThreads, 0, ws>>>(bs, bd, gv, cfg, kModePro, lms);
           prof.End(ws);
           ++g_launches;
           continue;
         }
         prof.Begin(0, ws);
-        plans[b].fn<<<plans[b].grid, kExpandThreads, plans[b].dyn, ws>>>(bd, gv, num_indices, plans[b].flags);
+        plans[b].fn<<<plans[b].grid, kExpandThreads, plans[b].dyn, ws>>>(bd, gv, num_indices, plans[b].flags, lms);
         prof.End(ws);
         prof.Begin(1, ws);
-        k_post<<<nb, kStreamThreads, 0, ws>>>(bs, bd, gv, cfg, kModeEpi | (f + 1 < steps ? kModePro : 0));
+        const int pm = kModeEpi | (f + 1 < steps ? kModePro : 0);
+        if (biglm) k_post<true><<<nb, kStreamThreads, 0, ws>>>(bs, bd, gv, cfg, pm, lms);
+        else k_post<false><<<nb, kStreamThreads, 0, ws>>>(bs, bd, gv, cfg, pm, lms);
         prof.End(ws);
         g_launches += 2;
       }
@@ -773,8 +875,14 @@ int asrd_get_best_path(asrd_decoder *const *decs, int32_t n, int32_t use_final_p
   CU_CHECK(sc.Alloc(&d_ac, tot));
   CU_CHECK(sc.Alloc(&d_n, (size_t)n));
   CU_CHECK(sc.Alloc(&d_st, (size_t)n));
-  k_best_path<<<n, kBestPathThreads, 0, s>>>(d_streams, decs[0]->graph->view, DevCfg(decs[0]), use_final_probs, cap, d_il,
-                                d_ol, d_gr, d_ac, d_n, d_st);
+  if (decs[0]->lm1)
+    k_best_path<true><<<n, kBestPathThreads, 0, s>>>(d_streams, decs[0]->graph->view, DevCfg(decs[0]),
+                                                     use_final_probs, cap, d_il, d_ol, d_gr, d_ac, d_n, d_st,
+                                                     Lms(decs[0]), decs[0]->finalized);
+  else
+    k_best_path<false><<<n, kBestPathThreads, 0, s>>>(d_streams, decs[0]->graph->view, DevCfg(decs[0]),
+                                                      use_final_probs, cap, d_il, d_ol, d_gr, d_ac, d_n, d_st,
+                                                      Lms(decs[0]), decs[0]->finalized);
   ++g_launches;
   CU_CHECK(cudaGetLastError());
   CU_CHECK(cudaMemcpyAsync(n_arcs, d_n, 4 * (size_t)n, cudaMemcpyDeviceToHost, s));
@@ -803,6 +911,7 @@ int asrd_get_raw_lattice(asrd_decoder *d, int32_t use_final_probs, asrd_lat_toke
   if (!d || !n_toks || !n_links || tok_cap < 0 || link_cap < 0 || tok_cap > 0x7FFFFFFF || link_cap > 0x7FFFFFFF)
     return ASRD_ERR_BAD_ARG;
   if (!d->initialized) return ASRD_ERR_STATE;
+  if (d->lm1) return ASRD_ERR_BAD_ARG;  // lattice generation is not built for the biglm decoder yet
   if (d->finalized && !use_final_probs) return ASRD_ERR_STATE;  // inl.h:879-884
   if (d->frames_decoded <= 0 || !d->d_ll_hist) {
     *n_toks = *n_links = 0;

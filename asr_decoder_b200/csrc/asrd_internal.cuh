@@ -8,7 +8,8 @@
 
 namespace asrd {
 
-constexpr uint32_t kEmptyKey = 0xFFFFFFFFu;
+constexpr uint32_t kEmptyKey = 0xFFFFFFFFu;                 // lattice maps (32-bit keys)
+constexpr unsigned long long kEmptyKey64 = 0xFFFFFFFFFFFFFFFFull;  // token map
 constexpr uint32_t kNoArc = 0xFFFFFFFFu;
 constexpr unsigned long long kInfVal = 0xFFFFFFFFFFFFFFFFull;
 constexpr uint32_t kOrdInf = 0xFF800000u;  // f2ord(+inf)
@@ -22,12 +23,25 @@ constexpr int kBestPathThreads = 512; // CTA size of the back-trace kernel
 constexpr int kMaxBatch = 65535;      // streams per launch (gridDim.y of k_expand)
 constexpr int kMinHashCapacity = 4096;
 
-// One slot of the per-frame state->token map.  val = (ordered cost << 32) | global arc id,
-// recombined with a single 64-bit atomicMin: lowest cost wins, equal cost -> lowest arc id.
+// One slot of the per-frame state->token map.  key = HCLG state (biglm: state | LM pair id << 32,
+// the reference's PairId, my-decoder/online-decoder-mempool-base-biglm.h:77-80).
+// val = (ordered cost << 32) | global arc id, recombined with a single 64-bit atomicMin: lowest
+// cost wins, equal cost -> lowest arc id.
 struct __align__(16) HashEntry {
-  uint32_t key;             // state id, kEmptyKey when free
-  uint32_t aux;             // eps-closure round stamp (de-duplicates the frontier queue)
+  unsigned long long key;   // kEmptyKey64 when free
   unsigned long long val;
+};
+
+// Device view of one LM FSA (reference Fsa, newlm/arpa2fsa.h:217-480): state 0 is the unigram
+// state and is direct-indexed by word id; other states hold word-sorted arcs and a back-off link.
+struct LmView {
+  const uint32_t *arc_off;     // [n_states + 1]
+  const int32_t *arc_word;     // [n_arcs]
+  const float *arc_weight;
+  const int32_t *arc_to;
+  const float *backoff_prob;   // [n_states]
+  const int32_t *backoff_id;
+  int32_t bos, eos, n_states;
 };
 
 // Device-resident graph: the reference's two flat arrays (src/newfst/optimize-fst.h:60-61)
@@ -52,6 +66,11 @@ struct StreamState {
   uint32_t *bm;         // claimed-slot bitmap of the map (capacity / 32 words)
   uint32_t *ebm;        // ... of which the state has eps arcs (seeds of the eps closure)
   uint32_t *queue[2];   // eps-closure frontier queues
+  uint32_t *stamp;      // [capacity] eps-closure round stamp per slot (de-duplicates the frontier queue)
+  uint32_t *tok_lm;     // biglm: token arena, LM pair id of every token
+  unsigned long long *pair_map;  // biglm: interned (lm1 state, lm2 state) pairs; the slot index is the pair id
+  uint32_t pair_mask;
+  uint32_t pad2;
   uint2 *tok_sc;        // token arena: {state, cost bits}
   uint32_t *tok_arc;    // token arena: arc that set the token's cost (kNoArc for the start token)
   uint32_t *frame_off;  // [max_frames + 2] arena offset of every frame's token span
@@ -85,7 +104,7 @@ struct __align__(16) FrameDesc {
   const uint2 *toks;    // tokens of frame t (being expanded)
   const float *ll;      // log-likelihood row of frame t
   HashEntry *hn;        // map of frame t+1
-  void *reserved0;
+  const uint32_t *toks_lm;  // biglm: LM pair ids of the tokens of frame t
   uint32_t *bm;         // claimed-slot bitmap of hn
   uint32_t *ebm;        // eps-seed bitmap of hn
   uint2 *out_sc;        // arena write window of frame t+1
@@ -164,6 +183,12 @@ __host__ __device__ inline float ord2f(uint32_t o) {
 
 }  // namespace asrd
 
+struct asrd_lm {
+  int device;
+  asrd::LmView view;
+  void *slab;
+};
+
 struct asrd_graph {
   int device;
   asrd::GraphView view;
@@ -174,6 +199,7 @@ struct asrd_graph {
 
 struct asrd_decoder {
   asrd_graph *graph;
+  asrd_lm *lm1, *lm2;          // biglm: old LM (already scaled by -1 by the caller) and new LM
   asrd_config cfg;
   asrd_device_options opts;
   asrd::StreamState *d_state;  // device copy

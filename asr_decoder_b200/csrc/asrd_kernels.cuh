@@ -30,6 +30,11 @@ __device__ __forceinline__ uint32_t hash_state(uint32_t s, uint32_t mask, uint32
   (void)mask;
   return (s * 0x9E3779B1u) >> shift;
 }
+__device__ __forceinline__ uint32_t hash_key(unsigned long long key, uint32_t mask, uint32_t shift) {
+  // plain decoders: key == state, same slot as hash_state(state); biglm: the LM pair id is mixed in
+  const uint32_t s = (uint32_t)key, p = (uint32_t)(key >> 32);
+  return ((s + p * 0x85EBCA6Bu) * 0x9E3779B1u) >> shift;
+}
 
 // L2 residency control.  The graph (arcs + rows, ~88 MB at config 2) is re-read every frame by
 // every stream at random and fits the 126 MB L2; the per-stream maps, token arena and
@@ -68,12 +73,12 @@ __device__ __forceinline__ bool par_bit(const uint32_t *bits, uint32_t arc) {
 
 // Find-or-claim the slot of `state` (FindOrAddToken, inl.h:88-136): CAS first, so a new
 // state costs one L2 round trip and an existing one as well.
-__device__ __forceinline__ bool hash_claim(HashEntry *tab, uint32_t mask, uint32_t h, uint32_t state,
+__device__ __forceinline__ bool hash_claim(HashEntry *tab, uint32_t mask, uint32_t h, unsigned long long state,
                                            uint32_t &slot, bool &is_new) {
   for (uint32_t probe = 0; probe <= mask; ++probe) {
-    const uint32_t k = atomicCAS(&tab[h].key, kEmptyKey, state);
-    if (k == kEmptyKey || k == state) {
-      is_new = (k == kEmptyKey);
+    const unsigned long long k = atomicCAS(&tab[h].key, kEmptyKey64, state);
+    if (k == kEmptyKey64 || k == state) {
+      is_new = (k == kEmptyKey64);
       slot = h;
       return true;
     }
@@ -84,21 +89,6 @@ __device__ __forceinline__ bool hash_claim(HashEntry *tab, uint32_t mask, uint32
 
 __device__ __forceinline__ bool eps_bit(const uint32_t *bits, uint32_t state) {
   return (__ldg(&bits[state >> 5]) >> (state & 31u)) & 1u;
-}
-
-__device__ __forceinline__ bool hash_find(const HashEntry *tab, uint32_t mask, uint32_t shift,
-                                          uint32_t state, unsigned long long &val) {
-  uint32_t h = hash_state(state, mask, shift);
-  for (uint32_t probe = 0; probe <= mask; ++probe) {
-    uint32_t k = __ldcg(&tab[h].key);
-    if (k == state) {
-      val = __ldcg(&tab[h].val);
-      return true;
-    }
-    if (k == kEmptyKey) return false;
-    h = (h + 1) & mask;
-  }
-  return false;
 }
 
 template <int NT>
@@ -175,6 +165,100 @@ __device__ __forceinline__ uint32_t block_sum_u32(uint32_t v, uint32_t *s_red) {
   return v;
 }
 
+// ------------------------------------------------------------------ biglm: LM-difference composition
+
+struct LmPair {  // kernel argument: old LM (pre-scaled by -1 by the caller) and new LM
+  LmView lm1, lm2;
+};
+
+// Fsa::GetArc (newlm/arpa2fsa.cc:244-262): word 0 = back-off link; the unigram state 0 is
+// direct-indexed by word id (arpa2fsa.h:211-214), other states are binary-searched (:194-210).
+__device__ __forceinline__ bool fsa_get_arc(const LmView &lm, int32_t id, int32_t word, float &weight, int32_t &to) {
+  const uint32_t b = __ldg(&lm.arc_off[id]);
+  if (id == 0) {
+    weight = __ldg(&lm.arc_weight[b + word]);
+    to = __ldg(&lm.arc_to[b + word]);
+    return true;
+  }
+  int start = 0, end = (int)(__ldg(&lm.arc_off[id + 1]) - b) - 1;
+  while (start <= end) {
+    const int mid = (start + end) / 2;
+    const int32_t w = __ldg(&lm.arc_word[b + mid]);
+    if (w > word) end = mid - 1;
+    else if (w < word) start = mid + 1;
+    else {
+      weight = __ldg(&lm.arc_weight[b + mid]);
+      to = __ldg(&lm.arc_to[b + mid]);
+      return true;
+    }
+  }
+  return false;
+}
+
+// ComposeArpaLm::GetArc (newlm/compose-arpalm.cc:52-70): walk the back-off chain, summing the
+// back-off weights in float, then the arc weight; Value1 = -(sum).
+__device__ __forceinline__ void clm_get_arc(const LmView &lm, int32_t s, int32_t word, int32_t &next, float &value1) {
+  float weight = 0.0f, w_arc = 0.0f;
+  int32_t to = 0;
+  while (!fsa_get_arc(lm, s, word, w_arc, to)) {
+    w_arc = __ldg(&lm.backoff_prob[s]);
+    to = __ldg(&lm.backoff_id[s]);
+    s = to;
+    weight += w_arc;
+  }
+  weight += w_arc;
+  value1 = -1 * weight;
+  next = to;
+}
+
+__device__ __forceinline__ float clm_final(const LmView &lm, int32_t s) {  // compose-arpalm.cc:15-29
+  int32_t next;
+  float v;
+  clm_get_arc(lm, s, lm.eos, next, v);
+  return v;
+}
+
+__device__ __forceinline__ int32_t clm_start(const LmView &lm) {  // compose-arpalm.cc:5-13
+  float w;
+  int32_t to;
+  fsa_get_arc(lm, 0, lm.bos, w, to);
+  return to;
+}
+
+// DiffArpaLm state table (newlm/diff-lm.h:92-103): (lm1 state, lm2 state) pairs interned in an
+// open-addressing table; the SLOT INDEX is the pair id, so no separate numbering is needed.
+__device__ __forceinline__ uint32_t pair_intern(unsigned long long *map, uint32_t pmask, int32_t n1, int32_t n2,
+                                                int32_t *status) {
+  const unsigned long long key = (((unsigned long long)(uint32_t)n1 << 32) | (uint32_t)n2) + 1ull;
+  uint32_t h = ((uint32_t)n1 * 0x9E3779B1u + (uint32_t)n2 * 0x85EBCA6Bu) & pmask;
+  for (uint32_t probe = 0; probe <= pmask; ++probe) {
+    unsigned long long k = __ldcg(&map[h]);
+    if (k == 0ull) k = atomicCAS(&map[h], 0ull, key);
+    if (k == 0ull || k == key) return h;
+    h = (h + 1) & pmask;
+  }
+  atomicMin(status, ASRD_ERR_HASH_OVERFLOW);
+  return 0;
+}
+
+// NextLmState (…-biglm.h:54-70) with the INTENDED DiffArpaLm semantics: both LMs advance from the
+// members of the pair (the reference passes the pair-state id itself, newlm/diff-lm.h:75-86 —
+// SURVEY.md Appendix B-6; on unigram-only LMs the two coincide).  Returns the LM-difference score
+// Times(w1, w2).Value1() and the successor LM states (not yet interned).
+__device__ __forceinline__ float lm_step(const LmPair &lms, const unsigned long long *map, uint32_t pair_id,
+                                         int32_t word, int32_t &n1, int32_t &n2) {
+  const unsigned long long pk = __ldcg(&map[pair_id]) - 1ull;
+  float v1, v2;
+  clm_get_arc(lms.lm1, (int32_t)(uint32_t)(pk >> 32), word, n1, v1);
+  clm_get_arc(lms.lm2, (int32_t)(uint32_t)pk, word, n2, v2);
+  return v1 + v2;
+}
+
+__device__ __forceinline__ float lm_final(const LmPair &lms, const unsigned long long *map, uint32_t pair_id) {
+  const unsigned long long pk = __ldcg(&map[pair_id]) - 1ull;  // DiffArpaLm::Final, diff-lm.h:48-55
+  return clm_final(lms.lm1, (int32_t)(uint32_t)(pk >> 32)) + clm_final(lms.lm2, (int32_t)(uint32_t)pk);
+}
+
 // ------------------------------------------------------------------ warp work splitting
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
@@ -217,7 +301,7 @@ __device__ __forceinline__ void clear_map_by_bitmap(HashEntry *h, uint32_t *bm, 
       const uint32_t bits = __shfl_sync(kFull, mine, k);
       if ((bits >> lane) & 1u) {
         HashEntry e;
-        e.key = kEmptyKey; e.aux = 0; e.val = kInfVal;
+        e.key = kEmptyKey64; e.val = kInfVal;
         h[(w0 + k) * 32 + lane] = e;
       }
     }
@@ -226,8 +310,9 @@ __device__ __forceinline__ void clear_map_by_bitmap(HashEntry *h, uint32_t *bm, 
 
 // InitDecoding (inl.h:41-67): forget the previous utterance and seed the start token; the
 // closure / finalize / cutoff kernels that follow complete frame 0 with cutoff = beam.
+template <bool BIGLM>
 __global__ void __launch_bounds__(kStreamThreads)
-k_init(StreamState *const *streams, FrameDesc *desc, GraphView g, DecoderConfigDev cfg) {
+k_init(StreamState *const *streams, FrameDesc *desc, GraphView g, DecoderConfigDev cfg, LmPair lms) {
   StreamState *st = streams[blockIdx.x];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t mask = st->hash_mask;
@@ -235,6 +320,9 @@ k_init(StreamState *const *streams, FrameDesc *desc, GraphView g, DecoderConfigD
   // the map is normally left clean by the last finalize phase; an aborted utterance may not have
   clear_map_by_bitmap(st->hash, st->bm, words, warp, lane, kStreamThreads / 32);
   for (uint32_t i = tid; i < words; i += kStreamThreads) st->ebm[i] = 0;
+  for (uint32_t i = tid; i <= mask; i += kStreamThreads) st->stamp[i] = 0;
+  if (BIGLM)  // DiffArpaLm::Reset (newlm/diff-lm.h:39-46): the pair table is per utterance
+    for (uint32_t i = tid; i <= st->pair_mask; i += kStreamThreads) st->pair_map[i] = 0ull;
   __syncthreads();
   if (tid == 0) {
     st->status = 0;
@@ -248,7 +336,11 @@ k_init(StreamState *const *streams, FrameDesc *desc, GraphView g, DecoderConfigD
     uint32_t slot;
     bool is_new;
     HashEntry *hn = st->hash;
-    hash_claim(hn, mask, hash_state((uint32_t)g.start, mask, st->hash_shift), (uint32_t)g.start, slot, is_new);
+    unsigned long long start_key = (uint32_t)g.start;
+    if (BIGLM)  // …-biglm.h:112: start pair = (graph start, DiffArpaLm::Start())
+      start_key |= (unsigned long long)pair_intern(st->pair_map, st->pair_mask, clm_start(lms.lm1),
+                                                   clm_start(lms.lm2), &st->status) << 32;
+    hash_claim(hn, mask, hash_key(start_key, mask, st->hash_shift), start_key, slot, is_new);
     atomicMin(&hn[slot].val, pack_val(0.0f, kNoArc));
     st->bm[slot >> 5] = 1u << (slot & 31u);
     if (eps_bit(g.eps_bits, (uint32_t)g.start)) st->ebm[slot >> 5] = 1u << (slot & 31u);
@@ -257,6 +349,7 @@ k_init(StreamState *const *streams, FrameDesc *desc, GraphView g, DecoderConfigD
     d.toks = nullptr;
     d.ll = nullptr;
     d.hn = hn;
+    d.toks_lm = nullptr;
     d.bm = st->bm;
     d.ebm = st->ebm;
     d.out_sc = st->tok_sc;
@@ -318,9 +411,9 @@ k_begin_advance(StreamState *const *streams, const AdvanceParams *params, int nu
 // in flight per iteration.  The stream's log-likelihood row is staged in shared memory once
 // per CTA (the only block barrier).  Token recombination: one 64-bit atomicMin per admitted
 // arc on (ordered cost << 32 | arc id) in the per-frame state->token map.
-template <int U, bool SMEM_LL>
-__global__ void __launch_bounds__(kExpandThreads, U == 1 ? 8 : 5)
-k_expand(FrameDesc *desc, GraphView g, int num_indices, int flags) {
+template <int U, bool SMEM_LL, bool BIGLM>
+__global__ void __launch_bounds__(kExpandThreads, (U == 1 && !BIGLM) ? 8 : 5)
+k_expand(FrameDesc *desc, GraphView g, int num_indices, int flags, LmPair lms) {
   extern __shared__ float s_ll[];
   FrameDesc *d = &desc[blockIdx.y];
   if (!d->stepping) return;
@@ -341,6 +434,9 @@ k_expand(FrameDesc *desc, GraphView g, int num_indices, int flags) {
   uint32_t *bm = d->bm, *ebm = d->ebm;
   const uint32_t mask = d->mask, shift = d->shift;
   uint32_t *next_cut = &d->next_cut_bits;
+  const uint32_t *__restrict__ toks_lm = d->toks_lm;
+  unsigned long long *pair_map = BIGLM ? d->st->pair_map : nullptr;
+  const uint32_t pair_mask = BIGLM ? d->st->pair_mask : 0;
   const bool hints = (flags & 1) != 0;
   const uint64_t pol_graph = hints ? l2_policy_evict_last() : 0, pol_stream = hints ? l2_policy_evict_first() : 0;
 
@@ -351,10 +447,11 @@ k_expand(FrameDesc *desc, GraphView g, int num_indices, int flags) {
     float nc = ord2f(__ldcg(next_cut));
     // ---- lane i: token i of the group and its emitting span
     const uint32_t i = grp * 32 + lane;
-    uint32_t deg = 0, base = 0, cost_bits = 0;
+    uint32_t deg = 0, base = 0, cost_bits = 0, my_pair = 0;
     if (i < n_cur) {
       const uint2 sc = hints ? ldg_u2(&toks[i], pol_stream) : __ldg(&toks[i]);
       cost_bits = sc.y;
+      if (BIGLM) my_pair = __ldg(&toks_lm[i]);
       if (__uint_as_float(sc.y) <= cur_cut) {  // inclusive, inl.h:315
         const uint2 er = hints ? ldg_u2(&g.erows[sc.x], pol_graph) : __ldg(&g.erows[sc.x]);
         base = er.x;
@@ -368,7 +465,7 @@ k_expand(FrameDesc *desc, GraphView g, int num_indices, int flags) {
 
     for (uint32_t jb = 0; jb < total; jb += 32 * U) {
       bool in[U];
-      uint32_t a[U];
+      uint32_t a[U], tpair[U];
       float tcost[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -378,6 +475,7 @@ k_expand(FrameDesc *desc, GraphView g, int num_indices, int flags) {
         const uint32_t off_l = __shfl_sync(kFull, off, l);
         const uint32_t base_l = __shfl_sync(kFull, base, l);
         tcost[u] = __uint_as_float(__shfl_sync(kFull, cost_bits, l));
+        tpair[u] = BIGLM ? __shfl_sync(kFull, my_pair, l) : 0u;
         a[u] = base_l + (j - off_l);
       }
       int4 arc[U];
@@ -388,22 +486,33 @@ k_expand(FrameDesc *desc, GraphView g, int num_indices, int flags) {
       bool adm[U];
       uint32_t h0[U];
       uint4 e0[U];
+      unsigned long long dkey[U];
       uint32_t cand_bits = 0xFFFFFFFFu;
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         adm[u] = false;
         tot[u] = 0.f;
         h0[u] = 0;
+        dkey[u] = 0;
         e0[u] = make_uint4(0, 0, 0, 0);
         if (in[u]) {
           const float ac = -(SMEM_LL ? s_ll[arc[u].x - 1] : __ldg(&ll[arc[u].x - 1]));
-          tot[u] = (tcost[u] + ac) + __int_as_float(arc[u].z);  // inl.h:326-329
+          float graph_cost = __int_as_float(arc[u].z);
+          int32_t n1 = 0, n2 = 0;
+          if (BIGLM && arc[u].y != 0)  // …-biglm.h:377-379: graph_cost = arc weight + LM-difference score
+            graph_cost = __int_as_float(arc[u].z) + lm_step(lms, pair_map, tpair[u], arc[u].y, n1, n2);
+          tot[u] = (tcost[u] + ac) + graph_cost;  // inl.h:326-329
           adm[u] = tot[u] < nc && !(flags & 2);   // (flags & 2): measurement aid, no map traffic
           if (adm[u]) {
             const float cand = tot[u] + abeam;  // inl.h:332-333
             if (cand < nc) cand_bits = min(cand_bits, f2ord(cand));
-            h0[u] = hash_state((uint32_t)arc[u].w & kStateMask, mask, shift);
-            // first probe: the whole 16-byte entry {key, stamp, val} in one request
+            dkey[u] = (uint32_t)arc[u].w & kStateMask;
+            if (BIGLM) {  // …-biglm.h:388: destination key = (arc target, next LM state)
+              const uint32_t np = arc[u].y != 0 ? pair_intern(pair_map, pair_mask, n1, n2, &d->st->status) : tpair[u];
+              dkey[u] |= (unsigned long long)np << 32;
+            }
+            h0[u] = hash_key(dkey[u], mask, shift);
+            // first probe: the whole 16-byte entry {key, val} in one request
             e0[u] = __ldcg(reinterpret_cast<const uint4 *>(&hn[h0[u]]));
           }
         }
@@ -417,10 +526,10 @@ k_expand(FrameDesc *desc, GraphView g, int num_indices, int flags) {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         if (adm[u]) {
-          const uint32_t state = (uint32_t)arc[u].w & kStateMask;
+          const unsigned long long state = dkey[u];
           const unsigned long long pk = pack_val(tot[u], a[u]);
           uint32_t slot = h0[u];
-          bool is_new = false, ok = e0[u].x == state;
+          bool is_new = false, ok = (((unsigned long long)e0[u].y << 32) | e0[u].x) == state;
           // the map value only ever decreases: if what we saw already beats us, so does the
           // current value — no atomic needed (most admitted arcs lose the recombination)
           const bool lost = ok && (((unsigned long long)e0[u].w << 32) | e0[u].z) <= pk;
@@ -503,10 +612,11 @@ __device__ float block_kth_smallest(const uint2 *tok_sc, uint32_t n, uint32_t k,
 
 // GetCutoff (inl.h:138-234) over the current frame's tokens, best-token pre-pass
 // (inl.h:282-300), and the descriptor of the next expansion.  Whole-CTA device function.
-template <int NT>
+template <int NT, bool BIGLM>
 __device__ __forceinline__ void cutoff_prologue(StreamState *st, FrameDesc *d, const GraphView &g,
-                                                const DecoderConfigDev &cfg, unsigned long long *s_red64,
-                                                uint32_t *s_red32, uint32_t *s_hist, uint32_t *s_misc) {
+                                                const DecoderConfigDev &cfg, const LmPair &lms,
+                                                unsigned long long *s_red64, uint32_t *s_red32,
+                                                uint32_t *s_hist, uint32_t *s_misc) {
   const int tid = threadIdx.x;
   const int t = st->frame;
   if (t >= st->target_frame) {
@@ -556,13 +666,26 @@ __device__ __forceinline__ void cutoff_prologue(StreamState *st, FrameDesc *d, c
         abeam = cur_cut - bc + cfg.beam_delta;
       }
     }
-    // best-token pre-pass (inl.h:282-300): association (cost + w) - loglike
-    const uint32_t sb = (uint32_t)best64;
+    // best-token pre-pass (inl.h:282-300): association (cost + w) - loglike;
+    // biglm (…-biglm.h:339-357): ((lm_score + cost) + w) - loglike.  In biglm mode best64 carries
+    // the token's index inside the frame instead of its state.
+    uint32_t sb = (uint32_t)best64, bpair = 0;
+    if (BIGLM) {
+      bpair = st->tok_lm[tok_off + sb];
+      sb = toks[sb].x;
+    }
     const uint2 er = __ldg(&g.erows[sb]);
     uint32_t mn = kOrdInf;
     for (uint32_t a = er.x + tid; a < er.y; a += NT) {
       const int4 arc = __ldg(&g.arcs[a]);
-      const float tot = bc + __int_as_float(arc.z) - __ldg(&ll[arc.x - 1]);
+      float tot;
+      if (BIGLM && arc.y != 0) {
+        int32_t n1, n2;
+        const float lm_score = lm_step(lms, st->pair_map, bpair, arc.y, n1, n2);
+        tot = lm_score + bc + __int_as_float(arc.z) - __ldg(&ll[arc.x - 1]);
+      } else {
+        tot = bc + __int_as_float(arc.z) - __ldg(&ll[arc.x - 1]);
+      }
       mn = min(mn, f2ord(tot + abeam));
     }
     const unsigned long long m64 = block_min_u64<NT>((unsigned long long)mn, s_red64);
@@ -575,6 +698,7 @@ __device__ __forceinline__ void cutoff_prologue(StreamState *st, FrameDesc *d, c
     nd.toks = toks;
     nd.ll = ll;
     nd.hn = st->hash;
+    nd.toks_lm = BIGLM ? st->tok_lm + tok_off : nullptr;
     nd.bm = st->bm;
     nd.ebm = st->ebm;
     nd.out_sc = st->tok_sc + out_base;
@@ -604,8 +728,9 @@ __device__ __forceinline__ void cutoff_prologue(StreamState *st, FrameDesc *d, c
 // carries it from the eps closure to the descriptor of the next expansion without going back
 // to the host-visible launch queue (three launches and their descriptor round trips saved).
 // The survivor counter and the best token live in shared memory instead of global atomics.
-__global__ void __launch_bounds__(kStreamThreads, 2)
-k_post(StreamState *const *streams, FrameDesc *desc, GraphView g, DecoderConfigDev cfg, int mode) {
+template <bool BIGLM>
+__global__ void __launch_bounds__(kStreamThreads, BIGLM ? 1 : 2)
+k_post(StreamState *const *streams, FrameDesc *desc, GraphView g, DecoderConfigDev cfg, int mode, LmPair lms) {
   constexpr int NT = kStreamThreads;
   __shared__ unsigned long long s_red64[NT / 32];
   __shared__ uint32_t s_red32[NT / 32];
@@ -635,21 +760,31 @@ k_post(StreamState *const *streams, FrameDesc *desc, GraphView g, DecoderConfigD
     __syncthreads();
 
     // ---- eps closure (ProcessNonemitting, inl.h:353-431)
+    uint32_t *stamp = st->stamp;
+    unsigned long long *pair_map = BIGLM ? st->pair_map : nullptr;
+    const uint32_t pair_mask = BIGLM ? st->pair_mask : 0;
+    const uint32_t stamp_base = (uint32_t)(t + 2) << 6;  // frame-unique round stamps: no clearing per frame
     auto relax_from = [&](uint32_t slot, uint32_t round) {
       const uint4 e = __ldcg(reinterpret_cast<const uint4 *>(&hn[slot]));
-      const uint32_t state = e.x;
+      const uint32_t state = e.x, pair = e.y;
       const float cost = ord2f(e.w);
       if (!(cost < nc)) return;  // inl.h:391
       const uint2 r = __ldg(&g.rows[state]);
       uint32_t *qout = ((round + 1) & 1) ? q1 : q0;
       for (uint32_t a = r.x; a < r.y; ++a) {
         const int4 arc = __ldg(&g.arcs[a]);
-        const float tot = cost + __int_as_float(arc.z);  // inl.h:413-414
-        if (tot < nc) {                                   // inl.h:415
+        float graph_cost = __int_as_float(arc.z);
+        int32_t n1 = 0, n2 = 0;
+        if (BIGLM && arc.y != 0)  // …-biglm.h:446-448
+          graph_cost = __int_as_float(arc.z) + lm_step(lms, pair_map, pair, arc.y, n1, n2);
+        const float tot = cost + graph_cost;  // inl.h:413-414
+        if (tot < nc) {                        // inl.h:415
           uint32_t slot2;
           bool is_new;
-          const uint32_t dst = (uint32_t)arc.w & kStateMask;
-          if (!hash_claim(hn, mask, hash_state(dst, mask, shift), dst, slot2, is_new)) {
+          unsigned long long dst = (uint32_t)arc.w & kStateMask;
+          if (BIGLM)
+            dst |= (unsigned long long)(arc.y != 0 ? pair_intern(pair_map, pair_mask, n1, n2, &st->status) : pair) << 32;
+          if (!hash_claim(hn, mask, hash_key(dst, mask, shift), dst, slot2, is_new)) {
             atomicMin(&st->status, ASRD_ERR_HASH_OVERFLOW);
             continue;
           }
@@ -657,8 +792,8 @@ k_post(StreamState *const *streams, FrameDesc *desc, GraphView g, DecoderConfigD
           const unsigned long long old = atomicMin(&hn[slot2].val, pk);
           if (is_new) atomicOr(&bm[slot2 >> 5], 1u << (slot2 & 31u));
           const bool changed = (uint32_t)(pk >> 32) < (uint32_t)(old >> 32);  // inl.h:115-127
-          if (changed && ((uint32_t)arc.w & kDestEpsBit) &&
-              atomicExch(&hn[slot2].aux, round + 1) != round + 1)
+          const uint32_t sv = stamp_base + min(round + 1, 63u);
+          if (changed && ((uint32_t)arc.w & kDestEpsBit) && (atomicMax(&stamp[slot2], sv) < sv || round >= 62u))
             qout[atomicAdd(&s_qn[(round + 1) & 1], 1u)] = slot2;  // inl.h:425-426
         }
       }
@@ -692,6 +827,7 @@ k_post(StreamState *const *streams, FrameDesc *desc, GraphView g, DecoderConfigD
       const uint32_t cap = d->out_cap;
       uint2 *out_sc = d->out_sc;
       uint32_t *out_arc = d->out_arc;
+      uint32_t *out_lm = BIGLM ? st->tok_lm + st->frame_off[t + 1] : nullptr;
       unsigned long long best64 = kInfVal;
       for (uint32_t grp = warp; grp < groups; grp += NT / 32) {
         const uint32_t word = __ldcg(&bm[grp * 32 + lane]);
@@ -707,13 +843,14 @@ k_post(StreamState *const *streams, FrameDesc *desc, GraphView g, DecoderConfigD
           const uint32_t wl = __shfl_sync(kFull, word, l);
           const uint32_t offl = __shfl_sync(kFull, off, l);
           bool alive = false;
-          uint32_t key = 0, rep = kNoArc;
+          uint32_t key = 0, pair = 0, rep = kNoArc;
           float cost = 0.f;
           if (it < total) {
             const uint32_t b = __fns(wl, 0, (int)(it - offl) + 1);
             const uint32_t slot = ((grp * 32 + l) << 5) + b;
             const uint4 e = __ldcg(reinterpret_cast<const uint4 *>(&hn[slot]));
             key = e.x;
+            pair = e.y;
             rep = e.z;
             cost = ord2f(e.w);
             alive = cost < nc;
@@ -728,9 +865,12 @@ k_post(StreamState *const *streams, FrameDesc *desc, GraphView g, DecoderConfigD
             if (idx < cap) {
               out_sc[idx] = make_uint2(key, __float_as_uint(cost));
               out_arc[idx] = rep;
+              if (BIGLM) out_lm[idx] = pair;
             }
-            const unsigned long long b64 = ((unsigned long long)f2ord(cost) << 32) | key;
-            best64 = b64 < best64 ? b64 : best64;
+            // best token: lowest cost, ties -> lowest state id; biglm keeps the token's index
+            // inside the frame instead (the pre-pass needs its LM state as well)
+            const unsigned long long b64 = ((unsigned long long)f2ord(cost) << 32) | (BIGLM ? idx : key);
+            if (!BIGLM || idx < cap) best64 = b64 < best64 ? b64 : best64;
           }
         }
         // The map of this frame dies here (the next expansion reads the arena, and so does the
@@ -745,7 +885,7 @@ k_post(StreamState *const *streams, FrameDesc *desc, GraphView g, DecoderConfigD
           const uint32_t bits = __shfl_sync(kFull, word, k);
           if ((bits >> lane) & 1u)
             __stcg(reinterpret_cast<uint4 *>(&hn[((grp * 32 + k) << 5) + lane]),
-                   make_uint4(kEmptyKey, 0u, 0xFFFFFFFFu, 0xFFFFFFFFu));
+                   make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu));
         }
       }
 #pragma unroll
@@ -788,7 +928,7 @@ k_post(StreamState *const *streams, FrameDesc *desc, GraphView g, DecoderConfigD
     __syncthreads();
   }
 
-  if (mode & kModePro) cutoff_prologue<NT>(st, d, g, cfg, s_red64, s_red32, s_hist, s_misc);
+  if (mode & kModePro) cutoff_prologue<NT, BIGLM>(st, d, g, cfg, lms, s_red64, s_red32, s_hist, s_misc);
 }
 
 // ------------------------------------------------------------------ raw lattice
@@ -1019,9 +1159,15 @@ __global__ void k_counters(StreamState *const *streams, int n, unsigned long lon
 // when link_extra_cost > lattice_beam (inl.h:524-542), which on the best path is
 // (tot' - tok.cost) > lattice_beam.  With parallel arcs pred.state -> tok.state that is the
 // highest-index admitted sibling within lattice_beam, not necessarily the cheapest one.
+//
+// biglm: tokens are keyed by (state, LM pair); the end token adds DiffArpaLm::Final of its LM
+// state (…-biglm.h:185-191) and the predecessor is the token of the source state whose LM
+// transition over the arc reproduces this token's LM state and cost.
+template <bool BIGLM>
 __global__ void __launch_bounds__(kBestPathThreads)
 k_best_path(StreamState *const *streams, GraphView g, DecoderConfigDev cfg, int use_final, int cap,
-            int32_t *o_il, int32_t *o_ol, float *o_gr, float *o_ac, int32_t *o_n, int32_t *o_status) {
+            int32_t *o_il, int32_t *o_ol, float *o_gr, float *o_ac, int32_t *o_n, int32_t *o_status,
+            LmPair lms, int finalized) {
   constexpr int NT = kBestPathThreads;
   __shared__ unsigned long long s_red64[NT / 32];
   __shared__ uint32_t s_found;
@@ -1036,21 +1182,43 @@ k_best_path(StreamState *const *streams, GraphView g, DecoderConfigDev cfg, int 
     }
     return;
   }
-  auto find_token = [&](int frame, uint32_t state) -> uint32_t {
+  const unsigned long long *pair_map = BIGLM ? st->pair_map : nullptr;
+  // Token of `state` in `frame`.  biglm: several tokens may share the state; take the one whose
+  // expansion over `arc` lands on (want_pair, want_cost) — `ll` is the row of that frame.
+  auto find_token = [&](int frame, uint32_t state, const int4 &arc, uint32_t want_pair, float want_cost,
+                        const float *ll) -> uint32_t {
     if (tid == 0) s_found = 0xFFFFFFFFu;
     __syncthreads();
     const uint32_t b = st->frame_off[frame], n = st->frame_off[frame + 1] - b;
     const uint2 *__restrict__ toks = st->tok_sc + b;
     for (uint32_t i0 = 0; i0 < n; i0 += NT * 4) {  // four independent loads in flight per thread
-      uint32_t k[4];
+      uint2 k[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const uint32_t i = i0 + u * NT + tid;
-        k[u] = i < n ? __ldg(&toks[i]).x : 0xFFFFFFFFu;
+        k[u] = i < n ? __ldg(&toks[i]) : make_uint2(0xFFFFFFFFu, 0u);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (k[u] == state) s_found = b + i0 + u * NT + tid;
+      for (int u = 0; u < 4; ++u) {
+        if (k[u].x != state) continue;
+        const uint32_t idx = b + i0 + u * NT + tid;
+        if (BIGLM && arc.x != -1) {
+          const uint32_t pp = st->tok_lm[idx];
+          const float pc = __uint_as_float(k[u].y);
+          float graph_cost = __int_as_float(arc.z);
+          if (arc.y != 0) {
+            int32_t n1, n2;
+            graph_cost = __int_as_float(arc.z) + lm_step(lms, pair_map, pp, arc.y, n1, n2);
+            // must land on the token's LM state pair
+            if ((((unsigned long long)(uint32_t)n1 << 32) | (uint32_t)n2) + 1ull != __ldcg(&pair_map[want_pair])) continue;
+          } else if (pp != want_pair) {
+            continue;
+          }
+          const float tot = arc.x != 0 ? (pc + (-ll[arc.x - 1])) + graph_cost : pc + graph_cost;
+          if (__float_as_uint(tot) != __float_as_uint(want_cost)) continue;
+        }
+        atomicMin(&s_found, idx);
+      }
     }
     __syncthreads();
     const uint32_t idx = s_found;
@@ -1059,30 +1227,54 @@ k_best_path(StreamState *const *streams, GraphView g, DecoderConfigDev cfg, int 
   };
   // end token
   const uint32_t b0 = st->frame_off[f], n0 = st->frame_off[f + 1] - b0;
-  unsigned long long best_all = kInfVal, best_fin = kInfVal;
+  unsigned long long best_all = kInfVal, best_fin = kInfVal, best_wf = kInfVal;
   for (uint32_t i = tid; i < n0; i += NT) {
     const uint2 sc = st->tok_sc[b0 + i];
-    const unsigned long long b = ((unsigned long long)f2ord(__uint_as_float(sc.y)) << 32) | sc.x;
-    best_all = b < best_all ? b : best_all;
-    if ((int32_t)sc.x == g.final_state) best_fin = b < best_fin ? b : best_fin;
+    const uint32_t low = BIGLM ? i : sc.x;  // biglm: index inside the frame (ties -> lowest index)
+    const unsigned long long bb = ((unsigned long long)f2ord(__uint_as_float(sc.y)) << 32) | low;
+    best_all = bb < best_all ? bb : best_all;
+    float c = __uint_as_float(sc.y);
+    if (BIGLM) {
+      // …-biglm.h:185-188: best_cost_with_final runs over ALL tokens
+      c += lm_final(lms, pair_map, st->tok_lm[b0 + i]);
+      const unsigned long long bw = ((unsigned long long)f2ord(c) << 32) | low;
+      best_wf = bw < best_wf ? bw : best_wf;
+    }
+    if ((int32_t)sc.x == g.final_state) {
+      const unsigned long long bf = ((unsigned long long)f2ord(c) << 32) | low;  // inl.h:1133-1134
+      best_fin = bf < best_fin ? bf : best_fin;
+    }
   }
   best_all = block_min_u64<NT>(best_all, s_red64);
   best_fin = block_min_u64<NT>(best_fin, s_red64);
-  const unsigned long long pick = (use_final && best_fin != kInfVal) ? best_fin : best_all;
-  if (pick == kInfVal) {
+  if (BIGLM) best_wf = block_min_u64<NT>(best_wf, s_red64);
+  const bool any_final = use_final && best_fin != kInfVal;
+  const unsigned long long pick = any_final ? best_fin : best_all;
+  // extra_cost of the end token after FinalizeDecoding (inl.h:775): 0 for the plain decoder; for
+  // biglm (cost + final) - final_best with final_best taken over all tokens, so it can be positive,
+  // and beyond lattice_beam the token is pruned away (inl.h:815-816) and nothing is returned.
+  float delta = 0.f;
+  if (BIGLM && finalized && pick != kInfVal) {
+    const float with_final = any_final ? ord2f((uint32_t)(pick >> 32))
+                                       : __uint_as_float(st->tok_sc[b0 + (uint32_t)pick].y);
+    delta = with_final - ord2f((uint32_t)(best_wf >> 32));
+  }
+  if (pick == kInfVal || delta > cfg.lattice_beam) {
     if (tid == 0) {
       o_n[blockIdx.x] = 0;
       o_status[blockIdx.x] = ASRD_ERR_NO_TOKENS;
     }
     return;
   }
-  uint32_t idx = find_token(f, (uint32_t)pick);
+  const int4 no_arc = make_int4(-1, 0, 0, 0);
+  uint32_t idx = BIGLM ? b0 + (uint32_t)pick : find_token(f, (uint32_t)pick, no_arc, 0, 0.f, nullptr);
   int n_out = 0;
   int status = idx == 0xFFFFFFFFu ? ASRD_ERR_STATE : ASRD_OK;
   while (status == ASRD_OK) {
     const uint2 sc = st->tok_sc[idx];
     const uint32_t state = sc.x;
     const float cost = __uint_as_float(sc.y);
+    const uint32_t pair = BIGLM ? st->tok_lm[idx] : 0u;
     uint32_t rep = st->tok_arc[idx];
     if (n_out >= cap) {
       status = ASRD_ERR_PATH_OVERFLOW;
@@ -1106,31 +1298,47 @@ k_best_path(StreamState *const *streams, GraphView g, DecoderConfigDev cfg, int 
       status = ASRD_ERR_STATE;
       break;
     }
-    const uint32_t pidx = find_token(fp, src);
+    const float *__restrict__ ll = emitting ? st->ll_hist + (size_t)fp * st->ll_stride : nullptr;
+    const uint32_t pidx = find_token(fp, src, arc, pair, cost, ll);
     if (pidx == 0xFFFFFFFFu) {
       status = ASRD_ERR_STATE;  // broken back-trace: cannot happen unless the arena overflowed
       break;
     }
-    const float *__restrict__ ll = emitting ? st->ll_hist + (size_t)fp * st->ll_stride : nullptr;
+    const float pc = __uint_as_float(st->tok_sc[pidx].y);
+    const uint32_t ppair = BIGLM ? st->tok_lm[pidx] : 0u;
+    float graph_cost = __int_as_float(arc.z);
+    if (BIGLM && arc.y != 0) {
+      int32_t n1, n2;
+      graph_cost = __int_as_float(arc.z) + lm_step(lms, pair_map, ppair, arc.y, n1, n2);
+    }
     if (par_bit(g.par_bits, rep)) {
-      const float pc = __uint_as_float(st->tok_sc[pidx].y);
       const float nc = st->frame_nc[f];
       const uint32_t hi = emitting ? __ldg(&g.erows[src]).y : __ldg(&g.rows[src]).y;
       for (uint32_t a2 = hi; a2-- > rep + 1;) {
         const int4 arc2 = __ldg(&g.arcs[a2]);
         if (((uint32_t)arc2.w & kStateMask) != state) continue;
+        float gc2 = __int_as_float(arc2.z);
+        if (BIGLM) {  // a sibling link reaches the SAME token only if it lands on the same LM state
+          if ((arc2.y != 0) != (arc.y != 0)) continue;
+          if (arc2.y != 0) {
+            int32_t n1, n2;
+            gc2 = __int_as_float(arc2.z) + lm_step(lms, pair_map, ppair, arc2.y, n1, n2);
+            if ((((unsigned long long)(uint32_t)n1 << 32) | (uint32_t)n2) + 1ull != __ldcg(&pair_map[pair])) continue;
+          }
+        }
         float tot2;
         bool admitted;
         if (emitting) {
-          tot2 = (pc + (-ll[arc2.x - 1])) + __int_as_float(arc2.z);  // inl.h:326-329
-          admitted = tot2 < nc;                                      // inl.h:330
+          tot2 = (pc + (-ll[arc2.x - 1])) + gc2;  // inl.h:326-329
+          admitted = tot2 < nc;                    // inl.h:330
         } else {
-          tot2 = pc + __int_as_float(arc2.z);                        // inl.h:413-414
-          admitted = pc < nc && tot2 < nc;                           // inl.h:391,415
+          tot2 = pc + gc2;                         // inl.h:413-414
+          admitted = pc < nc && tot2 < nc;         // inl.h:391,415
         }
-        if (admitted && !((tot2 - cost) > cfg.lattice_beam)) {       // inl.h:524-532
+        if (admitted && !((delta + (tot2 - cost)) > cfg.lattice_beam)) {  // inl.h:524-532
           rep = a2;
           arc = arc2;
+          graph_cost = gc2;
           break;
         }
       }
@@ -1138,7 +1346,7 @@ k_best_path(StreamState *const *streams, GraphView g, DecoderConfigDev cfg, int 
     if (tid == 0) {
       o_il[ob + n_out] = arc.x;
       o_ol[ob + n_out] = arc.y;
-      o_gr[ob + n_out] = __int_as_float(arc.z);
+      o_gr[ob + n_out] = graph_cost;
       o_ac[ob + n_out] = emitting ? -ll[arc.x - 1] : 0.f;
     }
     ++n_out;

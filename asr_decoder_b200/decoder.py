@@ -137,6 +137,34 @@ class CudaFst:
             pass
 
 
+class CudaLm:
+    """Device-resident LM FSA (the reference's ``ArpaLm``/``Fsa``, newlm/arpa2fsa.h:217-480).
+    Pass the OLD LM already rescaled by -1, like the reference's bin does
+    (kaldi-hclg-my-decoder-biglm.cc:55-60)."""
+
+    def __init__(self, lm, device: int = 0):
+        L = _lib.lib()
+        an = np.ascontiguousarray(lm.states["arc_num"], np.int32)
+        bp = np.ascontiguousarray(lm.states["backoff_prob"], np.float32)
+        bi = np.ascontiguousarray(lm.states["backoff_id"], np.int32)
+        arcs = np.ascontiguousarray(lm.arcs)
+        h = C.c_void_p()
+        check(L.asrd_lm_create(lm.bos, lm.eos, len(lm.states), an.ctypes.data, bp.ctypes.data, bi.ctypes.data,
+                               arcs.ctypes.data, len(arcs), device, C.byref(h)), "asrd_lm_create")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            _lib.lib().asrd_lm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def _as_ptr_and_keep(x):
     """(device?, pointer, n_frames, stride, keepalive) for a numpy array or a torch tensor."""
     if isinstance(x, np.ndarray):
@@ -155,10 +183,13 @@ class CudaDecoderBatch:
 
     def __init__(self, graph: CudaFst, config: LatticeFasterDecoderConfig, n: int,
                  max_frames: int = 0, hash_capacity: int = 0, token_capacity: int = 0,
-                 collect_stats: bool = False):
+                 collect_stats: bool = False, old_lm: "CudaLm" = None, new_lm: "CudaLm" = None):
+        """With ``old_lm``/``new_lm`` the decoders are the biglm variant
+        (``OnlineLatticeDecoderMempoolBiglm(&fst, opt, &lm1, &lm2)``)."""
         config.Check()
         L = _lib.lib()
         self.graph = graph
+        self._lms = (old_lm, new_lm)
         self.config = config
         self.n = n
         cfg = config.to_c()
@@ -167,8 +198,12 @@ class CudaDecoderBatch:
         self._created = 0
         for i in range(n):
             h = C.c_void_p()
-            check(L.asrd_decoder_create(graph.h, C.byref(cfg), C.byref(opts), C.byref(h)),
-                  "asrd_decoder_create")
+            if old_lm is not None:
+                check(L.asrd_decoder_create_biglm(graph.h, C.byref(cfg), C.byref(opts), old_lm.h, new_lm.h,
+                                                  C.byref(h)), "asrd_decoder_create_biglm")
+            else:
+                check(L.asrd_decoder_create(graph.h, C.byref(cfg), C.byref(opts), C.byref(h)),
+                      "asrd_decoder_create")
             self.handles[i] = h
             self._created += 1
         self.collect_stats = collect_stats

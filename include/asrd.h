@@ -105,7 +105,15 @@ typedef struct {
   float graph, acoustic;
 } asrd_lat_link;
 
+/* LM FSA arc, reference FsaArc (src/newlm/arpa2fsa.h:23-30) */
+typedef struct {
+  int32_t wordid;
+  float weight;    /* natural-log probability (cost = -weight) */
+  int32_t tostateid;
+} asrd_lm_arc;
+
 typedef struct asrd_graph asrd_graph;
+typedef struct asrd_lm asrd_lm;
 typedef struct asrd_decoder asrd_decoder;
 
 const char *asrd_strerror(int status);
@@ -127,12 +135,31 @@ int asrd_graph_destroy(asrd_graph *g);
 int asrd_graph_info(const asrd_graph *g, int32_t *total_states, int64_t *total_arcs,
                     int32_t *start, int32_t *final_state, int64_t *device_bytes);
 
+/* ---- LM: replaces ArpaLm / Fsa for the biglm path (src/newlm/arpa2fsa.h:217-480) -------- */
+
+/* The arrays ArpaLm::Read loads (arpa2fsa.h:399-439, arpa2fsa.cc:70-176): per state
+ * {arc_num, backoff_prob, backoff_id}, arcs grouped by state and sorted by word; state 0 is the
+ * unigram state and MUST hold one arc per word id (direct index, arpa2fsa.h:211-214).  As in the
+ * reference the caller rescales the OLD LM by -1 first (kaldi-hclg-my-decoder-biglm.cc:55-60). */
+int asrd_lm_create(int32_t bos, int32_t eos, int32_t n_states, const int32_t *arc_num,
+                   const float *backoff_prob, const int32_t *backoff_id, const asrd_lm_arc *arcs,
+                   int64_t n_arcs, int device, asrd_lm **out);
+int asrd_lm_destroy(asrd_lm *lm);
+
 /* ---- decoder: replaces OnlineLatticeDecoderMempool behind DecoderItf ----------------- */
 
 /* OnlineLatticeDecoderBase(FST*, const LatticeFasterDecoderConfig&), online-decoder-base.h:95.
  * The graph is shared and not owned (inl.h:24, _delete_fst(false)). */
 int asrd_decoder_create(asrd_graph *g, const asrd_config *cfg, const asrd_device_options *opts,
                         asrd_decoder **out);
+/* OnlineLatticeDecoderMempoolBaseBiglm(fst, config, oldlm, newlm)
+ * (my-decoder/online-decoder-mempool-base-biglm.h:21-30): on-the-fly composition with the
+ * LM-difference of two LMs; tokens are keyed by (HCLG state, LM state pair).  DiffArpaLm is
+ * implemented with its intended semantics (both LMs advance from the members of the state
+ * pair); the reference passes the pair-state id itself (newlm/diff-lm.h:75-86), which only
+ * coincides on unigram-only LMs — SURVEY.md Appendix B-6.  GetRawLattice is not available. */
+int asrd_decoder_create_biglm(asrd_graph *g, const asrd_config *cfg, const asrd_device_options *opts,
+                              asrd_lm *old_lm, asrd_lm *new_lm, asrd_decoder **out);
 int asrd_decoder_destroy(asrd_decoder *d);
 
 /* DecoderItf::InitDecoding (decoder-itf.h:15; inl.h:41-67), batched over n handles.

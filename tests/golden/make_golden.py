@@ -36,7 +36,42 @@ CASES = {
 }
 
 
+BIGLM_CASES = {
+    # unigram-only LM pair: the fixture on which the reference's DiffArpaLm::GetArc state-argument
+    # quirk is harmless, so bit-identity with the reference is meaningful
+    "b1": (dict(n_states=2000, avg_deg=5.0, n_pdfs=100, seed=12, n_words=50, eps_span=200),
+           [(80, 2.0, 4), (40, 2.5, 5)], dict(beam=13.0, max_active=2000, min_active=200, lattice_beam=8.0),
+           (50, 1, 2, 1)),   # (n_words, lm1 seed, lm2 seed, order)
+}
+
+
+def make_biglm():
+    from asr_decoder_b200 import lm as LM
+    for name, (gkw, utts, cfg, (nw, s1, s2, order)) in BIGLM_CASES.items():
+        fst = synth.make_graph(**gkw)
+        lls = [synth.make_loglikes(t, gkw["n_pdfs"], sig, seed=sd) for (t, sig, sd) in utts]
+        gp, lp = os.path.join(HERE, name + ".fst"), os.path.join(HERE, name + ".llb")
+        l1p, l2p = os.path.join(HERE, name + ".lm1"), os.path.join(HERE, name + ".lm2")
+        fstio.write_fst(gp, fst)
+        fstio.write_loglikes(lp, lls)
+        LM.write_lm(l1p, LM.make_lm(nw, seed=s1, order=order))
+        LM.write_lm(l2p, LM.make_lm(nw, seed=s2, order=order))
+        runs = {str(hr): O.run_ref_biglm(gp, lp, l1p, l2p, hash_ratio=hr, **cfg) for hr in (2.0, 1.0, 1.1)}
+        base = runs["2.0"]
+        stable = [all(runs[k][i]["words"] == base[i]["words"] and runs[k][i]["ali"] == base[i]["ali"] and
+                      runs[k][i]["tot_bits"] == base[i]["tot_bits"] for k in runs) for i in range(len(base))]
+        out = {"generator": "oracle/_ref/ref_decode_biglm (compiled reference OnlineLatticeDecoderMempoolBiglm)",
+               "config": cfg, "graph": gkw, "utts": utts, "lm": {"n_words": nw, "seeds": [s1, s2], "order": order},
+               "self_stable": stable, "reference": base,
+               "other_orders": {k: v for k, v in runs.items() if k != "2.0"}}
+        with open(os.path.join(HERE, name + ".json"), "w") as f:
+            json.dump(out, f)
+        print(name, "self_stable", stable, "tot", [r["tot"] for r in base])
+
+
 def main():
+    if O.have_ref_biglm():
+        make_biglm()
     if not O.have_ref():
         raise SystemExit("oracle/_ref/ref_decode missing: run `make -C oracle ref` where /root/reference exists")
     for name, (gkw, utts, cfg) in CASES.items():
