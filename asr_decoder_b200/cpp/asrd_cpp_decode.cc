@@ -50,7 +50,7 @@ unsigned Bits(float f) {
 }  // namespace
 
 int main(int argc, char **argv) {
-  std::string graph, loglikes;
+  std::string graph, loglikes, lm1f, lm2f;
   LatticeFasterDecoderConfig cfg;
   cfg._beam = 13.0f; cfg._max_active = 7000; cfg._min_active = 200; cfg._lattice_beam = 8.0f;
   int chunk = 0;
@@ -68,6 +68,8 @@ int main(int argc, char **argv) {
     else if (k == "--chunk") chunk = atoi(v.c_str());
     else if (k == "--pull") pull = true;
     else if (k == "--lattice") lattice = true;
+    else if (k == "--lm1") lm1f = v;
+    else if (k == "--lm2") lm2f = v;
     else { fprintf(stderr, "unknown arg %s\n", a.c_str()); return 2; }
   }
   FILE *fp = fopen(loglikes.c_str(), "rb");
@@ -86,8 +88,12 @@ int main(int argc, char **argv) {
   try {
     CudaFst fst;
     if (!fst.ReadFst(graph.c_str())) { fprintf(stderr, "load fst error.\n"); return 4; }
-    CudaLatticeDecoder decoder(&fst, cfg, max_t + 8);
-    DecoderItf *decode = &decoder;  // everything below goes through the reference interface
+    CudaLm lm1, lm2;  // kaldi-hclg-my-decoder-biglm.cc:55-60: lm1.Read, lm2.Read, lm1.Rescale(-1.0)
+    const bool biglm = !lm1f.empty();
+    if (biglm && (!lm1.Read(lm1f.c_str(), -1.0f) || !lm2.Read(lm2f.c_str()))) { fprintf(stderr, "load lm error.\n"); return 4; }
+    CudaLatticeDecoder plain(&fst, cfg, max_t + 8);
+    CudaLatticeDecoder rescoring(&fst, cfg, biglm ? &lm1 : NULL, biglm ? &lm2 : NULL, max_t + 8);
+    DecoderItf *decode = biglm ? &rescoring : &plain;  // everything below goes through the reference interface
     for (int i = 0; i < n; ++i) {
       decode->InitDecoding();
       PullDecodable pd(&utts[i]);

@@ -5,9 +5,49 @@
 
 namespace asrd_host {
 
+bool CudaLm::Read(const char *file, float scale, int device) {
+  FILE *fp = fopen(file, "rb");
+  if (!fp) return false;
+  int32_t hdr[3];
+  size_t n_orders = 0;
+  bool ok = fread(hdr, 4, 3, fp) == 3 && fread(&n_orders, sizeof(size_t), 1, fp) == 1 && n_orders < 64;
+  std::vector<int32_t> counts(n_orders);
+  ok = ok && fread(counts.data(), 4, n_orders, fp) == n_orders;
+  int32_t n_states = 0, n_arcs = 0;
+  ok = ok && fread(&n_states, 4, 1, fp) == 1 && n_states > 0;
+  struct Info { int32_t arc_num; float backoff_prob; int32_t backoff_id; };
+  std::vector<Info> info(ok ? n_states : 0);
+  ok = ok && fread(info.data(), sizeof(Info), n_states, fp) == (size_t)n_states;
+  ok = ok && fread(&n_arcs, 4, 1, fp) == 1 && n_arcs > 0;
+  std::vector<asrd_lm_arc> arcs(ok ? n_arcs : 0);
+  ok = ok && fread(arcs.data(), sizeof(asrd_lm_arc), n_arcs, fp) == (size_t)n_arcs;
+  fclose(fp);
+  if (!ok) return false;
+  std::vector<int32_t> an(n_states), bi(n_states);
+  std::vector<float> bp(n_states);
+  for (int32_t i = 0; i < n_states; ++i) {
+    an[i] = info[i].arc_num;
+    bp[i] = info[i].backoff_prob * scale;  // Fsa::Rescale, arpa2fsa.cc:264-276
+    bi[i] = info[i].backoff_id;
+  }
+  for (int32_t a = 0; a < n_arcs; ++a) arcs[a].weight *= scale;
+  return FromArrays(hdr[0], hdr[1], n_states, an.data(), bp.data(), bi.data(), arcs.data(), n_arcs, device);
+}
+
 CudaLatticeDecoder::CudaLatticeDecoder(CudaFst *graph, const LatticeFasterDecoderConfig &config, int max_frames,
                                        void *cuda_stream)
     : d_(NULL), stream_(cuda_stream), finalized_(false) {
+  Create(graph, config, NULL, NULL, max_frames);
+}
+
+CudaLatticeDecoder::CudaLatticeDecoder(CudaFst *graph, const LatticeFasterDecoderConfig &config, CudaLm *oldlm,
+                                       CudaLm *newlm, int max_frames, void *cuda_stream)
+    : d_(NULL), stream_(cuda_stream), finalized_(false) {
+  Create(graph, config, oldlm, newlm, max_frames);
+}
+
+void CudaLatticeDecoder::Create(CudaFst *graph, const LatticeFasterDecoderConfig &config, CudaLm *oldlm,
+                                CudaLm *newlm, int max_frames) {
   config.Check();
   asrd_config c;
   c.beam = config._beam;
@@ -21,7 +61,11 @@ CudaLatticeDecoder::CudaLatticeDecoder(CudaFst *graph, const LatticeFasterDecode
   asrd_device_options o = asrd_device_options();
   o.max_frames = max_frames;
   o.collect_stats = 1;
-  Check(asrd_decoder_create(graph ? graph->handle() : NULL, &c, &o, &d_), "asrd_decoder_create");
+  if (oldlm || newlm)
+    Check(asrd_decoder_create_biglm(graph ? graph->handle() : NULL, &c, &o, oldlm ? oldlm->handle() : NULL,
+                                    newlm ? newlm->handle() : NULL, &d_), "asrd_decoder_create_biglm");
+  else
+    Check(asrd_decoder_create(graph ? graph->handle() : NULL, &c, &o, &d_), "asrd_decoder_create");
 }
 
 CudaLatticeDecoder::~CudaLatticeDecoder() { asrd_decoder_destroy(d_); }

@@ -41,10 +41,37 @@ class CudaFst {
   asrd_graph *g_;
 };
 
+// Device-resident LM FSA: what replaces `ArpaLm` (newlm/arpa2fsa.h:217-480) for the biglm decoder.
+// The caller rescales the OLD LM by -1 before uploading, as the reference bin does
+// (kaldi-nnet3bin/kaldi-hclg-my-decoder-biglm.cc:55-60: lm1.Rescale(-1.0)).
+class CudaLm {
+ public:
+  CudaLm() : lm_(NULL) {}
+  ~CudaLm() { asrd_lm_destroy(lm_); }
+  // the arrays ArpaLm::Read loads (arpa2fsa.h:399-439)
+  bool FromArrays(int32_t bos, int32_t eos, int32_t n_states, const int32_t *arc_num, const float *backoff_prob,
+                  const int32_t *backoff_id, const asrd_lm_arc *arcs, int64_t n_arcs, int device = 0) {
+    asrd_lm_destroy(lm_);
+    lm_ = NULL;
+    return asrd_lm_create(bos, eos, n_states, arc_num, backoff_prob, backoff_id, arcs, n_arcs, device, &lm_) == ASRD_OK;
+  }
+  // ArpaLm::Read(const char*) file format; `scale` = the Rescale() factor applied while loading
+  bool Read(const char *file, float scale = 1.0f, int device = 0);
+  asrd_lm *handle() const { return lm_; }
+
+ private:
+  CudaLm(const CudaLm &);
+  CudaLm &operator=(const CudaLm &);
+  asrd_lm *lm_;
+};
+
 class CudaLatticeDecoder : public DecoderItf {
  public:
   CudaLatticeDecoder(CudaFst *graph, const LatticeFasterDecoderConfig &config, int max_frames = 0,
                      void *cuda_stream = NULL);
+  // biglm: OnlineLatticeDecoderMempoolBaseBiglm(fst, config, oldlm, newlm) (…-biglm.h:21-30)
+  CudaLatticeDecoder(CudaFst *graph, const LatticeFasterDecoderConfig &config, CudaLm *oldlm, CudaLm *newlm,
+                     int max_frames = 0, void *cuda_stream = NULL);
   virtual ~CudaLatticeDecoder();
 
   virtual void InitDecoding();
@@ -67,6 +94,7 @@ class CudaLatticeDecoder : public DecoderItf {
  private:
   void Check(int status, const char *what) const;  // LOG_ERR -> throw std::runtime_error
   void Upload(AmInterface *decodable, int32 first, int32 count);
+  void Create(CudaFst *graph, const LatticeFasterDecoderConfig &config, CudaLm *oldlm, CudaLm *newlm, int max_frames);
   asrd_decoder *d_;
   void *stream_;
   bool finalized_;

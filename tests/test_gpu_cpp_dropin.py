@@ -55,3 +55,17 @@ def test_get_raw_lattice_through_decoder_itf(oracle_mod):
         nt, nl = d.counts()
         assert (r["raw_states"], r["raw_arcs"]) == (nt, nl)
         assert r["raw_finals"] >= 1
+
+
+def test_biglm_through_decoder_itf():
+    """The C++ drop-in in its biglm form (constructor (fst, config, oldlm, newlm), LM files in the
+    reference's ArpaLm::Read format, old LM rescaled by -1) against the compiled biglm reference."""
+    meta = json.load(open(os.path.join(GOLD, "b1.json")))
+    cfg = meta["config"]
+    cmd = [BIN, f"--graph={GOLD}/b1.fst", f"--loglikes={GOLD}/b1.llb", f"--lm1={GOLD}/b1.lm1", f"--lm2={GOLD}/b1.lm2",
+           f"--beam={cfg['beam']}", f"--max-active={cfg['max_active']}", f"--min-active={cfg['min_active']}",
+           f"--lattice-beam={cfg['lattice_beam']}", "--chunk=25"]
+    out = subprocess.run(cmd, check=True, stdout=subprocess.PIPE).stdout.decode()
+    res = [json.loads(l) for l in out.splitlines() if l.startswith("{")]
+    for r, ref in zip(res, meta["reference"]):
+        assert r["ok"] and r["words"] == ref["words"] and r["ali"] == ref["ali"] and r["tot_bits"] == ref["tot_bits"]
