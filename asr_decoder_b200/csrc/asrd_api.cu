@@ -34,7 +34,7 @@ thread_local std::string g_last_error;
 constexpr int kHostChunkFrames = 16;
 
 // per-device side stream + events for overlapping host->device staging with the search
-constexpr int kMaxWorkers = 8;
+constexpr int kMaxWorkers = 32;
 struct DeviceCtx {
   cudaStream_t copy_stream = nullptr;
   cudaStream_t worker[kMaxWorkers] = {nullptr};

@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-utts", type=int, default=0, help="0 = 2 x host cores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--hash-capacity", type=int, default=0, help="0 = library default (8 x max-active)")
     return ap.parse_args()
 
 
@@ -219,7 +220,7 @@ def run_b200_arm(a):
                                      lattice_beam=a.lattice_beam)
     graph = CudaFst(fst, device=local)
     tok_cap = int(min(max(a.frames + 2, 64) * 12000, 1 << 23))
-    batch = CudaDecoderBatch(graph, cfg, n, max_frames=T + 8, token_capacity=tok_cap)
+    batch = CudaDecoderBatch(graph, cfg, n, max_frames=T + 8, token_capacity=tok_cap, hash_capacity=a.hash_capacity)
     stream = torch.cuda.current_stream().cuda_stream
 
     def ptr_arrays(base_ptr, row_stride_elems):
