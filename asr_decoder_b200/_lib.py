@@ -21,7 +21,7 @@ SYMBOLS = [
     "asrd_init_decoding", "asrd_advance_decoding", "asrd_finalize_decoding",
     "asrd_num_frames_decoded", "asrd_get_best_path", "asrd_path_to_vector",
     "asrd_frame_stats", "asrd_decoder_status", "asrd_synchronize",
-    "asrd_host_alloc", "asrd_host_free", "asrd_launch_count",
+    "asrd_host_alloc", "asrd_host_free", "asrd_launch_count", "asrd_last_fallback_frames", "asrd_last_phase_cycles",
     "asrd_get_raw_lattice", "asrd_get_counters", "asrd_profile_enable", "asrd_profile_reset", "asrd_profile_get",
 ]
 
@@ -105,6 +105,7 @@ def lib():
     L.asrd_host_alloc.argtypes = [C.POINTER(vp), i64]
     L.asrd_host_free.argtypes = [vp]
     L.asrd_launch_count.restype = i64
+    L.asrd_last_fallback_frames.restype = i64
     L.asrd_get_counters.argtypes = [vp, i32, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), vp]
     L.asrd_profile_enable.argtypes = [C.c_int]
     L.asrd_profile_get.argtypes = [C.POINTER(C.c_double), C.POINTER(i64)]

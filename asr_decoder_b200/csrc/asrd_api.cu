@@ -110,6 +110,9 @@ struct Profiler {
   }
 };
 
+int64_t g_last_fallback_frames = 0;
+int64_t g_last_phase_cycles[6] = {0, 0, 0, 0, 0, 0};
+
 int EnvInt(const char *name, int dflt) {
   const char *v = getenv(name);
   return v && *v ? atoi(v) : dflt;
@@ -125,6 +128,11 @@ int EnsureDevice(int device) {
     return ASRD_ERR_CUDA;
   }
   if (device < 0 || device >= n) return ASRD_ERR_BAD_ARG;
+  // a non-sticky error left behind by an earlier, unrelated runtime call must not be blamed on
+  // the launches of this entry point
+  const cudaError_t stale = cudaGetLastError();
+  if (stale != cudaSuccess && EnvInt("ASRD_TRACE", 0))
+    fprintf(stderr, "[asrd] discarding stale CUDA error: %s\n", cudaGetErrorString(stale));
   CU_CHECK(cudaSetDevice(device));
   if (!g_num_sms) {
     cudaDeviceProp p;
@@ -259,6 +267,35 @@ int PlanExpand(int n_streams, int num_indices, bool biglm, ExpandPlan *plan) {
   return ASRD_OK;
 }
 
+
+typedef void (*StreamFn)(StreamState *const *, const AdvanceParams *, GraphView, DecoderConfigDev, int);
+
+struct StreamPlan {
+  StreamFn fn = nullptr;  // null: use the k_expand / k_post pair
+  size_t dyn = 0;
+};
+
+// The on-chip frame loop (k_stream) serves plain decoders whose log-likelihood row fits next to
+// the shared-memory map; everything else runs the HBM-map kernels.
+int PlanStream(int num_indices, bool biglm, StreamPlan *plan) {
+  plan->fn = nullptr;
+  if (biglm || !EnvInt("ASRD_STREAM_KERNEL", 1)) return ASRD_OK;
+  const size_t map_bytes = (size_t)kSmemSlots * 13;
+  cudaFuncAttributes fa;
+  CU_CHECK(cudaFuncGetAttributes(&fa, k_stream<1, true>));
+  int dev = 0, max_optin = 0;
+  CU_CHECK(cudaGetDevice(&dev));
+  CU_CHECK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  const size_t room = (size_t)max_optin > fa.sharedSizeBytes + map_bytes ? (size_t)max_optin - fa.sharedSizeBytes - map_bytes : 0;
+  if ((size_t)max_optin < fa.sharedSizeBytes + map_bytes) return ASRD_OK;
+  const bool smem_ll = (size_t)num_indices * 4 <= room;
+  const int u = EnvInt("ASRD_STREAM_U", 2);
+  if (smem_ll) plan->fn = u >= 2 ? k_stream<2, true> : k_stream<1, true>;
+  else plan->fn = u >= 2 ? k_stream<2, false> : k_stream<1, false>;
+  plan->dyn = map_bytes + (smem_ll ? (size_t)num_indices * 4 : 0);
+  CU_CHECK(cudaFuncSetAttribute(plan->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->dyn));
+  return ASRD_OK;
+}
 
 }  // namespace
 
@@ -702,6 +739,8 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
   std::vector<ExpandPlan> plans(n_sub);
   for (int b = 0; b < n_sub; ++b)
     if ((rc = PlanExpand(std::min(sub, n - b * sub), num_indices, biglm, &plans[b]))) return rc;
+  StreamPlan splan;
+  if ((rc = PlanStream(num_indices, biglm, &splan))) return rc;
 
   // Host log-likelihoods: staged chunk by chunk through two device buffers, copied on a
   // side stream so the H2D of chunk k+1 overlaps the search of chunk k.
@@ -785,6 +824,19 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
     for (int w = 0; w < (single ? 0 : n_workers); ++w) CU_CHECK(cudaStreamWaitEvent(ctx->worker[w], ev_rows[k], 0));
     int32_t max_steps = 0;
     for (int b = 0; b < n_sub; ++b) max_steps = std::max(max_steps, steps_of[(size_t)k * n_sub + b]);
+    if (splan.fn) {  // on-chip frame loop: one launch per sub-batch carries the whole chunk
+      for (int b = 0; b < n_sub; ++b) {
+        if (steps_of[(size_t)k * n_sub + b] == 0) continue;
+        cudaStream_t ws = single ? s : ctx->worker[b % n_workers];
+        const int nb = std::min(sub, n - b * sub);
+        prof.Begin(2, ws);
+        splan.fn<<<nb, kStreamThreads, splan.dyn, ws>>>(d_streams + (size_t)b * sub, d_params + (size_t)k * n + (size_t)b * sub, gv, cfg,
+                                                         num_indices);
+        prof.End(ws);
+        ++g_launches;
+      }
+      max_steps = 0;
+    }
     for (int32_t f = -1; f < max_steps; ++f) {
       for (int b = 0; b < n_sub; ++b) {
         const int32_t steps = steps_of[(size_t)k * n_sub + b];
@@ -1073,17 +1125,25 @@ int asrd_get_counters(asrd_decoder *const *decs, int32_t n, int64_t *arcs_expand
   StreamState **d_streams;
   if ((rc = UploadStreams(decs, n, s, sc, &d_streams))) return rc;
   unsigned long long *d_out;
-  CU_CHECK(sc.Alloc(&d_out, 3));
-  CU_CHECK(cudaMemsetAsync(d_out, 0, 24, s));
+  CU_CHECK(sc.Alloc(&d_out, 10));
+  CU_CHECK(cudaMemsetAsync(d_out, 0, 80, s));
   k_counters<<<(n + 127) / 128, 128, 0, s>>>(d_streams, n, d_out);
   ++g_launches;
-  unsigned long long h[3];
-  CU_CHECK(cudaMemcpyAsync(h, d_out, 24, cudaMemcpyDeviceToHost, s));
+  unsigned long long h[10];
+  CU_CHECK(cudaMemcpyAsync(h, d_out, 80, cudaMemcpyDeviceToHost, s));
   CU_CHECK(cudaStreamSynchronize(s));
   if (arcs_expanded) *arcs_expanded = (int64_t)h[0];
   if (arcs_admitted) *arcs_admitted = (int64_t)h[1];
   if (tokens) *tokens = (int64_t)h[2];
+  g_last_fallback_frames = (int64_t)h[3];
+  for (int k = 0; k < 6; ++k) g_last_phase_cycles[k] = (int64_t)h[4 + k];
   return ASRD_OK;
+}
+
+int64_t asrd_last_fallback_frames(void) { return g_last_fallback_frames; }
+
+void asrd_last_phase_cycles(int64_t *out6) {
+  for (int k = 0; k < 6; ++k) out6[k] = g_last_phase_cycles[k];
 }
 
 int asrd_synchronize(void *stream) {

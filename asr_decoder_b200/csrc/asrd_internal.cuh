@@ -93,6 +93,8 @@ struct StreamState {
   // ---- utterance totals
   unsigned long long tot_arcs_expanded;
   unsigned long long tot_arcs_admitted;
+  unsigned long long tot_fallback_frames;  // frames k_stream had to redo through the HBM map
+  unsigned long long phase_cycles[6];      // k_stream: SM cycles per phase (cutoff, row, expand, closure, write-out, fallback)
 };
 
 // Per-stream descriptor of the frame step in flight: everything the grid-wide kernels need, in

@@ -332,7 +332,8 @@ k_init(StreamState *const *streams, FrameDesc *desc, GraphView g, DecoderConfigD
     st->frame_off[0] = 0;
     st->n_cur = 0;
     st->best64 = kInfVal;
-    st->tot_arcs_expanded = st->tot_arcs_admitted = 0;
+    st->tot_arcs_expanded = st->tot_arcs_admitted = st->tot_fallback_frames = 0;
+    for (int k = 0; k < 6; ++k) st->phase_cycles[k] = 0;
     uint32_t slot;
     bool is_new;
     HashEntry *hn = st->hash;
@@ -411,23 +412,16 @@ k_begin_advance(StreamState *const *streams, const AdvanceParams *params, int nu
 // in flight per iteration.  The stream's log-likelihood row is staged in shared memory once
 // per CTA (the only block barrier).  Token recombination: one 64-bit atomicMin per admitted
 // arc on (ordered cost << 32 | arc id) in the per-frame state->token map.
+// Body of the expansion: warp `warp_global` of `n_warps` walks the token groups of the frame
+// described by *d (global or shared memory).  s_ll: the frame's log-likelihood row in shared
+// memory (SMEM_LL) or unused.
 template <int U, bool SMEM_LL, bool BIGLM>
-__global__ void __launch_bounds__(kExpandThreads, (U == 1 && !BIGLM) ? 8 : 5)
-k_expand(FrameDesc *desc, GraphView g, int num_indices, int flags, LmPair lms) {
-  extern __shared__ float s_ll[];
-  FrameDesc *d = &desc[blockIdx.y];
-  if (!d->stepping) return;
+__device__ __forceinline__ void expand_frame(FrameDesc *d, const GraphView &g, const float *s_ll,
+                                             uint32_t warp_global, uint32_t n_warps, int flags, const LmPair &lms) {
   const uint32_t n_cur = d->n_cur;
   const uint32_t n_groups = (n_cur + 31) >> 5;
-  const int tid = threadIdx.x, lane = tid & 31;
-  const uint32_t warp_global = blockIdx.x * (kExpandThreads / 32) + (tid >> 5);
-  const uint32_t n_warps = gridDim.x * (kExpandThreads / 32);
-  if (blockIdx.x * (kExpandThreads / 32) >= n_groups) return;  // whole CTA idle
+  const int lane = threadIdx.x & 31;
   const float *__restrict__ ll = d->ll;
-  if (SMEM_LL) {
-    for (int c = tid; c < num_indices; c += kExpandThreads) s_ll[c] = __ldg(&ll[c]);
-    __syncthreads();
-  }
   const uint2 *__restrict__ toks = d->toks;
   const float cur_cut = d->cur_cut, abeam = d->abeam;
   HashEntry *hn = d->hn;
@@ -444,14 +438,15 @@ k_expand(FrameDesc *desc, GraphView g, int num_indices, int flags, LmPair lms) {
   for (uint32_t grp = warp_global; grp < n_groups; grp += n_warps) {
     // running cutoff (inl.h:330), refreshed once per group; our own tightenings are applied
     // locally below, other warps' arrive with the next group
-    float nc = ord2f(__ldcg(next_cut));
+    float nc = ord2f(*reinterpret_cast<volatile uint32_t *>(next_cut));  // (*d may live in shared memory)
     // ---- lane i: token i of the group and its emitting span
     const uint32_t i = grp * 32 + lane;
     uint32_t deg = 0, base = 0, cost_bits = 0, my_pair = 0;
     if (i < n_cur) {
-      const uint2 sc = hints ? ldg_u2(&toks[i], pol_stream) : __ldg(&toks[i]);
+      // (L2 loads, not ld.global.nc: inside k_stream the tokens were written by this very kernel)
+      const uint2 sc = hints ? ldg_u2(&toks[i], pol_stream) : __ldcg(&toks[i]);
       cost_bits = sc.y;
-      if (BIGLM) my_pair = __ldg(&toks_lm[i]);
+      if (BIGLM) my_pair = __ldcg(&toks_lm[i]);
       if (__uint_as_float(sc.y) <= cur_cut) {  // inclusive, inl.h:315
         const uint2 er = hints ? ldg_u2(&g.erows[sc.x], pol_graph) : __ldg(&g.erows[sc.x]);
         base = er.x;
@@ -553,6 +548,24 @@ k_expand(FrameDesc *desc, GraphView g, int num_indices, int flags, LmPair lms) {
     atomicAdd(&d->arcs_expanded, expanded);
     atomicAdd(&d->arcs_admitted, admitted);
   }
+}
+
+template <int U, bool SMEM_LL, bool BIGLM>
+__global__ void __launch_bounds__(kExpandThreads, (U == 1 && !BIGLM) ? 8 : 5)
+k_expand(FrameDesc *desc, GraphView g, int num_indices, int flags, LmPair lms) {
+  extern __shared__ float s_ll[];
+  FrameDesc *d = &desc[blockIdx.y];
+  if (!d->stepping) return;
+  const uint32_t n_groups = (d->n_cur + 31) >> 5;
+  const int tid = threadIdx.x;
+  if (blockIdx.x * (kExpandThreads / 32) >= n_groups) return;  // whole CTA idle
+  if (SMEM_LL) {
+    const float *__restrict__ ll = d->ll;
+    for (int c = tid; c < num_indices; c += kExpandThreads) s_ll[c] = __ldg(&ll[c]);
+    __syncthreads();
+  }
+  expand_frame<U, SMEM_LL, BIGLM>(d, g, s_ll, blockIdx.x * (kExpandThreads / 32) + (tid >> 5),
+                                  gridDim.x * (kExpandThreads / 32), flags, lms);
 }
 
 // ------------------------------------------------------------------ cutoff
@@ -728,22 +741,58 @@ __device__ __forceinline__ void cutoff_prologue(StreamState *st, FrameDesc *d, c
 // carries it from the eps closure to the descriptor of the next expansion without going back
 // to the host-visible launch queue (three launches and their descriptor round trips saved).
 // The survivor counter and the best token live in shared memory instead of global atomics.
-template <bool BIGLM>
-__global__ void __launch_bounds__(kStreamThreads, BIGLM ? 1 : 2)
-k_post(StreamState *const *streams, FrameDesc *desc, GraphView g, DecoderConfigDev cfg, int mode, LmPair lms) {
-  constexpr int NT = kStreamThreads;
-  __shared__ unsigned long long s_red64[NT / 32];
-  __shared__ uint32_t s_red32[NT / 32];
-  __shared__ uint32_t s_hist[256];
-  __shared__ uint32_t s_misc[4];
-  __shared__ uint32_t s_qn[2];
-  __shared__ uint32_t s_alive;
-  __shared__ unsigned long long s_best;
-  StreamState *st = streams[blockIdx.x];
-  FrameDesc *d = &desc[blockIdx.x];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+struct PostSmem {  // block-level scratch of the per-stream phases
+  unsigned long long red64[kStreamThreads / 32];
+  unsigned long long best;
+  uint32_t red32[kStreamThreads / 32];
+  uint32_t hist[256];
+  uint32_t misc[4];
+  uint32_t qn[2];
+  uint32_t alive;
+};
 
-  if ((mode & kModeEpi) && d->stepping) {
+// Frame bookkeeping once the survivors of frame t+1 are in the arena (thread 0 only).
+__device__ __forceinline__ void frame_commit(StreamState *st, FrameDesc *d, const DecoderConfigDev &cfg, float nc,
+                                             uint32_t n_alive, unsigned long long b64) {
+  const int t = d->t;
+  if (n_alive > d->out_cap) {
+    n_alive = d->out_cap;
+    atomicMin(&st->status, ASRD_ERR_ARENA_OVERFLOW);
+  }
+  const uint32_t out_base = st->frame_off[t + 1];
+  if (cfg.collect_stats && st->stats) {
+    asrd_frame_stat fs;
+    fs.n_in = d->n_cur;
+    fs.cur_cutoff = d->cur_cut;
+    fs.abeam = d->abeam;
+    fs.next_cutoff = nc;
+    fs.n_tokens = n_alive;
+    fs.best = b64 == kInfVal ? CUDART_INF_F : ord2f((uint32_t)(b64 >> 32));
+    fs.arcs_expanded = d->arcs_expanded;
+    fs.arcs_admitted = d->arcs_admitted;
+    st->stats[t + 1] = fs;
+  }
+  st->tot_arcs_expanded += d->arcs_expanded;
+  st->tot_arcs_admitted += d->arcs_admitted;
+  st->frame_off[t + 2] = out_base + n_alive;
+  st->frame_nc[t + 1] = nc;
+  st->frame = t + 1;
+  st->n_cur = n_alive;
+  st->best64 = b64;
+  d->stepping = 0;
+}
+
+// Eps closure + survivors -> arena + bookkeeping of the frame described by *d, over the
+// stream's map in HBM.  Whole-CTA device function (kStreamThreads threads).
+template <bool BIGLM>
+__device__ __forceinline__ void post_epilogue(StreamState *st, FrameDesc *d, const GraphView &g,
+                                              const DecoderConfigDev &cfg, const LmPair &lms, PostSmem &ps) {
+  constexpr int NT = kStreamThreads;
+  uint32_t *s_qn = ps.qn;
+  uint32_t &s_alive = ps.alive;
+  unsigned long long &s_best = ps.best;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  {
     const int t = d->t;
     const uint32_t mask = d->mask, shift = d->shift;
     const uint32_t groups = (mask + 1) >> 10;
@@ -896,39 +945,396 @@ k_post(StreamState *const *streams, FrameDesc *desc, GraphView g, DecoderConfigD
       if (lane == 0 && best64 != kInfVal) atomicMin(&s_best, best64);
     }
     __syncthreads();
-    if (tid == 0) {
-      uint32_t n_alive = s_alive;
-      if (n_alive > d->out_cap) {
-        n_alive = d->out_cap;
-        atomicMin(&st->status, ASRD_ERR_ARENA_OVERFLOW);
-      }
-      const unsigned long long b64 = s_best;
-      const uint32_t out_base = st->frame_off[t + 1];
-      if (cfg.collect_stats && st->stats) {
-        asrd_frame_stat fs;
-        fs.n_in = d->n_cur;
-        fs.cur_cutoff = d->cur_cut;
-        fs.abeam = d->abeam;
-        fs.next_cutoff = nc;
-        fs.n_tokens = n_alive;
-        fs.best = b64 == kInfVal ? CUDART_INF_F : ord2f((uint32_t)(b64 >> 32));
-        fs.arcs_expanded = d->arcs_expanded;
-        fs.arcs_admitted = d->arcs_admitted;
-        st->stats[t + 1] = fs;
-      }
-      st->tot_arcs_expanded += d->arcs_expanded;
-      st->tot_arcs_admitted += d->arcs_admitted;
-      st->frame_off[t + 2] = out_base + n_alive;
-      st->frame_nc[t + 1] = nc;
-      st->frame = t + 1;
-      st->n_cur = n_alive;
-      st->best64 = b64;
-      d->stepping = 0;
-    }
+    if (tid == 0) frame_commit(st, d, cfg, nc, s_alive, s_best);
     __syncthreads();
   }
+}
 
-  if (mode & kModePro) cutoff_prologue<NT, BIGLM>(st, d, g, cfg, lms, s_red64, s_red32, s_hist, s_misc);
+template <bool BIGLM>
+__global__ void __launch_bounds__(kStreamThreads, BIGLM ? 1 : 2)
+k_post(StreamState *const *streams, FrameDesc *desc, GraphView g, DecoderConfigDev cfg, int mode, LmPair lms) {
+  __shared__ PostSmem ps;
+  StreamState *st = streams[blockIdx.x];
+  FrameDesc *d = &desc[blockIdx.x];
+  if ((mode & kModeEpi) && d->stepping) post_epilogue<BIGLM>(st, d, g, cfg, lms, ps);
+  if (mode & kModePro) cutoff_prologue<kStreamThreads, BIGLM>(st, d, g, cfg, lms, ps.red64, ps.red32, ps.hist, ps.misc);
+}
+
+// ------------------------------------------------------------------ on-chip frame loop
+
+// k_stream: ONE CTA per stream runs the whole frame loop of an AdvanceDecoding call with the
+// per-frame state->token map in SHARED memory (the stream's private recombination state never
+// leaves the SM): GetCutoff + pre-pass, emitting expansion, eps closure and the survivor
+// write-out of every frame without going back to the launch queue.  HBM traffic per frame is
+// what the search really needs — arc records, row offsets, the previous frame's tokens, the
+// log-likelihood row — plus the append of the survivors to the token arena; the map's random
+// 32-byte sectors (the DRAM row-activation bound of the k_expand/k_post path) are gone.
+// A frame whose distinct destination states exceed the on-chip capacity is redone through the
+// HBM map of the stream by the same CTA (expand_frame + post_epilogue), so results never depend
+// on which path ran.  Plain (non-biglm) decoders only.
+constexpr int kSmemLog2 = 14;
+constexpr uint32_t kSmemSlots = 1u << kSmemLog2;
+constexpr uint32_t kSmemClaimLimit = kSmemSlots - 2 * kStreamThreads - 256;  // every thread may overshoot by U claims
+
+struct SmemMap {
+  unsigned long long *val;  // (ordered cost << 32) | arc id, kInfVal when free
+  uint32_t *key;            // state | kDestEpsBit, kEmptyKey when free
+  uint8_t *round;           // eps-closure round in which the slot has to be relaxed (0 = none)
+  uint32_t *claims;
+  uint32_t *overflow;
+  uint32_t claim_limit;
+};
+
+__device__ __forceinline__ uint4 lds_volatile_u4(const uint32_t *p) {
+  uint4 r;
+  asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "r"((uint32_t)__cvta_generic_to_shared(p)));
+  return r;
+}
+
+// FindOrAddToken (inl.h:88-136) on the on-chip map, called by the FULL warp: lanes with `act`
+// relax destination dstw (= state | kDestEpsBit) with value pk.
+// The key array is probed in BUCKETS of four slots (one 16-byte shared load compares four keys;
+// double hashing between buckets): heavy frames fill the map to 85 %, where slot-wise linear
+// probing needs ~20 probes per insert and the slowest lane of the warp many more.  The probe
+// loop is warp-uniform (a per-lane loop ran at 3 active threads per instruction); new claims are
+// counted once per call.  A key lives in the first bucket of its probe sequence that had a free
+// slot when it was inserted; slots are never freed within a frame, so a lookup may stop at the
+// first bucket that still has one.  Lanes give up when the claim budget is exhausted (the frame
+// is then redone through HBM).
+__device__ __forceinline__ void smem_relax(const SmemMap &m, bool act, uint32_t dstw, unsigned long long pk,
+                                           uint32_t next_round, uint32_t *s_any, int lane) {
+  constexpr uint32_t kBuckets = kSmemSlots / 4;
+  const uint32_t hsh = (dstw & kStateMask) * 0x9E3779B1u;
+  uint32_t b = hsh >> (32 - kSmemLog2 + 2);
+  const uint32_t step = (hsh >> 3) | 1u;  // odd: the sequence visits every bucket
+  bool pend = act;
+  uint32_t slot = 0xFFFFFFFFu, nclaim = 0;
+  while (__any_sync(kFull, pend)) {
+    if (pend) {
+      const uint4 kk = lds_volatile_u4(&m.key[b * 4]);
+      const int hit = kk.x == dstw ? 0 : kk.y == dstw ? 1 : kk.z == dstw ? 2 : kk.w == dstw ? 3 : -1;
+      const int emp = kk.x == kEmptyKey ? 0 : kk.y == kEmptyKey ? 1 : kk.z == kEmptyKey ? 2 : kk.w == kEmptyKey ? 3 : -1;
+      if (hit >= 0) {
+        slot = b * 4 + hit;
+        pend = false;
+      } else if (emp >= 0) {
+        if (*reinterpret_cast<volatile uint32_t *>(m.overflow)) {
+          pend = false;
+        } else {
+          const uint32_t old = atomicCAS(&m.key[b * 4 + emp], kEmptyKey, dstw);
+          if (old == kEmptyKey || old == dstw) {
+            slot = b * 4 + emp;
+            pend = false;
+            nclaim += old == kEmptyKey;
+          }  // else: somebody else's key took the slot — look at the bucket again
+        }
+      } else {
+        b = (b + step) & (kBuckets - 1);
+      }
+    }
+  }
+  if (__any_sync(kFull, nclaim != 0)) {
+    const uint32_t c = __reduce_add_sync(kFull, nclaim);
+    if (lane == 0 && atomicAdd(m.claims, c) + c > m.claim_limit) atomicExch(m.overflow, 1u);
+  }
+  if (slot != 0xFFFFFFFFu) {
+    // the value only ever decreases: an arc that cannot win needs no atomic
+    const unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&m.val[slot]);
+    if (cur > pk) {
+      const unsigned long long old = atomicMin(&m.val[slot], pk);
+      if ((dstw & kDestEpsBit) && (uint32_t)(pk >> 32) < (uint32_t)(old >> 32)) {  // cost changed: (re)queue, inl.h:115-127,425
+        m.round[slot] = (uint8_t)next_round;
+        if (s_any) *s_any = 1u;
+      }
+    }
+  }
+  __syncwarp();
+}
+
+template <int U, bool SMEM_LL>
+__global__ void __launch_bounds__(kStreamThreads, 1)
+k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, DecoderConfigDev cfg,
+         int num_indices) {
+  constexpr int NT = kStreamThreads;
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  __shared__ PostSmem ps;
+  __shared__ FrameDesc s_d;
+  __shared__ uint32_t s_claims, s_overflow, s_any;
+  __shared__ uint16_t s_wq[kStreamThreads / 32][64];
+  SmemMap m;
+  m.val = reinterpret_cast<unsigned long long *>(s_dyn);
+  m.key = reinterpret_cast<uint32_t *>(s_dyn + (size_t)kSmemSlots * 8);
+  m.round = reinterpret_cast<uint8_t *>(s_dyn + (size_t)kSmemSlots * 12);
+  m.claims = &s_claims;
+  m.overflow = &s_overflow;
+  m.claim_limit = (cfg.debug_flags >> 8) ? min((uint32_t)(cfg.debug_flags >> 8), kSmemClaimLimit) : kSmemClaimLimit;  // (test hook: smaller on-chip budget)
+  float *s_ll = reinterpret_cast<float *>(s_dyn + (size_t)kSmemSlots * 13);
+  StreamState *st = streams[blockIdx.x];
+  FrameDesc *d = &s_d;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const LmPair lms = {};
+  // this launch decodes the rows of ONE staged chunk: later chunks may already be raising
+  // target_frame while their rows are still being copied
+  const int limit = min(params[blockIdx.x].frame0 + params[blockIdx.x].n_frames, st->max_frames);
+
+  for (uint32_t i = tid; i < kSmemSlots; i += NT) {
+    m.val[i] = kInfVal;
+    m.key[i] = kEmptyKey;
+  }
+  for (uint32_t i = tid; i < kSmemSlots / 4; i += NT) reinterpret_cast<uint32_t *>(m.round)[i] = 0;
+  if (tid == 0) s_d.stepping = 0;
+  __syncthreads();
+
+  long long tph = clock64();
+  auto phase = [&](int k) {  // per-phase SM cycles (diagnostic; thread 0, called right after a barrier)
+    if (tid == 0) {
+      const long long now = clock64();
+      st->phase_cycles[k] += (unsigned long long)(now - tph);
+      tph = now;
+    }
+  };
+  for (;;) {
+    if (st->frame >= limit) break;  // uniform (written by thread 0 before the last barrier)
+    // ---- GetCutoff + best-token pre-pass of frame t; descriptor of the step into shared memory
+    cutoff_prologue<NT, false>(st, d, g, cfg, lms, ps.red64, ps.red32, ps.hist, ps.misc);
+    if (tid == 0) {
+      s_claims = 0;
+      s_overflow = (cfg.debug_flags & 8) ? 1u : 0u;  // test hook: every frame through the HBM map
+      s_any = 0;
+      ps.alive = 0;
+      ps.best = kInfVal;
+    }
+    __syncthreads();
+    if (!s_d.stepping) break;  // uniform: frame == target_frame
+    phase(0);
+    const float *__restrict__ ll = s_d.ll;
+    if (SMEM_LL) {
+      for (int c = tid; c < num_indices; c += NT) s_ll[c] = __ldg(&ll[c]);
+      __syncthreads();
+    }
+    phase(1);
+    const uint32_t n_cur = s_d.n_cur;
+    const uint32_t n_groups = (n_cur + 31) >> 5;
+    const uint2 *__restrict__ toks = s_d.toks;
+    const float cur_cut = s_d.cur_cut, abeam = s_d.abeam;
+    uint32_t *next_cut = &s_d.next_cut_bits;
+
+    // ---- emitting expansion (ProcessEmitting, inl.h:311-347) into the on-chip map
+    {
+      uint32_t expanded = 0, admitted = 0;
+      for (uint32_t grp = warp; grp < n_groups; grp += NT / 32) {
+        // warp-uniform decision (the lanes may not have reconverged after the map updates)
+        if (__any_sync(kFull, *reinterpret_cast<volatile uint32_t *>(&s_overflow) != 0u)) break;
+        float nc = ord2f(*reinterpret_cast<volatile uint32_t *>(next_cut));
+        const uint32_t i = grp * 32 + lane;
+        uint32_t deg = 0, base = 0, cost_bits = 0;
+        if (i < n_cur) {
+          const uint2 sc = __ldcg(&toks[i]);  // written by this kernel one frame ago: no ld.global.nc
+          cost_bits = sc.y;
+          if (__uint_as_float(sc.y) <= cur_cut) {  // inclusive, inl.h:315
+            const uint2 er = __ldg(&g.erows[sc.x]);
+            base = er.x;
+            deg = er.y - er.x;
+          }
+        }
+        const uint32_t incl = warp_incl_scan(deg, lane);
+        const uint32_t off = incl - deg;
+        const uint32_t total = __shfl_sync(kFull, incl, 31);
+        expanded += total;
+        for (uint32_t jb = 0; jb < total; jb += 32 * U) {
+          bool in[U];
+          uint32_t a[U];
+          float tcost[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const uint32_t j = jb + u * 32 + lane;
+            in[u] = j < total;
+            const int l = warp_owner(off, j);
+            const uint32_t off_l = __shfl_sync(kFull, off, l);
+            const uint32_t base_l = __shfl_sync(kFull, base, l);
+            tcost[u] = __uint_as_float(__shfl_sync(kFull, cost_bits, l));
+            a[u] = base_l + (j - off_l);
+          }
+          int4 arc[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            if (in[u]) arc[u] = __ldg(&g.arcs[a[u]]);
+          float tot[U];
+          bool adm[U];
+          uint32_t cand_bits = 0xFFFFFFFFu;
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            adm[u] = false;
+            tot[u] = 0.f;
+            if (in[u]) {
+              const float ac = -(SMEM_LL ? s_ll[arc[u].x - 1] : __ldg(&ll[arc[u].x - 1]));
+              tot[u] = (tcost[u] + ac) + __int_as_float(arc[u].z);  // inl.h:326-329
+              adm[u] = tot[u] < nc;
+              if (adm[u]) {
+                const float cand = tot[u] + abeam;  // inl.h:332-333
+                if (cand < nc) cand_bits = min(cand_bits, f2ord(cand));
+              }
+            }
+          }
+          if (__any_sync(kFull, cand_bits != 0xFFFFFFFFu)) {
+            const uint32_t wmin = __reduce_min_sync(kFull, cand_bits);
+            if (lane == 0) atomicMin(next_cut, wmin);
+            nc = fminf(nc, ord2f(wmin));
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            smem_relax(m, adm[u], (uint32_t)arc[u].w, pack_val(tot[u], a[u]), 1u, nullptr, lane);
+            admitted += adm[u];
+          }
+        }
+      }
+      admitted = __reduce_add_sync(kFull, admitted);
+      if (lane == 0 && expanded) {
+        atomicAdd(&s_d.arcs_expanded, expanded);
+        atomicAdd(&s_d.arcs_admitted, admitted);
+      }
+    }
+    __syncthreads();
+    phase(2);
+    const float nc = ord2f(s_d.next_cut_bits);  // the FINAL next_cutoff of this frame
+
+    // ---- eps closure (ProcessNonemitting, inl.h:353-431): round r relaxes the slots stamped r
+    if (!s_overflow) {
+      uint16_t *wq = s_wq[warp];  // this warp's compaction buffer of stamped slots
+      for (uint32_t round = 1;; ++round) {
+        const uint32_t rr = round < 255u ? round : 255u, nr = round < 255u ? round + 1 : 255u;
+        uint32_t nq = 0;
+        // the warp owns 512 consecutive slots: 16 windows of 32; stamped slots are compacted
+        // into wq and relaxed 32 at a time, so the row loads of a batch are issued together and
+        // the eps arcs of the batch are flattened over the lanes like the emitting arcs above
+        for (int k = 0; k < (int)(kSmemSlots / kStreamThreads); ++k) {
+          const uint32_t slot = ((uint32_t)warp * (kSmemSlots / (kStreamThreads / 32))) + (uint32_t)k * 32u + lane;
+          const bool stamped = m.round[slot] == (uint8_t)rr;
+          const unsigned sm = __ballot_sync(kFull, stamped);
+          if (sm) {
+            if (stamped) wq[nq + __popc(sm & ((1u << lane) - 1u))] = (uint16_t)slot;
+            nq += __popc(sm);
+            __syncwarp();
+          }
+          const bool last = k == (int)(kSmemSlots / kStreamThreads) - 1;
+          while (nq >= 32u || (last && nq > 0u)) {
+            const uint32_t cnt = nq < 32u ? nq : 32u;
+            uint32_t deg = 0, base = 0, cost_bits = 0;
+            if ((uint32_t)lane < cnt) {
+              const uint32_t sl = wq[lane];
+              const uint32_t state = m.key[sl] & kStateMask;
+              const uint32_t co = (uint32_t)(*reinterpret_cast<volatile unsigned long long *>(&m.val[sl]) >> 32);
+              cost_bits = __float_as_uint(ord2f(co));
+              if (ord2f(co) < nc) {  // inl.h:391
+                const uint2 r = __ldg(&g.rows[state]);
+                base = r.x;
+                deg = r.y - r.x;
+              }
+            }
+            __syncwarp();
+            if (nq > 32u) {  // keep the remainder for the next batch
+              const uint16_t keep = (uint32_t)lane + 32u < nq ? wq[lane + 32] : (uint16_t)0;
+              __syncwarp();
+              wq[lane] = keep;
+              __syncwarp();
+            }
+            nq -= cnt;
+            const uint32_t incl = warp_incl_scan(deg, lane);
+            const uint32_t off = incl - deg;
+            const uint32_t total = __shfl_sync(kFull, incl, 31);
+            for (uint32_t jb = 0; jb < total; jb += 32) {
+              const uint32_t j = jb + lane;
+              const bool in = j < total;
+              const int l = warp_owner(off, j);
+              const uint32_t off_l = __shfl_sync(kFull, off, l);
+              const uint32_t base_l = __shfl_sync(kFull, base, l);
+              const float cost = __uint_as_float(__shfl_sync(kFull, cost_bits, l));
+              const uint32_t a = base_l + (j - off_l);
+              int4 arc = make_int4(0, 0, 0, 0);
+              if (in) arc = __ldg(&g.arcs[a]);
+              const float tot = cost + __int_as_float(arc.z);  // inl.h:413-414
+              smem_relax(m, in && tot < nc, (uint32_t)arc.w, pack_val(tot, a), nr, &s_any, lane);  // inl.h:415
+            }
+          }
+        }
+        __syncthreads();
+        const bool more = s_any != 0 && !s_overflow;
+        __syncthreads();
+        if (!more) break;
+        if (tid == 0) s_any = 0;
+        __syncthreads();
+      }
+    }
+
+    phase(3);
+    if (s_overflow) {
+      // ---- too many distinct destinations for the on-chip map: wipe it and redo the frame
+      // through the stream's HBM map (identical results; the running cutoff stays valid)
+      for (uint32_t i = tid; i < kSmemSlots; i += NT) {
+        m.val[i] = kInfVal;
+        m.key[i] = kEmptyKey;
+      }
+      for (uint32_t i = tid; i < kSmemSlots / 4; i += NT) reinterpret_cast<uint32_t *>(m.round)[i] = 0;
+      if (tid == 0) {
+        s_d.arcs_expanded = 0;
+        s_d.arcs_admitted = 0;
+        st->tot_fallback_frames += 1;
+      }
+      __syncthreads();
+      expand_frame<1, SMEM_LL, false>(d, g, s_ll, (uint32_t)warp, NT / 32, 0, lms);
+      __syncthreads();
+      post_epilogue<false>(st, d, g, cfg, lms, ps);
+      phase(5);
+      continue;
+    }
+
+    // ---- survivors -> token arena (warp-compacted), slots recycled on the way
+    {
+      const uint32_t cap = s_d.out_cap;
+      uint2 *out_sc = s_d.out_sc;
+      uint32_t *out_arc = s_d.out_arc;
+      unsigned long long best64 = kInfVal;
+      for (uint32_t slot = tid; slot < kSmemSlots; slot += NT) {
+        const uint32_t kw = m.key[slot];
+        bool alive = false;
+        unsigned long long v = kInfVal;
+        if (kw != kEmptyKey) {
+          v = m.val[slot];
+          alive = ord2f((uint32_t)(v >> 32)) < nc;
+          m.key[slot] = kEmptyKey;
+          m.val[slot] = kInfVal;
+          m.round[slot] = 0;
+        }
+        const unsigned am = __ballot_sync(kFull, alive);
+        if (am == 0) continue;
+        uint32_t pos0 = 0;
+        if (lane == 0) pos0 = atomicAdd(&ps.alive, (uint32_t)__popc(am));
+        pos0 = __shfl_sync(kFull, pos0, 0);
+        if (alive) {
+          const uint32_t idx = pos0 + __popc(am & ((1u << lane) - 1u));
+          const uint32_t state = kw & kStateMask;
+          if (idx < cap) {
+            out_sc[idx] = make_uint2(state, __float_as_uint(ord2f((uint32_t)(v >> 32))));
+            out_arc[idx] = (uint32_t)v;
+          }
+          const unsigned long long b64 = (v & 0xFFFFFFFF00000000ull) | state;
+          best64 = b64 < best64 ? b64 : best64;
+        }
+      }
+#pragma unroll
+      for (int dlt = 16; dlt > 0; dlt >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(kFull, best64, dlt);
+        best64 = o < best64 ? o : best64;
+      }
+      if (lane == 0 && best64 != kInfVal) atomicMin(&ps.best, best64);
+    }
+    __syncthreads();
+    if (tid == 0) frame_commit(st, d, cfg, nc, ps.alive, ps.best);
+    __syncthreads();
+    phase(4);
+  }
 }
 
 // ------------------------------------------------------------------ raw lattice
@@ -1145,6 +1551,8 @@ __global__ void k_counters(StreamState *const *streams, int n, unsigned long lon
   atomicAdd(&out[0], st->tot_arcs_expanded);
   atomicAdd(&out[1], st->tot_arcs_admitted);
   atomicAdd(&out[2], (unsigned long long)st->frame_off[st->frame + 1]);
+  atomicAdd(&out[3], st->tot_fallback_frames);
+  for (int k = 0; k < 6; ++k) atomicAdd(&out[4 + k], st->phase_cycles[k]);
 }
 
 // ------------------------------------------------------------------ best path

@@ -295,8 +295,12 @@ def run_b200_arm(a):
     kms, kn = (C.c_double * 4)(), (C.c_int64 * 4)()
     L.asrd_profile_get(kms, kn)
     xm, xn = C.c_double(kms[0]), C.c_int64(kn[0])
-    knames = ["k_expand", "k_post"]
-    ktot = kms[0] + kms[1] + 1e-12
+    fallback_frames = int(L.asrd_last_fallback_frames())
+    on_chip = kn[2] > 0   # the on-chip frame loop (k_stream) served this run
+    knames = ["k_expand", "k_post", "k_stream"]
+    ktot = kms[0] + kms[1] + kms[2] + 1e-12
+    if on_chip:
+        xm, xn = C.c_double(kms[2]), C.c_int64(kn[2])
 
     # ---- end-to-end number: host (pinned) log-likelihoods through the C ABI
     e2e = None
@@ -349,7 +353,8 @@ def run_b200_arm(a):
         "arcs_expanded_per_step": arcs_all,
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "k_expand", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "hbm_map_fallback_frames": fallback_frames,
+        "roofline": {"bound": "hbm", "kernel": "k_stream" if on_chip else "k_expand", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_arc": 16, "arcs_per_launch": ae.value / max(1, xn.value),
                      "launch_ms": xm.value / max(1, xn.value), "launches_per_step": int(xn.value),

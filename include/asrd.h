@@ -230,12 +230,19 @@ int asrd_host_free(void *ptr);
 int asrd_get_counters(asrd_decoder *const *decs, int32_t n, int64_t *arcs_expanded,
                       int64_t *arcs_admitted, int64_t *tokens, void *stream);
 
+/* frames the on-chip frame loop had to redo through the HBM map (diagnostic; summed over the
+ * streams of the last asrd_get_counters call) */
+int64_t asrd_last_fallback_frames(void);
+/* SM cycles the on-chip frame loop spent per phase {cutoff, row load, expansion, eps closure,
+ * write-out, HBM-map fallback}, summed over the streams of the last asrd_get_counters call */
+void asrd_last_phase_cycles(int64_t *out6);
+
 /* Per-kernel device timing with CUDA events on the launching stream (measurement aid for
  * bench.py's roofline; adds gaps between launches, so keep it off in timed regions). */
 int asrd_profile_enable(int on);
 int asrd_profile_reset(void);
 /* kernel_ms[4], kernel_launches[4]: accumulated device time and launch counts of
- * {k_expand, k_post, unused, unused} since the last reset */
+ * {k_expand, k_post, k_stream, unused} since the last reset */
 int asrd_profile_get(double *kernel_ms, int64_t *kernel_launches);
 
 /* number of kernels launched by this library since load (bench.py "gpu_launches") */

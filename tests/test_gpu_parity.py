@@ -172,3 +172,39 @@ def test_arena_overflow_is_reported_not_silent():
     ll = synth.make_loglikes(40, 50, 2.0, seed=3)
     out = dec.Decode([ll])
     assert dec.status(0) == -5 and not out[0].ok and out[0].status == -5
+
+
+@pytest.mark.parametrize("env", [
+    {"ASRD_STREAM_KERNEL": "0"},                 # HBM-map kernels only (k_expand + k_post)
+    {"ASRD_DEBUG_FLAGS": "8"},                   # on-chip loop, every frame redone through the HBM map
+    {"ASRD_DEBUG_FLAGS": str(1500 << 8)},        # on-chip budget of 1500 states: overflow mid-frame
+    {"ASRD_STREAM_U": "1"},
+])
+def test_every_kernel_path_gives_the_same_search(oracle_mod, monkeypatch, env):
+    """The on-chip frame loop (k_stream), its mid-frame overflow into the HBM map and the HBM-map
+    kernels are three routes through the same search: identical one-best, per-frame cutoffs and
+    token counts, all equal to the canonical oracle."""
+    O = oracle_mod
+    fst = synth.make_graph(60000, 5.0, 500, seed=99)
+    lls = [synth.make_loglikes(120, 500, 2.0 + 0.5 * (i % 3), seed=910 + i) for i in range(5)]
+    cfg = _cfg()
+    g = CudaFst(fst)
+    base = CudaDecoderBatch(g, cfg, len(lls), max_frames=128, collect_stats=True)
+    out0 = base.Decode(lls)
+    st0 = [base.frame_stats(i) for i in range(len(lls))]
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    dec = CudaDecoderBatch(g, cfg, len(lls), max_frames=128, collect_stats=True)
+    out1 = dec.Decode(lls)
+    og = O.OracleGraph(fst)
+    for i in range(len(lls)):
+        assert dec.status(i) == 0
+        st1 = dec.frame_stats(i)
+        for f in ("n_in", "n_tokens", "arcs_expanded"):
+            assert np.array_equal(st0[i][f], st1[f]), (env, i, f)
+        for f in ("cur_cutoff", "abeam", "next_cutoff", "best"):
+            assert np.array_equal(st0[i][f].view(np.uint32), st1[f].view(np.uint32)), (env, i, f)
+        assert np.array_equal(out0[i].ilabel, out1[i].ilabel) and out0[i].tot_bits == out1[i].tot_bits
+        if i < 2:
+            ref, rst = _oracle_decode(O, og, cfg, lls[i])
+            _compare(out1[i], st1, ref, rst, f"{env} stream {i}")
