@@ -280,7 +280,7 @@ struct StreamPlan {
 int PlanStream(int num_indices, bool biglm, StreamPlan *plan) {
   plan->fn = nullptr;
   if (biglm || !EnvInt("ASRD_STREAM_KERNEL", 1)) return ASRD_OK;
-  const size_t map_bytes = (size_t)kSmemSlots * 13;
+  const size_t map_bytes = kSmemMapBytes;
   cudaFuncAttributes fa;
   CU_CHECK(cudaFuncGetAttributes(&fa, k_stream<1, true>));
   int dev = 0, max_optin = 0;
@@ -721,7 +721,9 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
   AdvanceParams *d_params;
   FrameDesc *d_desc;
   const size_t row = (size_t)num_indices;
-  const int32_t chunk = on_device ? max_nf : std::min<int32_t>(max_nf, std::max(1, EnvInt("ASRD_HOST_CHUNK", kHostChunkFrames)));
+  // resident rows are cut into chunks too: the chunk launches of the sub-batches interleave on the
+  // SMs, so a batch that is not a multiple of the SM count does not leave a ragged last wave
+  const int32_t chunk = std::min<int32_t>(max_nf, std::max(1, on_device ? EnvInt("ASRD_DEVICE_CHUNK", 32) : EnvInt("ASRD_HOST_CHUNK", kHostChunkFrames)));
   const int n_chunks = (max_nf + chunk - 1) / chunk;
   CU_CHECK(sc.Alloc(&d_params, (size_t)n * n_chunks));
   CU_CHECK(sc.Alloc(&d_desc, (size_t)n));

@@ -974,16 +974,32 @@ k_post(StreamState *const *streams, FrameDesc *desc, GraphView g, DecoderConfigD
 // on which path ran.  Plain (non-biglm) decoders only.
 constexpr int kSmemLog2 = 14;
 constexpr uint32_t kSmemSlots = 1u << kSmemLog2;
+constexpr size_t kSmemMapBytes = (size_t)kSmemSlots * 12 + 2 * (kSmemSlots / 32) * 4;  // vals, keys, round bitmaps
 constexpr uint32_t kSmemClaimLimit = kSmemSlots - 2 * kStreamThreads - 256;  // every thread may overshoot by U claims
 
 struct SmemMap {
   unsigned long long *val;  // (ordered cost << 32) | arc id, kInfVal when free
   uint32_t *key;            // state | kDestEpsBit, kEmptyKey when free
-  uint8_t *round;           // eps-closure round in which the slot has to be relaxed (0 = none)
+  uint32_t *qbits;          // [2][kSmemSlots / 32] slots to relax in the eps-closure round of that parity
   uint32_t *claims;
   uint32_t *overflow;
   uint32_t claim_limit;
 };
+
+// position of the r-th (0-based) set bit of mask (r < popc(mask))
+__device__ __forceinline__ int select_nth(uint32_t mask, int r) {
+  int pos = 0;
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) {
+    const uint32_t low = mask & ((1u << w) - 1u);
+    const int c = __popc(low);
+    const bool up = r >= c;
+    r -= up ? c : 0;
+    mask = up ? (mask >> w) : low;
+    pos += up ? w : 0;
+  }
+  return pos;
+}
 
 __device__ __forceinline__ uint4 lds_volatile_u4(const uint32_t *p) {
   uint4 r;
@@ -1045,7 +1061,7 @@ __device__ __forceinline__ void smem_relax(const SmemMap &m, bool act, uint32_t 
     if (cur > pk) {
       const unsigned long long old = atomicMin(&m.val[slot], pk);
       if ((dstw & kDestEpsBit) && (uint32_t)(pk >> 32) < (uint32_t)(old >> 32)) {  // cost changed: (re)queue, inl.h:115-127,425
-        m.round[slot] = (uint8_t)next_round;
+        atomicOr(&m.qbits[(next_round & 1u) * (kSmemSlots / 32) + (slot >> 5)], 1u << (slot & 31u));
         if (s_any) *s_any = 1u;
       }
     }
@@ -1066,11 +1082,11 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
   SmemMap m;
   m.val = reinterpret_cast<unsigned long long *>(s_dyn);
   m.key = reinterpret_cast<uint32_t *>(s_dyn + (size_t)kSmemSlots * 8);
-  m.round = reinterpret_cast<uint8_t *>(s_dyn + (size_t)kSmemSlots * 12);
+  m.qbits = reinterpret_cast<uint32_t *>(s_dyn + (size_t)kSmemSlots * 12);
   m.claims = &s_claims;
   m.overflow = &s_overflow;
   m.claim_limit = (cfg.debug_flags >> 8) ? min((uint32_t)(cfg.debug_flags >> 8), kSmemClaimLimit) : kSmemClaimLimit;  // (test hook: smaller on-chip budget)
-  float *s_ll = reinterpret_cast<float *>(s_dyn + (size_t)kSmemSlots * 13);
+  float *s_ll = reinterpret_cast<float *>(s_dyn + kSmemMapBytes);
   StreamState *st = streams[blockIdx.x];
   FrameDesc *d = &s_d;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1083,7 +1099,7 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
     m.val[i] = kInfVal;
     m.key[i] = kEmptyKey;
   }
-  for (uint32_t i = tid; i < kSmemSlots / 4; i += NT) reinterpret_cast<uint32_t *>(m.round)[i] = 0;
+  for (uint32_t i = tid; i < 2 * (kSmemSlots / 32); i += NT) m.qbits[i] = 0;
   if (tid == 0) s_d.stepping = 0;
   __syncthreads();
 
@@ -1124,6 +1140,10 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
     // ---- emitting expansion (ProcessEmitting, inl.h:311-347) into the on-chip map
     {
       uint32_t expanded = 0, admitted = 0;
+      bool p_valid = false;  // pending admitted arc of this lane: destination word and packed value
+      uint32_t p_w = 0;
+      unsigned long long p_pk = 0;
+      const uint32_t lt_mask = (1u << lane) - 1u;
       for (uint32_t grp = warp; grp < n_groups; grp += NT / 32) {
         // warp-uniform decision (the lanes may not have reconverged after the map updates)
         if (__any_sync(kFull, *reinterpret_cast<volatile uint32_t *>(&s_overflow) != 0u)) break;
@@ -1185,11 +1205,35 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
           }
 #pragma unroll
           for (int u = 0; u < U; ++u) {
-            smem_relax(m, adm[u], (uint32_t)arc[u].w, pack_val(tot[u], a[u]), 1u, nullptr, lane);
+            // Only about a third of the arcs are admitted: they are first gathered into a
+            // per-lane pending slot and the map is updated with all 32 lanes busy.
+            const unsigned nmask = __ballot_sync(kFull, adm[u]);
+            if (nmask == 0) continue;
             admitted += adm[u];
+            const unsigned long long pk = pack_val(tot[u], a[u]);
+            const unsigned freem = ~__ballot_sync(kFull, p_valid);
+            const int nfree = __popc(freem), nnew = __popc(nmask);
+            const int r = __popc(freem & lt_mask);  // rank among the free lanes
+            const bool take = !p_valid && r < nnew;
+            const int src = select_nth(nmask, take ? r : 0);
+            const uint32_t g_w = __shfl_sync(kFull, (uint32_t)arc[u].w, src);
+            const uint32_t g_lo = __shfl_sync(kFull, (uint32_t)pk, src);
+            const uint32_t g_hi = __shfl_sync(kFull, (uint32_t)(pk >> 32), src);
+            if (take) {
+              p_w = g_w;
+              p_pk = ((unsigned long long)g_hi << 32) | g_lo;
+              p_valid = true;
+            }
+            if (nnew >= nfree) {  // every lane holds an arc: update the map, keep the rest pending
+              smem_relax(m, true, p_w, p_pk, 1u, nullptr, lane);
+              p_valid = adm[u] && __popc(nmask & lt_mask) >= nfree;
+              p_w = (uint32_t)arc[u].w;
+              p_pk = pk;
+            }
           }
         }
       }
+      smem_relax(m, p_valid, p_w, p_pk, 1u, nullptr, lane);  // the last, partial set
       admitted = __reduce_add_sync(kFull, admitted);
       if (lane == 0 && expanded) {
         atomicAdd(&s_d.arcs_expanded, expanded);
@@ -1204,21 +1248,31 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
     if (!s_overflow) {
       uint16_t *wq = s_wq[warp];  // this warp's compaction buffer of stamped slots
       for (uint32_t round = 1;; ++round) {
-        const uint32_t rr = round < 255u ? round : 255u, nr = round < 255u ? round + 1 : 255u;
+        const uint32_t nr = round + 1;
         uint32_t nq = 0;
-        // the warp owns 512 consecutive slots: 16 windows of 32; stamped slots are compacted
-        // into wq and relaxed 32 at a time, so the row loads of a batch are issued together and
-        // the eps arcs of the batch are flattened over the lanes like the emitting arcs above
-        for (int k = 0; k < (int)(kSmemSlots / kStreamThreads); ++k) {
-          const uint32_t slot = ((uint32_t)warp * (kSmemSlots / (kStreamThreads / 32))) + (uint32_t)k * 32u + lane;
-          const bool stamped = m.round[slot] == (uint8_t)rr;
-          const unsigned sm = __ballot_sync(kFull, stamped);
+        // the warp owns 512 consecutive slots = 16 words of this round's bitmap; stamped slots are
+        // compacted into wq and relaxed 32 at a time, so the row loads of a batch are issued
+        // together and the eps arcs of the batch are flattened over the lanes like the emitting
+        // arcs above
+        constexpr int kWordsPerWarp = (int)(kSmemSlots / 32 / (kStreamThreads / 32));
+        uint32_t *qw = &m.qbits[(round & 1u) * (kSmemSlots / 32) + (uint32_t)warp * kWordsPerWarp];
+        uint32_t myword = 0;
+        if (lane < kWordsPerWarp) {
+          myword = qw[lane];
+          if (myword) qw[lane] = 0;
+        }
+        const unsigned nzw = __ballot_sync(kFull, myword != 0);
+        for (int k = 0; k < kWordsPerWarp; ++k) {
+          const bool last = k == kWordsPerWarp - 1;
+          if (!((nzw >> k) & 1u) && !(last && nq > 0u)) continue;
+          const uint32_t sm = __shfl_sync(kFull, myword, k);
+          const uint32_t slot = ((uint32_t)warp * kWordsPerWarp + (uint32_t)k) * 32u + lane;
+          const bool stamped = (sm >> lane) & 1u;
           if (sm) {
             if (stamped) wq[nq + __popc(sm & ((1u << lane) - 1u))] = (uint16_t)slot;
             nq += __popc(sm);
             __syncwarp();
           }
-          const bool last = k == (int)(kSmemSlots / kStreamThreads) - 1;
           while (nq >= 32u || (last && nq > 0u)) {
             const uint32_t cnt = nq < 32u ? nq : 32u;
             uint32_t deg = 0, base = 0, cost_bits = 0;
@@ -1276,7 +1330,7 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
         m.val[i] = kInfVal;
         m.key[i] = kEmptyKey;
       }
-      for (uint32_t i = tid; i < kSmemSlots / 4; i += NT) reinterpret_cast<uint32_t *>(m.round)[i] = 0;
+      for (uint32_t i = tid; i < 2 * (kSmemSlots / 32); i += NT) m.qbits[i] = 0;
       if (tid == 0) {
         s_d.arcs_expanded = 0;
         s_d.arcs_admitted = 0;
@@ -1305,7 +1359,6 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
           alive = ord2f((uint32_t)(v >> 32)) < nc;
           m.key[slot] = kEmptyKey;
           m.val[slot] = kInfVal;
-          m.round[slot] = 0;
         }
         const unsigned am = __ballot_sync(kFull, alive);
         if (am == 0) continue;
