@@ -289,7 +289,7 @@ int PlanStream(int num_indices, bool biglm, StreamPlan *plan) {
   const size_t room = (size_t)max_optin > fa.sharedSizeBytes + map_bytes ? (size_t)max_optin - fa.sharedSizeBytes - map_bytes : 0;
   if ((size_t)max_optin < fa.sharedSizeBytes + map_bytes) return ASRD_OK;
   const bool smem_ll = (size_t)num_indices * 4 <= room;
-  const int u = EnvInt("ASRD_STREAM_U", 2);
+  const int u = EnvInt("ASRD_STREAM_U", 1);
   if (smem_ll) plan->fn = u >= 2 ? k_stream<2, true> : k_stream<1, true>;
   else plan->fn = u >= 2 ? k_stream<2, false> : k_stream<1, false>;
   plan->dyn = map_bytes + (smem_ll ? (size_t)num_indices * 4 : 0);

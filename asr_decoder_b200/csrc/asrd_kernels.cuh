@@ -975,7 +975,7 @@ k_post(StreamState *const *streams, FrameDesc *desc, GraphView g, DecoderConfigD
 constexpr int kSmemLog2 = 14;
 constexpr uint32_t kSmemSlots = 1u << kSmemLog2;
 constexpr size_t kSmemMapBytes = (size_t)kSmemSlots * 12 + 2 * (kSmemSlots / 32) * 4;  // vals, keys, round bitmaps
-constexpr uint32_t kSmemClaimLimit = kSmemSlots - 2 * kStreamThreads - 256;  // every thread may overshoot by U claims
+constexpr uint32_t kSmemClaimLimit = kSmemSlots - kStreamThreads - 64;  // every warp may overshoot by 32 claims per map update
 
 struct SmemMap {
   unsigned long long *val;  // (ordered cost << 32) | arc id, kInfVal when free
@@ -1053,7 +1053,8 @@ __device__ __forceinline__ void smem_relax(const SmemMap &m, bool act, uint32_t 
   }
   if (__any_sync(kFull, nclaim != 0)) {
     const uint32_t c = __reduce_add_sync(kFull, nclaim);
-    if (lane == 0 && atomicAdd(m.claims, c) + c > m.claim_limit) atomicExch(m.overflow, 1u);
+    // (the flag carries the closure round that raised it, see the round loop of k_stream)
+    if (lane == 0 && atomicAdd(m.claims, c) + c > m.claim_limit) atomicCAS(m.overflow, 0u, next_round);
   }
   if (slot != 0xFFFFFFFFu) {
     // the value only ever decreases: an arc that cannot win needs no atomic
@@ -1077,7 +1078,7 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
   extern __shared__ __align__(16) unsigned char s_dyn[];
   __shared__ PostSmem ps;
   __shared__ FrameDesc s_d;
-  __shared__ uint32_t s_claims, s_overflow, s_any;
+  __shared__ uint32_t s_claims, s_overflow, s_any[3];
   __shared__ uint16_t s_wq[kStreamThreads / 32][64];
   SmemMap m;
   m.val = reinterpret_cast<unsigned long long *>(s_dyn);
@@ -1118,7 +1119,7 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
     if (tid == 0) {
       s_claims = 0;
       s_overflow = (cfg.debug_flags & 8) ? 1u : 0u;  // test hook: every frame through the HBM map
-      s_any = 0;
+      s_any[0] = s_any[1] = s_any[2] = 0;
       ps.alive = 0;
       ps.best = kInfVal;
     }
@@ -1138,98 +1139,148 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
     uint32_t *next_cut = &s_d.next_cut_bits;
 
     // ---- emitting expansion (ProcessEmitting, inl.h:311-347) into the on-chip map
+    // Software pipeline per warp: the arc records of step i+1 (the next U x 32 flattened arcs,
+    // possibly of the next token group) are requested before step i is scored and merged into
+    // the map, so the HBM/L2 latency of the arc fetch overlaps the shared-memory work.
     {
       uint32_t expanded = 0, admitted = 0;
       bool p_valid = false;  // pending admitted arc of this lane: destination word and packed value
       uint32_t p_w = 0;
       unsigned long long p_pk = 0;
       const uint32_t lt_mask = (1u << lane) - 1u;
-      for (uint32_t grp = warp; grp < n_groups; grp += NT / 32) {
-        // warp-uniform decision (the lanes may not have reconverged after the map updates)
-        if (__any_sync(kFull, *reinterpret_cast<volatile uint32_t *>(&s_overflow) != 0u)) break;
-        float nc = ord2f(*reinterpret_cast<volatile uint32_t *>(next_cut));
+      float nc = ord2f(*reinterpret_cast<volatile uint32_t *>(next_cut));
+      // fetch cursor: the token group whose arcs are being requested.  Two more groups are in
+      // flight behind it: the tokens of group +2 and the emitting-arc spans of group +1 (the
+      // span load needs the token's state), so a new group starts without waiting on HBM.
+      uint32_t f_grp = warp, f_off = 0, f_base = 0, f_cost = 0, f_total = 0, f_jb = 0;
+      bool f_open = false;
+      uint32_t t1_cost = 0, t1_base = 0, t1_deg = 0;  // group f_grp + 32: cost, span
+      uint2 t2 = make_uint2(0, 0);                    // group f_grp + 64: {state, cost}
+      bool t2_ok = false;
+      auto load_tokens = [&](uint32_t grp) {  // stage A
         const uint32_t i = grp * 32 + lane;
-        uint32_t deg = 0, base = 0, cost_bits = 0;
-        if (i < n_cur) {
-          const uint2 sc = __ldcg(&toks[i]);  // written by this kernel one frame ago: no ld.global.nc
-          cost_bits = sc.y;
-          if (__uint_as_float(sc.y) <= cur_cut) {  // inclusive, inl.h:315
-            const uint2 er = __ldg(&g.erows[sc.x]);
-            base = er.x;
-            deg = er.y - er.x;
+        t2_ok = grp < n_groups && i < n_cur;
+        if (t2_ok) t2 = __ldcg(&toks[i]);  // written by this kernel one frame ago: no ld.global.nc
+      };
+      auto load_spans = [&]() {  // stage B: consumes stage A
+        t1_cost = t2.y;
+        t1_base = 0;
+        t1_deg = 0;
+        if (t2_ok && __uint_as_float(t2.y) <= cur_cut) {  // inclusive, inl.h:315
+          const uint2 er = __ldg(&g.erows[t2.x]);
+          t1_base = er.x;
+          t1_deg = er.y - er.x;
+        }
+      };
+      load_tokens(warp);
+      load_spans();
+      load_tokens(warp + NT / 32);
+      // the step in flight
+      bool n_have = false, n_in[U];
+      uint32_t n_a[U];
+      float n_tc[U];
+      int4 n_arc[U];
+      auto issue = [&]() {
+        n_have = false;
+        while (!f_open || f_jb >= f_total) {
+          if (f_open) f_grp += NT / 32;
+          f_open = false;
+          if (f_grp >= n_groups) return;
+          // warp-uniform decision (the lanes may not have reconverged after the map updates)
+          if (__any_sync(kFull, *reinterpret_cast<volatile uint32_t *>(&s_overflow) != 0u)) {
+            f_grp = n_groups;
+            return;
+          }
+          // running cutoff (inl.h:330): other warps' tightenings arrive once per group
+          nc = fminf(nc, ord2f(*reinterpret_cast<volatile uint32_t *>(next_cut)));
+          f_cost = t1_cost;
+          f_base = t1_base;
+          const uint32_t deg = t1_deg;
+          load_spans();
+          load_tokens(f_grp + 2 * (NT / 32));
+          const uint32_t incl = warp_incl_scan(deg, lane);
+          f_off = incl - deg;
+          f_total = __shfl_sync(kFull, incl, 31);
+          f_jb = 0;
+          f_open = true;
+          expanded += f_total;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const uint32_t j = f_jb + u * 32 + lane;
+          n_in[u] = j < f_total;
+          const int l = warp_owner(f_off, j);
+          const uint32_t off_l = __shfl_sync(kFull, f_off, l);
+          const uint32_t base_l = __shfl_sync(kFull, f_base, l);
+          n_tc[u] = __uint_as_float(__shfl_sync(kFull, f_cost, l));
+          n_a[u] = base_l + (j - off_l);
+          if (n_in[u]) n_arc[u] = __ldg(&g.arcs[n_a[u]]);
+        }
+        f_jb += 32 * U;
+        n_have = true;
+      };
+      issue();
+      while (n_have) {
+        bool in[U];
+        uint32_t a[U];
+        float tcost[U];
+        int4 arc[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          in[u] = n_in[u];
+          a[u] = n_a[u];
+          tcost[u] = n_tc[u];
+          arc[u] = n_arc[u];
+        }
+        issue();
+        float tot[U];
+        bool adm[U];
+        uint32_t cand_bits = 0xFFFFFFFFu;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          adm[u] = false;
+          tot[u] = 0.f;
+          if (in[u]) {
+            const float ac = -(SMEM_LL ? s_ll[arc[u].x - 1] : __ldg(&ll[arc[u].x - 1]));
+            tot[u] = (tcost[u] + ac) + __int_as_float(arc[u].z);  // inl.h:326-329
+            adm[u] = tot[u] < nc;
+            if (adm[u]) {
+              const float cand = tot[u] + abeam;  // inl.h:332-333
+              if (cand < nc) cand_bits = min(cand_bits, f2ord(cand));
+            }
           }
         }
-        const uint32_t incl = warp_incl_scan(deg, lane);
-        const uint32_t off = incl - deg;
-        const uint32_t total = __shfl_sync(kFull, incl, 31);
-        expanded += total;
-        for (uint32_t jb = 0; jb < total; jb += 32 * U) {
-          bool in[U];
-          uint32_t a[U];
-          float tcost[U];
+        if (__any_sync(kFull, cand_bits != 0xFFFFFFFFu)) {
+          const uint32_t wmin = __reduce_min_sync(kFull, cand_bits);
+          if (lane == 0) atomicMin(next_cut, wmin);
+          nc = fminf(nc, ord2f(wmin));
+        }
 #pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const uint32_t j = jb + u * 32 + lane;
-            in[u] = j < total;
-            const int l = warp_owner(off, j);
-            const uint32_t off_l = __shfl_sync(kFull, off, l);
-            const uint32_t base_l = __shfl_sync(kFull, base, l);
-            tcost[u] = __uint_as_float(__shfl_sync(kFull, cost_bits, l));
-            a[u] = base_l + (j - off_l);
+        for (int u = 0; u < U; ++u) {
+          // Only about a third of the arcs are admitted: they are first gathered into a
+          // per-lane pending slot and the map is updated with all 32 lanes busy.
+          const unsigned nmask = __ballot_sync(kFull, adm[u]);
+          if (nmask == 0) continue;
+          admitted += adm[u];
+          const unsigned long long pk = pack_val(tot[u], a[u]);
+          const unsigned freem = ~__ballot_sync(kFull, p_valid);
+          const int nfree = __popc(freem), nnew = __popc(nmask);
+          const int r = __popc(freem & lt_mask);  // rank among the free lanes
+          const bool take = !p_valid && r < nnew;
+          const int src = select_nth(nmask, take ? r : 0);
+          const uint32_t g_w = __shfl_sync(kFull, (uint32_t)arc[u].w, src);
+          const uint32_t g_lo = __shfl_sync(kFull, (uint32_t)pk, src);
+          const uint32_t g_hi = __shfl_sync(kFull, (uint32_t)(pk >> 32), src);
+          if (take) {
+            p_w = g_w;
+            p_pk = ((unsigned long long)g_hi << 32) | g_lo;
+            p_valid = true;
           }
-          int4 arc[U];
-#pragma unroll
-          for (int u = 0; u < U; ++u)
-            if (in[u]) arc[u] = __ldg(&g.arcs[a[u]]);
-          float tot[U];
-          bool adm[U];
-          uint32_t cand_bits = 0xFFFFFFFFu;
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            adm[u] = false;
-            tot[u] = 0.f;
-            if (in[u]) {
-              const float ac = -(SMEM_LL ? s_ll[arc[u].x - 1] : __ldg(&ll[arc[u].x - 1]));
-              tot[u] = (tcost[u] + ac) + __int_as_float(arc[u].z);  // inl.h:326-329
-              adm[u] = tot[u] < nc;
-              if (adm[u]) {
-                const float cand = tot[u] + abeam;  // inl.h:332-333
-                if (cand < nc) cand_bits = min(cand_bits, f2ord(cand));
-              }
-            }
-          }
-          if (__any_sync(kFull, cand_bits != 0xFFFFFFFFu)) {
-            const uint32_t wmin = __reduce_min_sync(kFull, cand_bits);
-            if (lane == 0) atomicMin(next_cut, wmin);
-            nc = fminf(nc, ord2f(wmin));
-          }
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            // Only about a third of the arcs are admitted: they are first gathered into a
-            // per-lane pending slot and the map is updated with all 32 lanes busy.
-            const unsigned nmask = __ballot_sync(kFull, adm[u]);
-            if (nmask == 0) continue;
-            admitted += adm[u];
-            const unsigned long long pk = pack_val(tot[u], a[u]);
-            const unsigned freem = ~__ballot_sync(kFull, p_valid);
-            const int nfree = __popc(freem), nnew = __popc(nmask);
-            const int r = __popc(freem & lt_mask);  // rank among the free lanes
-            const bool take = !p_valid && r < nnew;
-            const int src = select_nth(nmask, take ? r : 0);
-            const uint32_t g_w = __shfl_sync(kFull, (uint32_t)arc[u].w, src);
-            const uint32_t g_lo = __shfl_sync(kFull, (uint32_t)pk, src);
-            const uint32_t g_hi = __shfl_sync(kFull, (uint32_t)(pk >> 32), src);
-            if (take) {
-              p_w = g_w;
-              p_pk = ((unsigned long long)g_hi << 32) | g_lo;
-              p_valid = true;
-            }
-            if (nnew >= nfree) {  // every lane holds an arc: update the map, keep the rest pending
-              smem_relax(m, true, p_w, p_pk, 1u, nullptr, lane);
-              p_valid = adm[u] && __popc(nmask & lt_mask) >= nfree;
-              p_w = (uint32_t)arc[u].w;
-              p_pk = pk;
-            }
+          if (nnew >= nfree) {  // every lane holds an arc: update the map, keep the rest pending
+            smem_relax(m, true, p_w, p_pk, 1u, nullptr, lane);
+            p_valid = adm[u] && __popc(nmask & lt_mask) >= nfree;
+            p_w = (uint32_t)arc[u].w;
+            p_pk = pk;
           }
         }
       }
@@ -1309,16 +1360,19 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
               int4 arc = make_int4(0, 0, 0, 0);
               if (in) arc = __ldg(&g.arcs[a]);
               const float tot = cost + __int_as_float(arc.z);  // inl.h:413-414
-              smem_relax(m, in && tot < nc, (uint32_t)arc.w, pack_val(tot, a), nr, &s_any, lane);  // inl.h:415
+              smem_relax(m, in && tot < nc, (uint32_t)arc.w, pack_val(tot, a), nr, &s_any[nr % 3u], lane);  // inl.h:415
             }
           }
         }
+        // one barrier per round: round r raises s_any[(r + 1) % 3] and reads it after the barrier;
+        // the flag the NEXT round raises is lowered here — its last readers passed the previous
+        // barrier, its next writers wait behind this one
+        if (tid == 0) s_any[(round + 2u) % 3u] = 0;
         __syncthreads();
-        const bool more = s_any != 0 && !s_overflow;
-        __syncthreads();
-        if (!more) break;
-        if (tid == 0) s_any = 0;
-        __syncthreads();
+        // an overflow raised by a warp that is already in round r + 1 carries the tag r + 2 and must
+        // not stop the slower warps one round early (the decision has to be uniform)
+        const uint32_t ovf = *reinterpret_cast<volatile uint32_t *>(&s_overflow);
+        if (s_any[nr % 3u] == 0 || (ovf != 0 && ovf <= nr)) break;
       }
     }
 
