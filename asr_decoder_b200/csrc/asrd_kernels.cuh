@@ -575,9 +575,11 @@ enum { kModeEpi = 2, kModePro = 4 };
 // exact k-th smallest (0-based) cost among the tokens with ordered key < limit_ord: what
 // std::nth_element yields in GetCutoff (inl.h:190-193, 211-216).  MSB-first radix select over
 // (ordered key - min key), starting at the top byte of `range` (an upper bound of that span).
-template <int NT>
-__device__ float block_kth_smallest(const uint2 *tok_sc, uint32_t n, uint32_t k, uint32_t min_ord,
-                                    uint32_t limit_ord, uint32_t range, uint32_t *s_hist, uint32_t *s_misc) {
+template <int NT, class OrdAt>
+__device__ __forceinline__ float block_kth_smallest(OrdAt ord_at, uint32_t n, uint32_t k, uint32_t min_ord,
+                                                    uint32_t limit_ord, uint32_t range, uint32_t *s_hist,
+                                                    uint32_t *s_misc) {
+  // ord_at(i), i < n: ordered cost key of item i, or 0xFFFFFFFF for "no token here"
   const int tid = threadIdx.x;
   int top = 24;
   while (top > 0 && (range >> top) == 0) top -= 8;
@@ -586,8 +588,8 @@ __device__ float block_kth_smallest(const uint2 *tok_sc, uint32_t n, uint32_t k,
     for (int b = tid; b < 256; b += NT) s_hist[b] = 0;
     __syncthreads();
     for (uint32_t i = tid; i < n; i += NT) {
-      const uint32_t key = f2ord(__uint_as_float(tok_sc[i].y));
-      if (key < limit_ord) {
+      const uint32_t key = ord_at(i);
+      if (key < limit_ord && key != 0xFFFFFFFFu) {
         const uint32_t rk = key - min_ord;
         if ((rk & pmask) == prefix) atomicAdd(&s_hist[(rk >> sh) & 255u], 1u);
       }
@@ -623,6 +625,86 @@ __device__ float block_kth_smallest(const uint2 *tok_sc, uint32_t n, uint32_t k,
   return ord2f(prefix + min_ord);
 }
 
+// GetCutoff (inl.h:138-234) over n tokens whose ordered cost keys are ord_at(i), i < n_items
+// (0xFFFFFFFF = no token): the frame's tokens in the arena, or the slots of the on-chip map.
+// best_ord = key of the best token.  Whole-CTA; every thread returns the same values.
+template <int NT, class OrdAt>
+__device__ __forceinline__ void get_cutoff(OrdAt ord_at, uint32_t n_items, uint32_t n, uint32_t best_ord,
+                                           const DecoderConfigDev &cfg, uint32_t *s_red32, uint32_t *s_hist,
+                                           uint32_t *s_misc, float &cur_cut, float &abeam) {
+  const int tid = threadIdx.x;
+  cur_cut = CUDART_INF_F;
+  abeam = cfg.beam;
+  if (n == 0) return;
+  const float bc = ord2f(best_ord);
+  const float beam_cut = bc + cfg.beam;  // inl.h:182
+  const uint32_t beam_ord = f2ord(beam_cut);
+  cur_cut = beam_cut;
+  if (n <= (uint32_t)cfg.min_active && n <= (uint32_t)cfg.max_active) {
+    // fewer tokens than min_active: min_active_cutoff stays +inf > beam_cutoff, nothing is
+    // pruned and the adaptive beam is infinite (inl.h:183,205,220-226)
+    cur_cut = CUDART_INF_F;
+    abeam = CUDART_INF_F;
+    return;
+  }
+  uint32_t lt = 0, le = 0;
+  for (uint32_t i = tid; i < n_items; i += NT) {
+    const uint32_t key = ord_at(i);
+    if (key != 0xFFFFFFFFu) {
+      const float c = ord2f(key);
+      lt += c < beam_cut;
+      le += c <= beam_cut;
+    }
+  }
+  lt = block_sum_u32<NT>(lt, s_red32);
+  le = block_sum_u32<NT>(le, s_red32);
+  if (lt > (uint32_t)cfg.max_active) {
+    // sorted[max_active] < beam_cutoff  <=>  more than max_active costs below it (inl.h:188-203)
+    cur_cut = block_kth_smallest<NT>(ord_at, n_items, (uint32_t)cfg.max_active, best_ord, beam_ord,
+                                     beam_ord - best_ord, s_hist, s_misc);
+    abeam = cur_cut - bc + cfg.beam_delta;
+  } else if (n <= (uint32_t)cfg.min_active) {
+    cur_cut = CUDART_INF_F;
+    abeam = CUDART_INF_F;
+  } else if (cfg.min_active > 0 && le <= (uint32_t)cfg.min_active) {
+    // sorted[min_active] > beam_cutoff  <=>  at most min_active costs <= it (inl.h:205-226)
+    cur_cut = block_kth_smallest<NT>(ord_at, n_items, (uint32_t)cfg.min_active, best_ord, 0xFFFFFFFFu,
+                                     0xFFFFFFFFu, s_hist, s_misc);
+    abeam = cur_cut - bc + cfg.beam_delta;
+  }
+}
+
+// Descriptor of the expansion of frame t (thread 0).
+__device__ __forceinline__ void fill_desc(StreamState *st, FrameDesc *d, int t, uint32_t n, uint32_t tok_off,
+                                          float cur_cut, float abeam, uint32_t next_bits, bool biglm) {
+  const uint32_t out_base = st->frame_off[t + 1];
+  FrameDesc nd;
+  nd.st = st;
+  nd.toks = st->tok_sc + tok_off;
+  nd.ll = st->ll_hist + (size_t)t * st->ll_stride;
+  nd.hn = st->hash;
+  nd.toks_lm = biglm ? st->tok_lm + tok_off : nullptr;
+  nd.bm = st->bm;
+  nd.ebm = st->ebm;
+  nd.out_sc = st->tok_sc + out_base;
+  nd.out_arc = st->tok_arc + out_base;
+  nd.best64 = kInfVal;
+  st->frame_cur[t] = cur_cut;
+  nd.n_cur = n;
+  nd.cur_cut = cur_cut;
+  nd.abeam = abeam;
+  nd.next_cut_bits = next_bits;
+  nd.mask = st->hash_mask;
+  nd.shift = st->hash_shift;
+  nd.out_cap = st->token_capacity > out_base ? st->token_capacity - out_base : 0;
+  nd.n_alive = 0;
+  nd.arcs_expanded = 0;
+  nd.arcs_admitted = 0;
+  nd.stepping = 1;
+  nd.t = t;
+  *d = nd;
+}
+
 // GetCutoff (inl.h:138-234) over the current frame's tokens, best-token pre-pass
 // (inl.h:282-300), and the descriptor of the next expansion.  Whole-CTA device function.
 template <int NT, bool BIGLM>
@@ -642,43 +724,12 @@ __device__ __forceinline__ void cutoff_prologue(StreamState *st, FrameDesc *d, c
   const float *__restrict__ ll = st->ll_hist + (size_t)t * st->ll_stride;
   // best token: lowest cost, ties -> lowest state id (inl.h:169-179); accumulated by k_finalize
   const unsigned long long best64 = st->best64;
-  float cur_cut = CUDART_INF_F, abeam = cfg.beam;
+  float cur_cut, abeam;
+  get_cutoff<NT>([&](uint32_t i) { return f2ord(__uint_as_float(toks[i].y)); }, n, n, (uint32_t)(best64 >> 32), cfg,
+                 s_red32, s_hist, s_misc, cur_cut, abeam);
   uint32_t next_bits = kOrdInf;
   if (n > 0) {
-    const uint32_t best_ord = (uint32_t)(best64 >> 32);
-    const float bc = ord2f(best_ord);
-    const float beam_cut = bc + cfg.beam;  // inl.h:182
-    const uint32_t beam_ord = f2ord(beam_cut);
-    cur_cut = beam_cut;
-    if (n <= (uint32_t)cfg.min_active && n <= (uint32_t)cfg.max_active) {
-      // fewer tokens than min_active: min_active_cutoff stays +inf > beam_cutoff, nothing is
-      // pruned and the adaptive beam is infinite (inl.h:183,205,220-226)
-      cur_cut = CUDART_INF_F;
-      abeam = CUDART_INF_F;
-    } else {
-      uint32_t lt = 0, le = 0;
-      for (uint32_t i = tid; i < n; i += NT) {
-        const float c = __uint_as_float(toks[i].y);
-        lt += c < beam_cut;
-        le += c <= beam_cut;
-      }
-      lt = block_sum_u32<NT>(lt, s_red32);
-      le = block_sum_u32<NT>(le, s_red32);
-      if (lt > (uint32_t)cfg.max_active) {
-        // sorted[max_active] < beam_cutoff  <=>  more than max_active costs below it (inl.h:188-203)
-        cur_cut = block_kth_smallest<NT>(toks, n, (uint32_t)cfg.max_active, best_ord, beam_ord,
-                                         beam_ord - best_ord, s_hist, s_misc);
-        abeam = cur_cut - bc + cfg.beam_delta;
-      } else if (n <= (uint32_t)cfg.min_active) {
-        cur_cut = CUDART_INF_F;
-        abeam = CUDART_INF_F;
-      } else if (cfg.min_active > 0 && le <= (uint32_t)cfg.min_active) {
-        // sorted[min_active] > beam_cutoff  <=>  at most min_active costs <= it (inl.h:205-226)
-        cur_cut = block_kth_smallest<NT>(toks, n, (uint32_t)cfg.min_active, best_ord, 0xFFFFFFFFu,
-                                         0xFFFFFFFFu, s_hist, s_misc);
-        abeam = cur_cut - bc + cfg.beam_delta;
-      }
-    }
+    const float bc = ord2f((uint32_t)(best64 >> 32));
     // best-token pre-pass (inl.h:282-300): association (cost + w) - loglike;
     // biglm (…-biglm.h:339-357): ((lm_score + cost) + w) - loglike.  In biglm mode best64 carries
     // the token's index inside the frame instead of its state.
@@ -704,34 +755,7 @@ __device__ __forceinline__ void cutoff_prologue(StreamState *st, FrameDesc *d, c
     const unsigned long long m64 = block_min_u64<NT>((unsigned long long)mn, s_red64);
     next_bits = (uint32_t)m64;
   }
-  if (tid == 0) {
-    const uint32_t out_base = st->frame_off[t + 1];
-    FrameDesc nd;
-    nd.st = st;
-    nd.toks = toks;
-    nd.ll = ll;
-    nd.hn = st->hash;
-    nd.toks_lm = BIGLM ? st->tok_lm + tok_off : nullptr;
-    nd.bm = st->bm;
-    nd.ebm = st->ebm;
-    nd.out_sc = st->tok_sc + out_base;
-    nd.out_arc = st->tok_arc + out_base;
-    nd.best64 = kInfVal;
-    st->frame_cur[t] = cur_cut;
-    nd.n_cur = n;
-    nd.cur_cut = cur_cut;
-    nd.abeam = abeam;
-    nd.next_cut_bits = next_bits;
-    nd.mask = st->hash_mask;
-    nd.shift = st->hash_shift;
-    nd.out_cap = st->token_capacity > out_base ? st->token_capacity - out_base : 0;
-    nd.n_alive = 0;
-    nd.arcs_expanded = 0;
-    nd.arcs_admitted = 0;
-    nd.stepping = 1;
-    nd.t = t;
-    *d = nd;
-  }
+  if (tid == 0) fill_desc(st, d, t, n, tok_off, cur_cut, abeam, next_bits, BIGLM);
 }
 
 // ------------------------------------------------------------------ fused per-stream post phase
@@ -1079,6 +1103,11 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
   __shared__ PostSmem ps;
   __shared__ FrameDesc s_d;
   __shared__ uint32_t s_claims, s_overflow, s_any[3];
+  __shared__ struct {  // GetCutoff result of the next frame, computed on chip
+    unsigned long long best;
+    float cur, abeam;
+    uint32_t n, off;
+  } s_h;
   __shared__ uint16_t s_wq[kStreamThreads / 32][64];
   SmemMap m;
   m.val = reinterpret_cast<unsigned long long *>(s_dyn);
@@ -1104,33 +1133,72 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
   if (tid == 0) s_d.stepping = 0;
   __syncthreads();
 
+  // per-phase SM cycles (diagnostic): accumulated in shared memory by thread 0 right after a
+  // barrier, written back once when the launch ends
+  __shared__ unsigned long long s_phase[6];
   long long tph = clock64();
-  auto phase = [&](int k) {  // per-phase SM cycles (diagnostic; thread 0, called right after a barrier)
+  if (tid < 6) s_phase[tid] = 0;
+  auto phase = [&](int k) {
     if (tid == 0) {
       const long long now = clock64();
-      st->phase_cycles[k] += (unsigned long long)(now - tph);
+      s_phase[k] += (unsigned long long)(now - tph);
       tph = now;
     }
   };
+  // Frame index and, after an on-chip frame, the GetCutoff result of the NEXT frame (computed from
+  // the map while it is still in shared memory): uniform registers, no HBM round trip per frame.
+  int t = st->frame;
+  bool have_cut = false;
+  const float *const ll_hist = st->ll_hist;
+  const int ll_stride = st->ll_stride;
   for (;;) {
-    if (st->frame >= limit) break;  // uniform (written by thread 0 before the last barrier)
-    // ---- GetCutoff + best-token pre-pass of frame t; descriptor of the step into shared memory
-    cutoff_prologue<NT, false>(st, d, g, cfg, lms, ps.red64, ps.red32, ps.hist, ps.misc);
+    if (t >= limit) break;
     if (tid == 0) {
       s_claims = 0;
       s_overflow = (cfg.debug_flags & 8) ? 1u : 0u;  // test hook: every frame through the HBM map
       s_any[0] = s_any[1] = s_any[2] = 0;
-      ps.alive = 0;
-      ps.best = kInfVal;
     }
-    __syncthreads();
-    if (!s_d.stepping) break;  // uniform: frame == target_frame
-    phase(0);
-    const float *__restrict__ ll = s_d.ll;
-    if (SMEM_LL) {
-      for (int c = tid; c < num_indices; c += NT) s_ll[c] = __ldg(&ll[c]);
+    if (!have_cut) {
+      // ---- first frame of the launch / after an HBM-map frame: GetCutoff + best-token pre-pass
+      // over the arena tokens; descriptor of the step into shared memory
+      cutoff_prologue<NT, false>(st, d, g, cfg, lms, ps.red64, ps.red32, ps.hist, ps.misc);
       __syncthreads();
+      if (!s_d.stepping) break;  // uniform: frame == target_frame
+      phase(0);
+      if (SMEM_LL) {
+        const float *__restrict__ llr = s_d.ll;
+        for (int c = tid; c < num_indices; c += NT) s_ll[c] = __ldg(&llr[c]);
+        __syncthreads();
+      }
+    } else {
+      // ---- cutoff known: stage the row, then the best-token pre-pass (inl.h:282-300) reads it
+      // from shared memory
+      const float *__restrict__ llr = ll_hist + (size_t)t * ll_stride;
+      const uint32_t h_n = s_h.n;
+      const float h_abeam = s_h.abeam;
+      const unsigned long long h_best = s_h.best;
+      if (tid == 0) fill_desc(st, d, t, h_n, s_h.off, s_h.cur, h_abeam, kOrdInf, false);
+      if (SMEM_LL)
+        for (int c = tid; c < num_indices; c += NT) s_ll[c] = __ldg(&llr[c]);
+      uint32_t mn = kOrdInf;
+      if (h_n > 0) {
+        const float bc = ord2f((uint32_t)(h_best >> 32));
+        const uint2 er = __ldg(&g.erows[(uint32_t)h_best]);
+        if (SMEM_LL) __syncthreads();
+        for (uint32_t a = er.x + tid; a < er.y; a += NT) {
+          const int4 arc = __ldg(&g.arcs[a]);
+          const float tot = bc + __int_as_float(arc.z) - (SMEM_LL ? s_ll[arc.x - 1] : __ldg(&llr[arc.x - 1]));
+          mn = min(mn, f2ord(tot + h_abeam));
+        }
+      } else if (SMEM_LL) {
+        __syncthreads();
+      }
+      const unsigned long long m64 = block_min_u64<NT>((unsigned long long)mn, ps.red64);
+      if (tid == 0) s_d.next_cut_bits = (uint32_t)m64;
+      __syncthreads();
+      phase(0);
     }
+    const float *__restrict__ ll = s_d.ll;
     phase(1);
     const uint32_t n_cur = s_d.n_cur;
     const uint32_t n_groups = (n_cur + 31) >> 5;
@@ -1395,16 +1463,49 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
       __syncthreads();
       post_epilogue<false>(st, d, g, cfg, lms, ps);
       phase(5);
+      ++t;
+      have_cut = false;
       continue;
     }
 
-    // ---- survivors -> token arena (warp-compacted), slots recycled on the way
+    // ---- the frame's tokens are final.  While the map is still on chip: count the survivors,
+    // find the best token (lowest cost, ties -> lowest state id, inl.h:169-179) and run GetCutoff
+    // for the next frame over the map slots; then append the survivors to the token arena in slot
+    // order (deterministic) and recycle the slots.
     {
+      auto ord_at = [&](uint32_t i) -> uint32_t {
+        if (m.key[i] == kEmptyKey) return 0xFFFFFFFFu;
+        const uint32_t o = (uint32_t)(m.val[i] >> 32);
+        return ord2f(o) < nc ? o : 0xFFFFFFFFu;
+      };
+      constexpr uint32_t kPerWarp = kSmemSlots / (NT / 32);  // each warp owns a contiguous run of slots
+      const uint32_t slot0 = (uint32_t)warp * kPerWarp;
+      unsigned long long best64 = kInfVal;
+      uint32_t cnt = 0;
+      for (uint32_t k = lane; k < kPerWarp; k += 32) {
+        const uint32_t slot = slot0 + k;
+        const uint32_t o = ord_at(slot);
+        if (o != 0xFFFFFFFFu) {
+          ++cnt;
+          const unsigned long long b64 = ((unsigned long long)o << 32) | (m.key[slot] & kStateMask);
+          best64 = b64 < best64 ? b64 : best64;
+        }
+      }
+      cnt = __reduce_add_sync(kFull, cnt);
+      if (lane == 0) ps.red32[warp] = cnt;
+      best64 = block_min_u64<NT>(best64, ps.red64);  // (barriers inside: ps.red32 is complete)
+      const uint32_t wc = ps.red32[lane];            // NT / 32 == 32 warps
+      const uint32_t n_alive = __reduce_add_sync(kFull, wc);
+      uint32_t pos = __reduce_add_sync(kFull, lane < warp ? wc : 0u);  // arena offset of this warp's run
+      __syncthreads();
+      float n_cur_cut, n_abeam;
+      get_cutoff<NT>(ord_at, kSmemSlots, n_alive, (uint32_t)(best64 >> 32), cfg, ps.red32, ps.hist, ps.misc,
+                     n_cur_cut, n_abeam);
       const uint32_t cap = s_d.out_cap;
       uint2 *out_sc = s_d.out_sc;
       uint32_t *out_arc = s_d.out_arc;
-      unsigned long long best64 = kInfVal;
-      for (uint32_t slot = tid; slot < kSmemSlots; slot += NT) {
+      for (uint32_t k = lane; k < kPerWarp; k += 32) {
+        const uint32_t slot = slot0 + k;
         const uint32_t kw = m.key[slot];
         bool alive = false;
         unsigned long long v = kInfVal;
@@ -1415,33 +1516,31 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
           m.val[slot] = kInfVal;
         }
         const unsigned am = __ballot_sync(kFull, alive);
-        if (am == 0) continue;
-        uint32_t pos0 = 0;
-        if (lane == 0) pos0 = atomicAdd(&ps.alive, (uint32_t)__popc(am));
-        pos0 = __shfl_sync(kFull, pos0, 0);
         if (alive) {
-          const uint32_t idx = pos0 + __popc(am & ((1u << lane) - 1u));
-          const uint32_t state = kw & kStateMask;
+          const uint32_t idx = pos + __popc(am & ((1u << lane) - 1u));
           if (idx < cap) {
-            out_sc[idx] = make_uint2(state, __float_as_uint(ord2f((uint32_t)(v >> 32))));
+            out_sc[idx] = make_uint2(kw & kStateMask, __float_as_uint(ord2f((uint32_t)(v >> 32))));
             out_arc[idx] = (uint32_t)v;
           }
-          const unsigned long long b64 = (v & 0xFFFFFFFF00000000ull) | state;
-          best64 = b64 < best64 ? b64 : best64;
         }
+        pos += __popc(am);
       }
-#pragma unroll
-      for (int dlt = 16; dlt > 0; dlt >>= 1) {
-        const unsigned long long o = __shfl_xor_sync(kFull, best64, dlt);
-        best64 = o < best64 ? o : best64;
+      if (tid == 0) {
+        s_h.off = st->frame_off[t + 1];
+        s_h.n = n_alive < cap ? n_alive : cap;
+        s_h.best = best64;
+        s_h.cur = n_cur_cut;
+        s_h.abeam = n_abeam;
+        frame_commit(st, d, cfg, nc, n_alive, best64);
       }
-      if (lane == 0 && best64 != kInfVal) atomicMin(&ps.best, best64);
+      have_cut = true;
+      ++t;
     }
-    __syncthreads();
-    if (tid == 0) frame_commit(st, d, cfg, nc, ps.alive, ps.best);
     __syncthreads();
     phase(4);
   }
+  __syncthreads();
+  if (tid < 6) st->phase_cycles[tid] += s_phase[tid];
 }
 
 // ------------------------------------------------------------------ raw lattice

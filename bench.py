@@ -336,7 +336,7 @@ def run_b200_arm(a):
     expand_s = xm.value / 1e3
     achieved = 16.0 * ae.value / expand_s / 1e9 if expand_s > 0 else 0.0
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "expand_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "stream_traffic.json" if on_chip else "expand_traffic.json")
     if os.path.exists(tpath):
         try:
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
@@ -359,6 +359,8 @@ def run_b200_arm(a):
                      "algorithmic_bytes_per_arc": 16, "arcs_per_launch": ae.value / max(1, xn.value),
                      "launch_ms": xm.value / max(1, xn.value), "launches_per_step": int(xn.value),
                      "timing": "CUDA events around every launch of one extra step run without sub-batch overlap",
+                     "launch": ("k_stream: one CTA per stream, 32 frames per launch" if on_chip else
+                                "k_expand: one frame of all streams per launch"),
                      "kernel_ms_per_launch": {k: kms[i] / max(1, kn[i]) for i, k in enumerate(knames)},
                      "kernel_share_of_step": {k: kms[i] / ktot for i, k in enumerate(knames)}},
     }
