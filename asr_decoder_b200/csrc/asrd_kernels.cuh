@@ -620,8 +620,9 @@ __device__ __forceinline__ float block_kth_smallest(OrdAt ord_at, uint32_t n, ui
     prefix |= s_misc[0] << sh;
     pmask |= 255u << sh;
     kk = s_misc[1];
-    __syncthreads();
+    // (no barrier here: s_misc is next written two barriers into the following pass)
   }
+  __syncthreads();
   return ord2f(prefix + min_ord);
 }
 
@@ -656,8 +657,14 @@ __device__ __forceinline__ void get_cutoff(OrdAt ord_at, uint32_t n_items, uint3
       le += c <= beam_cut;
     }
   }
-  lt = block_sum_u32<NT>(lt, s_red32);
-  le = block_sum_u32<NT>(le, s_red32);
+  if (n_items < 65536u) {  // both counts in one block reduction
+    const uint32_t both = block_sum_u32<NT>(lt | (le << 16), s_red32);
+    lt = both & 0xFFFFu;
+    le = both >> 16;
+  } else {
+    lt = block_sum_u32<NT>(lt, s_red32);
+    le = block_sum_u32<NT>(le, s_red32);
+  }
   if (lt > (uint32_t)cfg.max_active) {
     // sorted[max_active] < beam_cutoff  <=>  more than max_active costs below it (inl.h:188-203)
     cur_cut = block_kth_smallest<NT>(ord_at, n_items, (uint32_t)cfg.max_active, best_ord, beam_ord,
