@@ -9,6 +9,11 @@ import ctypes as C
 import os
 import subprocess
 
+# More hardware work queues than the driver's default of 8: the library runs its sub-batch frame
+# loops, staging copies and row scatter on a dozen streams, and streams that share a queue
+# serialise (see asrd_on_load in csrc/asrd_api.cu).  Read by the driver at context creation.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libasrd_b200.so")
 

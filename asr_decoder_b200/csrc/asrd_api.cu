@@ -5,6 +5,7 @@
 #include <atomic>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -37,6 +38,8 @@ constexpr int kHostChunkFrames = 16;
 constexpr int kMaxWorkers = 32;
 struct DeviceCtx {
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t sync = nullptr;  // event-only stream: joins the workers' per-chunk completion events
+  cudaStream_t prep = nullptr;  // high priority: row scatter (k_begin_advance) must not queue behind the frame loops
   cudaStream_t worker[kMaxWorkers] = {nullptr};
   cudaEvent_t ev_ready = nullptr, ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[kMaxWorkers] = {nullptr};
@@ -50,6 +53,10 @@ int GetCtx(int device, DeviceCtx **out) {
   DeviceCtx &c = g_ctx[device];
   if (!c.copy_stream) {
     CU_CHECK(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+    int prio_least = 0, prio_greatest = 0;
+    CU_CHECK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    CU_CHECK(cudaStreamCreateWithPriority(&c.prep, cudaStreamNonBlocking, prio_greatest));
+    CU_CHECK(cudaStreamCreateWithFlags(&c.sync, cudaStreamNonBlocking));
     CU_CHECK(cudaEventCreateWithFlags(&c.ev_ready, cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) {
       CU_CHECK(cudaEventCreateWithFlags(&c.ev_copied[i], cudaEventDisableTiming));
@@ -57,7 +64,7 @@ int GetCtx(int device, DeviceCtx **out) {
     }
     CU_CHECK(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
     for (int i = 0; i < kMaxWorkers; ++i) {
-      CU_CHECK(cudaStreamCreateWithFlags(&c.worker[i], cudaStreamNonBlocking));
+      CU_CHECK(cudaStreamCreateWithPriority(&c.worker[i], cudaStreamNonBlocking, prio_least));
       CU_CHECK(cudaEventCreateWithFlags(&c.ev_join[i], cudaEventDisableTiming));
     }
   }
@@ -109,6 +116,14 @@ struct Profiler {
     return ASRD_OK;
   }
 };
+
+// The frame loops of the sub-batches, the host->device staging copies and the row scatter run on
+// a dozen CUDA streams.  With the driver's default of 8 hardware work queues several of them share
+// a queue, and a sub-batch whose stream lands on the queue of the copy stream runs behind every
+// staged copy (measured: +12 ms per 256-stream step, one sub-batch finishing 15 ms after the
+// others).  The variable is read when the driver creates the context, so it is set when the
+// library is loaded; a value chosen by the application wins.
+__attribute__((constructor)) void asrd_on_load() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
 
 int64_t g_last_fallback_frames = 0;
 int64_t g_last_phase_cycles[6] = {0, 0, 0, 0, 0, 0};
@@ -782,11 +797,32 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
     }
   }
   CU_CHECK(cudaMemcpyAsync(d_params, hp.data(), sizeof(AdvanceParams) * hp.size(), cudaMemcpyHostToDevice, s));
+  // The row scatter of every chunk runs on a high-priority stream: the frame loops keep every SM
+  // busy (k_stream takes a whole SM), and a scatter queued at normal priority would wait for a
+  // free SM, stalling the staging double buffer and with it the host->device copies.
+  cudaStream_t ps = single ? s : ctx->prep;
+  if (!single) {
+    CU_CHECK(cudaEventRecord(ctx->ev_fork, s));  // stream table, parameters and staging buffers exist
+    CU_CHECK(cudaStreamWaitEvent(ps, ctx->ev_fork, 0));
+  }
 
   Profiler prof(g_profile.load());
   const bool trace = EnvInt("ASRD_TRACE", 0) != 0;
   const auto t_begin = std::chrono::steady_clock::now();
   auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
+  std::vector<cudaEvent_t> tr_copy, tr_rows, tr_w0, tr_join;  // ASRD_TRACE: device timeline of the pipeline
+  cudaEvent_t tr_start = nullptr;
+  if (trace) {
+    cudaEventCreate(&tr_start);
+    cudaEventRecord(tr_start, s);
+  }
+  auto tr_mark = [&](std::vector<cudaEvent_t> &v, cudaStream_t st) {
+    if (!trace) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    v.push_back(e);
+  };
   std::vector<cudaEvent_t> ev_rows;  // rows of chunk k are in the histories
   auto cleanup = [&]() { for (cudaEvent_t e : ev_rows) cudaEventDestroy(e); };
   for (int k = 0; k < n_chunks; ++k) {
@@ -809,17 +845,22 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
                                    (size_t)(loglikes[1] - loglikes[0]) * 4, (size_t)widest * row * 4, (size_t)n,
                                    cudaMemcpyHostToDevice, ctx->copy_stream));
       CU_CHECK(cudaEventRecord(ctx->ev_copied[k & 1], ctx->copy_stream));
-      CU_CHECK(cudaStreamWaitEvent(s, ctx->ev_copied[k & 1], 0));
+      tr_mark(tr_copy, ctx->copy_stream);
+      CU_CHECK(cudaStreamWaitEvent(ps, ctx->ev_copied[k & 1], 0));
     }
     if (trace) fprintf(stderr, "[asrd] chunk %d copies issued at %.2f ms\n", k, since());
-    k_begin_advance<<<dim3(8, (unsigned)n), 256, 0, s>>>(d_streams, d_params + (size_t)k * n, num_indices);
+    if (EnvInt("ASRD_SKIP_SCATTER", 0))  // measurement aid: rows assumed to be in the histories already
+      k_begin_advance<<<dim3(1, (unsigned)n), 32, 0, ps>>>(d_streams, d_params + (size_t)k * n, 0);
+    else
+      k_begin_advance<<<dim3(8, (unsigned)n), 256, 0, ps>>>(d_streams, d_params + (size_t)k * n, num_indices);
     ++g_launches;
     // the rows now live in the per-stream histories: the staging buffer may be refilled
-    if (!on_device) CU_CHECK(cudaEventRecord(ctx->ev_done[k & 1], s));
+    if (!on_device) CU_CHECK(cudaEventRecord(ctx->ev_done[k & 1], ps));
     cudaEvent_t ev;
     CU_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     ev_rows.push_back(ev);
-    CU_CHECK(cudaEventRecord(ev, s));
+    CU_CHECK(cudaEventRecord(ev, ps));
+    tr_mark(tr_rows, ps);
   }
   // ---- frame loops: one per sub-batch, on the worker streams (or on s when there is one)
   for (int k = 0; k < n_chunks; ++k) {
@@ -838,6 +879,7 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
         ++g_launches;
       }
       max_steps = 0;
+      tr_mark(tr_w0, single ? s : ctx->worker[0]);
     }
     for (int32_t f = -1; f < max_steps; ++f) {
       for (int b = 0; b < n_sub; ++b) {
@@ -873,6 +915,7 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
   }
   if (!single) {  // join the workers back into the caller's stream
     for (int w = 0; w < n_workers; ++w) {
+      tr_mark(tr_join, ctx->worker[w]);
       CU_CHECK(cudaEventRecord(ctx->ev_join[w], ctx->worker[w]));
       CU_CHECK(cudaStreamWaitEvent(s, ctx->ev_join[w], 0));
     }
@@ -887,6 +930,21 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
     fprintf(stderr, "[asrd] all issued at %.2f ms\n", since());
     cudaStreamSynchronize(s);
     fprintf(stderr, "[asrd] stream done at %.2f ms\n", since());
+    for (size_t k = 0; k < tr_rows.size(); ++k) {
+      float a = -1.f, b = -1.f, c = -1.f;
+      if (k < tr_copy.size()) cudaEventElapsedTime(&a, tr_start, tr_copy[k]);
+      cudaEventElapsedTime(&b, tr_start, tr_rows[k]);
+      if (k < tr_w0.size()) cudaEventElapsedTime(&c, tr_start, tr_w0[k]);
+      fprintf(stderr, "[asrd] chunk %zu: copied %.2f  rows in history %.2f  worker-0 chunk done %.2f ms\n", k, a, b, c);
+    }
+    for (size_t w = 0; w < tr_join.size(); ++w) {
+      float a = -1.f;
+      cudaEventElapsedTime(&a, tr_start, tr_join[w]);
+      fprintf(stderr, "[asrd] worker %zu done %.2f ms\n", w, a);
+    }
+    for (auto *v : {&tr_copy, &tr_rows, &tr_w0, &tr_join})
+      for (cudaEvent_t e : *v) cudaEventDestroy(e);
+    cudaEventDestroy(tr_start);
   }
   if ((rc = prof.Finish(s))) return rc;
   return ASRD_OK;

@@ -396,9 +396,11 @@ k_begin_advance(StreamState *const *streams, const AdvanceParams *params, int nu
     if (vec) {
       const float4 *s4 = reinterpret_cast<const float4 *>(src);
       float4 *d4 = reinterpret_cast<float4 *>(drow);
-      for (int c = threadIdx.x; c < (num_indices >> 2); c += blockDim.x) d4[c] = __ldg(&s4[c]);
+      // streaming (evict-first) on both sides: the rows pass through L2 once and must not push
+      // the graph out of it
+      for (int c = threadIdx.x; c < (num_indices >> 2); c += blockDim.x) __stcs(&d4[c], __ldcs(&s4[c]));
     } else {
-      for (int c = threadIdx.x; c < num_indices; c += blockDim.x) drow[c] = __ldg(&src[c]);
+      for (int c = threadIdx.x; c < num_indices; c += blockDim.x) __stcs(&drow[c], __ldcs(&src[c]));
     }
   }
 }
@@ -1115,7 +1117,10 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
     float cur, abeam;
     uint32_t n, off;
   } s_h;
-  __shared__ uint16_t s_wq[kStreamThreads / 32][64];
+  // per-warp scratch: staging of admitted arcs during the expansion (kStage x {u64 value, u32
+  // destination}); the eps closure reuses it as its compaction buffer of stamped slots (64 x u16)
+  constexpr int kStage = 44;
+  __shared__ __align__(8) unsigned char s_warp_scratch[kStreamThreads / 32][kStage * 12];
   SmemMap m;
   m.val = reinterpret_cast<unsigned long long *>(s_dyn);
   m.key = reinterpret_cast<uint32_t *>(s_dyn + (size_t)kSmemSlots * 8);
@@ -1174,7 +1179,7 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
       phase(0);
       if (SMEM_LL) {
         const float *__restrict__ llr = s_d.ll;
-        for (int c = tid; c < num_indices; c += NT) s_ll[c] = __ldg(&llr[c]);
+        for (int c = tid; c < num_indices; c += NT) s_ll[c] = __ldcs(&llr[c]);
         __syncthreads();
       }
     } else {
@@ -1186,7 +1191,7 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
       const unsigned long long h_best = s_h.best;
       if (tid == 0) fill_desc(st, d, t, h_n, s_h.off, s_h.cur, h_abeam, kOrdInf, false);
       if (SMEM_LL)
-        for (int c = tid; c < num_indices; c += NT) s_ll[c] = __ldg(&llr[c]);
+        for (int c = tid; c < num_indices; c += NT) s_ll[c] = __ldcs(&llr[c]);
       uint32_t mn = kOrdInf;
       if (h_n > 0) {
         const float bc = ord2f((uint32_t)(h_best >> 32));
@@ -1219,10 +1224,35 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
     // the map, so the HBM/L2 latency of the arc fetch overlaps the shared-memory work.
     {
       uint32_t expanded = 0, admitted = 0;
-      bool p_valid = false;  // pending admitted arc of this lane: destination word and packed value
-      uint32_t p_w = 0;
-      unsigned long long p_pk = 0;
+      // Only about a third of the arcs are admitted: they are staged in a warp-private buffer and
+      // the map is updated 32 arcs at a time with every lane busy.
+      unsigned long long *st_pk = reinterpret_cast<unsigned long long *>(s_warp_scratch[warp]);
+      uint32_t *st_w = reinterpret_cast<uint32_t *>(s_warp_scratch[warp] + kStage * 8);
+      uint32_t n_staged = 0;
       const uint32_t lt_mask = (1u << lane) - 1u;
+      auto flush = [&](uint32_t k) {  // the first k (<= 32) staged arcs go to the map, the rest moves up
+        const bool act = (uint32_t)lane < k;
+        const uint32_t w = act ? st_w[lane] : 0u;
+        const unsigned long long pk = act ? st_pk[lane] : 0ull;
+        const uint32_t rem = n_staged - k;
+        __syncwarp();
+        if (rem) {
+          uint32_t tw = 0;
+          unsigned long long tpk = 0;
+          if ((uint32_t)lane < rem) {
+            tw = st_w[k + lane];
+            tpk = st_pk[k + lane];
+          }
+          __syncwarp();
+          if ((uint32_t)lane < rem) {
+            st_w[lane] = tw;
+            st_pk[lane] = tpk;
+          }
+          __syncwarp();
+        }
+        n_staged = rem;
+        smem_relax(m, act, w, pk, 1u, nullptr, lane);
+      };
       float nc = ord2f(*reinterpret_cast<volatile uint32_t *>(next_cut));
       // fetch cursor: the token group whose arcs are being requested.  Two more groups are in
       // flight behind it: the tokens of group +2 and the emitting-arc spans of group +1 (the
@@ -1332,34 +1362,22 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          // Only about a third of the arcs are admitted: they are first gathered into a
-          // per-lane pending slot and the map is updated with all 32 lanes busy.
           const unsigned nmask = __ballot_sync(kFull, adm[u]);
           if (nmask == 0) continue;
           admitted += adm[u];
-          const unsigned long long pk = pack_val(tot[u], a[u]);
-          const unsigned freem = ~__ballot_sync(kFull, p_valid);
-          const int nfree = __popc(freem), nnew = __popc(nmask);
-          const int r = __popc(freem & lt_mask);  // rank among the free lanes
-          const bool take = !p_valid && r < nnew;
-          const int src = select_nth(nmask, take ? r : 0);
-          const uint32_t g_w = __shfl_sync(kFull, (uint32_t)arc[u].w, src);
-          const uint32_t g_lo = __shfl_sync(kFull, (uint32_t)pk, src);
-          const uint32_t g_hi = __shfl_sync(kFull, (uint32_t)(pk >> 32), src);
-          if (take) {
-            p_w = g_w;
-            p_pk = ((unsigned long long)g_hi << 32) | g_lo;
-            p_valid = true;
+          const uint32_t nnew = (uint32_t)__popc(nmask);
+          if (n_staged + nnew > (uint32_t)kStage) flush(n_staged);  // (n_staged < 32 here)
+          if (adm[u]) {
+            const uint32_t r = n_staged + (uint32_t)__popc(nmask & lt_mask);
+            st_w[r] = (uint32_t)arc[u].w;
+            st_pk[r] = pack_val(tot[u], a[u]);
           }
-          if (nnew >= nfree) {  // every lane holds an arc: update the map, keep the rest pending
-            smem_relax(m, true, p_w, p_pk, 1u, nullptr, lane);
-            p_valid = adm[u] && __popc(nmask & lt_mask) >= nfree;
-            p_w = (uint32_t)arc[u].w;
-            p_pk = pk;
-          }
+          n_staged += nnew;
+          __syncwarp();
+          if (n_staged >= 32u) flush(32u);
         }
       }
-      smem_relax(m, p_valid, p_w, p_pk, 1u, nullptr, lane);  // the last, partial set
+      flush(n_staged);  // the last, partial set
       admitted = __reduce_add_sync(kFull, admitted);
       if (lane == 0 && expanded) {
         atomicAdd(&s_d.arcs_expanded, expanded);
@@ -1372,7 +1390,7 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
 
     // ---- eps closure (ProcessNonemitting, inl.h:353-431): round r relaxes the slots stamped r
     if (!s_overflow) {
-      uint16_t *wq = s_wq[warp];  // this warp's compaction buffer of stamped slots
+      uint16_t *wq = reinterpret_cast<uint16_t *>(s_warp_scratch[warp]);  // this warp's compaction buffer of stamped slots
       for (uint32_t round = 1;; ++round) {
         const uint32_t nr = round + 1;
         uint32_t nq = 0;

@@ -28,6 +28,8 @@ import sys
 import tempfile
 import time
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # before the CUDA context exists (see _lib.py)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
