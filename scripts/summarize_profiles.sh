@@ -23,7 +23,7 @@ for K in "$@"; do
   F=gpurun_out/${TAG}_$K.ncu-rep
   [ -f $F ] || continue
   echo
-  echo "## $K  (ncu --set full, one launch mid-utterance, --frames 100 run)"
+  echo "## $K  (ncu --set full, one launch mid-utterance: 256 streams x 32 frames, sub-batch overlap off)"
   ncu -i $F --page details 2>/dev/null | grep -E "Duration|Elapsed Cycles|Executed Instructions |Registers Per|Theoretical Occ|Achieved Occ|Issue Slots Busy|L2 Hit|L1/TEX Hit|DRAM Throughput|Warp Cycles Per Issued|Grid Size|Block Size|Memory Throughput|Eligible Warps|Active Warps Per"
   ncu -i $F --page raw --csv 2>/dev/null | python -c "
 import csv,sys
@@ -34,7 +34,7 @@ for w in ['dram__bytes_read.sum','dram__bytes_write.sum','lts__t_sector_hit_rate
 "
   ncu -i $F --page source --csv --print-source cuda,sass 2>/dev/null > /tmp/ncu_src_$$.csv
   echo "   top stall lines (share of warp-stall samples, dominant reasons):"
-  python scripts/ncu_lines.py /tmp/ncu_src_$$.csv 14 | sed 's/^/    /'
+  python scripts/ncu_inst_lines.py /tmp/ncu_src_$$.csv 16 "# Samples" | cut -c1-190 | sed 's/^/    /'
   rm -f /tmp/ncu_src_$$.csv
 done
 } > $OUT
