@@ -1,18 +1,19 @@
 // Hand-written sm_100a kernels of the WFST token-passing beam search.
 //
-// Per decoded frame four launches serve ALL streams of a batch; all of them are warp-centric
-// (one warp per group of 32 tokens / 1024 map slots, work split by warp-shuffle prefix sums,
-// no block barriers on the hot paths):
-//   k_expand    — emitting-arc expansion (ProcessEmitting's hot loop,
-//                 reference src/my-decoder/online-decoder-base-inl.h:311-347)
-//   k_closure   — one CTA per stream: eps closure (ProcessNonemitting, inl.h:353-431) as
-//                 frontier rounds seeded from a bitmap of newly claimed eps states
-//   k_finalize  — over the claimed-slot bitmaps: survivors (cost < final cutoff) are appended to
-//                 the token arena with the arc the reference's trace-back would report
-//                 (inl.h:1169-1186 + the lattice-beam link pruning of inl.h:524-542)
-//   k_cutoff    — one CTA per stream: recycle the previous map, GetCutoff for the next frame
+//   k_stream    — the default path of plain decoders: ONE CTA per stream runs the whole frame loop
+//                 of an AdvanceDecoding chunk with the per-frame state->token map in shared memory
+//                 (GetCutoff, ProcessEmitting, ProcessNonemitting, survivor write-out;
+//                 reference src/my-decoder/online-decoder-base-inl.h:138-431)
+//   k_expand    — emitting-arc expansion over per-stream maps in HBM, all streams of a sub-batch
+//                 per launch (ProcessEmitting's hot loop, inl.h:311-347); biglm decoders and, as
+//                 the device function expand_frame, the overflow frames of k_stream
+//   k_post      — one CTA per stream over the HBM map: eps closure (inl.h:353-431) as frontier
+//                 rounds, survivors (cost < final cutoff) appended to the token arena with the
+//                 arc the reference's trace-back would report (inl.h:1169-1186 + the lattice-beam
+//                 link pruning of inl.h:524-542), map recycling, GetCutoff for the next frame
 //                 (inl.h:138-234, exact radix select) and the best-token pre-pass (inl.h:282-300)
-// k_best_path walks the back-trace (BestPathEnd / TraceBackBestPath, inl.h:1096-1200).
+//   k_best_path — back-trace (BestPathEnd / TraceBackBestPath, inl.h:1096-1200)
+//   k_lattice   — raw lattice with FinalizeDecoding's pruning (inl.h:725-975)
 #pragma once
 
 #include <math_constants.h>
