@@ -635,7 +635,8 @@ __device__ __forceinline__ float block_kth_smallest(OrdAt ord_at, uint32_t n, ui
 template <int NT, class OrdAt>
 __device__ __forceinline__ void get_cutoff(OrdAt ord_at, uint32_t n_items, uint32_t n, uint32_t best_ord,
                                            const DecoderConfigDev &cfg, uint32_t *s_red32, uint32_t *s_hist,
-                                           uint32_t *s_misc, float &cur_cut, float &abeam) {
+                                           uint32_t *s_misc, float &cur_cut, float &abeam,
+                                           float all_below = CUDART_INF_F) {
   const int tid = threadIdx.x;
   cur_cut = CUDART_INF_F;
   abeam = cfg.beam;
@@ -652,6 +653,11 @@ __device__ __forceinline__ void get_cutoff(OrdAt ord_at, uint32_t n_items, uint3
     return;
   }
   uint32_t lt = 0, le = 0;
+  if (all_below <= beam_cut) {
+    // every token is known to cost less than all_below (the frame's final next_cutoff, which the
+    // search keeps at or below best + adaptive beam): no counting pass needed
+    lt = le = n;
+  } else {
   for (uint32_t i = tid; i < n_items; i += NT) {
     const uint32_t key = ord_at(i);
     if (key != 0xFFFFFFFFu) {
@@ -667,6 +673,7 @@ __device__ __forceinline__ void get_cutoff(OrdAt ord_at, uint32_t n_items, uint3
   } else {
     lt = block_sum_u32<NT>(lt, s_red32);
     le = block_sum_u32<NT>(le, s_red32);
+  }
   }
   if (lt > (uint32_t)cfg.max_active) {
     // sorted[max_active] < beam_cutoff  <=>  more than max_active costs below it (inl.h:188-203)
@@ -1526,7 +1533,7 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
       __syncthreads();
       float n_cur_cut, n_abeam;
       get_cutoff<NT>(ord_at, kSmemSlots, n_alive, (uint32_t)(best64 >> 32), cfg, ps.red32, ps.hist, ps.misc,
-                     n_cur_cut, n_abeam);
+                     n_cur_cut, n_abeam, nc);
       const uint32_t cap = s_d.out_cap;
       uint2 *out_sc = s_d.out_sc;
       uint32_t *out_arc = s_d.out_arc;

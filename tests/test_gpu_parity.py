@@ -208,3 +208,27 @@ def test_every_kernel_path_gives_the_same_search(oracle_mod, monkeypatch, env):
         if i < 2:
             ref, rst = _oracle_decode(O, og, cfg, lls[i])
             _compare(out1[i], st1, ref, rst, f"{env} stream {i}")
+
+
+@pytest.mark.parametrize("case", ["wide-rows", "deep-eps", "tiny-beam"])
+def test_on_chip_loop_corner_shapes(oracle_mod, case):
+    """Shapes that take the less-travelled branches of the on-chip frame loop: (wide-rows) 6000 pdfs —
+    the log-likelihood row does not fit next to the shared-memory map and is read from global
+    memory; (deep-eps) 60 % of the states have an eps arc to a near state — many closure rounds
+    (round bitmaps, three-flag barrier protocol); (tiny-beam) a handful of tokens per frame."""
+    O = oracle_mod
+    if case == "wide-rows":
+        fst, P, T, cfg = synth.make_graph(20000, 5.0, 6000, seed=31), 6000, 60, _cfg()
+    elif case == "deep-eps":
+        fst, P, T, cfg = synth.make_graph(20000, 4.0, 300, seed=32, p_eps=0.6, eps_span=3), 300, 100, _cfg()
+    else:
+        fst, P, T, cfg = synth.make_graph(20000, 5.0, 300, seed=33), 300, 150, _cfg(beam=2.0, min_active=0)
+    lls = [synth.make_loglikes(T, P, 2.0, seed=500 + i) for i in range(3)]
+    g = CudaFst(fst)
+    dec = CudaDecoderBatch(g, cfg, len(lls), max_frames=T + 8, collect_stats=True)
+    out = dec.Decode(lls)
+    og = O.OracleGraph(fst)
+    for i, ll in enumerate(lls):
+        assert dec.status(i) == 0
+        ref, rst = _oracle_decode(O, og, cfg, ll)
+        _compare(out[i], dec.frame_stats(i), ref, rst, f"{case} stream {i}")
