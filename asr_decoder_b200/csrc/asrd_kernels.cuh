@@ -636,7 +636,7 @@ template <int NT, class OrdAt>
 __device__ __forceinline__ void get_cutoff(OrdAt ord_at, uint32_t n_items, uint32_t n, uint32_t best_ord,
                                            const DecoderConfigDev &cfg, uint32_t *s_red32, uint32_t *s_hist,
                                            uint32_t *s_misc, float &cur_cut, float &abeam,
-                                           float all_below = CUDART_INF_F) {
+                                           float all_below = 3.402823466e38f /* no bound known */) {
   const int tid = threadIdx.x;
   cur_cut = CUDART_INF_F;
   abeam = cfg.beam;
