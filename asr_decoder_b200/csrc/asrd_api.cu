@@ -1023,7 +1023,6 @@ int asrd_get_raw_lattice(asrd_decoder *d, int32_t use_final_probs, asrd_lat_toke
   if (!d || !n_toks || !n_links || tok_cap < 0 || link_cap < 0 || tok_cap > 0x7FFFFFFF || link_cap > 0x7FFFFFFF)
     return ASRD_ERR_BAD_ARG;
   if (!d->initialized) return ASRD_ERR_STATE;
-  if (d->lm1) return ASRD_ERR_BAD_ARG;  // lattice generation is not built for the biglm decoder yet
   if (d->finalized && !use_final_probs) return ASRD_ERR_STATE;  // inl.h:879-884
   if (d->frames_decoded <= 0 || !d->d_ll_hist) {
     *n_toks = *n_links = 0;
@@ -1048,11 +1047,20 @@ int asrd_get_raw_lattice(asrd_decoder *d, int32_t use_final_probs, asrd_lat_toke
   CU_CHECK(sc.Alloc(&h.links, (size_t)std::max<int64_t>(link_cap, 1)));
   h.map[0] = maps;
   h.map[1] = maps + H;
+  if (d->lm1) {
+    uint32_t *pairs;
+    CU_CHECK(sc.Alloc(&pairs, 2 * H));
+    h.map_pair[0] = pairs;
+    h.map_pair[1] = pairs + H;
+  }
   h.tok_cap = (uint32_t)tok_cap;
   h.link_cap = (uint32_t)link_cap;
   CU_CHECK(cudaMemsetAsync(maps, 0xFF, 2 * H * sizeof(LatEntry), s));
   CU_CHECK(cudaMemcpyAsync(d_out, &h, sizeof(h), cudaMemcpyHostToDevice, s));
-  k_lattice<<<1, kStreamThreads, 0, s>>>(d_streams, d_out, d->graph->view, DevCfg(d), use_final_probs ? 1 : 0);
+  if (d->lm1)
+    k_lattice<true><<<1, kStreamThreads, 0, s>>>(d_streams, d_out, d->graph->view, DevCfg(d), use_final_probs ? 1 : 0, Lms(d));
+  else
+    k_lattice<false><<<1, kStreamThreads, 0, s>>>(d_streams, d_out, d->graph->view, DevCfg(d), use_final_probs ? 1 : 0, Lms(d));
   ++g_launches;
   CU_CHECK(cudaGetLastError());
   LatticeOut r;
@@ -1075,7 +1083,9 @@ int asrd_get_raw_lattice(asrd_decoder *d, int32_t use_final_probs, asrd_lat_toke
   for (uint32_t i = 0; i < r.n_toks; ++i) order[i] = i;
   std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
     if (toks[a].frame != toks[b].frame) return toks[a].frame < toks[b].frame;
-    return toks[a].state < toks[b].state;
+    if (toks[a].state != toks[b].state) return toks[a].state < toks[b].state;
+    if (toks[a].cost != toks[b].cost) return toks[a].cost < toks[b].cost;  // biglm: several LM states per HCLG state
+    return arena[a] < arena[b];
   });
   std::vector<asrd_lat_token> sorted(r.n_toks);
   std::vector<std::pair<uint32_t, uint32_t>> a2i(r.n_toks);

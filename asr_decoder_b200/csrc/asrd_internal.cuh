@@ -140,6 +140,7 @@ struct LatticeOut {    // per-stream output window of k_lattice
   uint32_t *tok_arena_idx;   // arena index of every emitted token (links refer to arena indices)
   asrd_lat_link *links;
   LatEntry *map[2];
+  uint32_t *map_pair[2];     // biglm: LM pair id of the token in every map slot
   uint32_t tok_cap, link_cap;
   uint32_t n_toks, n_links;   // produced (may exceed the caps: then nothing beyond the cap was written)
 };

@@ -1587,12 +1587,15 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
 // inside a frame iterate to the exact fixed point), drops links with
 // link_extra_cost > lattice_beam and tokens without surviving links, and emits the survivors.
 // Two small per-frame maps (state -> cost, extra, arena index) replace the reference's pointers.
-__device__ __forceinline__ bool lat_find(const LatEntry *m, uint32_t mask, uint32_t shift, uint32_t state,
-                                         uint32_t &slot) {
-  uint32_t h = hash_state(state, mask, shift);
+// BIGLM: several tokens of a frame may share the HCLG state; the LM pair id of every slot sits in a
+// parallel array and the probe sequence starts at the hash of (state, pair).
+template <bool BIGLM>
+__device__ __forceinline__ bool lat_find(const LatEntry *m, const uint32_t *mp, uint32_t mask, uint32_t shift,
+                                         uint32_t state, uint32_t pair, uint32_t &slot) {
+  uint32_t h = BIGLM ? hash_key(((unsigned long long)pair << 32) | state, mask, shift) : hash_state(state, mask, shift);
   for (uint32_t probe = 0; probe <= mask; ++probe) {
     const uint32_t k = __ldcg(&m[h].key);
-    if (k == state) {
+    if (k == state && (!BIGLM || __ldcg(&mp[h]) == pair)) {
       slot = h;
       return true;
     }
@@ -1602,8 +1605,10 @@ __device__ __forceinline__ bool lat_find(const LatEntry *m, uint32_t mask, uint3
   return false;
 }
 
+template <bool BIGLM>
 __global__ void __launch_bounds__(kStreamThreads, 2)
-k_lattice(StreamState *const *streams, LatticeOut *outs, GraphView g, DecoderConfigDev cfg, int use_final) {
+k_lattice(StreamState *const *streams, LatticeOut *outs, GraphView g, DecoderConfigDev cfg, int use_final,
+          LmPair lms) {
   constexpr int NT = kStreamThreads;
   __shared__ unsigned long long s_red64[NT / 32];
   __shared__ uint32_t s_changed;
@@ -1620,25 +1625,40 @@ k_lattice(StreamState *const *streams, LatticeOut *outs, GraphView g, DecoderCon
   const float beam = cfg.lattice_beam;
   uint32_t *slots[2] = {st->queue[0], st->queue[1]};  // slot of token i of the frame in map[f & 1]
 
-  // ---- final costs (ComputeFinalCosts, inl.h:670-720): the token on the super-final state, if any
+  unsigned long long *pair_map = BIGLM ? st->pair_map : nullptr;
+  const uint32_t pair_mask = BIGLM ? st->pair_mask : 0;
+  // ---- final costs (ComputeFinalCosts, inl.h:670-720): the token on the super-final state, if any.
+  // biglm (…-biglm.h:157-215): a final token's final cost is DiffArpaLm::Final of its LM state, and
+  // the best cost with final is taken over ALL tokens of the frame.
   float final_best = 0.f;
   bool any_final = false;
   {
     const uint32_t b0 = st->frame_off[F], n0 = st->frame_off[F + 1] - b0;
-    unsigned long long best_all = kInfVal, best_fin = kInfVal;
+    unsigned long long best_all = kInfVal, best_fin = kInfVal, best_wf = kInfVal;
     for (uint32_t i = tid; i < n0; i += NT) {
       const uint2 sc = st->tok_sc[b0 + i];
       const unsigned long long b = ((unsigned long long)f2ord(__uint_as_float(sc.y)) << 32) | sc.x;
       best_all = b < best_all ? b : best_all;
       if ((int32_t)sc.x == g.final_state) best_fin = b < best_fin ? b : best_fin;
+      if (BIGLM) {
+        const float wf = __uint_as_float(sc.y) + lm_final(lms, pair_map, st->tok_lm[b0 + i]);
+        const unsigned long long bw = (unsigned long long)f2ord(wf) << 32;
+        best_wf = bw < best_wf ? bw : best_wf;
+      }
     }
     best_all = block_min_u64<NT>(best_all, s_red64);
     best_fin = block_min_u64<NT>(best_fin, s_red64);
+    if (BIGLM) best_wf = block_min_u64<NT>(best_wf, s_red64);
     any_final = use_final && best_fin != kInfVal;
-    final_best = ord2f((uint32_t)((any_final ? best_fin : best_all) >> 32));  // inl.h:709-719
+    if (BIGLM) {
+      const float wf = ord2f((uint32_t)(best_wf >> 32));
+      final_best = (use_final && best_wf != kInfVal && wf != CUDART_INF_F) ? wf : ord2f((uint32_t)(best_all >> 32));
+    } else {
+      final_best = ord2f((uint32_t)((any_final ? best_fin : best_all) >> 32));  // inl.h:709-719
+    }
   }
 
-  auto emit_link = [&](uint32_t src_idx, uint32_t dst_idx, const int4 &arc, float ac) {
+  auto emit_link = [&](uint32_t src_idx, uint32_t dst_idx, const int4 &arc, float graph_cost, float ac) {
     const uint32_t p = atomicAdd(&out->n_links, 1u);
     if (p < out->link_cap) {
       asrd_lat_link l;
@@ -1646,7 +1666,7 @@ k_lattice(StreamState *const *streams, LatticeOut *outs, GraphView g, DecoderCon
       l.dst = (int32_t)dst_idx;
       l.ilabel = arc.x;
       l.olabel = arc.y;
-      l.graph = __int_as_float(arc.z);
+      l.graph = graph_cost;
       l.acoustic = ac;
       out->links[p] = l;
     }
@@ -1655,9 +1675,12 @@ k_lattice(StreamState *const *streams, LatticeOut *outs, GraphView g, DecoderCon
   for (int f = F; f >= 0; --f) {
     LatEntry *mc = out->map[f & 1];        // this frame
     LatEntry *mn = out->map[(f + 1) & 1];  // frame f + 1 (complete)
+    uint32_t *pc = BIGLM ? out->map_pair[f & 1] : nullptr;
+    const uint32_t *pn = BIGLM ? out->map_pair[(f + 1) & 1] : nullptr;
     uint32_t *sl = slots[f & 1];
     const uint32_t b0 = st->frame_off[f], n = st->frame_off[f + 1] - b0;
     const float nc_f = st->frame_nc[f];
+    const uint32_t *tlm = BIGLM ? st->tok_lm + b0 : nullptr;  // LM pair ids of the frame's tokens
     // ---- recycle the map this frame reuses (it held frame f + 2)
     if (f + 2 <= F) {
       const uint32_t n2 = st->frame_off[f + 3] - st->frame_off[f + 2];
@@ -1672,16 +1695,19 @@ k_lattice(StreamState *const *streams, LatticeOut *outs, GraphView g, DecoderCon
     for (uint32_t i = tid; i < n; i += NT) {
       const uint2 sc = st->tok_sc[b0 + i];
       float init = CUDART_INF_F;
+      const uint32_t pair = BIGLM ? tlm[i] : 0u;
       if (f == F) {  // PruneForwardLinksFinal, inl.h:758-775, 815-816
-        const float fc = (!any_final || (int32_t)sc.x == g.final_state) ? 0.f : CUDART_INF_F;
+        float fc = 0.f;
+        if (any_final) fc = (int32_t)sc.x == g.final_state ? (BIGLM ? lm_final(lms, pair_map, pair) : 0.f) : CUDART_INF_F;
         init = __uint_as_float(sc.y) + fc - final_best;
         if (init > beam) init = CUDART_INF_F;
       }
-      uint32_t h = hash_state(sc.x, mask, shift);
+      uint32_t h = BIGLM ? hash_key(((unsigned long long)pair << 32) | sc.x, mask, shift) : hash_state(sc.x, mask, shift);
       for (;;) {
         if (atomicCAS(&mc[h].key, kEmptyKey, sc.x) == kEmptyKey) break;
         h = (h + 1) & mask;
       }
+      if (BIGLM) pc[h] = pair;
       mc[h].cost_bits = sc.y;
       mc[h].extra_ord = f2ord(init);
       mc[h].idx = b0 + i;
@@ -1698,20 +1724,25 @@ k_lattice(StreamState *const *streams, LatticeOut *outs, GraphView g, DecoderCon
         const float cost = __uint_as_float(sc.y);
         if (!(cost <= cur_cut)) continue;  // inl.h:315
         const uint2 er = __ldg(&g.erows[sc.x]);
+        const uint32_t pair = BIGLM ? tlm[i] : 0u;
         float best = CUDART_INF_F;
         for (uint32_t a = er.x; a < er.y; ++a) {
           const int4 arc = __ldg(&g.arcs[a]);
           const float ac = -__ldg(&ll[arc.x - 1]);
-          const float tot = (cost + ac) + __int_as_float(arc.z);  // inl.h:326-329
-          if (!(tot < nc_next)) continue;                           // inl.h:330, final cutoff
+          float graph_cost = __int_as_float(arc.z);
+          int32_t n1 = 0, n2 = 0;
+          if (BIGLM && arc.y != 0) graph_cost = __int_as_float(arc.z) + lm_step(lms, pair_map, pair, arc.y, n1, n2);
+          const float tot = (cost + ac) + graph_cost;  // inl.h:326-329
+          if (!(tot < nc_next)) continue;              // inl.h:330, final cutoff
+          const uint32_t dpair = (BIGLM && arc.y != 0) ? pair_intern(pair_map, pair_mask, n1, n2, &st->status) : pair;
           uint32_t ds;
-          if (!lat_find(mn, mask, shift, (uint32_t)arc.w & kStateMask, ds)) continue;
+          if (!lat_find<BIGLM>(mn, pn, mask, shift, (uint32_t)arc.w & kStateMask, dpair, ds)) continue;
           const float dextra = ord2f(__ldcg(&mn[ds].extra_ord));
           float le = dextra + (tot - __uint_as_float(__ldcg(&mn[ds].cost_bits)));  // inl.h:524-526
           if (le > beam) continue;                                                  // inl.h:532
           if (le < 0.f) le = 0.f;                                                   // inl.h:545-551
           best = fminf(best, le);
-          emit_link(b0 + i, __ldcg(&mn[ds].idx), arc, ac);
+          emit_link(b0 + i, __ldcg(&mn[ds].idx), arc, graph_cost, ac);
         }
         if (best < CUDART_INF_F) atomicMin(&mc[sl[i]].extra_ord, f2ord(best));
       }
@@ -1728,12 +1759,17 @@ k_lattice(StreamState *const *streams, LatticeOut *outs, GraphView g, DecoderCon
         const uint2 r = __ldg(&g.rows[sc.x]);
         if (r.y == r.x) continue;
         float mine = ord2f(__ldcg(&mc[sl[i]].extra_ord));
+        const uint32_t pair = BIGLM ? tlm[i] : 0u;
         for (uint32_t a = r.x; a < r.y; ++a) {
           const int4 arc = __ldg(&g.arcs[a]);
-          const float tot = cost + __int_as_float(arc.z);  // inl.h:413-414
-          if (!(tot < nc_f)) continue;                      // inl.h:415
+          float graph_cost = __int_as_float(arc.z);
+          int32_t n1 = 0, n2 = 0;
+          if (BIGLM && arc.y != 0) graph_cost = __int_as_float(arc.z) + lm_step(lms, pair_map, pair, arc.y, n1, n2);
+          const float tot = cost + graph_cost;  // inl.h:413-414
+          if (!(tot < nc_f)) continue;           // inl.h:415
+          const uint32_t dpair = (BIGLM && arc.y != 0) ? pair_intern(pair_map, pair_mask, n1, n2, &st->status) : pair;
           uint32_t ds;
-          if (!lat_find(mc, mask, shift, (uint32_t)arc.w & kStateMask, ds)) continue;
+          if (!lat_find<BIGLM>(mc, pc, mask, shift, (uint32_t)arc.w & kStateMask, dpair, ds)) continue;
           float le = ord2f(__ldcg(&mc[ds].extra_ord)) + (tot - __uint_as_float(__ldcg(&mc[ds].cost_bits)));
           if (le > beam) continue;
           if (le < 0.f) le = 0.f;
@@ -1766,15 +1802,20 @@ k_lattice(StreamState *const *streams, LatticeOut *outs, GraphView g, DecoderCon
       }
       if (!(cost < nc_f)) continue;
       const uint2 r = __ldg(&g.rows[sc.x]);
+      const uint32_t pair = BIGLM ? tlm[i] : 0u;
       for (uint32_t a = r.x; a < r.y; ++a) {
         const int4 arc = __ldg(&g.arcs[a]);
-        const float tot = cost + __int_as_float(arc.z);
+        float graph_cost = __int_as_float(arc.z);
+        int32_t n1 = 0, n2 = 0;
+        if (BIGLM && arc.y != 0) graph_cost = __int_as_float(arc.z) + lm_step(lms, pair_map, pair, arc.y, n1, n2);
+        const float tot = cost + graph_cost;
         if (!(tot < nc_f)) continue;
+        const uint32_t dpair = (BIGLM && arc.y != 0) ? pair_intern(pair_map, pair_mask, n1, n2, &st->status) : pair;
         uint32_t ds;
-        if (!lat_find(mc, mask, shift, (uint32_t)arc.w & kStateMask, ds)) continue;
+        if (!lat_find<BIGLM>(mc, pc, mask, shift, (uint32_t)arc.w & kStateMask, dpair, ds)) continue;
         const float le = ord2f(__ldcg(&mc[ds].extra_ord)) + (tot - __uint_as_float(__ldcg(&mc[ds].cost_bits)));
         if (le > beam) continue;
-        emit_link(b0 + i, __ldcg(&mc[ds].idx), arc, 0.f);
+        emit_link(b0 + i, __ldcg(&mc[ds].idx), arc, graph_cost, 0.f);
       }
     }
     __syncthreads();

@@ -40,7 +40,7 @@ FRAME_STAT_DTYPE = np.dtype([
 LAT_TOK_DTYPE = np.dtype([("frame", "<i4"), ("state", "<i4"), ("tot", "<f4"), ("extra", "<f4")])
 LAT_LINK_DTYPE = np.dtype([("src_frame", "<i4"), ("src_state", "<i4"), ("dst_frame", "<i4"),
                            ("dst_state", "<i4"), ("ilabel", "<i4"), ("olabel", "<i4"),
-                           ("graph", "<f4"), ("acoustic", "<f4")])
+                           ("graph", "<f4"), ("acoustic", "<f4"), ("src_tot", "<f4"), ("dst_tot", "<f4")])
 
 _lib = None
 

@@ -1174,6 +1174,8 @@ int64_t orc_dump_lattice(const OrcDecoder *d, OrcLatTok *toks, int64_t tok_cap, 
           links[nl].olabel = l->olabel;
           links[nl].graph = l->graph;
           links[nl].acoustic = l->ac;
+          links[nl].src_tot = t->tot;
+          links[nl].dst_tot = l->next_tok->tot;
         }
         ++nl;
       }

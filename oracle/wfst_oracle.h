@@ -66,6 +66,7 @@ typedef struct {
   int32_t dst_frame, dst_state;
   int32_t ilabel, olabel;
   float graph, acoustic;
+  float src_tot, dst_tot; /* costs of the two tokens: tell apart the biglm tokens that share a state */
 } OrcLatLink;
 
 enum { ORC_MODE_REFERENCE = 0, ORC_MODE_CANONICAL = 1 };

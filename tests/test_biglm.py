@@ -112,3 +112,41 @@ def test_cuda_biglm_equals_compiled_reference_golden():
         for bp, ref in zip(out, meta["reference"]):
             assert bp.ok and bp.words == ref["words"] and bp.ali == ref["ali"] and bp.tot_bits == ref["tot_bits"]
             assert abs(bp.tot - ref["tot"]) <= 1e-4 * abs(ref["tot"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("order", [1, 2])
+def test_cuda_biglm_raw_lattice_equals_canonical_oracle(oracle_mod, order):
+    """GetRawLattice of the biglm decoder (the reference inherits it from the base class,
+    online-decoder-base-inl.h:868-975, with the final costs of …-biglm.h:157-215): surviving tokens
+    (cost and extra_cost bits) and forward links (labels, graph cost incl. the LM-difference score,
+    acoustic cost) equal the canonical oracle's.  Tokens that share an HCLG state are told apart by
+    their cost."""
+    from asr_decoder_b200.decoder import CudaDecoderBatch, CudaFst, CudaLm, LatticeFasterDecoderConfig
+    O = oracle_mod
+    fst = synth.make_graph(3000, 5.0, 90, seed=41, n_words=60, eps_span=250)
+    lm1 = LM.make_lm(60, seed=7, order=order).Rescale(-1.0)
+    lm2 = LM.make_lm(60, seed=8, order=order, bigram_density=0.2)
+    lls = [synth.make_loglikes(t, 90, s, seed=300 + t) for t, s in ((70, 2.0), (33, 2.5))]
+    cfg = LatticeFasterDecoderConfig(beam=12.0, max_active=2500, min_active=150, lattice_beam=7.0)
+    dec = CudaDecoderBatch(CudaFst(fst), cfg, len(lls), max_frames=96, old_lm=CudaLm(lm1), new_lm=CudaLm(lm2))
+    dec.Decode(lls)
+    og, o1, o2 = O.OracleGraph(fst), O.OracleLm(lm1), O.OracleLm(lm2)
+    bits = lambda x: int(np.float32(x).view(np.uint32))
+    for i, ll in enumerate(lls):
+        d = O.OracleDecoder(og, O.make_config(cfg.beam, cfg.max_active, cfg.min_active, cfg.lattice_beam),
+                            O.MODE_CANONICAL, o1, o2)
+        d.decode(ll)
+        otoks, olinks = d.dump_lattice()
+        toks, links = dec.GetRawLattice(i)
+        gt = sorted((int(x["frame"]), int(x["state"]), bits(x["cost"]), bits(x["extra"])) for x in toks)
+        ot = sorted((int(x["frame"]), int(x["state"]), bits(x["tot"]), bits(x["extra"])) for x in otoks)
+        assert gt == ot, (order, i, len(gt), len(ot))
+        gl = sorted((int(toks[x["src"]]["frame"]), int(toks[x["src"]]["state"]), bits(toks[x["src"]]["cost"]),
+                     int(toks[x["dst"]]["frame"]), int(toks[x["dst"]]["state"]), bits(toks[x["dst"]]["cost"]),
+                     int(x["ilabel"]), int(x["olabel"]), bits(x["graph"]), bits(x["acoustic"])) for x in links)
+        ol = sorted((int(x["src_frame"]), int(x["src_state"]), bits(x["src_tot"]), int(x["dst_frame"]),
+                     int(x["dst_state"]), bits(x["dst_tot"]), int(x["ilabel"]), int(x["olabel"]), bits(x["graph"]),
+                     bits(x["acoustic"])) for x in olinks)
+        assert gl == ol, (order, i, len(gl), len(ol))
+        assert toks["is_final"].sum() >= 1
