@@ -69,3 +69,29 @@ def test_biglm_through_decoder_itf():
     res = [json.loads(l) for l in out.splitlines() if l.startswith("{")]
     for r, ref in zip(res, meta["reference"]):
         assert r["ok"] and r["words"] == ref["words"] and r["ali"] == ref["ali"] and r["tot_bits"] == ref["tot_bits"]
+
+
+def test_biglm_raw_lattice_through_decoder_itf(oracle_mod):
+    """DecoderItf::GetRawLattice of the biglm drop-in: Lattice state / arc counts equal the canonical
+    biglm oracle's surviving tokens / links on the golden biglm fixture."""
+    from asr_decoder_b200 import fstio, lm as LM
+    O = oracle_mod
+    meta = json.load(open(os.path.join(GOLD, "b1.json")))
+    cfg = meta["config"]
+    cmd = [BIN, f"--graph={GOLD}/b1.fst", f"--loglikes={GOLD}/b1.llb", f"--lm1={GOLD}/b1.lm1", f"--lm2={GOLD}/b1.lm2",
+           f"--beam={cfg['beam']}", f"--max-active={cfg['max_active']}", f"--min-active={cfg['min_active']}",
+           f"--lattice-beam={cfg['lattice_beam']}", "--lattice"]
+    out = subprocess.run(cmd, check=True, stdout=subprocess.PIPE).stdout.decode()
+    res = [json.loads(l) for l in out.splitlines() if l.startswith("{")]
+    fst = fstio.read_fst(os.path.join(GOLD, "b1.fst"))
+    lls = fstio.read_loglikes(os.path.join(GOLD, "b1.llb"))
+    lm1 = LM.read_lm(os.path.join(GOLD, "b1.lm1")).Rescale(-1.0)
+    lm2 = LM.read_lm(os.path.join(GOLD, "b1.lm2"))
+    og, o1, o2 = O.OracleGraph(fst), O.OracleLm(lm1), O.OracleLm(lm2)
+    assert len(res) == len(lls)
+    for r, ll in zip(res, lls):
+        d = O.OracleDecoder(og, O.make_config(**cfg), O.MODE_CANONICAL, o1, o2)
+        d.decode(ll)
+        nt, nl = d.counts()
+        assert (r["raw_states"], r["raw_arcs"]) == (nt, nl)
+        assert r["raw_finals"] >= 1
