@@ -1492,7 +1492,8 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
         st->tot_fallback_frames += 1;
       }
       __syncthreads();
-      expand_frame<1, SMEM_LL, false>(d, g, s_ll, (uint32_t)warp, NT / 32, 0, lms);
+      // (two arc steps in flight per lane: a single CTA is latency-bound on the HBM map)
+      expand_frame<2, SMEM_LL, false>(d, g, s_ll, (uint32_t)warp, NT / 32, 0, lms);
       __syncthreads();
       post_epilogue<false>(st, d, g, cfg, lms, ps);
       phase(5);
