@@ -43,6 +43,7 @@ struct DeviceCtx {
   cudaStream_t worker[kMaxWorkers] = {nullptr};
   cudaEvent_t ev_ready = nullptr, ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[kMaxWorkers] = {nullptr};
+  std::mutex issue_mu;  // one AdvanceDecoding call at a time ISSUES work on a device (the events above are shared)
 };
 std::mutex g_ctx_mu;
 DeviceCtx g_ctx[16];
@@ -730,6 +731,10 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
   const LmPair lms = Lms(decs[0]);
   DeviceCtx *ctx = nullptr;
   if ((rc = GetCtx(decs[0]->graph->device, &ctx))) return rc;
+  // Host threads may call the ABI concurrently on different decoder handles (the reference runs one
+  // decoder per worker thread): the side streams and events of the device are shared, so the issue
+  // phases of two calls must not interleave.  The device work itself still overlaps.
+  std::lock_guard<std::mutex> issue_lock(ctx->issue_mu);
   Scratch sc(s);
   StreamState **d_streams;
   if ((rc = UploadStreams(decs, n, s, sc, &d_streams))) return rc;
