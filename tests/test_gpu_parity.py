@@ -232,3 +232,39 @@ def test_on_chip_loop_corner_shapes(oracle_mod, case):
         assert dec.status(i) == 0
         ref, rst = _oracle_decode(O, og, cfg, ll)
         _compare(out[i], dec.frame_stats(i), ref, rst, f"{case} stream {i}")
+
+
+def test_concurrent_host_threads_on_different_handles(oracle_mod):
+    """The reference runs one decoder object per worker thread (v2-asr-service.cc:95-104); the C ABI
+    must therefore accept concurrent calls on DIFFERENT handles.  Four host threads decode their own
+    batches at the same time on their own CUDA streams (ctypes releases the GIL); every result equals
+    the single-threaded one."""
+    import threading
+    import torch
+    fst = synth.make_graph(30000, 5.0, 400, seed=55)
+    g = CudaFst(fst)
+    cfg = _cfg()
+    jobs = [[synth.make_loglikes(80 + 10 * k, 400, 2.0 + 0.25 * (i % 3), seed=700 + 10 * k + i) for i in range(40)]
+            for k in range(4)]
+    ref = []
+    for lls in jobs:
+        dec = CudaDecoderBatch(g, cfg, len(lls), max_frames=128)
+        ref.append(dec.Decode(lls))
+    outs, errs = [None] * len(jobs), []
+
+    def work(k):
+        try:
+            st = torch.cuda.Stream()
+            dec = CudaDecoderBatch(g, cfg, len(jobs[k]), max_frames=128)
+            for _ in range(3):
+                outs[k] = dec.Decode(jobs[k], stream=st.cuda_stream)
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(len(jobs))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    for k in range(len(jobs)):
+        for a, b in zip(ref[k], outs[k]):
+            assert a.ok == b.ok and a.tot_bits == b.tot_bits and np.array_equal(a.ilabel, b.ilabel)
