@@ -7,7 +7,8 @@ from asr_decoder_b200.decoder import CudaDecoderBatch, CudaFst, LatticeFasterDec
 n, T, P = 256, 333, 3000
 fst = synth.make_graph(1_000_000, 5.0, P, seed=12345)
 g = CudaFst(fst)
-cfg = LatticeFasterDecoderConfig(beam=13.0, max_active=7000, min_active=200, lattice_beam=8.0)
+BEAM = float(os.environ.get('BEAM', '13.0'))
+cfg = LatticeFasterDecoderConfig(beam=BEAM, max_active=7000, min_active=200, lattice_beam=8.0)
 host = torch.empty((n, T, P), dtype=torch.float32).pin_memory()
 gen = [synth.make_loglikes(T, P, 2.0, seed=100 + i) for i in range(8)]
 for i in range(n):
@@ -37,26 +38,10 @@ def timed(a, od, reps=3):
         torch.cuda.synchronize(); t0 = time.perf_counter(); step(a, od); torch.cuda.synchronize()
         best = min(best, 1e3 * (time.perf_counter() - t0))
     return round(best, 2)
-for w in (0,):
-    os.environ["ASRD_GRID_WINDOW"] = str(w)
-    print("window", w, "resident", timed(da, True), "host", timed(ha, False), flush=True)
-
-
-os.environ["ASRD_DEVICE_CHUNK"] = "16"
-side = torch.cuda.Stream(); main = torch.cuda.Stream()
-ms = C.c_void_p(main.cuda_stream)
-def step_on(a, on_device, st):
-    batch.InitDecoding(st); batch.AdvanceDecodingRaw(a[0], a[1], a[2], P, on_device, -1, st)
-    batch.FinalizeDecoding(st); return batch.GetBestPath(True, st, vectors=False)
-dummy = torch.empty_like(dev)
-def run(kind):
-    torch.cuda.synchronize(); t0 = time.perf_counter()
-    if kind == "h2d":
-        with torch.cuda.stream(side): dummy.copy_(host, non_blocking=True)
-    step_on(da, True, ms); torch.cuda.synchronize()
-    return round(1e3 * (time.perf_counter() - t0), 2)
-print("resident on own stream", [run("none") for _ in range(3)], "with concurrent 1GB H2D", [run("h2d") for _ in range(3)], flush=True)
-def host_on():
-    torch.cuda.synchronize(); t0 = time.perf_counter(); step_on(ha, False, ms); torch.cuda.synchronize()
-    return round(1e3 * (time.perf_counter() - t0), 2)
-print("host rows on own stream", [host_on() for _ in range(3)], flush=True)
+print("beam", BEAM, "resident", timed(da, True), "host", timed(ha, False), flush=True)
+for ch in (8, 16, 32, 64):
+    os.environ["ASRD_HOST_CHUNK"] = str(ch)
+    print("host chunk", ch, timed(ha, False), flush=True)
+os.environ["ASRD_HOST_CHUNK"] = "16"
+os.environ["ASRD_TRACE"] = "1"
+step(ha, False)
