@@ -11,7 +11,8 @@ beam = float(sys.argv[4]) if len(sys.argv) > 4 else 13.0
 maxa = int(sys.argv[5]) if len(sys.argv) > 5 else 7000
 P = 3000
 fst = synth.make_graph(S, 5.0, P, seed=12345)
-lls = [synth.make_loglikes(T, P, 2.0 if i % 2 == 0 else 3.0, seed=4000 + i) for i in range(n)]
+SIG = os.environ.get('SIGMA')
+lls = [synth.make_loglikes(T, P, float(SIG) if SIG else (2.0 if i % 2 == 0 else 3.0), seed=4000 + i) for i in range(n)]
 cfg = LatticeFasterDecoderConfig(beam=beam, max_active=maxa, min_active=200, lattice_beam=8.0)
 g = CudaFst(fst)
 dec = CudaDecoderBatch(g, cfg, n, max_frames=T + 8, token_capacity=T * 30000, collect_stats=True)
