@@ -74,7 +74,7 @@ int GetCtx(int device, DeviceCtx **out) {
 }
 
 // Optional per-kernel timing with CUDA events on the launching stream (asrd_profile_*):
-// class 0 = k_expand, 1 = k_closure, 2 = k_finalize, 3 = k_cutoff.  Off by default: events
+// class 0 = k_expand, 1 = k_post, 2 = k_stream, 3 = unused.  Off by default: events
 // between launches add gaps.
 std::atomic<int> g_profile{0};
 std::mutex g_prof_mu;

@@ -99,7 +99,7 @@ struct StreamState {
 
 // Per-stream descriptor of the frame step in flight: everything the grid-wide kernels need, in
 // one contiguous 128-byte record per stream (one L2 round trip instead of a pointer chase
-// through StreamState).  Rebuilt by k_cutoff(PRO) / k_init for every step; the running cutoff,
+// through StreamState).  Rebuilt by k_post(PRO) / k_stream / k_init for every step; the running cutoff,
 // survivor counter and best token are accumulated here with atomics.
 struct __align__(16) FrameDesc {
   StreamState *st;

@@ -27,7 +27,7 @@ namespace asrd {
 __device__ __forceinline__ uint32_t hash_state(uint32_t s, uint32_t mask, uint32_t shift) {
   // Fibonacci hashing: the active states of a frame come in dense runs of neighbouring ids;
   // the multiplicative scramble spreads them uniformly over the map, which keeps linear-probe
-  // chains short AND balances the per-1024-slot work groups of k_closure / k_finalize.
+  // chains short AND balances the per-1024-slot work groups of the closure and write-out walks of k_post.
   (void)mask;
   return (s * 0x9E3779B1u) >> shift;
 }
@@ -739,7 +739,7 @@ __device__ __forceinline__ void cutoff_prologue(StreamState *st, FrameDesc *d, c
   const uint32_t tok_off = st->frame_off[t];
   const uint2 *toks = st->tok_sc + tok_off;
   const float *__restrict__ ll = st->ll_hist + (size_t)t * st->ll_stride;
-  // best token: lowest cost, ties -> lowest state id (inl.h:169-179); accumulated by k_finalize
+  // best token: lowest cost, ties -> lowest state id (inl.h:169-179); accumulated by the write-out of the previous step
   const unsigned long long best64 = st->best64;
   float cur_cut, abeam;
   get_cutoff<NT>([&](uint32_t i) { return f2ord(__uint_as_float(toks[i].y)); }, n, n, (uint32_t)(best64 >> 32), cfg,
@@ -777,7 +777,7 @@ __device__ __forceinline__ void cutoff_prologue(StreamState *st, FrameDesc *d, c
 
 // ------------------------------------------------------------------ fused per-stream post phase
 
-// k_closure + k_finalize + k_cutoff for one stream in ONE CTA: everything that follows the
+// Eps closure + survivor write-out + GetCutoff for one stream in ONE CTA: everything that follows the
 // emitting expansion of a frame only touches the stream's own state, so a single resident CTA
 // carries it from the eps closure to the descriptor of the next expansion without going back
 // to the host-visible launch queue (three launches and their descriptor round trips saved).
