@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(HERE, "libasrd_b200.so")
 
 # every symbol include/asrd.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
-    "asrd_strerror", "asrd_abi_version", "asrd_device_count",
+    "asrd_strerror", "asrd_abi_version", "asrd_device_count", "asrd_configure_process",
     "asrd_graph_create", "asrd_graph_read", "asrd_graph_destroy", "asrd_graph_info",
     "asrd_lm_create", "asrd_lm_destroy",
     "asrd_decoder_create", "asrd_decoder_create_biglm", "asrd_decoder_destroy",
@@ -47,7 +47,7 @@ class asrd_config(C.Structure):
 class asrd_device_options(C.Structure):
     _fields_ = [("hash_capacity", C.c_int32), ("token_capacity", C.c_int64),
                 ("max_frames", C.c_int32), ("collect_stats", C.c_int32),
-                ("reserved", C.c_int32 * 4)]
+                ("lm_pair_capacity", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 class asrd_frame_stat(C.Structure):

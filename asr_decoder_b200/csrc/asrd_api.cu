@@ -18,6 +18,7 @@ using namespace asrd;
 namespace {
 
 std::atomic<long long> g_launches{0};
+std::mutex g_ref_mu;  // reference counts of graphs and LMs (shared by decoders, src/my-decoder/online-decoder-base-inl.h:24)
 thread_local std::string g_last_error;
 
 #define CU_CHECK(expr)                                                                   \
@@ -122,12 +123,12 @@ struct Profiler {
 // a dozen CUDA streams.  With the driver's default of 8 hardware work queues several of them share
 // a queue, and a sub-batch whose stream lands on the queue of the copy stream runs behind every
 // staged copy (measured: +12 ms per 256-stream step, one sub-batch finishing 15 ms after the
-// others).  The variable is read when the driver creates the context, so it is set when the
-// library is loaded; a value chosen by the application wins.
-__attribute__((constructor)) void asrd_on_load() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+// others).  CUDA_DEVICE_MAX_CONNECTIONS is read when the driver creates the context, so a host
+// that wants the extra queues calls asrd_configure_process() (or sets the variable itself) before
+// its first CUDA call; the library no longer touches the environment when it is loaded.
 
-int64_t g_last_fallback_frames = 0;
-int64_t g_last_phase_cycles[6] = {0, 0, 0, 0, 0, 0};
+std::atomic<int64_t> g_last_fallback_frames{0};
+std::atomic<int64_t> g_last_phase_cycles[6];
 
 int EnvInt(const char *name, int dflt) {
   const char *v = getenv(name);
@@ -136,6 +137,12 @@ int EnvInt(const char *name, int dflt) {
 
 int g_num_sms = 0;
 
+// The library's stream-ordered scratch (staging buffers, descriptors, result windows) comes from a
+// PRIVATE memory pool per device, kept cached across the synchronising calls; the device's default
+// pool — which other code in the host process may use — is left alone.
+cudaMemPool_t g_pool[64] = {nullptr};
+std::mutex g_pool_mu;
+
 int EnsureDevice(int device) {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
@@ -143,40 +150,32 @@ int EnsureDevice(int device) {
     g_last_error = "no CUDA device";
     return ASRD_ERR_CUDA;
   }
-  if (device < 0 || device >= n) return ASRD_ERR_BAD_ARG;
-  // a non-sticky error left behind by an earlier, unrelated runtime call must not be blamed on
-  // the launches of this entry point
-  const cudaError_t stale = cudaGetLastError();
-  if (stale != cudaSuccess && EnvInt("ASRD_TRACE", 0))
-    fprintf(stderr, "[asrd] discarding stale CUDA error: %s\n", cudaGetErrorString(stale));
+  if (device < 0 || device >= n || device >= 64) return ASRD_ERR_BAD_ARG;
   CU_CHECK(cudaSetDevice(device));
   if (!g_num_sms) {
     cudaDeviceProp p;
     CU_CHECK(cudaGetDeviceProperties(&p, device));
     g_num_sms = p.multiProcessorCount;
   }
-  static bool pool_tuned[64] = {false};
-  if (device < 64 && !pool_tuned[device]) {
-    // keep the stream-ordered scratch (staging buffers, descriptors) cached across the
-    // synchronising calls instead of returning it to the driver at every sync
-    // L2 set-aside for the evict_last (persisting) graph loads of k_expand / k_post
-    if (EnvInt("ASRD_L2_PERSIST", 0)) {
-      cudaDeviceProp p;
-      if (cudaGetDeviceProperties(&p, device) == cudaSuccess && p.persistingL2CacheMaxSize > 0) {
-        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)p.persistingL2CacheMaxSize);
-        if (EnvInt("ASRD_TRACE", 0))
-          fprintf(stderr, "[asrd] L2 %d MB, persisting set-aside %d MB\n", p.l2CacheSize >> 20,
-                  p.persistingL2CacheMaxSize >> 20);
-      }
-    }
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-      unsigned long long keep = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-    pool_tuned[device] = true;
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  if (!g_pool[device]) {
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof(props));
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    CU_CHECK(cudaMemPoolCreate(&g_pool[device], &props));
+    unsigned long long keep = ~0ull;
+    CU_CHECK(cudaMemPoolSetAttribute(g_pool[device], cudaMemPoolAttrReleaseThreshold, &keep));
   }
   return ASRD_OK;
+}
+
+cudaMemPool_t CurrentPool() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < 64) ? g_pool[dev] : nullptr;
 }
 
 uint32_t NextPow2(uint64_t v) {
@@ -195,7 +194,7 @@ struct Scratch {  // stream-ordered device scratch released on scope exit
   template <typename T>
   cudaError_t Alloc(T **out, size_t count) {
     void *p = nullptr;
-    cudaError_t e = cudaMallocAsync(&p, std::max<size_t>(count * sizeof(T), 16), s);
+    cudaError_t e = cudaMallocFromPoolAsync(&p, std::max<size_t>(count * sizeof(T), 16), CurrentPool(), s);
     if (e == cudaSuccess) ptrs.push_back(p);
     *out = (T *)p;
     return e;
@@ -284,31 +283,39 @@ int PlanExpand(int n_streams, int num_indices, bool biglm, ExpandPlan *plan) {
 }
 
 
-typedef void (*StreamFn)(StreamState *const *, const AdvanceParams *, GraphView, DecoderConfigDev, int);
+typedef void (*StreamFn)(StreamState *const *, const AdvanceParams *, GraphView, DecoderConfigDev, int, uint32_t);
 
 struct StreamPlan {
   StreamFn fn = nullptr;  // null: use the k_expand / k_post pair
   size_t dyn = 0;
+  uint32_t n_buckets = 0;
 };
 
-// The on-chip frame loop (k_stream) serves plain decoders whose log-likelihood row fits next to
-// the shared-memory map; everything else runs the HBM-map kernels.
-int PlanStream(int num_indices, bool biglm, StreamPlan *plan) {
+// The on-chip frame loop (k_stream) serves plain decoders; everything else runs the HBM-map
+// kernels.  The map takes whatever shared memory the log-likelihood row, the warp scratch and the
+// closure queues leave (8 bytes per slot, buckets of four): ~20 k slots at 3000 pdfs.  Rows too
+// wide to leave a useful map are read from global memory instead.
+int PlanStream(const asrd_graph *graph, int num_indices, bool biglm, StreamPlan *plan) {
   plan->fn = nullptr;
   if (biglm || !EnvInt("ASRD_STREAM_KERNEL", 1)) return ASRD_OK;
-  const size_t map_bytes = kSmemMapBytes;
+  if (graph->total_arcs >= (int64_t)kMaxStreamArcs) return ASRD_OK;  // work items pack (arc index << 2 | count)
   cudaFuncAttributes fa;
-  CU_CHECK(cudaFuncGetAttributes(&fa, k_stream<1, true>));
+  CU_CHECK(cudaFuncGetAttributes(&fa, k_stream<true>));
   int dev = 0, max_optin = 0;
   CU_CHECK(cudaGetDevice(&dev));
   CU_CHECK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  const size_t room = (size_t)max_optin > fa.sharedSizeBytes + map_bytes ? (size_t)max_optin - fa.sharedSizeBytes - map_bytes : 0;
-  if ((size_t)max_optin < fa.sharedSizeBytes + map_bytes) return ASRD_OK;
-  const bool smem_ll = (size_t)num_indices * 4 <= room;
-  const int u = EnvInt("ASRD_STREAM_U", 1);
-  if (smem_ll) plan->fn = u >= 2 ? k_stream<2, true> : k_stream<1, true>;
-  else plan->fn = u >= 2 ? k_stream<2, false> : k_stream<1, false>;
-  plan->dyn = map_bytes + (smem_ll ? (size_t)num_indices * 4 : 0);
+  const size_t room = (size_t)max_optin > fa.sharedSizeBytes + 64 ? (size_t)max_optin - fa.sharedSizeBytes - 64 : 0;
+  constexpr size_t kMinMapBytes = (size_t)8192 * 8;
+  bool smem_ll = stream_fixed_dyn_bytes(num_indices) + 2 * kMinMapBytes <= room;
+  const size_t fixed = stream_fixed_dyn_bytes(smem_ll ? num_indices : 0);
+  if (fixed + kMinMapBytes > room) return ASRD_OK;
+  // n_slots must be a multiple of 32 (the write-out walks rows of 32 slots) and fit a u16 slot id
+  uint32_t n_buckets = (uint32_t)std::min<size_t>((room - fixed) / 32, 16376) & ~7u;
+  const int force = EnvInt("ASRD_STREAM_BUCKETS", 0);  // (measurement aid)
+  if (force >= 64 && (uint32_t)force < n_buckets) n_buckets = (uint32_t)force & ~7u;
+  plan->fn = smem_ll ? k_stream<true> : k_stream<false>;
+  plan->n_buckets = n_buckets;
+  plan->dyn = fixed + (size_t)n_buckets * 32;
   CU_CHECK(cudaFuncSetAttribute(plan->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->dyn));
   return ASRD_OK;
 }
@@ -324,6 +331,7 @@ const char *asrd_strerror(int status) {
     case ASRD_ERR_CUDA: return g_last_error.empty() ? "CUDA error" : g_last_error.c_str();
     case ASRD_ERR_NOMEM: return "out of memory";
     case ASRD_ERR_HASH_OVERFLOW: return "state->token map overflow (raise hash_capacity)";
+    case ASRD_ERR_LM_PAIRS_OVERFLOW: return "biglm LM state-pair table full (raise lm_pair_capacity)";
     case ASRD_ERR_ARENA_OVERFLOW: return "token arena overflow (raise token_capacity)";
     case ASRD_ERR_FRAMES_OVERFLOW: return "more frames than max_frames";
     case ASRD_ERR_NO_TOKENS: return "no surviving tokens / nothing decoded";
@@ -335,6 +343,12 @@ const char *asrd_strerror(int status) {
 }
 
 int asrd_abi_version(void) { return ASRD_ABI_VERSION; }
+
+int asrd_configure_process(void) {
+  // more hardware work queues than the driver's default of 8 (see the note above); a value chosen
+  // by the application wins.  Only effective before the process creates its CUDA context.
+  return setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0) == 0 ? ASRD_OK : ASRD_ERR_BAD_ARG;
+}
 
 int asrd_device_count(void) {
   int n = 0;
@@ -411,31 +425,55 @@ int asrd_graph_create(const asrd_arc *arcs, const uint32_t *num_arcs, const uint
     if ((epsb[ns >> 5] >> (ns & 31)) & 1u) parc[a].nextstate = (int32_t)(ns | kDestEpsBit);
   }
 
+  // incoming-arc index (counting sort by destination; arc ids ascend inside a group): the
+  // trace-back of plain decoders finds the arc that set a token's cost through it (k_best_path_rev)
+  std::vector<uint32_t> in_off((size_t)S + 1, 0u), in_arc((size_t)std::max<int64_t>(A, 1));
+  int32_t max_ilabel = 0;
+  for (int64_t a = 0; a < A; ++a) {
+    ++in_off[((uint32_t)parc[a].nextstate & kStateMask) + 1];
+    max_ilabel = std::max(max_ilabel, parc[a].ilabel);
+  }
+  for (int32_t s2 = 0; s2 < S; ++s2) in_off[s2 + 1] += in_off[s2];
+  {
+    std::vector<uint32_t> fill(in_off.begin(), in_off.end() - 1);
+    for (int64_t a = 0; a < A; ++a) in_arc[fill[(uint32_t)parc[a].nextstate & kStateMask]++] = (uint32_t)a;
+  }
+
   asrd_graph *g = new asrd_graph();
   memset(g, 0, sizeof(*g));
+  g->refs = 1;
   g->device = device;
   g->total_arcs = A;
+  g->max_ilabel = max_ilabel;
   const size_t b_arcs = sizeof(asrd_arc) * parc.size(), b_rows = sizeof(uint2) * rows.size(),
                b_src = sizeof(uint32_t) * src.size(), b_par = sizeof(uint32_t) * par.size(),
-               b_eps = sizeof(uint32_t) * epsb.size(), b_erows = sizeof(uint2) * std::max<size_t>(erows.size(), 1);
-  if (cudaMalloc(&g->d_arcs, b_arcs) != cudaSuccess || cudaMalloc(&g->d_rows, b_rows) != cudaSuccess ||
-      cudaMalloc(&g->d_erows, b_erows) != cudaSuccess ||
-      cudaMalloc(&g->d_arc_src, b_src) != cudaSuccess || cudaMalloc(&g->d_par, b_par) != cudaSuccess ||
-      cudaMalloc(&g->d_eps, b_eps) != cudaSuccess) {
-    asrd_graph_destroy(g);
-    return ASRD_ERR_NOMEM;
+               b_eps = sizeof(uint32_t) * epsb.size(), b_erows = sizeof(uint2) * std::max<size_t>(erows.size(), 1),
+               b_ioff = sizeof(uint32_t) * in_off.size(), b_iarc = sizeof(uint32_t) * in_arc.size();
+  struct Up { void **dst; const void *src; size_t bytes; };
+  const Up ups[] = {{&g->d_arcs, parc.data(), b_arcs}, {&g->d_rows, rows.data(), b_rows},
+                    {&g->d_erows, erows.data(), sizeof(uint2) * erows.size()}, {&g->d_arc_src, src.data(), b_src},
+                    {&g->d_par, par.data(), b_par}, {&g->d_eps, epsb.data(), b_eps},
+                    {&g->d_in_off, in_off.data(), b_ioff}, {&g->d_in_arc, in_arc.data(), b_iarc}};
+  for (const Up &u : ups) {
+    if (cudaMalloc(u.dst, std::max<size_t>(u.bytes, 16)) != cudaSuccess) {
+      cudaGetLastError();
+      asrd_graph_destroy(g);
+      return ASRD_ERR_NOMEM;
+    }
+    const cudaError_t e = cudaMemcpy(*u.dst, u.src, u.bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      g_last_error = std::string("graph upload: ") + cudaGetErrorString(e);
+      asrd_graph_destroy(g);
+      return ASRD_ERR_CUDA;
+    }
   }
-  CU_CHECK(cudaMemcpy(g->d_arcs, parc.data(), b_arcs, cudaMemcpyHostToDevice));
-  CU_CHECK(cudaMemcpy(g->d_rows, rows.data(), b_rows, cudaMemcpyHostToDevice));
-  CU_CHECK(cudaMemcpy(g->d_arc_src, src.data(), b_src, cudaMemcpyHostToDevice));
-  CU_CHECK(cudaMemcpy(g->d_par, par.data(), b_par, cudaMemcpyHostToDevice));
-  CU_CHECK(cudaMemcpy(g->d_eps, epsb.data(), b_eps, cudaMemcpyHostToDevice));
-  CU_CHECK(cudaMemcpy(g->d_erows, erows.data(), sizeof(uint2) * erows.size(), cudaMemcpyHostToDevice));
-  g->device_bytes = (int64_t)(b_arcs + b_rows + b_erows + b_src + b_par + b_eps);
+  g->device_bytes = (int64_t)(b_arcs + b_rows + b_erows + b_src + b_par + b_eps + b_ioff + b_iarc);
   g->view.arcs = (const int4 *)g->d_arcs;
   g->view.rows = (const uint2 *)g->d_rows;
   g->view.erows = (const uint2 *)g->d_erows;
   g->view.arc_src = (const uint32_t *)g->d_arc_src;
+  g->view.in_off = (const uint32_t *)g->d_in_off;
+  g->view.in_arc = (const uint32_t *)g->d_in_arc;
   g->view.par_bits = (const uint32_t *)g->d_par;
   g->view.eps_bits = (const uint32_t *)g->d_eps;
   g->view.n_states = S;
@@ -472,8 +510,15 @@ int asrd_graph_read(const char *path, int device, asrd_graph **out) {
   return asrd_graph_create(arcs.data(), na.data(), ne.data(), S, A, hdr[0], hdr[1], device, out);
 }
 
+// The handle is reference counted: decoders built on a graph keep it alive, so the caller may
+// release graph and decoders in any order (the reference shares one read-only Fst among its
+// decoder threads and never frees it under them).
 int asrd_graph_destroy(asrd_graph *g) {
   if (!g) return ASRD_OK;
+  {
+    std::lock_guard<std::mutex> lk(g_ref_mu);
+    if (--g->refs > 0) return ASRD_OK;
+  }
   cudaSetDevice(g->device);
   cudaFree(g->d_arcs);
   cudaFree(g->d_rows);
@@ -481,6 +526,8 @@ int asrd_graph_destroy(asrd_graph *g) {
   cudaFree(g->d_arc_src);
   cudaFree(g->d_par);
   cudaFree(g->d_eps);
+  cudaFree(g->d_in_off);
+  cudaFree(g->d_in_arc);
   delete g;
   return ASRD_OK;
 }
@@ -511,6 +558,7 @@ static int DecoderCreate(asrd_graph *g, const asrd_config *cfg, const asrd_devic
   if (rc) return rc;
   asrd_decoder *d = new asrd_decoder();
   memset((void *)d, 0, sizeof(*d));
+  d->device = g->device;
   d->graph = g;
   d->lm1 = lm1;
   d->lm2 = lm2;
@@ -525,19 +573,30 @@ static int DecoderCreate(asrd_graph *g, const asrd_config *cfg, const asrd_devic
     o.hash_capacity = (int32_t)std::max<uint32_t>(NextPow2((uint64_t)o.hash_capacity), kMinHashCapacity);
   }
   if (o.max_frames <= 0) o.max_frames = 2048;
-  if (o.token_capacity <= 0)  // 16 bytes per token record; ~1.5 x max_active survivors per frame
+  if (o.token_capacity <= 0)  // 8 bytes per token record {state, cost}; ~1.5 x max_active survivors per frame
     o.token_capacity = std::min<int64_t>((int64_t)o.max_frames * std::min<int64_t>(cfg->max_active, 1 << 16) * 3 / 2,
                                          (int64_t)1 << 23);
-  if (o.token_capacity >= 0xFFFFFFF0ll) return ASRD_ERR_BAD_ARG;
+  if (o.token_capacity >= 0xFFFFFFF0ll) {
+    delete d;
+    return ASRD_ERR_BAD_ARG;
+  }
   const size_t H = (size_t)o.hash_capacity;
   auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  // biglm: interned (lm1 state, lm2 state) pairs of one utterance (the reference's unordered_map
+  // is unbounded, newlm/diff-lm.h:92-103); sized by lm_pair_capacity, default 2^16
+  size_t pair_cap = 0;
+  if (lm1) {
+    if (o.lm_pair_capacity <= 0) o.lm_pair_capacity = 1 << 16;
+    pair_cap = NextPow2((uint64_t)std::max(o.lm_pair_capacity, 1024));
+    o.lm_pair_capacity = (int32_t)pair_cap;
+  }
   const size_t b_hash = align(H * sizeof(HashEntry)), b_list = align(H * 4), b_bm = align(H / 8),
-               b_tok = align((size_t)o.token_capacity * 8), b_arc = align((size_t)o.token_capacity * 4),
+               b_tok = align((size_t)o.token_capacity * 8),
+               b_arc = lm1 ? align((size_t)o.token_capacity * 4) : 0,  // plain decoders keep no arc per token
                b_off = align(((size_t)o.max_frames + 4) * 4),
                b_stats = o.collect_stats ? align(((size_t)o.max_frames + 1) * sizeof(asrd_frame_stat)) : 0,
                b_state = align(sizeof(StreamState));
-  const size_t pair_cap = lm1 ? (size_t)1 << 16 : 0;
-  const size_t b_lm = lm1 ? b_arc : 0, b_pair = align(pair_cap * 8);
+  const size_t b_lm = b_arc, b_pair = align(pair_cap * 8);
   const size_t total = b_state + b_hash + 2 * b_bm + 3 * b_list + b_tok + b_arc + 3 * b_off + b_stats + b_lm + b_pair;
   if (cudaMalloc(&d->slab, total) != cudaSuccess) {
     cudaGetLastError();
@@ -560,7 +619,7 @@ static int DecoderCreate(asrd_graph *g, const asrd_config *cfg, const asrd_devic
     h.pair_mask = (uint32_t)pair_cap - 1;
   }
   h.tok_sc = (uint2 *)p; p += b_tok;
-  h.tok_arc = (uint32_t *)p; p += b_arc;
+  h.tok_arc = lm1 ? (uint32_t *)p : nullptr; p += b_arc;
   h.frame_off = (uint32_t *)p; p += b_off;
   h.frame_nc = (float *)p; p += b_off;
   h.frame_cur = (float *)p; p += b_off;
@@ -578,6 +637,14 @@ static int DecoderCreate(asrd_graph *g, const asrd_config *cfg, const asrd_devic
     cudaFree(d->slab);
     delete d;
     return ASRD_ERR_CUDA;
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_ref_mu);
+    ++g->refs;
+    if (lm1) {
+      ++lm1->refs;
+      ++lm2->refs;
+    }
   }
   *out = d;
   return ASRD_OK;
@@ -622,6 +689,7 @@ int asrd_lm_create(int32_t bos, int32_t eos, int32_t n_states, const int32_t *ar
   const size_t b_off = align(off.size() * 4), b_a = align((size_t)n_arcs * 4), b_s = align((size_t)n_states * 4);
   asrd_lm *lm = new asrd_lm();
   memset(lm, 0, sizeof(*lm));
+  lm->refs = 1;
   lm->device = device;
   if (cudaMalloc(&lm->slab, b_off + 3 * b_a + 2 * b_s) != cudaSuccess) {
     cudaGetLastError();
@@ -629,12 +697,23 @@ int asrd_lm_create(int32_t bos, int32_t eos, int32_t n_states, const int32_t *ar
     return ASRD_ERR_NOMEM;
   }
   char *p = (char *)lm->slab;
-  lm->view.arc_off = (const uint32_t *)p; CU_CHECK(cudaMemcpy(p, off.data(), off.size() * 4, cudaMemcpyHostToDevice)); p += b_off;
-  lm->view.arc_word = (const int32_t *)p; CU_CHECK(cudaMemcpy(p, word.data(), (size_t)n_arcs * 4, cudaMemcpyHostToDevice)); p += b_a;
-  lm->view.arc_weight = (const float *)p; CU_CHECK(cudaMemcpy(p, weight.data(), (size_t)n_arcs * 4, cudaMemcpyHostToDevice)); p += b_a;
-  lm->view.arc_to = (const int32_t *)p; CU_CHECK(cudaMemcpy(p, to.data(), (size_t)n_arcs * 4, cudaMemcpyHostToDevice)); p += b_a;
-  lm->view.backoff_prob = (const float *)p; CU_CHECK(cudaMemcpy(p, backoff_prob, (size_t)n_states * 4, cudaMemcpyHostToDevice)); p += b_s;
-  lm->view.backoff_id = (const int32_t *)p; CU_CHECK(cudaMemcpy(p, backoff_id, (size_t)n_states * 4, cudaMemcpyHostToDevice)); p += b_s;
+  struct Up { const void **view; const void *src; size_t bytes, stride; };
+  const Up ups[] = {{(const void **)&lm->view.arc_off, off.data(), off.size() * 4, b_off},
+                    {(const void **)&lm->view.arc_word, word.data(), (size_t)n_arcs * 4, b_a},
+                    {(const void **)&lm->view.arc_weight, weight.data(), (size_t)n_arcs * 4, b_a},
+                    {(const void **)&lm->view.arc_to, to.data(), (size_t)n_arcs * 4, b_a},
+                    {(const void **)&lm->view.backoff_prob, backoff_prob, (size_t)n_states * 4, b_s},
+                    {(const void **)&lm->view.backoff_id, backoff_id, (size_t)n_states * 4, b_s}};
+  for (const Up &u : ups) {
+    *u.view = p;
+    const cudaError_t e = cudaMemcpy(p, u.src, u.bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      g_last_error = std::string("LM upload: ") + cudaGetErrorString(e);
+      asrd_lm_destroy(lm);
+      return ASRD_ERR_CUDA;
+    }
+    p += u.stride;
+  }
   lm->view.bos = bos;
   lm->view.eos = eos;
   lm->view.n_states = n_states;
@@ -644,6 +723,10 @@ int asrd_lm_create(int32_t bos, int32_t eos, int32_t n_states, const int32_t *ar
 
 int asrd_lm_destroy(asrd_lm *lm) {
   if (!lm) return ASRD_OK;
+  {
+    std::lock_guard<std::mutex> lk(g_ref_mu);
+    if (--lm->refs > 0) return ASRD_OK;
+  }
   cudaSetDevice(lm->device);
   cudaFree(lm->slab);
   delete lm;
@@ -652,9 +735,12 @@ int asrd_lm_destroy(asrd_lm *lm) {
 
 int asrd_decoder_destroy(asrd_decoder *d) {
   if (!d) return ASRD_OK;
-  cudaSetDevice(d->graph->device);
+  cudaSetDevice(d->device);
   cudaFree(d->slab);
   cudaFree(d->d_ll_hist);
+  asrd_graph_destroy(d->graph);  // drops this decoder's references
+  asrd_lm_destroy(d->lm1);
+  asrd_lm_destroy(d->lm2);
   delete d;
   return ASRD_OK;
 }
@@ -704,9 +790,12 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
     if (n_frames[i] < 0 || stride[i] < num_indices || (n_frames[i] > 0 && !loglikes[i])) return ASRD_ERR_BAD_ARG;
     nf[i] = n_frames[i];
     if (max_num_frames >= 0) nf[i] = std::min(nf[i], max_num_frames);  // inl.h:643-648
-    nf[i] = std::min(nf[i], decs[i]->opts.max_frames - decs[i]->frames_decoded);
+    // frames beyond max_frames are never dropped silently: the call fails before anything is decoded
+    if (nf[i] > decs[i]->opts.max_frames - decs[i]->frames_decoded) return ASRD_ERR_FRAMES_OVERFLOW;
     max_nf = std::max(max_nf, nf[i]);
   }
+  // the graph's ilabels index the rows (column = ilabel - 1): a narrower matrix would be read out of bounds
+  if (num_indices < decs[0]->graph->max_ilabel) return ASRD_ERR_BAD_ARG;
   if (max_nf == 0) return ASRD_OK;
   // log-likelihood history (read by the search and by the trace-back); sized on first use
   for (int i = 0; i < n; ++i) {
@@ -762,7 +851,7 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
   for (int b = 0; b < n_sub; ++b)
     if ((rc = PlanExpand(std::min(sub, n - b * sub), num_indices, biglm, &plans[b]))) return rc;
   StreamPlan splan;
-  if ((rc = PlanStream(num_indices, biglm, &splan))) return rc;
+  if ((rc = PlanStream(decs[0]->graph, num_indices, biglm, &splan))) return rc;
 
   // Host log-likelihoods: staged chunk by chunk through two device buffers, copied on a
   // side stream so the H2D of chunk k+1 overlaps the search of chunk k.
@@ -828,8 +917,13 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
     cudaEventRecord(e, st);
     v.push_back(e);
   };
-  std::vector<cudaEvent_t> ev_rows;  // rows of chunk k are in the histories
-  auto cleanup = [&]() { for (cudaEvent_t e : ev_rows) cudaEventDestroy(e); };
+  struct EventList {  // rows of chunk k are in the histories; destroyed on every exit path
+    std::vector<cudaEvent_t> v;
+    ~EventList() {
+      for (cudaEvent_t e : v) cudaEventDestroy(e);
+    }
+  } ev_rows_holder;
+  std::vector<cudaEvent_t> &ev_rows = ev_rows_holder.v;
   for (int k = 0; k < n_chunks; ++k) {
     const int32_t f0 = k * chunk;
     float *stage = d_stage[k & 1];
@@ -861,7 +955,7 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
     ++g_launches;
     // the rows now live in the per-stream histories: the staging buffer may be refilled
     if (!on_device) CU_CHECK(cudaEventRecord(ctx->ev_done[k & 1], ps));
-    cudaEvent_t ev;
+    cudaEvent_t ev = nullptr;
     CU_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     ev_rows.push_back(ev);
     CU_CHECK(cudaEventRecord(ev, ps));
@@ -879,7 +973,7 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
         const int nb = std::min(sub, n - b * sub);
         prof.Begin(2, ws);
         splan.fn<<<nb, kStreamThreads, splan.dyn, ws>>>(d_streams + (size_t)b * sub, d_params + (size_t)k * n + (size_t)b * sub, gv, cfg,
-                                                         num_indices);
+                                                         num_indices, splan.n_buckets);
         prof.End(ws);
         ++g_launches;
       }
@@ -913,10 +1007,7 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
         g_launches += 2;
       }
     }
-    if (cudaGetLastError() != cudaSuccess) {
-      cleanup();
-      return ASRD_ERR_CUDA;
-    }
+    CU_CHECK(cudaGetLastError());
   }
   if (!single) {  // join the workers back into the caller's stream
     for (int w = 0; w < n_workers; ++w) {
@@ -929,7 +1020,6 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
     // the copy stream must not run ahead into a later call's (recycled) staging memory
     CU_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[(n_chunks - 1) & 1], 0));
   }
-  cleanup();
   for (int i = 0; i < n; ++i) decs[i]->frames_decoded += nf[i];
   if (trace) {
     fprintf(stderr, "[asrd] all issued at %.2f ms\n", since());
@@ -977,6 +1067,8 @@ int asrd_get_best_path(asrd_decoder *const *decs, int32_t n, int32_t use_final_p
   for (int i = 0; i < n; ++i) {
     if (!decs[i]->initialized) return ASRD_ERR_STATE;
     if (decs[i]->finalized && !use_final_probs) return ASRD_ERR_STATE;  // inl.h:1100-1102
+    // (the biglm end-token pruning depends on FinalizeDecoding: one launch serves one state)
+    if (decs[i]->finalized != decs[0]->finalized) return ASRD_ERR_BAD_ARG;
   }
   if ((rc = EnsureDevice(decs[0]->graph->device))) return rc;
   cudaStream_t s = (cudaStream_t)stream;
@@ -997,9 +1089,8 @@ int asrd_get_best_path(asrd_decoder *const *decs, int32_t n, int32_t use_final_p
                                                      use_final_probs, cap, d_il, d_ol, d_gr, d_ac, d_n, d_st,
                                                      Lms(decs[0]), decs[0]->finalized);
   else
-    k_best_path<false><<<n, kBestPathThreads, 0, s>>>(d_streams, decs[0]->graph->view, DevCfg(decs[0]),
-                                                      use_final_probs, cap, d_il, d_ol, d_gr, d_ac, d_n, d_st,
-                                                      Lms(decs[0]), decs[0]->finalized);
+    k_best_path_rev<<<n, kBestPathThreads, 0, s>>>(d_streams, decs[0]->graph->view, DevCfg(decs[0]), use_final_probs,
+                                                   cap, d_il, d_ol, d_gr, d_ac, d_n, d_st);
   ++g_launches;
   CU_CHECK(cudaGetLastError());
   CU_CHECK(cudaMemcpyAsync(n_arcs, d_n, 4 * (size_t)n, cudaMemcpyDeviceToHost, s));
@@ -1210,15 +1301,15 @@ int asrd_get_counters(asrd_decoder *const *decs, int32_t n, int64_t *arcs_expand
   if (arcs_expanded) *arcs_expanded = (int64_t)h[0];
   if (arcs_admitted) *arcs_admitted = (int64_t)h[1];
   if (tokens) *tokens = (int64_t)h[2];
-  g_last_fallback_frames = (int64_t)h[3];
-  for (int k = 0; k < 6; ++k) g_last_phase_cycles[k] = (int64_t)h[4 + k];
+  g_last_fallback_frames.store((int64_t)h[3]);
+  for (int k = 0; k < 6; ++k) g_last_phase_cycles[k].store((int64_t)h[4 + k]);
   return ASRD_OK;
 }
 
-int64_t asrd_last_fallback_frames(void) { return g_last_fallback_frames; }
+int64_t asrd_last_fallback_frames(void) { return g_last_fallback_frames.load(); }
 
 void asrd_last_phase_cycles(int64_t *out6) {
-  for (int k = 0; k < 6; ++k) out6[k] = g_last_phase_cycles[k];
+  for (int k = 0; k < 6; ++k) out6[k] = g_last_phase_cycles[k].load();
 }
 
 int asrd_synchronize(void *stream) {

@@ -51,6 +51,8 @@ struct GraphView {
   const uint2 *rows;       // [S+1] {row_off, emit_off}: eps span [x, y)
   const uint2 *erows;      // [S]   {emit_off, row_end}: emitting span [x, y) — one 8-byte load per token
   const uint32_t *arc_src; // [A] source state of every arc
+  const uint32_t *in_off;  // [S+1] incoming-arc index: arcs INTO state s are in_arc[in_off[s] .. in_off[s+1])
+  const uint32_t *in_arc;  // [A] arc ids grouped by destination state, ascending inside a group
   const uint32_t *par_bits;// [ceil(A/32)] arc has a same-class sibling with the same (src, dst)
   const uint32_t *eps_bits;// [ceil(S/32)] state has at least one input-epsilon arc
   int32_t n_states;
@@ -72,7 +74,9 @@ struct StreamState {
   uint32_t pair_mask;
   uint32_t pad2;
   uint2 *tok_sc;        // token arena: {state, cost bits}
-  uint32_t *tok_arc;    // token arena: arc that set the token's cost (kNoArc for the start token)
+  uint32_t *tok_arc;    // biglm: token arena, arc that set the token's cost (kNoArc for the start token);
+                        // plain decoders keep {state, cost} only — the trace-back finds the arc through
+                        // the graph's incoming-arc index (k_best_path_rev)
   uint32_t *frame_off;  // [max_frames + 2] arena offset of every frame's token span
   float *frame_nc;      // [max_frames + 2] final next_cutoff of the step that produced each frame
   float *frame_cur;     // [max_frames + 2] GetCutoff result of each frame (which tokens were expanded)
@@ -163,18 +167,18 @@ struct DecoderConfigDev {
   int32_t debug_flags;   // measurement aids (ASRD_DEBUG_FLAGS)
 };
 
-// order-preserving float <-> uint32 map (handles negative costs)
+// order-preserving float <-> uint32 map (handles negative costs): two instructions each way
 __host__ __device__ inline uint32_t f2ord(float f) {
 #ifdef __CUDA_ARCH__
-  uint32_t u = __float_as_uint(f);
+  const uint32_t u = __float_as_uint(f);
 #else
   uint32_t u;
   memcpy(&u, &f, 4);
 #endif
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);  // negative: flip all bits; else: set the sign bit
 }
 __host__ __device__ inline float ord2f(uint32_t o) {
-  uint32_t u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+  const uint32_t u = o ^ (~(uint32_t)((int32_t)o >> 31) | 0x80000000u);
 #ifdef __CUDA_ARCH__
   return __uint_as_float(u);
 #else
@@ -187,20 +191,24 @@ __host__ __device__ inline float ord2f(uint32_t o) {
 }  // namespace asrd
 
 struct asrd_lm {
+  int refs;  // the handle + one per decoder built on it (guarded by g_ref_mu); freed when it reaches 0
   int device;
   asrd::LmView view;
   void *slab;
 };
 
 struct asrd_graph {
+  int refs;  // the handle + one per decoder built on it (guarded by g_ref_mu); freed when it reaches 0
   int device;
   asrd::GraphView view;
-  void *d_arcs, *d_rows, *d_erows, *d_arc_src, *d_par, *d_eps;
+  void *d_arcs, *d_rows, *d_erows, *d_arc_src, *d_par, *d_eps, *d_in_off, *d_in_arc;
+  int32_t max_ilabel;
   int64_t device_bytes;
   int64_t total_arcs;
 };
 
 struct asrd_decoder {
+  int device;
   asrd_graph *graph;
   asrd_lm *lm1, *lm2;          // biglm: old LM (already scaled by -1 by the caller) and new LM
   asrd_config cfg;

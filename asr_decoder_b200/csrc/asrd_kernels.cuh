@@ -232,13 +232,14 @@ __device__ __forceinline__ uint32_t pair_intern(unsigned long long *map, uint32_
                                                 int32_t *status) {
   const unsigned long long key = (((unsigned long long)(uint32_t)n1 << 32) | (uint32_t)n2) + 1ull;
   uint32_t h = ((uint32_t)n1 * 0x9E3779B1u + (uint32_t)n2 * 0x85EBCA6Bu) & pmask;
-  for (uint32_t probe = 0; probe <= pmask; ++probe) {
+  // (bounded: a nearly full table must fail, not crawl — linear probing degrades to O(capacity))
+  for (uint32_t probe = 0; probe <= pmask && probe < 2048u; ++probe) {
     unsigned long long k = __ldcg(&map[h]);
     if (k == 0ull) k = atomicCAS(&map[h], 0ull, key);
     if (k == 0ull || k == key) return h;
     h = (h + 1) & pmask;
   }
-  atomicMin(status, ASRD_ERR_HASH_OVERFLOW);
+  atomicMin(status, ASRD_ERR_LM_PAIRS_OVERFLOW);
   return 0;
 }
 
@@ -785,7 +786,7 @@ __device__ __forceinline__ void cutoff_prologue(StreamState *st, FrameDesc *d, c
 struct PostSmem {  // block-level scratch of the per-stream phases
   unsigned long long red64[kStreamThreads / 32];
   unsigned long long best;
-  uint32_t red32[kStreamThreads / 32];
+  uint32_t red32[kStreamThreads / 32 + 1];  // (+1: block_exclusive_scan keeps the total behind the warp sums)
   uint32_t hist[256];
   uint32_t misc[4];
   uint32_t qn[2];
@@ -954,8 +955,10 @@ __device__ __forceinline__ void post_epilogue(StreamState *st, FrameDesc *d, con
             const uint32_t idx = pos0 + __popc(am & ((1u << lane) - 1u));
             if (idx < cap) {
               out_sc[idx] = make_uint2(key, __float_as_uint(cost));
-              out_arc[idx] = rep;
-              if (BIGLM) out_lm[idx] = pair;
+              if (BIGLM) {
+                out_arc[idx] = rep;
+                out_lm[idx] = pair;
+              }
             }
             // best token: lowest cost, ties -> lowest state id; biglm keeps the token's index
             // inside the frame instead (the pre-pass needs its LM state as well)
@@ -1467,6 +1470,206 @@ k_best_path(StreamState *const *streams, GraphView g, DecoderConfigDev cfg, int 
       o_ol[ob + n_out] = arc.y;
       o_gr[ob + n_out] = graph_cost;
       o_ac[ob + n_out] = emitting ? -ll[arc.x - 1] : 0.f;
+    }
+    ++n_out;
+    f = fp;
+    idx = pidx;
+  }
+  if (tid == 0) {
+    o_n[blockIdx.x] = n_out;
+    o_status[blockIdx.x] = status;
+  }
+}
+
+
+// ------------------------------------------------------------------ best path, plain decoders
+
+// Plain decoders keep {state, cost} per token and nothing else: the frame loop never records which
+// arc set a token's cost.  The trace-back recovers it for the tokens of the best path only.  For
+// token (frame f, state d, cost c) the winning arc is the LOWEST-INDEX arc a : s -> d for which a
+// token p of state s exists with
+//     emitting a:  p in frame f-1, p.cost <= cur_cutoff(f-1) (inl.h:315), (p.cost + ac) + w == c  (inl.h:326-329)
+//     eps a:       p in frame f,   p.cost <  next_cutoff(f)  (inl.h:391),  p.cost + w == c        (inl.h:413-414)
+// bit for bit — exactly the relaxation (lowest cost, then lowest arc index) the search performs with
+// the arc packed next to the cost.  (An eps relaxation made while p's cost was not yet final gives
+// tot' >= the one with the final cost, so it cannot be the only witness of c.)  Candidates come
+// from the graph's incoming-arc index; their source states go into a small shared-memory hash and
+// the tokens of frames f and f-1 are streamed past it once.
+constexpr int kRevCand = 1024;  // incoming arcs examined per round
+constexpr int kRevHash = 2048;
+
+__global__ void __launch_bounds__(kBestPathThreads)
+k_best_path_rev(StreamState *const *streams, GraphView g, DecoderConfigDev cfg, int use_final, int cap,
+                int32_t *o_il, int32_t *o_ol, float *o_gr, float *o_ac, int32_t *o_n, int32_t *o_status) {
+  constexpr int NT = kBestPathThreads;
+  __shared__ unsigned long long s_red64[NT / 32];
+  __shared__ unsigned long long s_win;  // (arc id << 32) | arena index of the predecessor
+  __shared__ uint32_t s_found, s_classes;
+  __shared__ uint32_t s_csrc[kRevCand], s_carc[kRevCand];
+  __shared__ int32_t s_cnext[kRevCand], s_head[kRevHash];
+  StreamState *st = streams[blockIdx.x];
+  const int tid = threadIdx.x;
+  const size_t ob = (size_t)blockIdx.x * cap;
+  int f = st->frame;
+  if (st->status < 0 || f <= 0) {  // inl.h:1104-1108
+    if (tid == 0) {
+      o_n[blockIdx.x] = 0;
+      o_status[blockIdx.x] = st->status < 0 ? st->status : ASRD_ERR_NO_TOKENS;
+    }
+    return;
+  }
+  // ---- end token (BestPathEnd, inl.h:1096-1158): the token on the super-final state when
+  // use_final_probs and one is alive, else the cheapest; ties -> lowest state id
+  const uint32_t b0 = st->frame_off[f], n0 = st->frame_off[f + 1] - b0;
+  unsigned long long best_all = kInfVal, best_fin = kInfVal;
+  for (uint32_t i = tid; i < n0; i += NT) {
+    const uint2 sc = st->tok_sc[b0 + i];
+    const unsigned long long bb = ((unsigned long long)f2ord(__uint_as_float(sc.y)) << 32) | sc.x;
+    best_all = bb < best_all ? bb : best_all;
+    if ((int32_t)sc.x == g.final_state) best_fin = bb < best_fin ? bb : best_fin;
+  }
+  best_all = block_min_u64<NT>(best_all, s_red64);
+  best_fin = block_min_u64<NT>(best_fin, s_red64);
+  const unsigned long long pick = (use_final && best_fin != kInfVal) ? best_fin : best_all;
+  if (pick == kInfVal) {
+    if (tid == 0) {
+      o_n[blockIdx.x] = 0;
+      o_status[blockIdx.x] = ASRD_ERR_NO_TOKENS;
+    }
+    return;
+  }
+  if (tid == 0) s_found = 0xFFFFFFFFu;
+  __syncthreads();
+  for (uint32_t i = tid; i < n0; i += NT)
+    if (st->tok_sc[b0 + i].x == (uint32_t)pick) atomicMin(&s_found, b0 + i);
+  __syncthreads();
+  uint32_t idx = s_found;
+  int n_out = 0;
+  int status = idx == 0xFFFFFFFFu ? ASRD_ERR_STATE : ASRD_OK;
+  while (status == ASRD_OK) {
+    const uint2 sc = st->tok_sc[idx];
+    const uint32_t state = sc.x;
+    const float cost = __uint_as_float(sc.y);
+    if (n_out >= cap) {
+      status = ASRD_ERR_PATH_OVERFLOW;
+      break;
+    }
+    if (f == 0 && (int32_t)state == g.start && sc.y == 0u) {
+      // start token: label-free arc with unit weight (inl.h:1193-1198)
+      if (tid == 0) {
+        o_il[ob + n_out] = 0;
+        o_ol[ob + n_out] = 0;
+        o_gr[ob + n_out] = 0.f;
+        o_ac[ob + n_out] = 0.f;
+      }
+      ++n_out;
+      break;
+    }
+    const float nc_f = st->frame_nc[f];
+    const float cur_prev = f > 0 ? st->frame_cur[f - 1] : 0.f;
+    const float *__restrict__ ll_prev = f > 0 ? st->ll_hist + (size_t)(f - 1) * st->ll_stride : nullptr;
+    const uint32_t ib = __ldg(&g.in_off[state]), ie = __ldg(&g.in_off[state + 1]);
+    if (tid == 0) s_win = kInfVal;
+    for (uint32_t r0 = ib; r0 < ie; r0 += kRevCand) {
+      const uint32_t ncand = min((uint32_t)kRevCand, ie - r0);
+      for (int i = tid; i < kRevHash; i += NT) s_head[i] = -1;
+      if (tid == 0) s_classes = 0;
+      __syncthreads();
+      for (uint32_t i = tid; i < ncand; i += NT) {
+        const uint32_t a = __ldg(&g.in_arc[r0 + i]);
+        const uint32_t src = __ldg(&g.arc_src[a]);
+        const bool eps = __ldg(&g.arcs[a]).x == 0;
+        if (!eps && f == 0) {  // no frame before the first
+          s_csrc[i] = 0xFFFFFFFFu;
+          continue;
+        }
+        s_csrc[i] = src;
+        s_carc[i] = a;
+        s_cnext[i] = atomicExch(&s_head[(src * 0x9E3779B1u) >> 21], (int32_t)i);
+        atomicOr(&s_classes, eps ? 1u : 2u);
+      }
+      __syncthreads();
+      const uint32_t classes = s_classes;
+      for (int cls = 0; cls < 2; ++cls) {  // 0: eps candidates against frame f, 1: emitting against f - 1
+        if (!(classes & (1u << cls))) continue;
+        const int fr = cls == 0 ? f : f - 1;
+        const uint32_t tb = st->frame_off[fr], tn = st->frame_off[fr + 1] - tb;
+        const uint2 *__restrict__ toks = st->tok_sc + tb;
+        for (uint32_t i0 = 0; i0 < tn; i0 += NT * 4) {  // four independent loads in flight per thread
+          uint2 k[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t i = i0 + u * NT + tid;
+            k[u] = i < tn ? __ldg(&toks[i]) : make_uint2(0xFFFFFFFFu, 0u);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (k[u].x == 0xFFFFFFFFu) continue;
+            for (int32_t j = s_head[(k[u].x * 0x9E3779B1u) >> 21]; j >= 0; j = s_cnext[j]) {
+              if (s_csrc[j] != k[u].x) continue;
+              const uint32_t a = s_carc[j];
+              const int4 arc = __ldg(&g.arcs[a]);
+              if ((arc.x == 0) != (cls == 0)) continue;
+              const float pc = __uint_as_float(k[u].y);
+              float tot;
+              if (cls == 0) {
+                if (!(pc < nc_f)) continue;              // inl.h:391
+                tot = pc + __int_as_float(arc.z);        // inl.h:413-414
+              } else {
+                if (!(pc <= cur_prev)) continue;         // inl.h:315
+                tot = (pc + (-ll_prev[arc.x - 1])) + __int_as_float(arc.z);  // inl.h:326-329
+              }
+              if (__float_as_uint(tot) != sc.y) continue;
+              atomicMin(&s_win, ((unsigned long long)a << 32) | (tb + i0 + u * NT + tid));
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+    __syncthreads();
+    const unsigned long long win = s_win;
+    __syncthreads();
+    if (win == kInfVal) {
+      status = ASRD_ERR_STATE;  // broken back-trace: cannot happen unless the arena overflowed
+      break;
+    }
+    uint32_t rep = (uint32_t)(win >> 32);
+    const uint32_t pidx = (uint32_t)win;
+    int4 arc = __ldg(&g.arcs[rep]);
+    const bool emitting = arc.x != 0;
+    const int fp = emitting ? f - 1 : f;
+    const float pc = __uint_as_float(st->tok_sc[pidx].y);
+    // For every step pred -> tok the reference reports the most recently added surviving forward
+    // link (inl.h:1169-1186): with parallel arcs pred.state -> tok.state that is the highest-index
+    // admitted sibling within lattice_beam, not necessarily the cheapest one (see k_best_path).
+    if (par_bit(g.par_bits, rep)) {
+      const uint32_t src = __ldg(&g.arc_src[rep]);
+      const uint32_t hi = emitting ? __ldg(&g.erows[src]).y : __ldg(&g.rows[src]).y;
+      for (uint32_t a2 = hi; a2-- > rep + 1;) {
+        const int4 arc2 = __ldg(&g.arcs[a2]);
+        if (((uint32_t)arc2.w & kStateMask) != state) continue;
+        float tot2;
+        bool admitted;
+        if (emitting) {
+          tot2 = (pc + (-ll_prev[arc2.x - 1])) + __int_as_float(arc2.z);  // inl.h:326-329
+          admitted = tot2 < nc_f;                                          // inl.h:330
+        } else {
+          tot2 = pc + __int_as_float(arc2.z);                              // inl.h:413-414
+          admitted = pc < nc_f && tot2 < nc_f;                             // inl.h:391,415
+        }
+        if (admitted && !((tot2 - cost) > cfg.lattice_beam)) {  // inl.h:524-532
+          rep = a2;
+          arc = arc2;
+          break;
+        }
+      }
+    }
+    if (tid == 0) {
+      o_il[ob + n_out] = arc.x;
+      o_ol[ob + n_out] = arc.y;
+      o_gr[ob + n_out] = __int_as_float(arc.z);
+      o_ac[ob + n_out] = emitting ? -ll_prev[arc.x - 1] : 0.f;
     }
     ++n_out;
     f = fp;

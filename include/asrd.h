@@ -41,7 +41,8 @@ enum {
   ASRD_ERR_NO_TOKENS = -7,      /* reference: GetBestPath returns false (inl.h:1078-1079) */
   ASRD_ERR_PATH_OVERFLOW = -8,  /* best path longer than the caller's buffer */
   ASRD_ERR_STATE = -9,          /* call order violated (e.g. Advance after Finalize, inl.h:634) */
-  ASRD_ERR_IO = -10
+  ASRD_ERR_IO = -10,
+  ASRD_ERR_LM_PAIRS_OVERFLOW = -11 /* biglm: LM state-pair table full (raise lm_pair_capacity) */
 };
 
 /* newfst StdArc, src/newfst/arc.h:23-26 (16 bytes, kept verbatim in HBM) */
@@ -72,7 +73,10 @@ typedef struct {
   int64_t token_capacity;  /* token records kept per utterance (all frames) */
   int32_t max_frames;      /* frames per utterance */
   int32_t collect_stats;   /* keep per-frame statistics for asrd_frame_stats */
-  int32_t reserved[4];
+  int32_t lm_pair_capacity;/* biglm: distinct (old LM state, new LM state) pairs one utterance may reach
+                            * (DiffArpaLm's state table, src/newlm/diff-lm.h:92-103); rounded up to a
+                            * power of two, default 65536 */
+  int32_t reserved[3];
 } asrd_device_options;
 
 /* per-frame statistics; index 0 = after InitDecoding (what the reference logs under
@@ -120,6 +124,11 @@ const char *asrd_strerror(int status);
 int asrd_abi_version(void);
 /* number of usable sm_100 devices; 0 or a negative status when none */
 int asrd_device_count(void);
+/* Optional, once, BEFORE the host process makes its first CUDA call: asks the driver for 32
+ * hardware work queues (CUDA_DEVICE_MAX_CONNECTIONS, unless the application already set it) so the
+ * library's copy / scatter / frame-loop streams do not share a queue.  The library never changes
+ * process-wide state on its own: not when it is loaded, not in any other entry point. */
+int asrd_configure_process(void);
 
 /* ---- graph: replaces Fst (src/newfst/optimize-fst.h:53-307) -------------------------- */
 
@@ -157,7 +166,8 @@ int asrd_decoder_create(asrd_graph *g, const asrd_config *cfg, const asrd_device
  * LM-difference of two LMs; tokens are keyed by (HCLG state, LM state pair).  DiffArpaLm is
  * implemented with its intended semantics (both LMs advance from the members of the state
  * pair); the reference passes the pair-state id itself (newlm/diff-lm.h:75-86), which only
- * coincides on unigram-only LMs — SURVEY.md Appendix B-6.  GetRawLattice is not available. */
+ * coincides on unigram-only LMs — SURVEY.md Appendix B-6.  GetBestPath and GetRawLattice both
+ * work; lattice links carry arc weight + LM-difference score as their graph cost. */
 int asrd_decoder_create_biglm(asrd_graph *g, const asrd_config *cfg, const asrd_device_options *opts,
                               asrd_lm *old_lm, asrd_lm *new_lm, asrd_decoder **out);
 int asrd_decoder_destroy(asrd_decoder *d);
@@ -167,6 +177,9 @@ int asrd_decoder_destroy(asrd_decoder *d);
 int asrd_init_decoding(asrd_decoder *const *decs, int32_t n, void *stream);
 
 /* DecoderItf::AdvanceDecoding (decoder-itf.h:16; inl.h:630-668), batched.
+ * Fails with ASRD_ERR_FRAMES_OVERFLOW — before decoding anything — when a stream would pass
+ * max_frames, and with ASRD_ERR_BAD_ARG when num_indices is smaller than the graph's largest
+ * ilabel: frames are never dropped and rows never read out of bounds.
  * loglikes[i] points at the row of frame NumFramesDecoded(i) of stream i — what
  * AmInterface::LogLikelihood(frame, index) would return for index = column + 1
  * (src/itf/decodable-itf.h:55-62; caller inl.h:295,326).  n_frames[i] rows with

@@ -163,6 +163,35 @@ def test_no_frames_and_error_paths(oracle_mod):
     with pytest.raises(_lib.AsrdError):                                     # fewer columns than ilabels
         dec.InitDecoding()
         dec.AdvanceDecoding([ll[:, :10], ll[:, :10]])
+    # the same check inside the C ABI (callers that do not go through the Python mirror)
+    import ctypes as C
+    L = _lib.lib()
+    narrow = np.ascontiguousarray(ll[:, :10])
+    ptrs = (C.c_void_p * 2)(narrow.ctypes.data, narrow.ctypes.data)
+    nfr, strides = (C.c_int32 * 2)(5, 5), (C.c_int32 * 2)(10, 10)
+    dec.InitDecoding()
+    assert L.asrd_advance_decoding(dec.handles, 2, ptrs, nfr, strides, 10, -1, 0, None) == -1
+
+
+def test_frames_beyond_max_frames_fail_loudly():
+    """More frames than max_frames are never dropped silently: AdvanceDecoding fails with
+    ASRD_ERR_FRAMES_OVERFLOW before decoding anything, and the stream stays usable."""
+    from asr_decoder_b200 import _lib
+    fst = synth.make_graph(400, 4.0, 20, seed=2)
+    g = CudaFst(fst)
+    dec = CudaDecoderBatch(g, _cfg(), 1, max_frames=16)
+    ll = synth.make_loglikes(24, 20, 2.0, seed=1)
+    dec.InitDecoding()
+    with pytest.raises(_lib.AsrdError) as e:
+        dec.AdvanceDecoding([ll])
+    assert e.value.status == -6 and dec.NumFramesDecoded(0) == 0
+    dec.AdvanceDecoding([ll[:10]])
+    with pytest.raises(_lib.AsrdError) as e:           # 10 decoded + 10 more > 16
+        dec.AdvanceDecoding([ll[10:20]])
+    assert e.value.status == -6 and dec.NumFramesDecoded(0) == 10
+    dec.AdvanceDecoding([ll[10:16]])
+    dec.FinalizeDecoding()
+    assert dec.GetBestPath()[0].ok and dec.NumFramesDecoded(0) == 16
 
 
 def test_arena_overflow_is_reported_not_silent():
@@ -210,15 +239,17 @@ def test_every_kernel_path_gives_the_same_search(oracle_mod, monkeypatch, env):
             _compare(out1[i], st1, ref, rst, f"{env} stream {i}")
 
 
-@pytest.mark.parametrize("case", ["wide-rows", "deep-eps", "tiny-beam"])
+@pytest.mark.parametrize("case", ["wide-rows", "very-wide-rows", "deep-eps", "tiny-beam"])
 def test_on_chip_loop_corner_shapes(oracle_mod, case):
     """Shapes that take the less-travelled branches of the on-chip frame loop: (wide-rows) 6000 pdfs —
-    the log-likelihood row does not fit next to the shared-memory map and is read from global
-    memory; (deep-eps) 60 % of the states have an eps arc to a near state — many closure rounds
-    (round bitmaps, three-flag barrier protocol); (tiny-beam) a handful of tokens per frame."""
+    a 24 KB log-likelihood row next to a smaller shared-memory map; (very-wide-rows) 30000 pdfs — the row
+    does not fit and is read from global memory; (deep-eps) 60 % of the states have an eps arc to a near state — many closure rounds
+    (worklists, three-counter barrier protocol); (tiny-beam) a handful of tokens per frame."""
     O = oracle_mod
     if case == "wide-rows":
         fst, P, T, cfg = synth.make_graph(20000, 5.0, 6000, seed=31), 6000, 60, _cfg()
+    elif case == "very-wide-rows":   # 30000 pdfs: the row is read from global memory (k_stream<false>)
+        fst, P, T, cfg = synth.make_graph(20000, 5.0, 30000, seed=34), 30000, 40, _cfg()
     elif case == "deep-eps":
         fst, P, T, cfg = synth.make_graph(20000, 4.0, 300, seed=32, p_eps=0.6, eps_span=3), 300, 100, _cfg()
     else:
