@@ -309,10 +309,10 @@ int PlanStream(const asrd_graph *graph, int num_indices, bool biglm, StreamPlan 
   bool smem_ll = stream_fixed_dyn_bytes(num_indices) + 2 * kMinMapBytes <= room;
   const size_t fixed = stream_fixed_dyn_bytes(smem_ll ? num_indices : 0);
   if (fixed + kMinMapBytes > room) return ASRD_OK;
-  // n_slots must be a multiple of 32 (the write-out walks rows of 32 slots) and fit a u16 slot id
-  uint32_t n_buckets = (uint32_t)std::min<size_t>((room - fixed) / 32, 16376) & ~7u;
+  // n_buckets must be a multiple of 32 (the write-out walks 32 buckets per warp step) and fit a u16 slot id
+  uint32_t n_buckets = (uint32_t)std::min<size_t>((room - fixed) / 32, 16352) & ~31u;
   const int force = EnvInt("ASRD_STREAM_BUCKETS", 0);  // (measurement aid)
-  if (force >= 64 && (uint32_t)force < n_buckets) n_buckets = (uint32_t)force & ~7u;
+  if (force >= 64 && (uint32_t)force < n_buckets) n_buckets = (uint32_t)force & ~31u;
   plan->fn = smem_ll ? k_stream<true> : k_stream<false>;
   plan->n_buckets = n_buckets;
   plan->dyn = fixed + (size_t)n_buckets * 32;
@@ -439,6 +439,17 @@ int asrd_graph_create(const asrd_arc *arcs, const uint32_t *num_arcs, const uint
     for (int64_t a = 0; a < A; ++a) in_arc[fill[(uint32_t)parc[a].nextstate & kStateMask]++] = (uint32_t)a;
   }
 
+  // eps rows with the first eps arc inline (the closure of k_stream)
+  std::vector<uint4> eps_rows((size_t)S);
+  for (int32_t s2 = 0; s2 < S; ++s2) {
+    uint4 r = make_uint4(rows[s2].x, rows[s2].y, 0u, 0u);
+    if (r.y > r.x) {
+      memcpy(&r.z, &parc[r.x].weight, 4);
+      r.w = (uint32_t)parc[r.x].nextstate;
+    }
+    eps_rows[s2] = r;
+  }
+
   asrd_graph *g = new asrd_graph();
   memset(g, 0, sizeof(*g));
   g->refs = 1;
@@ -448,12 +459,14 @@ int asrd_graph_create(const asrd_arc *arcs, const uint32_t *num_arcs, const uint
   const size_t b_arcs = sizeof(asrd_arc) * parc.size(), b_rows = sizeof(uint2) * rows.size(),
                b_src = sizeof(uint32_t) * src.size(), b_par = sizeof(uint32_t) * par.size(),
                b_eps = sizeof(uint32_t) * epsb.size(), b_erows = sizeof(uint2) * std::max<size_t>(erows.size(), 1),
-               b_ioff = sizeof(uint32_t) * in_off.size(), b_iarc = sizeof(uint32_t) * in_arc.size();
+               b_ioff = sizeof(uint32_t) * in_off.size(), b_iarc = sizeof(uint32_t) * in_arc.size(),
+               b_epsr = sizeof(uint4) * eps_rows.size();
   struct Up { void **dst; const void *src; size_t bytes; };
   const Up ups[] = {{&g->d_arcs, parc.data(), b_arcs}, {&g->d_rows, rows.data(), b_rows},
                     {&g->d_erows, erows.data(), sizeof(uint2) * erows.size()}, {&g->d_arc_src, src.data(), b_src},
                     {&g->d_par, par.data(), b_par}, {&g->d_eps, epsb.data(), b_eps},
-                    {&g->d_in_off, in_off.data(), b_ioff}, {&g->d_in_arc, in_arc.data(), b_iarc}};
+                    {&g->d_in_off, in_off.data(), b_ioff}, {&g->d_in_arc, in_arc.data(), b_iarc},
+                    {&g->d_eps_rows, eps_rows.data(), b_epsr}};
   for (const Up &u : ups) {
     if (cudaMalloc(u.dst, std::max<size_t>(u.bytes, 16)) != cudaSuccess) {
       cudaGetLastError();
@@ -467,10 +480,11 @@ int asrd_graph_create(const asrd_arc *arcs, const uint32_t *num_arcs, const uint
       return ASRD_ERR_CUDA;
     }
   }
-  g->device_bytes = (int64_t)(b_arcs + b_rows + b_erows + b_src + b_par + b_eps + b_ioff + b_iarc);
+  g->device_bytes = (int64_t)(b_arcs + b_rows + b_erows + b_src + b_par + b_eps + b_ioff + b_iarc + b_epsr);
   g->view.arcs = (const int4 *)g->d_arcs;
   g->view.rows = (const uint2 *)g->d_rows;
   g->view.erows = (const uint2 *)g->d_erows;
+  g->view.eps_rows = (const uint4 *)g->d_eps_rows;
   g->view.arc_src = (const uint32_t *)g->d_arc_src;
   g->view.in_off = (const uint32_t *)g->d_in_off;
   g->view.in_arc = (const uint32_t *)g->d_in_arc;
@@ -523,6 +537,7 @@ int asrd_graph_destroy(asrd_graph *g) {
   cudaFree(g->d_arcs);
   cudaFree(g->d_rows);
   cudaFree(g->d_erows);
+  cudaFree(g->d_eps_rows);
   cudaFree(g->d_arc_src);
   cudaFree(g->d_par);
   cudaFree(g->d_eps);

@@ -50,6 +50,8 @@ struct GraphView {
   const int4 *arcs;        // {ilabel, olabel, weight bits, nextstate | kDestEpsBit if the destination has eps arcs}
   const uint2 *rows;       // [S+1] {row_off, emit_off}: eps span [x, y)
   const uint2 *erows;      // [S]   {emit_off, row_end}: emitting span [x, y) — one 8-byte load per token
+  const uint4 *eps_rows;   // [S]   {row_off, emit_off, weight bits and nextstate word of the FIRST eps arc}: a
+                           //       state with one eps arc (the common case) is relaxed with a single load
   const uint32_t *arc_src; // [A] source state of every arc
   const uint32_t *in_off;  // [S+1] incoming-arc index: arcs INTO state s are in_arc[in_off[s] .. in_off[s+1])
   const uint32_t *in_arc;  // [A] arc ids grouped by destination state, ascending inside a group
@@ -201,7 +203,7 @@ struct asrd_graph {
   int refs;  // the handle + one per decoder built on it (guarded by g_ref_mu); freed when it reaches 0
   int device;
   asrd::GraphView view;
-  void *d_arcs, *d_rows, *d_erows, *d_arc_src, *d_par, *d_eps, *d_in_off, *d_in_arc;
+  void *d_arcs, *d_rows, *d_erows, *d_eps_rows, *d_arc_src, *d_par, *d_eps, *d_in_off, *d_in_arc;
   int32_t max_ilabel;
   int64_t device_bytes;
   int64_t total_arcs;

@@ -23,22 +23,45 @@ namespace asrd {
 // A frame whose distinct destination states exceed the on-chip capacity is redone through the
 // HBM map of the stream by the same CTA (expand_frame + post_epilogue), so results never depend
 // on which path ran.  Plain (non-biglm) decoders only.
-constexpr int kQuad = 4;                  // arcs per work item: four lanes fetch 64 contiguous bytes
-constexpr int kItemBuf = 64;              // work items per warp buffer
+#ifndef ASRD_ITEM_ARCS
+#define ASRD_ITEM_ARCS 4
+#endif
+
+constexpr int kItemArcs = ASRD_ITEM_ARCS;  // arcs per work item (2 or 4): that many lanes fetch one item's consecutive records
+constexpr int kBatch = 32 / kItemArcs;    // items per step (32 arc slots)
+constexpr int kItemRing = 8 * kBatch;     // work-item ring per warp (refilled when fewer than two steps are left)
 constexpr int kStageCap = 64;             // admitted-arc staging ring per warp
-constexpr int kWarpScratch = (kItemBuf + kStageCap) * 8;  // bytes per warp
+constexpr int kWarpScratch = (kItemRing + kStageCap) * 8;  // bytes per warp
 constexpr int kEpsQueueCap = 4096;        // eps-closure worklist entries (u16 slot ids), two buffers
 constexpr int kHistBins = 2048;           // cost histogram of GetCutoff (aliases the warp scratch)
 constexpr int kCandCap = 2048;            // candidates of the exact k-th selection (aliases the warp scratch)
 constexpr uint32_t kFreeCost = 0xFFFFFFFFu;
 constexpr uint32_t kNoSlot = 0xFFFFFFFFu;
 constexpr int kMaxProbe = 48;             // buckets probed before a frame is declared too big for the map
-constexpr uint32_t kMaxStreamArcs = 1u << 30;  // work items pack (arc index << 2 | count - 1)
+constexpr int kItemShift = kItemArcs == 4 ? 2 : 1;
+constexpr uint32_t kMaxStreamArcs = 1u << (32 - kItemShift);  // work items pack (arc index << shift | count - 1)
 static_assert(kHistBins * 4 + kCandCap * 4 <= (kStreamThreads / 32) * kWarpScratch, "histogram + candidates alias the warp scratch");
+static_assert(kItemRing >= 4 * kBatch && kStageCap >= 64, "ring sizes");
 
-// shared-memory bytes of k_stream besides the map: log-likelihood row, warp scratch, closure queues
+// Counters of the frame in flight, at the start of the dynamic shared memory (one base register
+// addresses them all; static __shared__ scalars cost a window-address computation per access).
+struct StreamHot {
+  uint32_t claims;      // distinct states claimed in the map
+  uint32_t overflow;    // 0, or WHEN the frame outgrew the map (1 = expansion, r + 2 = closure round r)
+  uint32_t best_ord;    // lowest ordered cost that entered the map
+  uint32_t best_state;  // lowest state id among the tokens with that cost
+  uint32_t alive;       // survivors appended to the arena
+  uint32_t ncand;
+  uint32_t qn[3];       // closure worklist lengths, indexed by round % 3
+  uint32_t next_group;  // token groups handed out to the warps so far (expansion)
+  uint32_t pad[6];
+};
+static_assert(sizeof(StreamHot) == 64, "StreamHot is 64 bytes");
+
+// shared-memory bytes of k_stream besides the map: counters, log-likelihood row, warp scratch, closure queues
 __host__ __device__ constexpr size_t stream_fixed_dyn_bytes(int ll_floats) {
-  return (size_t)((ll_floats + 3) & ~3) * 4 + (size_t)(kStreamThreads / 32) * kWarpScratch + 2 * (size_t)kEpsQueueCap * 2;
+  return sizeof(StreamHot) + (size_t)((ll_floats + 3) & ~3) * 4 + (size_t)(kStreamThreads / 32) * kWarpScratch +
+         2 * (size_t)kEpsQueueCap * 2;
 }
 
 __device__ __forceinline__ uint4 lds_volatile_u4(const uint32_t *p) {
@@ -51,35 +74,92 @@ __device__ __forceinline__ uint4 lds_volatile_u4(const uint32_t *p) {
 __device__ __forceinline__ uint32_t lds_volatile_u32(const uint32_t *p) {
   return *reinterpret_cast<const volatile uint32_t *>(p);
 }
+__device__ __forceinline__ uint32_t lanemask_lt() {
+  uint32_t m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Shared memory by 32-bit shared-state-space address: the hot loop keeps a handful of base
+// addresses in registers and every access is one LDS / STS / ATOMS with a register base (through
+// generic pointers each access site recomputes the shared window base first).
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ float lds_f32_ro(uint32_t a) {  // read-only within the phase (the log-likelihood row)
+  float v;
+  asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint2 lds_u2(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u2(uint32_t a, uint32_t x, uint32_t y) {
+  asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t x) {
+  asm volatile("st.volatile.shared.u16 [%0], %1;" ::"r"(a), "h"((unsigned short)x) : "memory");
+}
+__device__ __forceinline__ uint32_t atoms_cas(uint32_t a, uint32_t cmp, uint32_t val) {
+  uint32_t old;
+  asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "r"(a), "r"(cmp), "r"(val) : "memory");
+  return old;
+}
+__device__ __forceinline__ uint32_t atoms_min(uint32_t a, uint32_t val) {
+  uint32_t old;
+  asm volatile("atom.shared.min.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(val) : "memory");
+  return old;
+}
+__device__ __forceinline__ void reds_min(uint32_t a, uint32_t val) {
+  asm volatile("red.shared.min.u32 [%0], %1;" ::"r"(a), "r"(val) : "memory");
+}
+__device__ __forceinline__ uint32_t atoms_add(uint32_t a, uint32_t val) {
+  uint32_t old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(val) : "memory");
+  return old;
+}
 
 struct SmemMap {
   uint32_t *key;    // [4 * n_buckets] state | kDestEpsBit, kEmptyKey when free
   uint32_t *cost;   // [4 * n_buckets] ordered cost, kFreeCost when free
   uint32_t n_buckets;
+  uint32_t key_sa;  // shared-space address of key[]; cost[] follows at key_sa + 16 * n_buckets
 };
 
 // FindOrAddToken's lookup half (inl.h:88-136) on the on-chip map: slot of key dstw, claiming a
-// free one if the key is new (n_new counts the claims of this thread).  Buckets of four keys —
-// one 16-byte shared load compares four slots —, double hashing between buckets.  A key lives
-// in the first bucket of its probe sequence that had a free slot when it was inserted; slots are
-// never freed within a frame, so a lookup may stop at the first bucket that still has one.
-// kNoSlot: the probe budget ran out (the frame is then redone through the HBM map).
-__device__ __forceinline__ uint32_t smem_find_or_claim(const SmemMap &m, uint32_t dstw, uint32_t &n_new) {
+// free one if the key is new (is_new).  Buckets of four keys — one 16-byte shared load compares
+// four slots —, double hashing between buckets.  A key lives in the first bucket of its probe
+// sequence that had a free slot when it was inserted; slots are never freed within a frame and
+// fill a bucket front to back, so a lookup may stop at the first bucket that still has a free
+// slot.  kNoSlot: the probe budget ran out (the frame is then redone through the HBM map).
+__device__ __forceinline__ uint32_t smem_find_or_claim(const SmemMap &m, uint32_t dstw, bool &is_new) {
   const uint32_t hsh = (dstw & kStateMask) * 0x9E3779B1u;
   uint32_t b = __umulhi(hsh, m.n_buckets);
   const uint32_t step = ((hsh >> 4) & 31u) + 1u;
 #pragma unroll 1
   for (int probe = 0; probe < kMaxProbe; ++probe) {
-    const uint4 kk = lds_volatile_u4(&m.key[b * 4]);
+    const uint32_t ba = m.key_sa + b * 16u;
+    const uint4 kk = lds_u4(ba);
     if (kk.x == dstw) return b * 4;
     if (kk.y == dstw) return b * 4 + 1;
     if (kk.z == dstw) return b * 4 + 2;
     if (kk.w == dstw) return b * 4 + 3;
-    const int emp = kk.x == kEmptyKey ? 0 : kk.y == kEmptyKey ? 1 : kk.z == kEmptyKey ? 2 : kk.w == kEmptyKey ? 3 : -1;
-    if (emp >= 0) {
-      const uint32_t old = atomicCAS(&m.key[b * 4 + emp], kEmptyKey, dstw);
+    if (kk.w == kEmptyKey) {  // the bucket has a free slot: the first one
+      const uint32_t emp = kk.x == kEmptyKey ? 0u : kk.y == kEmptyKey ? 1u : kk.z == kEmptyKey ? 2u : 3u;
+      const uint32_t old = atoms_cas(ba + emp * 4u, kEmptyKey, dstw);
       if (old == kEmptyKey) {
-        ++n_new;
+        is_new = true;
         return b * 4 + emp;
       }
       if (old == dstw) return b * 4 + emp;
@@ -97,39 +177,39 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
          int num_indices, uint32_t n_buckets) {
   constexpr int NT = kStreamThreads;
   constexpr int NW = NT / 32;
-  constexpr int U = 2;  // work-item batches (8 items = 32 arc slots each) in flight per warp
   extern __shared__ __align__(16) unsigned char s_dyn[];
   __shared__ PostSmem ps;
   __shared__ FrameDesc s_d;
-  __shared__ uint32_t s_claims, s_overflow, s_best_ord, s_best_state, s_alive, s_ncand;
-  __shared__ uint32_t s_qn[3];  // closure worklist lengths, indexed by round % 3
   __shared__ struct {  // GetCutoff result of the next frame, computed on chip
     unsigned long long best;
     float cur, abeam;
     uint32_t n, off;
   } s_h;
   const uint32_t n_slots = n_buckets * 4;
+  StreamHot *hot = reinterpret_cast<StreamHot *>(s_dyn);
   SmemMap m;
-  m.key = reinterpret_cast<uint32_t *>(s_dyn);
+  m.key = reinterpret_cast<uint32_t *>(s_dyn + sizeof(StreamHot));
   m.cost = m.key + n_slots;
   m.n_buckets = n_buckets;
+  m.key_sa = smem_addr(m.key);
   float *s_ll = reinterpret_cast<float *>(m.cost + n_slots);
   unsigned char *s_scratch = reinterpret_cast<unsigned char *>(s_ll + (SMEM_LL ? ((num_indices + 3) & ~3) : 0));
   uint16_t *s_eq = reinterpret_cast<uint16_t *>(s_scratch + NW * kWarpScratch);  // [2][kEpsQueueCap]
   uint32_t *s_hist = reinterpret_cast<uint32_t *>(s_scratch);                    // [kHistBins]   (write-out phase only)
   uint32_t *s_cand = s_hist + kHistBins;                                         // [kCandCap]
+  // every warp may run ahead of the shared claim counter by what it has not reported yet
+  const uint32_t slack = n_slots / 16 > 1024u ? n_slots / 16 : 1024u;
   // (test hook: a smaller on-chip budget forces overflow frames)
-  const uint32_t claim_limit = (cfg.debug_flags >> 8) ? min((uint32_t)(cfg.debug_flags >> 8), n_slots - n_slots / 16)
-                                                       : n_slots - n_slots / 16;
+  const uint32_t claim_limit = (cfg.debug_flags >> 8) ? min((uint32_t)(cfg.debug_flags >> 8), n_slots - slack)
+                                                       : n_slots - slack;
   StreamState *st = streams[blockIdx.x];
   FrameDesc *d = &s_d;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t lt_mask = (1u << lane) - 1u;
   const LmPair lms = {};
-  // The overflow flag carries WHEN it was raised (1 = expansion, r + 2 = closure round r; first
-  // writer wins): a warp that is already one phase ahead must not change the decision the slower
-  // warps are still taking about the phase behind it (the decisions have to be uniform).
-  auto raise_overflow = [&](uint32_t tag) { atomicCAS(&s_overflow, 0u, tag); };
+  // The overflow flag carries WHEN it was raised (first writer wins): a warp that is already one
+  // phase ahead must not change the decision the slower warps are still taking about the phase
+  // behind it (the decisions have to be uniform).
+  auto raise_overflow = [&](uint32_t tag) { atomicCAS(&hot->overflow, 0u, tag); };
   // this launch decodes the rows of ONE staged chunk: later chunks may already be raising
   // target_frame while their rows are still being copied
   const int limit = min(params[blockIdx.x].frame0 + params[blockIdx.x].n_frames, st->max_frames);
@@ -162,17 +242,18 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
   for (;;) {
     if (t >= limit) break;
     if (tid == 0) {
-      s_claims = 0;
-      s_overflow = (cfg.debug_flags & 8) ? 1u : 0u;  // test hook: every frame through the HBM map
-      s_best_ord = 0xFFFFFFFFu;
-      s_best_state = 0xFFFFFFFFu;
-      s_alive = 0;
-      s_ncand = 0;
-      s_qn[0] = s_qn[1] = s_qn[2] = 0;
+      hot->claims = 0;
+      hot->overflow = (cfg.debug_flags & 8) ? 1u : 0u;  // test hook: every frame through the HBM map
+      hot->best_ord = 0xFFFFFFFFu;
+      hot->best_state = 0xFFFFFFFFu;
+      hot->alive = 0;
+      hot->ncand = 0;
+      hot->qn[0] = hot->qn[1] = hot->qn[2] = 0;
+      hot->next_group = 0;
     }
     if (t + 1 < limit) {  // the next frame's row: into L2 while this frame is searched
       const char *nxt = reinterpret_cast<const char *>(ll_hist + (size_t)(t + 1) * ll_stride);
-      if (tid * 128 < num_indices * 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + tid * 128));
+      if (tid * 128 < num_indices * 4) prefetch_l2(nxt + tid * 128);
     }
     if (!have_cut) {
       // ---- first frame of the launch / after an HBM-map frame: GetCutoff + best-token pre-pass
@@ -219,158 +300,208 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
     const uint2 *__restrict__ toks = s_d.toks;
     const float cur_cut = s_d.cur_cut, abeam = s_d.abeam;
     uint32_t *next_cut = &s_d.next_cut_bits;
-    uint32_t my_best = 0xFFFFFFFFu;  // lowest cost this warp has reported to s_best_ord
 
     // ---- emitting expansion (ProcessEmitting, inl.h:311-347) into the on-chip map.
-    // A warp takes a group of 32 tokens: lane i loads token i and its emitting span and cuts the
-    // span into work items of up to four consecutive arcs, written to a warp-private buffer at
-    // the lane's prefix-sum offset.  Item k is then fetched by the four lanes 4k..4k+3 — 64
-    // contiguous bytes, one 16-byte LDG.128 per lane —, so mapping a lane to its arc costs one
-    // 8-byte shared load instead of a binary search over the prefix sums.  About a third of the
-    // arcs pass the running cutoff; they are staged in a warp-private ring and go to the map 32
-    // at a time with every lane busy.
+    // A warp takes groups of 32 tokens: lane i loads token i and its emitting span and cuts the
+    // span into work items of up to kItemArcs consecutive arcs, appended to a warp-private ring at
+    // the lane's prefix-sum offset.  The ring is drained one STEP (32 arc slots = kBatch items) at
+    // a time — item k by the kItemArcs lanes k * kItemArcs .., each one 16-byte LDG.128 —, so
+    // mapping a lane to its arc costs one 8-byte shared load instead of a binary search over the
+    // prefix sums, and what a group leaves over is carried into the next one (every step but the
+    // last is full).  The loads of step i+1 are issued BEFORE step i is scored and merged, so
+    // the HBM / L2 latency of the arc fetch hides behind the shared-memory work.  About a third
+    // of the arcs pass the running cutoff; they are staged in a second warp-private ring and go to
+    // the map 32 at a time with every lane busy.
     {
-      uint2 *ibuf = reinterpret_cast<uint2 *>(s_scratch + warp * kWarpScratch);
-      uint2 *ring = ibuf + kItemBuf;
-      uint32_t head = 0, n_staged = 0;
-      uint32_t expanded = 0, admitted = 0;
+      // (Register diet: at 64 registers per thread every spill costs an L2 round trip here — the
+      // L1 is all but gone to the shared-memory carve-out.  Only two shared-memory base addresses
+      // are kept; flags are folded into values (an arc slot without an arc carries cost +inf) or
+      // recomputed from the group ids.)
+      const uint32_t base_sa = smem_addr(hot);
+      const uint32_t iring_sa = smem_addr(s_scratch + warp * kWarpScratch);
+      constexpr uint32_t kHotClaims = 0, kHotOverflow = 4, kHotBest = 8, kHotQn0 = 24, kHotNextGroup = 36;
+      static_assert(offsetof(StreamHot, overflow) == kHotOverflow && offsetof(StreamHot, best_ord) == kHotBest &&
+                        offsetof(StreamHot, qn) == kHotQn0 && offsetof(StreamHot, claims) == kHotClaims &&
+                        offsetof(StreamHot, next_group) == kHotNextGroup,
+                    "StreamHot layout");
+      auto sring_at = [&](uint32_t i) { return iring_sa + kItemRing * 8 + ((i & (kStageCap - 1)) << 3); };
+      auto iring_at = [&](uint32_t i) { return iring_sa + ((i & (kItemRing - 1)) << 3); };
+      auto cost_at = [&](uint32_t slot) { return base_sa + (uint32_t)sizeof(StreamHot) + n_buckets * 16u + slot * 4u; };
+      auto ll_at = [&](uint32_t c) { return base_sa + (uint32_t)sizeof(StreamHot) + n_buckets * 32u + c * 4u; };
+      uint32_t ihead = 0, itail = 0, shead = 0, stail = 0;
+      uint32_t expanded = 0, unreported = 0;
+      uint32_t my_best = 0xFFFFFFFFu;  // lowest cost this warp has reported to hot->best_ord
+      float nc = ord2f(lds_u32(smem_addr(next_cut)));
       auto flush = [&](uint32_t cnt) {  // the first cnt (<= 32) staged arcs go to the map
         const bool act = (uint32_t)lane < cnt;
         uint2 e = make_uint2(0u, 0xFFFFFFFFu);
-        if (act) e = ring[(head + lane) & (kStageCap - 1)];
-        head += cnt;
-        n_staged -= cnt;
-        uint32_t n_new = 0, slot = kNoSlot;
-        if (act) slot = smem_find_or_claim(m, e.x, n_new);
+        if (act) e = lds_u2(sring_at(shead + lane));
+        shead += cnt;
+        bool is_new = false;
+        if (act) {
+          const uint32_t slot = smem_find_or_claim(m, e.x, is_new);
+          if (slot != kNoSlot) {
+            reds_min(cost_at(slot), e.y);
+            if (is_new && (e.x & kDestEpsBit)) {
+              // a new state with eps arcs: closure seed (inl.h:376-381); its eps row will be wanted soon
+              const uint32_t qi = atomicAdd(&hot->qn[0], 1u);
+              if (qi < (uint32_t)kEpsQueueCap) s_eq[qi] = (uint16_t)slot;
+              else raise_overflow(1u);
+              prefetch_l2(&g.eps_rows[e.x & kStateMask]);
+            }
+          } else {
+            raise_overflow(1u);
+          }
+        }
         const uint32_t wmin = __reduce_min_sync(kFull, e.y);
         if (wmin < my_best) {  // best cost of the frame (inl.h:169-179), tracked where costs enter the map
           my_best = wmin;
-          if (lane == 0) atomicMin(&s_best_ord, wmin);
+          if (lane == 0) reds_min(base_sa + kHotBest, wmin);
         }
-        bool seed = false;
-        if (slot != kNoSlot) {
-          atomicMin(&m.cost[slot], e.y);
-          seed = n_new != 0 && (e.x & kDestEpsBit) != 0;  // a new state with eps arcs: closure seed (inl.h:376-381)
+        // claims are reported to the shared counter 32 at a time (the limit leaves that slack)
+        unreported += (uint32_t)__popc(__ballot_sync(kFull, is_new));
+        if (unreported >= 32u) {
+          if (lane == 0 && atoms_add(base_sa + kHotClaims, unreported) + unreported > claim_limit) raise_overflow(1u);
+          unreported = 0;
         }
-        const unsigned sm = __ballot_sync(kFull, seed);
-        const unsigned fm = __ballot_sync(kFull, act && slot == kNoSlot);
-        const uint32_t nn = __reduce_add_sync(kFull, n_new);
-        uint32_t qb = 0;
-        if (lane == 0) {
-          if ((nn && atomicAdd(&s_claims, nn) + nn > claim_limit) || fm) raise_overflow(1u);
-          if (sm) qb = atomicAdd(&s_qn[0], (uint32_t)__popc(sm));
+      };
+      // a step: its arc records and the cost of the token each one leaves (+inf: no arc in this slot)
+      struct Step {
+        int4 arc;
+        float tcost;
+      };
+      // (Every lane loads — lanes without an arc re-read their item's last one, or record 0 —: a
+      // predicated load with a default value makes ptxas write the default into the load's
+      // destination registers AFTER the request, and that write waits for the data: measured,
+      // the warp then sits out the whole fetch latency at the request.)
+      auto issue = [&](uint32_t cnt) -> Step {  // cnt (<= kBatch) items from the head of the item ring
+        Step sp;
+        const uint32_t it = (uint32_t)lane >> kItemShift;
+        const bool have = it < cnt;
+        const uint2 item = lds_u2(iring_at(ihead + (have ? it : 0u)));
+        const uint32_t r = (uint32_t)lane & (kItemArcs - 1), last = item.x & (kItemArcs - 1);
+        sp.tcost = (have && r <= last) ? __uint_as_float(item.y) : CUDART_INF_F;
+        sp.arc = __ldg(&g.arcs[(item.x >> kItemShift) + (r < last ? r : last)]);
+        ihead += cnt;
+        return sp;
+      };
+      auto process = [&](const Step &sp) {
+        // (a slot without an arc may hold an eps record, ilabel 0: the row index is clamped)
+        const int li = sp.arc.x > 0 ? sp.arc.x - 1 : 0;
+        const float ac = -(SMEM_LL ? lds_f32_ro(ll_at((uint32_t)li)) : __ldg(&ll[li]));
+        const float tot = (sp.tcost + ac) + __int_as_float(sp.arc.z);  // inl.h:326-329
+        // (the olabel is not needed, but its register must stay reserved until the record has arrived:
+        // ptxas reuses the register of an unused component as a temporary right after the request, and
+        // that write waits for the whole fetch.  No olabel is 0x80000001; the test costs one predicate input.)
+        const bool adm = tot < nc && sp.arc.y != (int)0x80000001;  // inl.h:330 (tot is +inf where there is no arc)
+        const float cand = adm ? tot + abeam : CUDART_INF_F;       // inl.h:332-333
+        if (__any_sync(kFull, cand < nc)) {
+          const uint32_t wmin = __reduce_min_sync(kFull, f2ord(cand));
+          if (lane == 0) reds_min(smem_addr(next_cut), wmin);
+          nc = fminf(nc, ord2f(wmin));
         }
-        if (sm) {
-          qb = __shfl_sync(kFull, qb, 0);
-          if (seed) {
-            const uint32_t qi = qb + (uint32_t)__popc(sm & lt_mask);
-            if (qi < (uint32_t)kEpsQueueCap) s_eq[qi] = (uint16_t)slot;
-            else raise_overflow(1u);
-          }
-        }
+        const unsigned am = __ballot_sync(kFull, adm);
+        if (adm) sts_u2(sring_at(stail + (uint32_t)__popc(am & lanemask_lt())), (uint32_t)sp.arc.w, f2ord(tot));
+        stail += (uint32_t)__popc(am);
         __syncwarp();
+        if (stail - shead >= 32u) flush(32u);
       };
-      float nc = ord2f(lds_volatile_u32(next_cut));
-      // Two more groups are in flight behind the one being walked: the tokens of group +2 and the
-      // emitting-arc spans of group +1 (the span load needs the token's state), so a new group
-      // starts without waiting on HBM.
-      uint32_t t1_cost = 0, t1_base = 0, t1_deg = 0;  // next group: cost, span
-      uint2 t2 = make_uint2(0, 0);                    // group after that: {state, cost}
-      bool t2_ok = false;
-      auto load_tokens = [&](uint32_t grp) {
-        const uint32_t i = grp * 32 + lane;
-        t2_ok = grp < n_groups && i < n_cur;
-        if (t2_ok) t2 = __ldcg(&toks[i]);  // written by this kernel one frame ago: no ld.global.nc
+      // Two more groups are in flight behind the one being cut into items: the tokens of group id2
+      // and the emitting-arc spans of group id1 (the span load needs the token's state), so a new
+      // group starts without waiting on HBM.  Unconditional loads with clamped indices: a
+      // predicated load that keeps the old value needs a move out of the load's destination, which
+      // waits for the data.
+      uint32_t t1_cost = 0;
+      uint2 t1_er = make_uint2(0, 0), t2 = make_uint2(0, 0);
+      uint32_t id1, id2;
+      auto load_tokens = [&](uint32_t id) {
+        const uint32_t i = id * 32 + lane;
+        t2 = __ldcg(&toks[i < n_cur ? i : 0u]);  // written by this kernel one frame ago: no ld.global.nc
       };
-      auto load_spans = [&]() {
+      auto load_spans = [&](uint32_t id) {  // id: the group whose tokens are in t2
         t1_cost = t2.y;
-        t1_base = 0;
-        t1_deg = 0;
-        if (t2_ok && __uint_as_float(t2.y) <= cur_cut) {  // inclusive, inl.h:315
-          const uint2 er = __ldg(&g.erows[t2.x]);
-          t1_base = er.x;
-          t1_deg = er.y - er.x;
+        t1_er = __ldg(&g.erows[id * 32 + lane < n_cur ? t2.x : 0u]);
+      };
+      // Token groups are handed out dynamically (one shared counter): the warp schedulers favour
+      // some warps over others, and with a fixed share per warp the favoured ones would wait at the
+      // barrier while the rest finish alone, with nothing left to hide their latencies behind.
+      auto acquire = [&]() -> uint32_t {
+        uint32_t id = 0;
+        if (lane == 0) id = atoms_add(base_sa + kHotNextGroup, 1u);
+        return __shfl_sync(kFull, id, 0);
+      };
+      id1 = acquire();
+      load_tokens(id1);
+      load_spans(id1);
+      id2 = acquire();
+      load_tokens(id2);
+      // The group being cut into items keeps its place in registers (a group with more items than
+      // the ring has room for is appended slice by slice).
+      uint32_t g_cost = 0, g_base = 0, g_deg = 0, g_off = 0, g_total = 0, g_r0 = 0;
+      auto top_up = [&]() {  // keep two steps' worth of items in the ring while there are tokens left
+        for (;;) {
+          const uint32_t avail = itail - ihead;
+          if (avail >= 2u * kBatch) return;
+          if (g_r0 >= g_total) {
+            if (id1 >= n_groups) return;
+            // next group of tokens; warp-uniform decision (the lanes may not have reconverged after the map updates)
+            if (__any_sync(kFull, lds_u32(base_sa + kHotOverflow) != 0u)) {
+              id1 = id2 = 0xFFFFFFFFu;  // the frame is being redone anyway: drop what is queued
+              ihead = itail;
+              return;
+            }
+            // running cutoff (inl.h:330): other warps' tightenings arrive once per group
+            nc = fminf(nc, ord2f(lds_u32(smem_addr(next_cut))));
+            g_cost = t1_cost;
+            g_base = t1_er.x;
+            // inclusive token test, inl.h:315
+            g_deg = (id1 * 32 + lane < n_cur && __uint_as_float(t1_cost) <= cur_cut) ? t1_er.y - t1_er.x : 0u;
+            load_spans(id2);
+            id1 = id2;
+            id2 = acquire();
+            load_tokens(id2);
+            const uint32_t nit = (g_deg + kItemArcs - 1) / kItemArcs;
+            const uint32_t incl = warp_incl_scan(nit, lane);
+            g_off = incl - nit;
+            g_total = __shfl_sync(kFull, incl, 31);
+            g_r0 = 0;
+            expanded += g_deg;
+            if (g_total == 0) continue;
+          }
+          // items [g_r0, g_r0 + take) of the group -> ring
+          const uint32_t room = (uint32_t)kItemRing - avail;
+          const uint32_t take = room < g_total - g_r0 ? room : g_total - g_r0;
+          const uint32_t nit = (g_deg + kItemArcs - 1) / kItemArcs;
+          for (uint32_t k = g_off < g_r0 ? g_r0 - g_off : 0u; k < nit && g_off + k < g_r0 + take; ++k) {
+            const uint32_t left = g_deg - k * kItemArcs;
+            sts_u2(iring_at(itail + g_off + k - g_r0),
+                   ((g_base + k * kItemArcs) << kItemShift) | ((left < (uint32_t)kItemArcs ? left : (uint32_t)kItemArcs) - 1u), g_cost);
+          }
+          itail += take;
+          g_r0 += take;
+          __syncwarp();
         }
       };
-      load_tokens(warp);
-      load_spans();
-      load_tokens(warp + NW);
-      for (uint32_t grp = warp; grp < n_groups; grp += NW) {
-        // warp-uniform decision (the lanes may not have reconverged after the map updates)
-        if (__any_sync(kFull, lds_volatile_u32(&s_overflow) != 0u)) break;
-        // running cutoff (inl.h:330): other warps' tightenings arrive once per group
-        nc = fminf(nc, ord2f(lds_volatile_u32(next_cut)));
-        const uint32_t cost_bits = t1_cost, base = t1_base, deg = t1_deg;
-        load_spans();
-        load_tokens(grp + 2 * NW);
-        const uint32_t nit = (deg + kQuad - 1) / kQuad;
-        const uint32_t incl = warp_incl_scan(nit, lane);
-        const uint32_t off = incl - nit;
-        const uint32_t total = __shfl_sync(kFull, incl, 31);
-        expanded += deg;
-        for (uint32_t ib = 0; ib < total; ib += kItemBuf) {
-          // ---- this lane's items with index in [ib, ib + kItemBuf) -> buffer
-          for (uint32_t k = off < ib ? ib - off : 0u; k < nit && off + k < ib + kItemBuf; ++k) {
-            const uint32_t left = deg - k * kQuad;
-            ibuf[off + k - ib] = make_uint2(((base + k * kQuad) << 2) | ((left < (uint32_t)kQuad ? left : (uint32_t)kQuad) - 1u),
-                                            cost_bits);
-          }
-          __syncwarp();
-          const uint32_t nbuf = total - ib < (uint32_t)kItemBuf ? total - ib : (uint32_t)kItemBuf;
-          for (uint32_t i0 = 0; i0 < nbuf; i0 += 8 * U) {
-            bool in[U];
-            float tcost[U];
-            int4 arc[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-              const uint32_t it = i0 + u * 8 + (lane >> 2);
-              uint2 item = make_uint2(0u, 0u);
-              const bool have = it < nbuf;
-              if (have) item = ibuf[it];
-              const uint32_t r = lane & 3u;
-              in[u] = have && r <= (item.x & 3u);
-              tcost[u] = __uint_as_float(item.y);
-              arc[u] = make_int4(1, 0, 0, 0);
-              if (in[u]) arc[u] = __ldg(&g.arcs[(item.x >> 2) + r]);
-            }
-            float tot[U];
-            bool adm[U];
-            uint32_t cand_bits = 0xFFFFFFFFu;
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-              const float ac = -(SMEM_LL ? s_ll[arc[u].x - 1] : __ldg(&ll[arc[u].x - 1]));
-              tot[u] = (tcost[u] + ac) + __int_as_float(arc[u].z);  // inl.h:326-329
-              adm[u] = in[u] && tot[u] < nc;                        // inl.h:330
-              const float cand = tot[u] + abeam;                    // inl.h:332-333
-              if (adm[u] && cand < nc) cand_bits = min(cand_bits, f2ord(cand));
-            }
-            if (__any_sync(kFull, cand_bits != 0xFFFFFFFFu)) {
-              const uint32_t wmin = __reduce_min_sync(kFull, cand_bits);
-              if (lane == 0) atomicMin(next_cut, wmin);
-              nc = fminf(nc, ord2f(wmin));
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-              const unsigned am = __ballot_sync(kFull, adm[u]);
-              if (am == 0) continue;
-              if (adm[u])
-                ring[(head + n_staged + (uint32_t)__popc(am & lt_mask)) & (kStageCap - 1)] =
-                    make_uint2((uint32_t)arc[u].w, f2ord(tot[u]));
-              const uint32_t nnew = (uint32_t)__popc(am);
-              n_staged += nnew;
-              admitted += nnew;
-              __syncwarp();
-              if (n_staged >= 32u) flush(32u);
-            }
-          }
-          __syncwarp();  // every lane is done with the item buffer
+      Step sA, sB;
+      for (;;) {  // two steps requested back to back, then scored
+        top_up();
+        const uint32_t avail = itail - ihead;
+        if (avail == 0) break;
+        sA = issue(avail < (uint32_t)kBatch ? avail : (uint32_t)kBatch);
+        if (avail > (uint32_t)kBatch) {
+          sB = issue(avail - kBatch < (uint32_t)kBatch ? avail - kBatch : (uint32_t)kBatch);
+          process(sA);
+          process(sB);
+        } else {
+          process(sA);
         }
       }
-      if (n_staged) flush(n_staged);  // the last, partial set (n_staged < 32)
+      while (stail != shead) flush(stail - shead < 32u ? stail - shead : 32u);  // what is still staged
+      if (unreported && lane == 0 && atoms_add(base_sa + kHotClaims, unreported) + unreported > claim_limit) raise_overflow(1u);
       expanded = __reduce_add_sync(kFull, expanded);
       if (lane == 0 && expanded) {
         atomicAdd(&s_d.arcs_expanded, expanded);
-        atomicAdd(&s_d.arcs_admitted, admitted);
+        atomicAdd(&s_d.arcs_admitted, stail);  // every staged arc was admitted against the running cutoff
       }
     }
     __syncthreads();
@@ -382,55 +513,70 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
     // the eps arcs of the slots queued for it (round 0: every new state with eps arcs, queued when
     // it was claimed) and queues the destinations whose cost it lowered for round r + 1.  A slot
     // whose cost is lowered twice is queued twice; relaxing is idempotent.  The min-plus fixed
-    // point is unique, so the costs equal the reference's LIFO order.
-    if (const uint32_t ovf0 = lds_volatile_u32(&s_overflow); !(ovf0 != 0u && ovf0 <= 1u)) {
-      // (the warp scratch is idle from here on: clear the cost histogram of the write-out phase)
-      for (int i = tid; i < kHistBins; i += NT) s_hist[i] = 0;
+    // point is unique, so the costs equal the reference's LIFO order.  The eps row of a state
+    // carries its first eps arc inline (most states have one): one load per relaxed state.
+    if (const uint32_t ovf0 = lds_volatile_u32(&hot->overflow); !(ovf0 != 0u && ovf0 <= 1u)) {
       for (uint32_t round = 0;; ++round) {
-        const uint32_t nq = min(s_qn[round % 3u], (uint32_t)kEpsQueueCap);
+        const uint32_t nq = min(hot->qn[round % 3u], (uint32_t)kEpsQueueCap);
         const uint16_t *qin = s_eq + (round & 1u) * kEpsQueueCap;
         uint16_t *qout = s_eq + ((round + 1u) & 1u) * kEpsQueueCap;
-        uint32_t *qn_out = &s_qn[(round + 1u) % 3u];
-        for (uint32_t i = tid; i < nq; i += NT) {
-          const uint32_t sl = qin[i];
-          const uint32_t co = lds_volatile_u32(&m.cost[sl]);
-          if (!(co < nc_ord)) continue;  // inl.h:391
-          const float cost = ord2f(co);
-          const uint2 r = __ldg(&g.rows[m.key[sl] & kStateMask]);
-          for (uint32_t a = r.x; a < r.y; ++a) {
-            const int4 arc = __ldg(&g.arcs[a]);
-            const float tot = cost + __int_as_float(arc.z);  // inl.h:413-414
-            if (!(tot < nc)) continue;                       // inl.h:415
-            const uint32_t to = f2ord(tot);
-            uint32_t n_new = 0;
-            const uint32_t s2 = smem_find_or_claim(m, (uint32_t)arc.w, n_new);
-            if (s2 == kNoSlot) {
-              raise_overflow(round + 2u);
-              continue;
+        uint32_t *qn_out = &hot->qn[(round + 1u) % 3u];
+        auto relax = [&](float cost, float w, uint32_t dstw) {
+          const float tot = cost + w;  // inl.h:413-414
+          if (!(tot < nc)) return;     // inl.h:415
+          const uint32_t to = f2ord(tot);
+          bool is_new = false;
+          const uint32_t s2 = smem_find_or_claim(m, dstw, is_new);
+          if (s2 == kNoSlot) {
+            raise_overflow(round + 2u);
+            return;
+          }
+          if (is_new && atomicAdd(&hot->claims, 1u) + 1u > claim_limit) raise_overflow(round + 2u);
+          const uint32_t old = atomicMin(&m.cost[s2], to);
+          if (to < old) {  // cost changed (inl.h:115-127)
+            atomicMin(&hot->best_ord, to);
+            if (dstw & kDestEpsBit) {  // inl.h:425-426
+              const uint32_t qi = atomicAdd(qn_out, 1u);
+              if (qi < (uint32_t)kEpsQueueCap) qout[qi] = (uint16_t)s2;
+              else raise_overflow(round + 2u);
+              prefetch_l2(&g.eps_rows[dstw & kStateMask]);
             }
-            if (n_new && atomicAdd(&s_claims, 1u) + 1u > claim_limit) raise_overflow(round + 2u);
-            const uint32_t old = atomicMin(&m.cost[s2], to);
-            if (to < old) {  // cost changed (inl.h:115-127)
-              atomicMin(&s_best_ord, to);
-              if ((uint32_t)arc.w & kDestEpsBit) {  // inl.h:425-426
-                const uint32_t qi = atomicAdd(qn_out, 1u);
-                if (qi < (uint32_t)kEpsQueueCap) qout[qi] = (uint16_t)s2;
-                else raise_overflow(round + 2u);
-              }
+          }
+        };
+        for (uint32_t i0 = tid; i0 < nq; i0 += 4 * NT) {  // up to four worklist entries per thread, loads batched
+          float cost[4];
+          uint4 er[4];
+          bool go[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {  // (unconditional loads, clamped: see load_tokens)
+            const uint32_t i = i0 + j * NT;
+            const uint32_t sl = qin[i < nq ? i : 0u];
+            const uint32_t co = lds_volatile_u32(&m.cost[sl]);
+            go[j] = i < nq && co < nc_ord;  // inl.h:391
+            cost[j] = ord2f(co);
+            er[j] = __ldg(&g.eps_rows[m.key[sl] & kStateMask]);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (!go[j] || er[j].y == er[j].x) continue;
+            relax(cost[j], __uint_as_float(er[j].z), er[j].w);
+            for (uint32_t a = er[j].x + 1; a < er[j].y; ++a) {
+              const int4 arc = __ldg(&g.arcs[a]);
+              relax(cost[j], __int_as_float(arc.z), (uint32_t)arc.w);
             }
           }
         }
-        // one barrier per round: round r reads s_qn[r % 3] and raises s_qn[(r + 1) % 3]; the
+        // one barrier per round: round r reads qn[r % 3] and raises qn[(r + 1) % 3]; the
         // counter round r + 1 raises is lowered here — its last readers passed the previous barrier
-        if (tid == 0) s_qn[(round + 2u) % 3u] = 0;
+        if (tid == 0) hot->qn[(round + 2u) % 3u] = 0;
         __syncthreads();
-        const uint32_t ovf = lds_volatile_u32(&s_overflow);
-        if (s_qn[(round + 1u) % 3u] == 0 || (ovf != 0u && ovf <= round + 2u)) break;
+        const uint32_t ovf = lds_volatile_u32(&hot->overflow);
+        if (hot->qn[(round + 1u) % 3u] == 0 || (ovf != 0u && ovf <= round + 2u)) break;
       }
     }
     phase(2);
 
-    if (s_overflow) {
+    if (hot->overflow) {
       // ---- too many distinct destinations for the on-chip map: wipe it and redo the frame
       // through the stream's HBM map (identical results; the running cutoff stays valid)
       __syncthreads();
@@ -454,59 +600,60 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
       continue;
     }
 
-    // ---- the frame's tokens are final.  ONE pass over the map: survivors (cost < next_cutoff) are
-    // appended to the token arena, their costs binned for GetCutoff, the best token's state
-    // resolved (lowest cost — known from the tracking above —, ties -> lowest state id,
-    // inl.h:169-179), the slots recycled.
+    // ---- the frame's tokens are final.  ONE pass over the map, a bucket (four slots, two 16-byte
+    // shared loads) per lane: survivors (cost < next_cutoff) are appended to the token arena, the
+    // best token's state resolved (lowest cost — known from the tracking above —, ties -> lowest
+    // state id, inl.h:169-179), the slots recycled.
     {
-      const uint32_t best_ord = s_best_ord;
+      const uint32_t best_ord = hot->best_ord;
       const float bc = ord2f(best_ord);
-      // GetCutoff (inl.h:138-234) needs the exact max_active-th smallest cost when more tokens
-      // than that survive.  All survivors lie in [best, next_cutoff): a 2048-bin histogram over
-      // that range (monotone in the cost) locates the bin holding that rank; its few members are
-      // then selected exactly.  Only when at least max_active states were claimed at all.
-      const bool want_hist = s_claims > (uint32_t)cfg.max_active && best_ord != 0xFFFFFFFFu && nc < CUDART_INF_F;
-      const float h_scale = want_hist ? (float)kHistBins / fmaxf(nc - bc, 1e-6f) : 0.f;
-      auto bin_of = [&](float c) -> uint32_t {
-        const float x = (c - bc) * h_scale;
-        return x >= (float)(kHistBins - 1) ? (uint32_t)(kHistBins - 1) : (uint32_t)(int)fmaxf(x, 0.f);
-      };
       const uint32_t cap = s_d.out_cap;
       uint2 *out_sc = s_d.out_sc;
-      const uint32_t rows = n_slots >> 5;  // n_slots is a multiple of 32
-      for (uint32_t row = warp; row < rows; row += NW) {
-        const uint32_t slot = row * 32 + lane;
-        const uint32_t kw = m.key[slot];
-        if (!__any_sync(kFull, kw != kEmptyKey)) continue;
-        bool alive = false;
-        uint32_t co = kFreeCost;
-        if (kw != kEmptyKey) {
-          co = m.cost[slot];
-          alive = co < nc_ord;
-          m.key[slot] = kEmptyKey;
-          m.cost[slot] = kFreeCost;
+      // GetCutoff (inl.h:138-234) needs the exact max_active-th smallest cost when more tokens than
+      // that survive: only possible when more states than that were claimed at all
+      const bool want_hist = hot->claims > (uint32_t)cfg.max_active && best_ord != 0xFFFFFFFFu && nc < CUDART_INF_F;
+      for (int i = tid; i < kHistBins; i += NT) s_hist[i] = 0;  // (the warp scratch is idle from here on)
+      const uint32_t blocks = n_buckets >> 5;  // n_buckets is a multiple of 32
+      for (uint32_t blk = warp; blk < blocks; blk += NW) {
+        const uint32_t s0 = (blk * 32 + lane) * 4;
+        const uint4 kw = *reinterpret_cast<const uint4 *>(&m.key[s0]);
+        uint32_t cnt = 0;
+        uint4 co = make_uint4(kFreeCost, kFreeCost, kFreeCost, kFreeCost);
+        if (kw.x != kEmptyKey) {  // (slots fill a bucket front to back)
+          co = *reinterpret_cast<const uint4 *>(&m.cost[s0]);
+          *reinterpret_cast<uint4 *>(&m.key[s0]) = make_uint4(kEmptyKey, kEmptyKey, kEmptyKey, kEmptyKey);
+          *reinterpret_cast<uint4 *>(&m.cost[s0]) = make_uint4(kFreeCost, kFreeCost, kFreeCost, kFreeCost);
+          cnt = (co.x < nc_ord) + (co.y < nc_ord) + (co.z < nc_ord) + (co.w < nc_ord);
         }
-        const unsigned am = __ballot_sync(kFull, alive);
-        if (am == 0) continue;
+        const uint32_t incl = warp_incl_scan(cnt, lane);
+        const uint32_t total = __shfl_sync(kFull, incl, 31);
+        if (total == 0) continue;
         uint32_t pos = 0;
-        if (lane == 0) pos = atomicAdd(&s_alive, (uint32_t)__popc(am));
-        pos = __shfl_sync(kFull, pos, 0);
-        if (alive) {
-          const float c = ord2f(co);
-          const uint32_t idx = pos + (uint32_t)__popc(am & lt_mask);
-          if (idx < cap) out_sc[idx] = make_uint2(kw & kStateMask, __float_as_uint(c));
-          if (want_hist) atomicAdd(&s_hist[bin_of(c)], 1u);
-          if (co == best_ord) atomicMin(&s_best_state, kw & kStateMask);
+        if (lane == 0) pos = atomicAdd(&hot->alive, total);
+        pos = __shfl_sync(kFull, pos, 0) + incl - cnt;
+        auto put = [&](uint32_t k, uint32_t c) {
+          if (c < nc_ord) {
+            if (pos < cap) out_sc[pos] = make_uint2(k & kStateMask, __float_as_uint(ord2f(c)));
+            ++pos;
+            if (c == best_ord) atomicMin(&hot->best_state, k & kStateMask);
+          }
+        };
+        if (cnt) {
+          put(kw.x, co.x);
+          put(kw.y, co.y);
+          put(kw.z, co.z);
+          put(kw.w, co.w);
         }
       }
       __syncthreads();
       phase(3);
-      const uint32_t n_alive = s_alive;
+      const uint32_t n_alive = hot->alive;
       const unsigned long long best64 =
-          n_alive ? (((unsigned long long)best_ord << 32) | s_best_state) : kInfVal;
+          n_alive ? (((unsigned long long)best_ord << 32) | hot->best_state) : kInfVal;
       const uint32_t n_kept = n_alive < cap ? n_alive : cap;
       float n_cur_cut = CUDART_INF_F, n_abeam = cfg.beam;
       const float beam_cut = bc + cfg.beam;  // inl.h:182
+      auto arena_ord = [&](uint32_t i) { return f2ord(__uint_as_float(__ldcg(&out_sc[i]).y)); };
       if (n_alive == 0) {
         // nothing survived: the next frame has nothing to expand
       } else if (n_alive <= (uint32_t)cfg.min_active && n_alive <= (uint32_t)cfg.max_active) {
@@ -516,7 +663,17 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
         n_cur_cut = beam_cut;  // every token is below best + beam and max_active does not bind (inl.h:227-232)
         n_abeam = cfg.beam;
       } else if (nc <= beam_cut && want_hist && n_kept == n_alive) {
-        // ---- sorted[max_active] over the survivors (inl.h:188-203): bin of that rank, then exact
+        // ---- sorted[max_active] over the survivors (inl.h:188-203).  All of them lie in
+        // [best, next_cutoff): a 2048-bin histogram over that range (monotone in the cost) locates
+        // the bin holding that rank; its few members are then selected exactly.  Both passes read
+        // the survivors back from the arena (coalesced, L2-resident: they were written just now).
+        const float h_scale = (float)kHistBins / fmaxf(nc - bc, 1e-6f);
+        auto bin_of = [&](float c) -> uint32_t {
+          const float x = (c - bc) * h_scale;
+          return x >= (float)(kHistBins - 1) ? (uint32_t)(kHistBins - 1) : (uint32_t)(int)fmaxf(x, 0.f);
+        };
+        for (uint32_t i = tid; i < n_alive; i += NT) atomicAdd(&s_hist[bin_of(__uint_as_float(__ldcg(&out_sc[i]).y))], 1u);
+        __syncthreads();
         const uint32_t k = (uint32_t)cfg.max_active;
         uint32_t total = 0;
         const uint32_t h0 = s_hist[2 * tid], h1 = s_hist[2 * tid + 1];
@@ -532,21 +689,20 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
         if (kcount <= (uint32_t)kCandCap) {
           for (uint32_t i = tid; i < n_alive; i += NT) {
             const float c = __uint_as_float(__ldcg(&out_sc[i]).y);
-            if (bin_of(c) == kbin) s_cand[atomicAdd(&s_ncand, 1u)] = f2ord(c);
+            if (bin_of(c) == kbin) s_cand[atomicAdd(&hot->ncand, 1u)] = f2ord(c);
           }
           __syncthreads();
           n_cur_cut = block_kth_smallest<NT>([&](uint32_t i) { return s_cand[i]; }, kcount, kk, best_ord, 0xFFFFFFFFu,
                                              nc_ord - best_ord, ps.hist, ps.misc);
         } else {  // (a degenerate cost distribution: select over all survivors)
-          n_cur_cut = block_kth_smallest<NT>([&](uint32_t i) { return f2ord(__uint_as_float(__ldcg(&out_sc[i]).y)); },
-                                             n_alive, k, best_ord, 0xFFFFFFFFu, nc_ord - best_ord, ps.hist, ps.misc);
+          n_cur_cut = block_kth_smallest<NT>(arena_ord, n_alive, k, best_ord, 0xFFFFFFFFu, nc_ord - best_ord, ps.hist,
+                                             ps.misc);
         }
         n_abeam = n_cur_cut - bc + cfg.beam_delta;
       } else {
         // ---- general case (the adaptive beam of this frame was wider than the beam, or the arena
         // is full): GetCutoff over the survivors in the arena
-        get_cutoff<NT>([&](uint32_t i) { return f2ord(__uint_as_float(__ldcg(&out_sc[i]).y)); }, n_kept, n_kept,
-                       best_ord, cfg, ps.red32, ps.hist, ps.misc, n_cur_cut, n_abeam);
+        get_cutoff<NT>(arena_ord, n_kept, n_kept, best_ord, cfg, ps.red32, ps.hist, ps.misc, n_cur_cut, n_abeam);
       }
       if (tid == 0) {
         s_h.off = st->frame_off[t + 1];
