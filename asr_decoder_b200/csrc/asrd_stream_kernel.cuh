@@ -79,6 +79,11 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
   return m;
 }
+// asynchronous 16-byte global -> shared copy (LDGSTS): no register, no scoreboard wait at the request
+__device__ __forceinline__ void cp_async16(uint32_t smem_a, const void *gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_a), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // Shared memory by 32-bit shared-state-space address: the hot loop keeps a handful of base
@@ -237,6 +242,7 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
   // the survivors while they are written out): no HBM round trip per frame.
   int t = st->frame;
   bool have_cut = false;
+  bool row_staged = false;  // the row of frame t is already in s_ll (copied behind the previous frame's closure)
   const float *const ll_hist = st->ll_hist;
   const int ll_stride = st->ll_stride;
   for (;;) {
@@ -274,8 +280,12 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
       const float h_abeam = s_h.abeam;
       const unsigned long long h_best = s_h.best;
       if (tid == 0) fill_desc(st, d, t, h_n, s_h.off, s_h.cur, h_abeam, kOrdInf, false);
-      if (SMEM_LL)
-        for (int c = tid; c < num_indices; c += NT) s_ll[c] = __ldcs(&llr[c]);
+      if (SMEM_LL) {
+        if (row_staged) cp_async_wait_all();  // (made visible to the other threads by the barrier below)
+        else
+          for (int c = tid; c < num_indices; c += NT) s_ll[c] = __ldcs(&llr[c]);
+      }
+      row_staged = false;
       uint32_t mn = kOrdInf;
       if (h_n > 0) {
         const float bc = ord2f((uint32_t)(h_best >> 32));
@@ -509,38 +519,82 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
     const float nc = ord2f(s_d.next_cut_bits);  // the FINAL next_cutoff of this frame
     const uint32_t nc_ord = s_d.next_cut_bits;
 
-    // ---- eps closure (ProcessNonemitting, inl.h:353-431) over worklists of slots: round r relaxes
-    // the eps arcs of the slots queued for it (round 0: every new state with eps arcs, queued when
-    // it was claimed) and queues the destinations whose cost it lowered for round r + 1.  A slot
-    // whose cost is lowered twice is queued twice; relaxing is idempotent.  The min-plus fixed
-    // point is unique, so the costs equal the reference's LIFO order.  The eps row of a state
-    // carries its first eps arc inline (most states have one): one load per relaxed state.
+    // ---- eps closure (ProcessNonemitting, inl.h:353-431) over worklists of slots: round 0 relaxes
+    // the eps arcs of every new state with eps arcs (queued when it was claimed).  A thread that
+    // lowers the cost of a destination which has eps arcs itself FOLLOWS it at once (depth first, like
+    // the reference's LIFO) instead of waiting for the next round: a chain of eps arcs costs one load
+    // per hop and no barrier; only when a state fans out to several such destinations do the extra
+    // ones go to the worklist of the next round.  A slot whose cost is lowered twice is relaxed
+    // twice; relaxing is idempotent.  The min-plus fixed point is unique, so the costs equal the
+    // reference's.  The eps row of a state carries its first eps arc inline (most states have
+    // one): one load per relaxed state.
     if (const uint32_t ovf0 = lds_volatile_u32(&hot->overflow); !(ovf0 != 0u && ovf0 <= 1u)) {
+      // The expansion was the last reader of this frame's log-likelihood row: the next frame's row
+      // is copied into its place now, asynchronously, behind the closure and the write-out.
+      if (SMEM_LL && t + 1 < limit && (ll_stride & 3) == 0) {
+        const float *nrow = ll_hist + (size_t)(t + 1) * ll_stride;
+        const uint32_t ll_sa = smem_addr(s_ll);
+        for (int c = tid * 4; c < num_indices; c += NT * 4) cp_async16(ll_sa + c * 4, nrow + c);
+        row_staged = true;
+      }
       for (uint32_t round = 0;; ++round) {
         const uint32_t nq = min(hot->qn[round % 3u], (uint32_t)kEpsQueueCap);
         const uint16_t *qin = s_eq + (round & 1u) * kEpsQueueCap;
         uint16_t *qout = s_eq + ((round + 1u) & 1u) * kEpsQueueCap;
         uint32_t *qn_out = &hot->qn[(round + 1u) % 3u];
-        auto relax = [&](float cost, float w, uint32_t dstw) {
+        // relaxes dstw with cost + w; true when the destination's cost was lowered and it has eps arcs
+        auto relax = [&](float cost, float w, uint32_t dstw, float &new_cost, uint32_t &s2) -> bool {
           const float tot = cost + w;  // inl.h:413-414
-          if (!(tot < nc)) return;     // inl.h:415
+          if (!(tot < nc)) return false;  // inl.h:415
           const uint32_t to = f2ord(tot);
           bool is_new = false;
-          const uint32_t s2 = smem_find_or_claim(m, dstw, is_new);
+          s2 = smem_find_or_claim(m, dstw, is_new);
           if (s2 == kNoSlot) {
             raise_overflow(round + 2u);
-            return;
+            return false;
           }
           if (is_new && atomicAdd(&hot->claims, 1u) + 1u > claim_limit) raise_overflow(round + 2u);
           const uint32_t old = atomicMin(&m.cost[s2], to);
-          if (to < old) {  // cost changed (inl.h:115-127)
-            atomicMin(&hot->best_ord, to);
-            if (dstw & kDestEpsBit) {  // inl.h:425-426
-              const uint32_t qi = atomicAdd(qn_out, 1u);
-              if (qi < (uint32_t)kEpsQueueCap) qout[qi] = (uint16_t)s2;
-              else raise_overflow(round + 2u);
-              prefetch_l2(&g.eps_rows[dstw & kStateMask]);
+          if (!(to < old)) return false;  // cost unchanged (inl.h:115-127)
+          atomicMin(&hot->best_ord, to);
+          new_cost = tot;
+          return (dstw & kDestEpsBit) != 0;  // inl.h:425-426
+        };
+        // relaxes every eps arc of a state (er: its eps row) from `cost`, then follows one lowered
+        // destination after the other; further ones are queued for the next round
+        auto relax_chain = [&](float cost, uint4 er) {
+          for (int hop = 0; hop < 64; ++hop) {
+            uint32_t next_w = 0;
+            float next_cost = 0.f;
+            bool have_next = false;
+            for (uint32_t a = er.x; a < er.y; ++a) {
+              float w;
+              uint32_t dstw;
+              if (a == er.x) {
+                w = __uint_as_float(er.z);
+                dstw = er.w;
+              } else {
+                const int4 arc = __ldg(&g.arcs[a]);
+                w = __int_as_float(arc.z);
+                dstw = (uint32_t)arc.w;
+              }
+              float c2;
+              uint32_t s2;
+              if (relax(cost, w, dstw, c2, s2)) {
+                if (!have_next && hop < 63) {
+                  have_next = true;
+                  next_w = dstw;
+                  next_cost = c2;
+                } else {
+                  const uint32_t qi = atomicAdd(qn_out, 1u);
+                  if (qi < (uint32_t)kEpsQueueCap) qout[qi] = (uint16_t)s2;
+                  else raise_overflow(round + 2u);
+                }
+              }
             }
+            if (!have_next) return;
+            cost = next_cost;
+            er = __ldg(&g.eps_rows[next_w & kStateMask]);
           }
         };
         for (uint32_t i0 = tid; i0 < nq; i0 += 4 * NT) {  // up to four worklist entries per thread, loads batched
@@ -557,14 +611,8 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
             er[j] = __ldg(&g.eps_rows[m.key[sl] & kStateMask]);
           }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (!go[j] || er[j].y == er[j].x) continue;
-            relax(cost[j], __uint_as_float(er[j].z), er[j].w);
-            for (uint32_t a = er[j].x + 1; a < er[j].y; ++a) {
-              const int4 arc = __ldg(&g.arcs[a]);
-              relax(cost[j], __int_as_float(arc.z), (uint32_t)arc.w);
-            }
-          }
+          for (int j = 0; j < 4; ++j)
+            if (go[j]) relax_chain(cost[j], er[j]);
         }
         // one barrier per round: round r reads qn[r % 3] and raises qn[(r + 1) % 3]; the
         // counter round r + 1 raises is lowered here — its last readers passed the previous barrier
@@ -589,6 +637,13 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
         s_d.arcs_admitted = 0;
         st->tot_fallback_frames += 1;
       }
+      if (SMEM_LL && row_staged) {  // the next frame's row has taken this one's place: fetch it again
+        cp_async_wait_all();
+        __syncthreads();
+        const float *__restrict__ llr = s_d.ll;
+        for (int c = tid; c < num_indices; c += NT) s_ll[c] = __ldcs(&llr[c]);
+      }
+      row_staged = false;
       __syncthreads();
       // (two arc steps in flight per lane: a single CTA is latency-bound on the HBM map)
       expand_frame<2, SMEM_LL, false>(d, g, s_ll, (uint32_t)warp, NW, 0, lms);
@@ -672,7 +727,21 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
           const float x = (c - bc) * h_scale;
           return x >= (float)(kHistBins - 1) ? (uint32_t)(kHistBins - 1) : (uint32_t)(int)fmaxf(x, 0.f);
         };
-        for (uint32_t i = tid; i < n_alive; i += NT) atomicAdd(&s_hist[bin_of(__uint_as_float(__ldcg(&out_sc[i]).y))], 1u);
+        // (the survivors' costs are read from the arena once and kept in registers for both passes
+        // when there are at most eight per thread)
+        constexpr int kKeep = 8;
+        const bool keep = n_alive <= (uint32_t)(kKeep * NT);
+        float cv[kKeep];
+#pragma unroll
+        for (int j = 0; j < kKeep; ++j) {
+          const uint32_t i = tid + j * NT;
+          cv[j] = __uint_as_float(__ldcg(&out_sc[i < n_alive ? i : 0u]).y);
+        }
+#pragma unroll
+        for (int j = 0; j < kKeep; ++j)
+          if (tid + j * NT < n_alive) atomicAdd(&s_hist[bin_of(cv[j])], 1u);
+        for (uint32_t i = tid + kKeep * NT; i < n_alive; i += NT)
+          atomicAdd(&s_hist[bin_of(__uint_as_float(__ldcg(&out_sc[i]).y))], 1u);
         __syncthreads();
         const uint32_t k = (uint32_t)cfg.max_active;
         uint32_t total = 0;
@@ -687,17 +756,36 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
         __syncthreads();
         const uint32_t kbin = ps.misc[0], kk = ps.misc[1], kcount = ps.misc[2];
         if (kcount <= (uint32_t)kCandCap) {
-          for (uint32_t i = tid; i < n_alive; i += NT) {
+#pragma unroll
+          for (int j = 0; j < kKeep; ++j)
+            if (tid + j * NT < n_alive && bin_of(cv[j]) == kbin) s_cand[atomicAdd(&hot->ncand, 1u)] = f2ord(cv[j]);
+          for (uint32_t i = tid + kKeep * NT; i < n_alive; i += NT) {
             const float c = __uint_as_float(__ldcg(&out_sc[i]).y);
             if (bin_of(c) == kbin) s_cand[atomicAdd(&hot->ncand, 1u)] = f2ord(c);
           }
           __syncthreads();
-          n_cur_cut = block_kth_smallest<NT>([&](uint32_t i) { return s_cand[i]; }, kcount, kk, best_ord, 0xFFFFFFFFu,
-                                             nc_ord - best_ord, ps.hist, ps.misc);
+          if (kcount <= 64u) {
+            // a handful of candidates (the usual case): rank by counting, two warps
+            if (tid < (int)kcount) {
+              const uint32_t mine = s_cand[tid];
+              uint32_t rank = 0;
+              for (uint32_t j = 0; j < kcount; ++j) {
+                const uint32_t o = s_cand[j];
+                rank += (o < mine) || (o == mine && j < (uint32_t)tid);
+              }
+              if (rank == kk) ps.misc[3] = mine;
+            }
+            __syncthreads();
+            n_cur_cut = ord2f(ps.misc[3]);
+          } else {
+            n_cur_cut = block_kth_smallest<NT>([&](uint32_t i) { return s_cand[i]; }, kcount, kk, best_ord, 0xFFFFFFFFu,
+                                               nc_ord - best_ord, ps.hist, ps.misc);
+          }
         } else {  // (a degenerate cost distribution: select over all survivors)
           n_cur_cut = block_kth_smallest<NT>(arena_ord, n_alive, k, best_ord, 0xFFFFFFFFu, nc_ord - best_ord, ps.hist,
                                              ps.misc);
         }
+        (void)keep;
         n_abeam = n_cur_cut - bc + cfg.beam_delta;
       } else {
         // ---- general case (the adaptive beam of this frame was wider than the beam, or the arena
