@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(HERE, "libasrd_b200.so")
 # every symbol include/asrd.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "asrd_strerror", "asrd_abi_version", "asrd_device_count", "asrd_configure_process",
-    "asrd_graph_create", "asrd_graph_read", "asrd_graph_destroy", "asrd_graph_info",
+    "asrd_graph_create", "asrd_graph_read", "asrd_graph_read_const", "asrd_graph_destroy", "asrd_graph_info",
     "asrd_lm_create", "asrd_lm_destroy",
     "asrd_decoder_create", "asrd_decoder_create_biglm", "asrd_decoder_destroy",
     "asrd_init_decoding", "asrd_advance_decoding", "asrd_finalize_decoding",
@@ -59,6 +59,20 @@ class asrd_frame_stat(C.Structure):
 _lib = None
 
 
+def kernel_source_sha() -> str:
+    """sha1 over the CUDA sources and the ABI header: ties a committed ncu capture
+    (profiles/stream_traffic.json) to the code it was taken from."""
+    import glob
+    import hashlib
+    h = hashlib.sha1()
+    files = sorted(glob.glob(os.path.join(HERE, "csrc", "*.cu")) + glob.glob(os.path.join(HERE, "csrc", "*.cuh")))
+    files.append(os.path.join(os.path.dirname(HERE), "include", "asrd.h"))
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
 def build(force: bool = False) -> str:
     """Compile ``csrc/`` for sm_100a into ``libasrd_b200.so`` (in-tree)."""
     src_dir = os.path.join(HERE, "csrc")
@@ -84,6 +98,7 @@ def lib():
     L.asrd_device_count.restype = C.c_int
     L.asrd_graph_create.argtypes = [vp, vp, vp, i32, i64, i32, i32, C.c_int, C.POINTER(vp)]
     L.asrd_graph_read.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
+    L.asrd_graph_read_const.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
     L.asrd_graph_destroy.argtypes = [vp]
     L.asrd_graph_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i64), C.POINTER(i32), C.POINTER(i32),
                                   C.POINTER(i64)]

@@ -11,9 +11,39 @@
 #include <vector>
 
 #include "asrd.h"
+
+// Two ways to compile this class:
+//  * inside the reference tree (-DASRD_REFERENCE_TREE, include root = the reference checkout): it
+//    derives from the reference's OWN DecoderItf and fills the reference's own Lattice, so it can
+//    be handed to DeterminizeLatticeWrapper / NShortestPath and selected by --graph-type like the
+//    CPU decoders; CudaFst::FromFst uploads an already loaded reference Fst.
+//  * stand-alone: against decoder-itf.h next to this file, a from-scratch mirror of the same
+//    surface (so the class and its tests build where the reference sources are absent).
+#ifdef ASRD_REFERENCE_TREE
+#include "src/my-decoder/decoder-itf.h"
+#include "src/my-decoder/lattice-faster-decoder-conf.h"
+#include "src/newfst/lattice-fst.h"
+#include "src/newfst/optimize-fst.h"
+namespace asrd_host {
+#ifdef NAMESPACE
+using namespace datemoon;
+#endif
+typedef int int32;
+}  // namespace asrd_host
+#else
 #include "decoder-itf.h"
+#endif
 
 namespace asrd_host {
+
+// A decodable that already holds the matrix: AdvanceDecoding uploads rows without T x P
+// virtual calls (SURVEY.md section 8b "input side").  Any other AmInterface is served through
+// LogLikelihood(frame, index) calls (the reference's pull model, itf/decodable-itf.h:65-104).
+class MatrixDecodableInterface : public AmInterface {
+ public:
+  virtual const BaseFloat *Data() const = 0;  // row-major, column = index - 1
+  virtual int32 Stride() const = 0;           // floats between rows
+};
 
 // Device-resident HCLG: what replaces `Fst` (newfst/optimize-fst.h:53-307) for this decoder.
 class CudaFst {
@@ -26,6 +56,14 @@ class CudaFst {
     g_ = NULL;
     return asrd_graph_read(file, device, &g_) == ASRD_OK;
   }
+  // ConstFst::Read + Fst(const ConstFst&) (newfst/const-fst.h:189-221, optimize-fst.h:82-134):
+  // an OpenFst const file, e.g. a Kaldi HCLG.fst (--fst-type=const in OnlineDecoderInfo,
+  // kaldi-nnet3/kaldi-online-nnet3-my-decoder.h:210-220)
+  bool ReadConstFst(const char *file, int device = 0) {
+    asrd_graph_destroy(g_);
+    g_ = NULL;
+    return asrd_graph_read_const(file, device, &g_) == ASRD_OK;
+  }
   // from the arrays an already loaded reference `Fst` holds
   bool FromArrays(const asrd_arc *arcs, const uint32_t *num_arcs, const uint32_t *niepsilons, int32_t states,
                   int64_t n_arcs, int32_t start, int32_t final_state, int device = 0) {
@@ -33,6 +71,22 @@ class CudaFst {
     g_ = NULL;
     return asrd_graph_create(arcs, num_arcs, niepsilons, states, n_arcs, start, final_state, device, &g_) == ASRD_OK;
   }
+#ifdef ASRD_REFERENCE_TREE
+  // Upload a graph the host already holds as the reference's Fst (Fst::ReadFst or
+  // Fst(const ConstFst&), newfst/optimize-fst.h:82-134,208-280): its two flat arrays are read in place.
+  bool FromFst(Fst &fst, int device = 0) {
+    const int32_t S = fst.TotState();
+    std::vector<uint32_t> na((size_t)S), ne((size_t)S);
+    int32_t final_state = -1;
+    for (int32_t s = 0; s < S; ++s) {
+      na[s] = fst.GetState(s)->_num_arcs;
+      ne[s] = fst.GetState(s)->_niepsilons;
+      if (fst.IsFinal(s)) final_state = s;
+    }
+    return FromArrays(reinterpret_cast<const asrd_arc *>(fst.GetArc(0)), na.data(), ne.data(), S, fst.TotArc(),
+                      fst.Start(), final_state, device);
+  }
+#endif
   asrd_graph *handle() const { return g_; }
 
  private:

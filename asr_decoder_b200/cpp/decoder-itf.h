@@ -35,14 +35,6 @@ class DecodableInterface {
 };
 typedef DecodableInterface AmInterface;
 
-// A decodable that already holds the matrix: AdvanceDecoding uploads rows without T x P
-// virtual calls (SURVEY.md §8b "input side").
-class MatrixDecodableInterface : public DecodableInterface {
- public:
-  virtual const BaseFloat *Data() const = 0;  // row-major, column = index - 1
-  virtual int32 Stride() const = 0;           // floats between rows
-};
-
 class LatticeWeight {
  public:
   LatticeWeight() : v1_(0.0f), v2_(0.0f) {}

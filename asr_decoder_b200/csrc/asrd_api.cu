@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -522,6 +523,70 @@ int asrd_graph_read(const char *path, int device, asrd_graph **out) {
     ne[s] = info[(size_t)s * 3 + 1];
   }
   return asrd_graph_create(arcs.data(), na.data(), ne.data(), S, A, hdr[0], hdr[1], device, out);
+}
+
+int asrd_graph_read_const(const char *path, int device, asrd_graph **out) {
+  // ConstFst<StdArc, int>::Read (src/newfst/const-fst.h:46-80,189-221) + Fst(const ConstFst&)
+  // (src/newfst/optimize-fst.h:82-134): an OpenFst "const" FST over the standard (tropical) arc
+  // becomes the flat graph — one super-final state appended, every final state gets
+  // 0:0/final_weight -> super-final as its FIRST arc.  Like the reference's reader: no symbol
+  // tables, no alignment padding.
+  if (!path || !out) return ASRD_ERR_BAD_ARG;
+  FILE *fp = fopen(path, "rb");
+  if (!fp) return ASRD_ERR_IO;
+  auto fail = [&]() {
+    fclose(fp);
+    return ASRD_ERR_IO;
+  };
+  auto read_string = [&](std::string *str) {
+    int32_t n = 0;
+    if (fread(&n, 4, 1, fp) != 1 || n < 0 || n > 64) return false;
+    str->resize((size_t)n);
+    return n == 0 || fread(&(*str)[0], 1, (size_t)n, fp) == (size_t)n;
+  };
+  int32_t magic = 0, version = 0, flags = 0;
+  uint64_t properties = 0;
+  int64_t start = 0, n_states = 0, n_arcs = 0;
+  std::string fsttype, arctype;
+  if (fread(&magic, 4, 1, fp) != 1 || magic != 2125659606 || !read_string(&fsttype) || !read_string(&arctype) ||
+      fsttype != "const" || arctype != "standard" || fread(&version, 4, 1, fp) != 1 || fread(&flags, 4, 1, fp) != 1 ||
+      fread(&properties, 8, 1, fp) != 1 || fread(&start, 8, 1, fp) != 1 || fread(&n_states, 8, 1, fp) != 1 ||
+      fread(&n_arcs, 8, 1, fp) != 1 || n_states <= 0 || n_states >= 0x7FFFFFF0ll || n_arcs < 0 || n_arcs >= 0xFFFFFFF0ll)
+    return fail();
+  struct ConstState {  // const-fst.h:206-215
+    float weight;
+    int32_t pos, narcs, niepsilons, noepsilons;
+  };
+  std::vector<ConstState> cs((size_t)n_states);
+  std::vector<asrd_arc> in((size_t)std::max<int64_t>(n_arcs, 1));
+  if (fread(cs.data(), sizeof(ConstState), (size_t)n_states, fp) != (size_t)n_states ||
+      fread(in.data(), sizeof(asrd_arc), (size_t)n_arcs, fp) != (size_t)n_arcs)
+    return fail();
+  fclose(fp);
+  const int32_t S = (int32_t)n_states + 1;
+  int64_t n_final = 0;
+  for (int64_t s = 0; s < n_states; ++s) n_final += cs[s].weight != std::numeric_limits<float>::infinity();
+  std::vector<asrd_arc> arcs((size_t)std::max<int64_t>(n_arcs + n_final, 1));
+  std::vector<uint32_t> na((size_t)S, 0u), ne((size_t)S, 0u);
+  int64_t w = 0;
+  for (int64_t s = 0; s < n_states; ++s) {
+    const ConstState &c = cs[s];
+    if (c.pos < 0 || c.narcs < 0 || (int64_t)c.pos + c.narcs > n_arcs) return ASRD_ERR_IO;
+    const bool fin = c.weight != std::numeric_limits<float>::infinity();  // Weight::Zero() marks non-final states
+    if (fin) {
+      asrd_arc a;
+      a.ilabel = 0;
+      a.olabel = 0;
+      a.weight = c.weight;
+      a.nextstate = S - 1;
+      arcs[w++] = a;
+    }
+    std::copy(in.begin() + c.pos, in.begin() + c.pos + c.narcs, arcs.begin() + w);
+    w += c.narcs;
+    na[s] = (uint32_t)c.narcs + (fin ? 1u : 0u);
+    ne[s] = (uint32_t)c.niepsilons + (fin ? 1u : 0u);
+  }
+  return asrd_graph_create(arcs.data(), na.data(), ne.data(), S, w, (int32_t)start, S - 1, device, out);
 }
 
 // The handle is reference counted: decoders built on a graph keep it alive, so the caller may

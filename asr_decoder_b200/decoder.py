@@ -120,6 +120,20 @@ class CudaFst:
         """``Fst::ReadFst`` (optimize-fst.h:208-280)."""
         return cls(read_fst(path), device)
 
+    @classmethod
+    def ReadConstFst(cls, path: str, device: int = 0) -> "CudaFst":
+        """``ConstFst::Read`` + ``Fst(const ConstFst&)`` (const-fst.h:189-221, optimize-fst.h:82-134):
+        an OpenFst const file; the conversion runs inside the library (``asrd_graph_read_const``)."""
+        from .fstio import read_const_fst
+        self = cls.__new__(cls)
+        self.host = None
+        self.device = device
+        h = C.c_void_p()
+        check(_lib.lib().asrd_graph_read_const(path.encode(), device, C.byref(h)), "asrd_graph_read_const")
+        self.h = h
+        self.max_ilabel = int(read_const_fst(path).arcs["ilabel"].max())
+        return self
+
     def device_bytes(self) -> int:
         b = C.c_int64(0)
         check(_lib.lib().asrd_graph_info(self.h, None, None, None, None, C.byref(b)), "asrd_graph_info")

@@ -127,3 +127,90 @@ def read_loglikes(path: str):
             t, p = (int(x) for x in np.frombuffer(f.read(8), dtype="<i4"))
             out.append(np.frombuffer(f.read(4 * t * p), dtype="<f4").reshape(t, p).copy())
     return out
+
+
+# --------------------------------------------------------------------------- OpenFst const files
+#
+# ``ConstFst<StdArc, int>::Read`` (reference ``src/newfst/const-fst.h:46-80,189-221``) followed by
+# ``Fst(const ConstFst&)`` (``src/newfst/optimize-fst.h:82-134``): a real Kaldi ``HCLG.fst`` saved as
+# an OpenFst "const" FST becomes the flat graph the decoders read — one super-final state is
+# appended and every originally-final state gets ``0:0/final_weight -> super-final`` as its FIRST arc.
+# Like the reference's reader, no alignment padding is handled (files written with ``--align`` are
+# refused by the magic/size checks downstream).
+
+FST_MAGIC = 2125659606
+CONST_STATE_DTYPE = np.dtype([("weight", "<f4"), ("pos", "<i4"), ("narcs", "<i4"), ("niepsilons", "<i4"),
+                              ("noepsilons", "<i4")])
+
+
+def _read_string(f) -> str:
+    n = int(np.frombuffer(f.read(4), dtype="<i4")[0])
+    return f.read(n).decode()
+
+
+def read_const_fst(path: str) -> Fst:
+    with open(path, "rb") as f:
+        if int(np.frombuffer(f.read(4), dtype="<i4")[0]) != FST_MAGIC:
+            raise IOError(f"{path}: bad FST header")
+        fsttype, arctype = _read_string(f), _read_string(f)
+        if fsttype != "const":
+            raise IOError(f"{path}: FST not of type const")
+        if arctype != "standard":
+            raise IOError(f"{path}: arc type {arctype!r}, want standard")
+        np.frombuffer(f.read(8), dtype="<i4")                 # version, flags
+        np.frombuffer(f.read(8), dtype="<u8")                 # properties
+        start, n_states, n_arcs = (int(x) for x in np.frombuffer(f.read(24), dtype="<i8"))
+        states = np.frombuffer(f.read(CONST_STATE_DTYPE.itemsize * n_states), dtype=CONST_STATE_DTYPE)
+        arcs_in = np.frombuffer(f.read(16 * n_arcs), dtype=ARC_DTYPE)
+    if states.shape[0] != n_states or arcs_in.shape[0] != n_arcs:
+        raise IOError(f"{path}: truncated const FST")
+    is_final = ~np.isposinf(states["weight"])                 # Weight::Zero() is +inf
+    n_final = int(is_final.sum())
+    S = n_states + 1
+    num_arcs = np.zeros(S, np.uint32)
+    nie = np.zeros(S, np.uint32)
+    noe = np.zeros(S, np.uint32)
+    num_arcs[:n_states] = states["narcs"] + is_final
+    nie[:n_states] = states["niepsilons"] + is_final
+    noe[:n_states] = states["noepsilons"] + is_final
+    arcs = np.zeros(n_arcs + n_final, ARC_DTYPE)
+    shift = np.cumsum(is_final) - is_final                    # final arcs inserted before each state's row
+    dst_pos = states["pos"].astype(np.int64) + shift + is_final
+    # scatter every state's arcs behind its (optional) final arc
+    src_idx = np.arange(n_arcs, dtype=np.int64)
+    owner = np.repeat(np.arange(n_states), states["narcs"])
+    arcs[dst_pos[owner] + (src_idx - states["pos"][owner])] = arcs_in
+    fpos = (states["pos"].astype(np.int64) + shift)[is_final]
+    arcs["weight"][fpos] = states["weight"][is_final]
+    arcs["nextstate"][fpos] = n_states
+    return Fst(start, n_states, arcs, num_arcs, nie, noe)
+
+
+def write_const_fst(path: str, fst: Fst) -> None:
+    """Inverse of :func:`read_const_fst` (test fixture writer): the super-final state and the
+    leading final arcs of a flat graph become OpenFst final weights again."""
+    S = fst.total_states - 1
+    assert fst.final_state == S and int(fst.num_arcs[S]) == 0
+    off = fst.row_off
+    first = fst.arcs[np.minimum(off[:S], max(fst.total_arcs - 1, 0))]
+    is_final = (fst.num_arcs[:S] > 0) & (first["ilabel"] == 0) & (first["olabel"] == 0) & (first["nextstate"] == S)
+    assert not (fst.arcs["nextstate"] == S)[np.setdiff1d(np.arange(fst.total_arcs), off[:S][is_final])].any(), \
+        "arcs into the super-final state must lead their rows"
+    states = np.zeros(S, CONST_STATE_DTYPE)
+    states["weight"] = np.where(is_final, first["weight"], np.float32(np.inf))
+    states["narcs"] = fst.num_arcs[:S] - is_final
+    states["niepsilons"] = fst.niepsilons[:S] - is_final
+    states["noepsilons"] = fst.noepsilons[:S] - is_final
+    states["pos"] = np.concatenate([[0], np.cumsum(states["narcs"])[:-1]])
+    keep = np.ones(fst.total_arcs, bool)
+    keep[off[:S][is_final]] = False
+    arcs = fst.arcs[keep]
+    with open(path, "wb") as f:
+        f.write(np.array([FST_MAGIC], "<i4").tobytes())
+        for s in ("const", "standard"):
+            f.write(np.array([len(s)], "<i4").tobytes() + s.encode())
+        f.write(np.array([1, 0], "<i4").tobytes())            # version, flags (no symbol tables, not aligned)
+        f.write(np.array([0], "<u8").tobytes())               # properties
+        f.write(np.array([fst.start, S, arcs.shape[0]], "<i8").tobytes())
+        f.write(states.tobytes())
+        f.write(np.ascontiguousarray(arcs).tobytes())

@@ -57,10 +57,27 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--hash-capacity", type=int, default=0, help="0 = library default (8 x max-active)")
-    return ap.parse_args()
+    ap.add_argument("--workload", default="offline", choices=["offline", "streaming"],
+                    help="offline = BASELINE.json configs[1] (the headline); streaming = configs[4]: "
+                         "--streams concurrent streams fed in --chunk-frames chunks, sharded over the GPUs")
+    ap.add_argument("--regime", default="busy", choices=["busy", "peaked", "deployed"],
+                    help="SURVEY.md section 8d regimes: busy = sigma 2 (default, max-active binding); peaked = sigma 3; "
+                         "deployed = beam 10 / lattice-beam 7 (v2-asrbin/conf/decoder.conf)")
+    ap.add_argument("--streams", type=int, default=4096, help="streaming: concurrent streams over ALL GPUs")
+    ap.add_argument("--chunk-frames", type=int, default=30)
+    a = ap.parse_args()
+    if a.regime == "peaked":
+        a.sigma = 3.0
+    elif a.regime == "deployed":
+        a.beam, a.lattice_beam = 10.0, 7.0
+    return a
 
 
 def workload_name(a):
+    if a.workload == "streaming":
+        return (f"streaming: synthetic HCLG {a.states} states avg-degree 5, {a.pdfs} pdfs; {a.streams} concurrent streams x "
+                f"{a.frames} frames fed in {a.chunk_frames}-frame chunks (30 ms/frame), sigma={a.sigma}; beam={a.beam} "
+                f"max-active={a.max_active} min-active={a.min_active}; one-best")
     return (f"synthetic HCLG {a.states} states avg-degree 5, {a.pdfs} pdfs; {a.utts} utts x {a.frames} frames "
             f"(30 ms/frame), sigma={a.sigma}; beam={a.beam} max-active={a.max_active} "
             f"min-active={a.min_active}; one-best")
@@ -89,9 +106,10 @@ def cpu_reference_run(a, fst, gen, n_utts, repeats=1, threads=None):
             fstio.write_fst(gp, fst)
             fstio.write_loglikes(lp, lls)
             secs = []
+            answers = None
             for _ in range(repeats):
-                _, summ = O.run_ref(gp, lp, stats=False, threads=cores, beam=a.beam, max_active=a.max_active,
-                                    min_active=a.min_active, lattice_beam=a.lattice_beam)
+                answers, summ = O.run_ref(gp, lp, stats=False, threads=cores, beam=a.beam, max_active=a.max_active,
+                                          min_active=a.min_active, lattice_beam=a.lattice_beam)
                 secs.append(summ["wall_s"])
         finally:
             shutil.rmtree(tmp, ignore_errors=True)
@@ -99,6 +117,7 @@ def cpu_reference_run(a, fst, gen, n_utts, repeats=1, threads=None):
     else:
         # the C port in reference token order, one decoder object per thread
         from concurrent.futures import ThreadPoolExecutor
+        answers = None
         og = O.OracleGraph(fst)
         cfg = O.make_config(a.beam, a.max_active, a.min_active, a.lattice_beam)
         decs = [O.OracleDecoder(og, cfg, O.MODE_REFERENCE) for _ in range(cores)]
@@ -113,7 +132,7 @@ def cpu_reference_run(a, fst, gen, n_utts, repeats=1, threads=None):
                 list(ex.map(work, range(cores)))
             secs.append(time.perf_counter() - t0)
         kind = "port"
-    return dict(seconds=secs, value=audio / float(np.mean(secs)), kind=kind, cores=cores,
+    return dict(seconds=secs, value=audio / float(np.mean(secs)), kind=kind, cores=cores, answers=answers,
                 sample=f"{n_utts} of the workload's utterances x {a.frames} frames, {cores} threads "
                        f"(one decoder object per thread, shared graph)")
 
@@ -197,7 +216,7 @@ def run_b200_arm(a):
     import torch
     import torch.distributed as dist
     from asr_decoder_b200 import _lib
-    from asr_decoder_b200.decoder import CudaDecoderBatch, CudaFst, LatticeFasterDecoderConfig
+    from asr_decoder_b200.decoder import CudaDecoderBatch, CudaFst, LatticeFasterDecoderConfig, LatticeToVector
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -337,18 +356,24 @@ def run_b200_arm(a):
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
     expand_s = xm.value / 1e3
     achieved = 16.0 * ae.value / expand_s / 1e9 if expand_s > 0 else 0.0
-    traffic = None
+    traffic, traffic_note = None, None
     tpath = os.path.join(ROOT, "profiles", "stream_traffic.json" if on_chip else "expand_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
+            tj = json.load(open(tpath))
+            if tj.get("kernel_src_sha") == _lib.kernel_source_sha():
+                traffic = tj.get("dram_bytes_per_launch")
+                traffic_note = f"ncu --set full capture {tj.get('ncu_tag')} of these very sources ({tj.get('kernel_src_sha')})"
+            else:  # a capture of other sources says nothing about this build
+                traffic_note = (f"stale: profiles/{os.path.basename(tpath)} was captured from sources "
+                                f"{tj.get('kernel_src_sha')}, this build is {_lib.kernel_source_sha()}")
+        except Exception as e:  # noqa: BLE001
+            traffic_note = f"unreadable: {e}"
     line = {
         "metric": "batched decode RTFx", "value": audio_all / (ms_value / 1e3), "unit": "x realtime",
         "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_value,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "parallelism": f"replica-per-gpu x{world}, streams sharded",
+        "config": {"workload": workload_name(a), "regime": a.regime, "parallelism": f"replica-per-gpu x{world}, streams sharded",
                    "l2": "inputs (1.02 GB of log-likelihoods + per-stream maps) exceed the 126 MB L2; no flush needed",
                    "arena_tokens_per_stream": tok_cap},
         "arcs_expanded_per_s": arcs_all / (ms_value / 1e3),
@@ -357,10 +382,11 @@ def run_b200_arm(a):
         "clocks": clocks,
         "hbm_map_fallback_frames": fallback_frames,
         "roofline": {"bound": "hbm", "kernel": "k_stream" if on_chip else "k_expand", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
                      "algorithmic_bytes_per_arc": 16, "arcs_per_launch": ae.value / max(1, xn.value),
                      "launch_ms": xm.value / max(1, xn.value), "launches_per_step": int(xn.value),
                      "timing": "CUDA events around every launch of one extra step run without sub-batch overlap",
+                     "kernel_src_sha": _lib.kernel_source_sha(),
                      "launch": ("k_stream: one CTA per stream, 32 frames per launch" if on_chip else
                                 "k_expand: one frame of all streams per launch"),
                      "kernel_ms_per_launch": {k: kms[i] / max(1, kn[i]) for i, k in enumerate(knames)},
@@ -376,6 +402,160 @@ def run_b200_arm(a):
         res = cpu_reference_run(a, fst, gen, k, repeats=1)
         line["cpu_baseline"] = {"value": res["value"], "unit": "x realtime", "cores": res["cores"],
                                 "kind": res["kind"], "sample": res["sample"]}
+        if res.get("answers"):
+            # The reference decoded these very utterances: where does the CUDA one-best stand to ITS
+            # answer under this one token order (hash ratio 2.0)?  tests/golden/census.json holds the
+            # same comparison under seven orders (the reference disagrees with itself on half of them).
+            same = cheaper = dearer = 0
+            for r, g in zip(res["answers"], res_dev):
+                words, ali, tot, _ = LatticeToVector(g.ilabel, g.olabel, g.graph, g.acoustic)
+                tb = int(np.float32(tot).view(np.uint32))
+                if words == r["words"] and ali == r["ali"] and tb == r["tot_bits"]:
+                    same += 1
+                elif tot <= r["tot"]:
+                    cheaper += 1
+                else:
+                    dearer += 1
+            line["parity_vs_reference"] = {
+                "utterances": len(res["answers"]), "identical_one_best": same, "different_cheaper_or_equal_cost": cheaper,
+                "different_dearer": dearer, "reference_token_order": "hash_ratio 2.0, one decoder object per thread",
+                "note": "the reference's one-best depends on its token visiting order (SURVEY.md Appendix B-2); "
+                        "see tests/golden/census.json and DESIGN.md section 5.1"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------- streaming (config 5)
+
+def run_streaming_arm(a):
+    """BASELINE.json configs[4]: `--streams` concurrent utterance streams (over all GPUs, sharded
+    stream_id mod N: strong scaling of one pool), every stream fed `--chunk-frames` frames per
+    AdvanceDecoding call like the reference's service loop (kaldi-online-nnet3-my-decoder.cc:10-48).
+    A step = InitDecoding, all chunks of all streams, FinalizeDecoding, GetBestPath."""
+    import torch
+    import torch.distributed as dist
+    from asr_decoder_b200 import _lib, synth
+    from asr_decoder_b200.decoder import CudaDecoderBatch, CudaFst, LatticeFasterDecoderConfig
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L = _lib.lib()
+    fst = synth.make_graph(a.states, 5.0, a.pdfs, seed=12345)
+    T, P, CH = a.frames, a.pdfs, a.chunk_frames
+    my_streams = [s for s in range(a.streams) if s % world == rank]   # stream_id mod N
+    n = len(my_streams)
+    n_distinct = min(n, 256)                                          # distinct utterances; streams reuse them
+    host = torch.empty((n_distinct, T, P), dtype=torch.float32).pin_memory()
+    hv = host.numpy()
+    for i in range(n_distinct):
+        hv[i] = synth.make_loglikes(T, P, a.sigma, seed=1000 + i)
+    dev = host.to(f"cuda:{local}")
+    cfg = LatticeFasterDecoderConfig(beam=a.beam, max_active=a.max_active, min_active=a.min_active,
+                                     lattice_beam=a.lattice_beam)
+    graph = CudaFst(fst, device=local)
+    tok_cap = int((T + 2) * 9000)
+    free0 = torch.cuda.mem_get_info()[0]
+    batch = CudaDecoderBatch(graph, cfg, n, max_frames=T + 8, token_capacity=tok_cap, hash_capacity=a.hash_capacity)
+    stream = torch.cuda.current_stream().cuda_stream
+    chunks = [(f0, min(CH, T - f0)) for f0 in range(0, T, CH)]
+
+    def args_for(base_ptr, f0, c):
+        ptrs = (C.c_void_p * n)(*[base_ptr + 4 * ((i % n_distinct) * T + f0) * P for i in range(n)])
+        return ptrs, (C.c_int32 * n)(*([c] * n)), (C.c_int32 * n)(*([P] * n))
+
+    dev_args = [args_for(dev.data_ptr(), f0, c) for f0, c in chunks]
+    host_args = [args_for(host.data_ptr(), f0, c) for f0, c in chunks]
+
+    def step(args, on_device, lat=None):
+        batch.InitDecoding(stream)
+        for k, (ptrs, nfr, strides) in enumerate(args):
+            t0 = time.perf_counter()
+            batch.AdvanceDecodingRaw(ptrs, nfr, strides, P, on_device, -1, stream)
+            if lat is not None:          # per-chunk latency: the caller waits for the chunk like a service would
+                torch.cuda.synchronize()
+                lat.append(1e3 * (time.perf_counter() - t0))
+        batch.FinalizeDecoding(stream)
+        return batch.GetBestPath(True, stream, vectors=False)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce(x, op):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    for _ in range(a.warmup):
+        res = step(dev_args, True)
+    slab_used = free0 - torch.cuda.mem_get_info()[0]
+    bad = [r.status for r in res if not r.ok]
+    if bad:
+        raise SystemExit(f"decode failed: statuses {sorted(set(bad))}")
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = L.asrd_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        res = step(dev_args, True)
+    e1.record()
+    barrier()
+    launches = L.asrd_launch_count() - l0
+    ms_value = reduce(e0.elapsed_time(e1) / a.steps, dist.ReduceOp.MAX if world > 1 else None)
+    clocks = sampler.stop() if sampler else None
+    ae, aa, tk = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+    L.asrd_get_counters(batch.handles, n, C.byref(ae), C.byref(aa), C.byref(tk), stream)
+    fallback_frames = int(L.asrd_last_fallback_frames())
+    # per-chunk latency (device inputs), then end to end from pinned host memory
+    lat = []
+    step(dev_args, True, lat)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        res_host = step(host_args, False)
+    torch.cuda.synchronize()
+    ms_e2e = reduce(1e3 * (time.perf_counter() - t0) / a.steps, dist.ReduceOp.MAX if world > 1 else None)
+    same = all(np.array_equal(x.ilabel, y.ilabel) for x, y in zip(res, res_host))
+    d2h = int(sum(16 * len(r.ilabel) for r in res_host) + 8 * n)
+    audio_all = reduce(n * T * FRAME_SECONDS, dist.ReduceOp.SUM if world > 1 else None)
+    arcs_all = reduce(float(ae.value), dist.ReduceOp.SUM if world > 1 else None)
+    lat_max = reduce(max(lat), dist.ReduceOp.MAX if world > 1 else None)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    line = {
+        "metric": "streaming decode RTFx", "value": audio_all / (ms_value / 1e3), "unit": "x realtime",
+        "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_value,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "regime": a.regime,
+                   "parallelism": f"graph replica per GPU, one pool of {a.streams} streams sharded stream_id mod {world}",
+                   "streams_per_gpu": n, "chunks_per_utterance": len(chunks),
+                   "l2": "inputs and per-stream state exceed the 126 MB L2; no flush needed"},
+        "arcs_expanded_per_s": arcs_all / (ms_value / 1e3), "gpu_launches": int(launches), "clocks": clocks,
+        "hbm_map_fallback_frames": fallback_frames,
+        "chunk_latency_ms": {"mean": float(np.mean(lat)), "max_over_ranks": lat_max, "chunk_frames": CH,
+                             "audio_ms_per_chunk": 1e3 * CH * FRAME_SECONDS,
+                             "note": "one AdvanceDecoding call over all of this GPU's streams, synchronised"},
+        "memory_per_stream_bytes": int(slab_used / max(n, 1)),
+        "memory_note": f"token arena sized for {T}-frame utterances ({tok_cap} records of 8 B) + log-likelihood history + "
+                       "HBM-map fallback structures; grows with utterance length (no arena garbage collection yet)",
+        "e2e": {"value": audio_all / (ms_e2e / 1e3), "unit": "x realtime", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": int(n * T * P * 4) * world, "d2h_bytes_per_step": d2h * world,
+                "matches_resident_run": bool(same)},
+    }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -385,6 +565,8 @@ def main():
     a = parse_args()
     if a.impl == "reference":
         run_reference_arm(a)
+    elif a.workload == "streaming":
+        run_streaming_arm(a)
     else:
         run_b200_arm(a)
 

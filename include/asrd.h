@@ -140,6 +140,11 @@ int asrd_graph_create(const asrd_arc *arcs, const uint32_t *num_arcs, const uint
                       int device, asrd_graph **out);
 /* Fst::ReadFst(const char*), optimize-fst.h:208-219: same file format */
 int asrd_graph_read(const char *path, int device, asrd_graph **out);
+/* ConstFst<StdArc,int>::Read + Fst(const ConstFst&) (src/newfst/const-fst.h:189-221,
+ * src/newfst/optimize-fst.h:82-134): load an OpenFst "const" FST (e.g. a Kaldi HCLG.fst converted
+ * with fstconvert --fst_type=const); final weights become leading 0:0 arcs to an appended
+ * super-final state, exactly like the reference's conversion. */
+int asrd_graph_read_const(const char *path, int device, asrd_graph **out);
 int asrd_graph_destroy(asrd_graph *g);
 int asrd_graph_info(const asrd_graph *g, int32_t *total_states, int64_t *total_arcs,
                     int32_t *start, int32_t *final_state, int64_t *device_bytes);

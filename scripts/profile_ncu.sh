@@ -8,6 +8,7 @@ TAG=${1:-r01}
 shift
 KERNELS=${*:-k_stream}
 export ASRD_SUBBATCH=0
+python -c "from asr_decoder_b200 import _lib; print(_lib.kernel_source_sha())" > gpurun_out/${TAG}_src_sha.txt
 # launch list of one full config-2 step (k_begin_advance + one k_stream per 32-frame chunk, back-trace)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
     --log-file gpurun_out/${TAG}_launches.csv \

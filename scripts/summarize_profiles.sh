@@ -38,5 +38,26 @@ for w in ['dram__bytes_read.sum','dram__bytes_write.sum','lts__t_sector_hit_rate
   rm -f /tmp/ncu_src_$$.csv
 done
 } > $OUT
+# DRAM traffic of the dominant kernel, tied to the sources it was captured from (bench.py refuses a stale one)
+if [ -f gpurun_out/${TAG}_k_stream.ncu-rep ]; then
+ncu -i gpurun_out/${TAG}_k_stream.ncu-rep --page raw --csv 2>/dev/null | TAG=$TAG python -c "
+import csv, sys, json, os, subprocess
+rows = list(csv.reader(sys.stdin)); hdr = rows[0]
+def val(name):
+    i = hdr.index(name); unit = rows[1][i]; v = float(rows[2][i].replace(',', ''))
+    return v * {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1}[unit]
+tag = os.environ['TAG']
+rd, wr = val('dram__bytes_read.sum'), val('dram__bytes_write.sum')
+sha_file = 'gpurun_out/%s_src_sha.txt' % tag
+out = {'kernel': 'k_stream<true>', 'ncu_tag': tag,
+       'launch': '256 streams x 32 frames (5th launch of a config-2 step, ASRD_SUBBATCH=0)',
+       'source': 'profiles/%s_summary.txt (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum)' % tag,
+       'kernel_src_sha': open(sha_file).read().strip() if os.path.exists(sha_file) else None,
+       'git_commit_when_summarised': subprocess.run(['git', 'rev-parse', '--short', 'HEAD'], stdout=subprocess.PIPE).stdout.decode().strip(),
+       'dram_bytes_read': rd, 'dram_bytes_write': wr, 'dram_bytes_per_launch': rd + wr}
+json.dump(out, open('profiles/stream_traffic.json', 'w'), indent=1)
+print('profiles/stream_traffic.json:', out)
+"
+fi
 cp gpurun_out/${TAG}_launches.csv profiles/${TAG}_launches.csv
 echo wrote $OUT

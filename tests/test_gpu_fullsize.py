@@ -115,6 +115,29 @@ def test_config5_many_streams_chunked(big):
     assert all(_same(out[3], out[i]) for i in same_in)
 
 
+def test_config5_4096_streams_in_30_frame_chunks(big):
+    """BASELINE.json configs[4] at its stated size on one GPU: 4096 concurrent streams on the
+    1M-state graph, 30-frame chunks.  Every stream equals the single-stream decode of its input
+    (sampled), equal inputs in different slots give equal outputs, no stream reports an error."""
+    fst, g = big
+    n, P, T = 4096, 3000, 75
+    base = [synth.make_loglikes(T, P, 2.0 + 0.5 * (k % 3), seed=9900 + k) for k in range(32)]
+    lls = [base[i % 32] for i in range(n)]
+    cfg = _cfg()
+    dec = CudaDecoderBatch(g, cfg, n, max_frames=T + 5, token_capacity=(T + 2) * 9000, hash_capacity=1 << 15)
+    dec.InitDecoding()
+    for f0 in range(0, T, 30):
+        dec.AdvanceDecoding([ll[f0:f0 + 30] for ll in lls])
+    dec.FinalizeDecoding()
+    out = dec.GetBestPath()
+    assert all(o.ok and len(o.ali) == T for o in out)
+    assert all(dec.status(i) == 0 for i in range(0, n, 97))
+    one = CudaDecoderBatch(g, cfg, 1, max_frames=T + 5, token_capacity=(T + 2) * 9000, hash_capacity=1 << 15)
+    for k in (0, 1, 2, 31):
+        ref = one.Decode([base[k]])[0]
+        assert all(_same(ref, out[i]) for i in range(k, n, 32)), k
+
+
 def test_config3_large_graph_lattice(oracle_mod):
     """Trigram-sized graph shape at reduced scale (8M states / 24M arcs resident in HBM; the full
     50M / 150M case only changes the upload size): one-best + raw lattice equal the canonical
