@@ -192,6 +192,38 @@ def _as_ptr_and_keep(x):
     return bool(t.is_cuda), int(t.data_ptr()), int(t.shape[0]), int(t.stride(0)), t
 
 
+def get_best_paths(handles, n: int, max_frames_decoded: int, use_final_probs: bool = True, stream: int = 0,
+                   vectors: bool = True) -> List[BestPath]:
+    """``DecoderItf::GetBestPath`` (inl.h:1071-1200) for ``n`` decoder handles in one batched call."""
+    L = _lib.lib()
+    cap = 4 * max_frames_decoded + 64
+    while True:
+        il = np.zeros((n, cap), np.int32)
+        ol = np.zeros((n, cap), np.int32)
+        gr = np.zeros((n, cap), np.float32)
+        ac = np.zeros((n, cap), np.float32)
+        na = np.zeros(n, np.int32)
+        st = np.zeros(n, np.int32)
+        check(L.asrd_get_best_path(handles, n, int(use_final_probs), cap, il.ctypes.data,
+                                   ol.ctypes.data, gr.ctypes.data, ac.ctypes.data, na.ctypes.data,
+                                   st.ctypes.data, stream), "asrd_get_best_path")
+        if (st == -8).any():  # ASRD_ERR_PATH_OVERFLOW
+            cap *= 4
+            continue
+        break
+    out = []
+    for i in range(n):
+        m = int(na[i])
+        ok = st[i] == 0 and m > 0
+        if ok and vectors:
+            words, ali, tot, lm = LatticeToVector(il[i, :m], ol[i, :m], gr[i, :m], ac[i, :m])
+        else:
+            words, ali, tot, lm = [], [], 0.0, 0.0
+        out.append(BestPath(bool(ok), int(st[i]), il[i, :m].copy(), ol[i, :m].copy(), gr[i, :m].copy(),
+                            ac[i, :m].copy(), words, ali, tot, lm))
+    return out
+
+
 class CudaDecoderBatch:
     """N decoder objects stepped together.  ``decoders[i]`` is one stream."""
 
@@ -283,34 +315,8 @@ class CudaDecoderBatch:
         check(_lib.lib().asrd_synchronize(stream), "asrd_synchronize")
 
     def GetBestPath(self, use_final_probs: bool = True, stream: int = 0, vectors: bool = True) -> List[BestPath]:
-        L = _lib.lib()
         maxf = max(self.NumFramesDecoded(i) for i in range(self.n))
-        cap = 4 * maxf + 64
-        while True:
-            il = np.zeros((self.n, cap), np.int32)
-            ol = np.zeros((self.n, cap), np.int32)
-            gr = np.zeros((self.n, cap), np.float32)
-            ac = np.zeros((self.n, cap), np.float32)
-            na = np.zeros(self.n, np.int32)
-            st = np.zeros(self.n, np.int32)
-            check(L.asrd_get_best_path(self.handles, self.n, int(use_final_probs), cap, il.ctypes.data,
-                                       ol.ctypes.data, gr.ctypes.data, ac.ctypes.data, na.ctypes.data,
-                                       st.ctypes.data, stream), "asrd_get_best_path")
-            if (st == -8).any():  # ASRD_ERR_PATH_OVERFLOW
-                cap *= 4
-                continue
-            break
-        out = []
-        for i in range(self.n):
-            m = int(na[i])
-            ok = st[i] == 0 and m > 0
-            if ok and vectors:
-                words, ali, tot, lm = LatticeToVector(il[i, :m], ol[i, :m], gr[i, :m], ac[i, :m])
-            else:
-                words, ali, tot, lm = [], [], 0.0, 0.0
-            out.append(BestPath(bool(ok), int(st[i]), il[i, :m].copy(), ol[i, :m].copy(), gr[i, :m].copy(),
-                                ac[i, :m].copy(), words, ali, tot, lm))
-        return out
+        return get_best_paths(self.handles, self.n, maxf, use_final_probs, stream, vectors)
 
     def GetRawLattice(self, i: int = 0, use_final_probs: bool = True, stream: int = 0):
         """``DecoderItf::GetRawLattice`` for stream ``i`` (inl.h:868-975), after the lattice-beam

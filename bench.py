@@ -449,7 +449,8 @@ def run_streaming_arm(a):
     L = _lib.lib()
     fst = synth.make_graph(a.states, 5.0, a.pdfs, seed=12345)
     T, P, CH = a.frames, a.pdfs, a.chunk_frames
-    my_streams = [s for s in range(a.streams) if s % world == rank]   # stream_id mod N
+    from asr_decoder_b200 import sharding
+    my_streams = sharding.shard_indices(a.streams, rank, world)      # stream_id mod N
     n = len(my_streams)
     n_distinct = min(n, 256)                                          # distinct utterances; streams reuse them
     host = torch.empty((n_distinct, T, P), dtype=torch.float32).pin_memory()
