@@ -936,19 +936,28 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
   // Host log-likelihoods: staged chunk by chunk through two device buffers, copied on a
   // side stream so the H2D of chunk k+1 overlaps the search of chunk k.
   float *d_stage[2] = {nullptr, nullptr};
-  bool contiguous = false;
+  // Host rows of neighbouring streams that sit at one fixed distance from each other (one
+  // [k, T, P] block, or several such blocks) are copied with ONE pitched copy per run and chunk
+  // instead of one per stream.
+  struct CopyRun { int first, count; };
+  std::vector<CopyRun> runs;
   if (!on_device) {
     const int nbuf = max_nf > chunk ? 2 : 1;
     for (int b = 0; b < nbuf; ++b) CU_CHECK(sc.Alloc(&d_stage[b], (size_t)n * chunk * row));
     if (nbuf == 1) d_stage[1] = d_stage[0];
     CU_CHECK(cudaEventRecord(ctx->ev_ready, s));  // staging buffers exist from here on
     CU_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_ready, 0));
-    // one [n, T, P] block with equal lengths -> a single pitched copy per chunk
-    contiguous = n > 1;
-    for (int i = 0; i < n && contiguous; ++i)
-      contiguous = nf[i] == nf[0] && stride[i] == num_indices &&
-                   (i == 0 || loglikes[i] - loglikes[i - 1] == loglikes[1] - loglikes[0]);
-    if (contiguous && (loglikes[1] - loglikes[0]) < (ptrdiff_t)((size_t)nf[0] * row)) contiguous = false;
+    for (int i = 0; i < n;) {
+      int j = i + 1;
+      if (j < n && stride[i] == num_indices && nf[i] > 0) {
+        const ptrdiff_t pitch = loglikes[j] - loglikes[i];
+        while (j < n && nf[j] == nf[i] && stride[j] == num_indices && loglikes[j] - loglikes[j - 1] == pitch &&
+               pitch >= (ptrdiff_t)((size_t)nf[i] * row))
+          ++j;
+      }
+      runs.push_back(CopyRun{i, j - i});
+      i = j;
+    }
   }
   std::vector<AdvanceParams> hp((size_t)n * n_chunks);
   std::vector<int32_t> steps_of((size_t)n_chunks * n_sub, 0);
@@ -1010,19 +1019,19 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
     // ---- rows of this chunk -> device (copy stream) -> per-stream histories (stream s)
     if (!on_device) {
       if (k >= 2) CU_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[k & 1], 0));
-      int32_t widest = 0;
-      for (int i = 0; i < n; ++i) {
+      for (const CopyRun &r : runs) {
+        const int i = r.first;
         const int32_t c = hp[(size_t)k * n + i].n_frames;
-        widest = std::max(widest, c);
-        if (c > 0 && !contiguous)
-          CU_CHECK(cudaMemcpy2DAsync(stage + (size_t)i * chunk * row, row * 4,
-                                     loglikes[i] + (size_t)f0 * stride[i], (size_t)stride[i] * 4, row * 4,
-                                     (size_t)c, cudaMemcpyHostToDevice, ctx->copy_stream));
+        if (c <= 0) continue;
+        if (r.count == 1)
+          CU_CHECK(cudaMemcpy2DAsync(stage + (size_t)i * chunk * row, row * 4, loglikes[i] + (size_t)f0 * stride[i],
+                                     (size_t)stride[i] * 4, row * 4, (size_t)c, cudaMemcpyHostToDevice,
+                                     ctx->copy_stream));
+        else  // c rows of every stream of the run are one contiguous piece: `count` pieces at a fixed pitch
+          CU_CHECK(cudaMemcpy2DAsync(stage + (size_t)i * chunk * row, (size_t)chunk * row * 4,
+                                     loglikes[i] + (size_t)f0 * row, (size_t)(loglikes[i + 1] - loglikes[i]) * 4,
+                                     (size_t)c * row * 4, (size_t)r.count, cudaMemcpyHostToDevice, ctx->copy_stream));
       }
-      if (contiguous)
-        CU_CHECK(cudaMemcpy2DAsync(stage, (size_t)chunk * row * 4, loglikes[0] + (size_t)f0 * row,
-                                   (size_t)(loglikes[1] - loglikes[0]) * 4, (size_t)widest * row * 4, (size_t)n,
-                                   cudaMemcpyHostToDevice, ctx->copy_stream));
       CU_CHECK(cudaEventRecord(ctx->ev_copied[k & 1], ctx->copy_stream));
       tr_mark(tr_copy, ctx->copy_stream);
       CU_CHECK(cudaStreamWaitEvent(ps, ctx->ev_copied[k & 1], 0));

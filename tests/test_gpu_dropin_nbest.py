@@ -41,10 +41,11 @@ def compare(cuda, ref, tag, exact_lattice):
         assert c["words"] == r["words"] and c["ali"] == r["ali"], t
         assert c["tot_bits"] == r["tot_bits"] and c["lm_bits"] == r["lm_bits"], t
         # raw lattice: one state per surviving token, one arc per surviving link.  The canonical
-        # search keeps no order-dependent extras, so it is never larger than the reference's by more
-        # than the few tokens a different admission order moves across the lattice beam.
+        # search keeps no order-dependent extras (tokens the reference admitted before its running
+        # cutoff tightened), so its raw lattice is the smaller one — by up to a
+        # third on these inputs — while the determinised n-best below is the same.
         assert c["raw_states"] > 0 and c["det_states"] > 0, t
-        assert 0.7 * r["raw_states"] <= c["raw_states"] <= 1.1 * r["raw_states"], (t, c["raw_states"], r["raw_states"])
+        assert 0.5 * r["raw_states"] <= c["raw_states"] <= 1.05 * r["raw_states"], (t, c["raw_states"], r["raw_states"])
         # determinised n-best: same word sequences with the same costs, in the same order.  (Costs are
         # float sums over different but equivalent lattices: compared to 1e-4 relative, the
         # north_star tolerance; ties may swap neighbours, so sequences are matched by words.)
