@@ -57,9 +57,11 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--hash-capacity", type=int, default=0, help="0 = library default (8 x max-active)")
-    ap.add_argument("--workload", default="offline", choices=["offline", "streaming"],
+    ap.add_argument("--workload", default="offline", choices=["offline", "streaming", "biglm", "lattice"],
                     help="offline = BASELINE.json configs[1] (the headline); streaming = configs[4]: "
-                         "--streams concurrent streams fed in --chunk-frames chunks, sharded over the GPUs")
+                         "--streams concurrent streams fed in --chunk-frames chunks, sharded over the GPUs; "
+                         "biglm = configs[3] (on-the-fly LM-difference composition); lattice = configs[2]'s shape "
+                         "(raw lattice from the device + the reference's host determinisation)")
     ap.add_argument("--regime", default="busy", choices=["busy", "peaked", "deployed"],
                     help="SURVEY.md section 8d regimes: busy = sigma 2 (default, max-active binding); peaked = sigma 3; "
                          "deployed = beam 10 / lattice-beam 7 (v2-asrbin/conf/decoder.conf)")
@@ -562,12 +564,154 @@ def run_streaming_arm(a):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------- biglm / lattice lines
+
+def run_side_workload(a):
+    """One-GPU measurement lines for BASELINE.json configs[3] (biglm) and configs[2] (lattice mode),
+    with the reference's CPU implementation timed beside them.  Not the driver's headline."""
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+    from asr_decoder_b200 import _lib, fstio, synth, lm as LM
+    from asr_decoder_b200.decoder import CudaDecoderBatch, CudaFst, CudaLm, LatticeFasterDecoderConfig
+    from oracle import oracle as O
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    L = _lib.lib()
+    cores = os.cpu_count() or 1
+    cfg = LatticeFasterDecoderConfig(beam=a.beam, max_active=a.max_active, min_active=a.min_active,
+                                     lattice_beam=a.lattice_beam)
+    stream = torch.cuda.current_stream().cuda_stream
+    T, P = a.frames, a.pdfs
+    if a.workload == "biglm":
+        n = min(a.utts, 64)
+        fst = synth.make_graph(a.states, 5.0, P, seed=12345)
+        nw = 20000
+        lm1, lm2 = LM.make_lm(nw, seed=1, order=2, bigram_density=0.002), LM.make_lm(nw, seed=2, order=2, bigram_density=0.002)
+        lls = [synth.make_loglikes(T, P, a.sigma, seed=1000 + i) for i in range(n)]
+        graph = CudaFst(fst)
+        batch = CudaDecoderBatch(graph, cfg, n, max_frames=T + 8, token_capacity=(T + 2) * 14000,
+                                 old_lm=CudaLm(lm1.Rescale(-1.0)), new_lm=CudaLm(lm2))
+        dev = [torch.from_numpy(x).cuda() for x in lls]
+
+        def step():
+            batch.InitDecoding(stream)
+            batch.AdvanceDecoding(dev, stream=stream)
+            batch.FinalizeDecoding(stream)
+            return batch.GetBestPath(True, stream, vectors=False)
+        for _ in range(a.warmup):
+            res = step()
+        bad = [r.status for r in res if not r.ok]
+        if bad:
+            raise SystemExit(f"decode failed: statuses {sorted(set(bad))}")
+        torch.cuda.synchronize()
+        l0 = L.asrd_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.steps):
+            res = step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / a.steps
+        ae, aa, tk = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        L.asrd_get_counters(batch.handles, n, C.byref(ae), C.byref(aa), C.byref(tk), stream)
+        line = {"metric": "biglm decode RTFx", "value": n * T * FRAME_SECONDS / (ms / 1e3), "unit": "x realtime", "n_gpus": 1,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"biglm: synthetic HCLG {a.states} states, {P} pdfs, two bigram LMs over {nw} words "
+                                       f"(old LM scaled by -1); {n} utts x {T} frames, sigma={a.sigma}; beam={a.beam} "
+                                       f"max-active={a.max_active}; one-best", "kernels": "k_expand<BIGLM> + k_post<BIGLM> (HBM map)"},
+                "arcs_expanded_per_s": ae.value / (ms / 1e3), "gpu_launches": int((L.asrd_launch_count() - l0) / a.steps)}
+        if O.have_ref_biglm() and not a.no_cpu_baseline:
+            tmp = tempfile.mkdtemp(prefix="asrd_biglm_")
+            try:
+                gp = os.path.join(tmp, "g.fst")
+                fstio.write_fst(gp, fst)
+                l1, l2 = os.path.join(tmp, "lm1"), os.path.join(tmp, "lm2")
+                LM.write_lm(l1, lm1)
+                LM.write_lm(l2, lm2)
+                k = min(cores, n)
+
+                def one(i):
+                    lp = os.path.join(tmp, f"ll{i}")
+                    fstio.write_loglikes(lp, [lls[i]])
+                    return O.run_ref_biglm(gp, lp, l1, l2, beam=a.beam, max_active=a.max_active, min_active=a.min_active,
+                                           lattice_beam=a.lattice_beam)[0]
+                with ThreadPoolExecutor(k) as ex:   # one reference process per core, one utterance each, concurrently
+                    outs = list(ex.map(one, range(k)))
+                wall = max(o["seconds"] for o in outs)
+                line["cpu_baseline"] = {"value": k * T * FRAME_SECONDS / wall, "unit": "x realtime", "cores": k, "kind": "reference",
+                                        "sample": f"{k} utterances, one OnlineLatticeDecoderMempoolBiglm process per core run "
+                                                  "concurrently; slowest decode time (graph / LM load excluded)"}
+            finally:
+                shutil.rmtree(tmp, ignore_errors=True)
+        print(json.dumps(line), flush=True)
+        return
+    # ---- lattice mode: config 3's shape (average degree 3), flat scores so that thousands of tokens survive
+    binp = os.path.join(ROOT, "oracle", "_ref", "dropin_nbest")
+    states = min(a.states, 2_000_000)
+    fst = synth.make_graph(states, 3.0, P, seed=777)
+    n = min(a.utts, 16)
+    Tl = min(T, 100)
+    lls = [synth.make_loglikes(Tl, P, 1.2, seed=50 + i) for i in range(n)]
+    graph = CudaFst(fst)
+    batch = CudaDecoderBatch(graph, cfg, n, max_frames=Tl + 8)
+    batch.Decode(lls)
+    t_lat, sizes = [], []
+    for rep in range(a.warmup + a.steps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        lat = [batch.GetRawLattice(i) for i in range(n)]
+        torch.cuda.synchronize()
+        if rep >= a.warmup:
+            t_lat.append(1e3 * (time.perf_counter() - t0) / n)
+        sizes = [(len(x[0]), len(x[1])) for x in lat]
+    d2h = int(np.mean([20 * t + 24 * l for t, l in sizes]))
+    line = {"metric": "raw lattice extraction ms per utterance", "value": float(np.mean(t_lat)), "unit": "ms",
+            "n_gpus": 1, "steps": a.steps, "warmup": a.warmup, "ms_per_step": float(np.mean(t_lat)) * n,
+            "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"lattice: synthetic HCLG {states} states avg-degree 3, {P} pdfs; {n} utts x {Tl} frames, "
+                                   f"sigma=1.2; beam={a.beam} max-active={a.max_active} lattice-beam={a.lattice_beam}",
+                       "what": "asrd_get_raw_lattice per utterance: k_lattice (link regeneration + lattice-beam prune on the "
+                               "device) + D2H of the survivors + host sort"},
+            "raw_lattice_states_links_mean": [float(np.mean([s[0] for s in sizes])), float(np.mean([s[1] for s in sizes]))],
+            "d2h_bytes_per_utterance": d2h}
+    if os.path.exists(binp) and not a.no_cpu_baseline:
+        tmp = tempfile.mkdtemp(prefix="asrd_lat_")
+        try:
+            gp, lp = os.path.join(tmp, "g.fst"), os.path.join(tmp, "l.llb")
+            fstio.write_fst(gp, fst)
+            fstio.write_loglikes(lp, lls)
+            out = {}
+            for which in ("cuda", "ref"):
+                r = subprocess.run([binp, f"--graph={gp}", f"--loglikes={lp}", f"--decoder={which}", "--nbest=10",
+                                    f"--beam={a.beam}", f"--max-active={a.max_active}", f"--min-active={a.min_active}",
+                                    f"--lattice-beam={a.lattice_beam}"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                   check=True).stdout.decode()
+                out[which] = [json.loads(x) for x in r.splitlines() if x.startswith("{")]
+            same = sum([p["words"] for p in c["nbest"]] == [p["words"] for p in r["nbest"]] for c, r in zip(out["cuda"], out["ref"]))
+            for which in ("cuda", "ref"):
+                o = out[which]
+                line[f"reference_post_pass_{which}"] = {
+                    "decode_ms": 1e3 * float(np.mean([x["decode_s"] for x in o])),
+                    "get_raw_lattice_ms": 1e3 * float(np.mean([x["raw_lattice_s"] for x in o])),
+                    "determinize_nbest_ms": 1e3 * float(np.mean([x["determinize_nbest_s"] for x in o])),
+                    "raw_states": float(np.mean([x["raw_states"] for x in o])), "det_states": float(np.mean([x["det_states"] for x in o]))}
+            line["nbest10_word_sequences_identical"] = f"{same} of {n} utterances"
+            line["post_pass_note"] = ("oracle/_ref/dropin_nbest: the drop-in class and the reference decoder behind one DecoderItf*, "
+                                      "both through the reference's own DeterminizeLatticeWrapper + NShortestPath (one stream at a time, 1 host core)")
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+    print(json.dumps(line), flush=True)
+
+
 def main():
     a = parse_args()
     if a.impl == "reference":
         run_reference_arm(a)
     elif a.workload == "streaming":
         run_streaming_arm(a)
+    elif a.workload in ("biglm", "lattice"):
+        run_side_workload(a)
     else:
         run_b200_arm(a)
 

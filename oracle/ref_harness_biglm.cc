@@ -6,6 +6,7 @@
 //   lm1.Read, lm2.Read, lm1.Rescale(-1.0); decoder(&fst, opt, &lm1, &lm2);
 //   InitDecoding -> AdvanceDecoding -> FinalizeDecoding -> GetBestPath -> LatticeToVector
 // One JSON object per utterance.  Only tests and bench baselines may execute this binary.
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -92,6 +93,7 @@ int main(int argc, char **argv) {
   fclose(fp);
   Probe dec(&fst, cfg, &lm1, &lm2);
   for (int i = 0; i < n; ++i) {
+    const auto t_begin = std::chrono::steady_clock::now();
     dec.stats.clear();
     dec.InitDecoding();
     MatrixDecodable decodable(&utts[i]);
@@ -102,8 +104,9 @@ int main(int argc, char **argv) {
     float tot = 0, lm = 0;
     bool ok = dec.GetBestPath(&best_path);
     if (ok) ok = LatticeToVector(best_path, words, ali, tot, lm);
-    fprintf(real_out, "{\"utt\": %d, \"ok\": %s, \"frames\": %d, \"tot\": %.9g, \"tot_bits\": %u, \"lm_bits\": %u, \"words\": [",
-            i, ok ? "true" : "false", utts[i].T, tot, Bits(tot), Bits(lm));
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count();
+    fprintf(real_out, "{\"utt\": %d, \"ok\": %s, \"frames\": %d, \"seconds\": %.6f, \"tot\": %.9g, \"tot_bits\": %u, \"lm_bits\": %u, \"words\": [",
+            i, ok ? "true" : "false", utts[i].T, secs, tot, Bits(tot), Bits(lm));
     for (size_t k = 0; k < words.size(); ++k) fprintf(real_out, "%s%d", k ? "," : "", words[k]);
     fprintf(real_out, "], \"ali\": [");
     for (size_t k = 0; k < ali.size(); ++k) fprintf(real_out, "%s%d", k ? "," : "", ali[k]);
