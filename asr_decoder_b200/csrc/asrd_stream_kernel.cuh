@@ -311,6 +311,67 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
     const float cur_cut = s_d.cur_cut, abeam = s_d.abeam;
     uint32_t *next_cut = &s_d.next_cut_bits;
 
+    // ---- eps relaxation (ProcessNonemitting's inner step, inl.h:413-426), used by the closure rounds.
+    // (Relaxing eagerly inside the expansion — whenever a state with eps arcs gets cheaper — was
+    // measured: the closure phase all but vanishes, but the divergent chain walks inside the map
+    // update cost three times what they save, 58 vs 48 ms per step.)  relax_one: dstw gets cost + w if that is below `cut`;
+    // true when the destination's cost was lowered and it has eps arcs itself.  relax_chain: every
+    // eps arc of a state (er: its eps row, first arc inline) from `cost`, then the lowered
+    // destinations one after the other (depth first, like the reference's LIFO); when a state fans
+    // out to several such destinations the extra ones go to worklist `qsel` for a later round.
+    auto relax_one = [&](float cost, float w, uint32_t dstw, float cut, uint32_t tag, float &new_cost, uint32_t &s2) -> bool {
+      const float tot = cost + w;  // inl.h:413-414
+      if (!(tot < cut)) return false;  // inl.h:415
+      const uint32_t to = f2ord(tot);
+      bool is_new = false;
+      s2 = smem_find_or_claim(m, dstw, is_new);
+      if (s2 == kNoSlot) {
+        raise_overflow(tag);
+        return false;
+      }
+      if (is_new && atomicAdd(&hot->claims, 1u) + 1u > claim_limit) raise_overflow(tag);
+      const uint32_t old = atomicMin(&m.cost[s2], to);
+      if (!(to < old)) return false;  // cost unchanged (inl.h:115-127)
+      atomicMin(&hot->best_ord, to);
+      new_cost = tot;
+      return (dstw & kDestEpsBit) != 0;  // inl.h:425-426
+    };
+    auto relax_chain = [&](float cost, uint4 er, float cut, uint32_t tag, uint32_t qsel) {
+      for (int hop = 0; hop < 64; ++hop) {
+        uint32_t next_w = 0;
+        float next_cost = 0.f;
+        bool have_next = false;
+        for (uint32_t a = er.x; a < er.y; ++a) {
+          float w;
+          uint32_t dstw;
+          if (a == er.x) {
+            w = __uint_as_float(er.z);
+            dstw = er.w;
+          } else {
+            const int4 arc = __ldg(&g.arcs[a]);
+            w = __int_as_float(arc.z);
+            dstw = (uint32_t)arc.w;
+          }
+          float c2;
+          uint32_t s2;
+          if (relax_one(cost, w, dstw, cut, tag, c2, s2)) {
+            if (!have_next && hop < 63) {
+              have_next = true;
+              next_w = dstw;
+              next_cost = c2;
+            } else {
+              const uint32_t qi = atomicAdd(&hot->qn[qsel % 3u], 1u);
+              if (qi < (uint32_t)kEpsQueueCap) s_eq[(qsel & 1u) * kEpsQueueCap + qi] = (uint16_t)s2;
+              else raise_overflow(tag);
+            }
+          }
+        }
+        if (!have_next) return;
+        cost = next_cost;
+        er = __ldg(&g.eps_rows[next_w & kStateMask]);
+      }
+    };
+
     // ---- emitting expansion (ProcessEmitting, inl.h:311-347) into the on-chip map.
     // A warp takes groups of 32 tokens: lane i loads token i and its emitting span and cuts the
     // span into work items of up to kItemArcs consecutive arcs, appended to a warp-private ring at
@@ -540,63 +601,6 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
       for (uint32_t round = 0;; ++round) {
         const uint32_t nq = min(hot->qn[round % 3u], (uint32_t)kEpsQueueCap);
         const uint16_t *qin = s_eq + (round & 1u) * kEpsQueueCap;
-        uint16_t *qout = s_eq + ((round + 1u) & 1u) * kEpsQueueCap;
-        uint32_t *qn_out = &hot->qn[(round + 1u) % 3u];
-        // relaxes dstw with cost + w; true when the destination's cost was lowered and it has eps arcs
-        auto relax = [&](float cost, float w, uint32_t dstw, float &new_cost, uint32_t &s2) -> bool {
-          const float tot = cost + w;  // inl.h:413-414
-          if (!(tot < nc)) return false;  // inl.h:415
-          const uint32_t to = f2ord(tot);
-          bool is_new = false;
-          s2 = smem_find_or_claim(m, dstw, is_new);
-          if (s2 == kNoSlot) {
-            raise_overflow(round + 2u);
-            return false;
-          }
-          if (is_new && atomicAdd(&hot->claims, 1u) + 1u > claim_limit) raise_overflow(round + 2u);
-          const uint32_t old = atomicMin(&m.cost[s2], to);
-          if (!(to < old)) return false;  // cost unchanged (inl.h:115-127)
-          atomicMin(&hot->best_ord, to);
-          new_cost = tot;
-          return (dstw & kDestEpsBit) != 0;  // inl.h:425-426
-        };
-        // relaxes every eps arc of a state (er: its eps row) from `cost`, then follows one lowered
-        // destination after the other; further ones are queued for the next round
-        auto relax_chain = [&](float cost, uint4 er) {
-          for (int hop = 0; hop < 64; ++hop) {
-            uint32_t next_w = 0;
-            float next_cost = 0.f;
-            bool have_next = false;
-            for (uint32_t a = er.x; a < er.y; ++a) {
-              float w;
-              uint32_t dstw;
-              if (a == er.x) {
-                w = __uint_as_float(er.z);
-                dstw = er.w;
-              } else {
-                const int4 arc = __ldg(&g.arcs[a]);
-                w = __int_as_float(arc.z);
-                dstw = (uint32_t)arc.w;
-              }
-              float c2;
-              uint32_t s2;
-              if (relax(cost, w, dstw, c2, s2)) {
-                if (!have_next && hop < 63) {
-                  have_next = true;
-                  next_w = dstw;
-                  next_cost = c2;
-                } else {
-                  const uint32_t qi = atomicAdd(qn_out, 1u);
-                  if (qi < (uint32_t)kEpsQueueCap) qout[qi] = (uint16_t)s2;
-                  else raise_overflow(round + 2u);
-                }
-              }
-            }
-            if (!have_next) return;
-            cost = next_cost;
-            er = __ldg(&g.eps_rows[next_w & kStateMask]);
-          }
-        };
         for (uint32_t i0 = tid; i0 < nq; i0 += 4 * NT) {  // up to four worklist entries per thread, loads batched
           float cost[4];
           uint4 er[4];
@@ -612,7 +616,7 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            if (go[j]) relax_chain(cost[j], er[j]);
+            if (go[j]) relax_chain(cost[j], er[j], nc, round + 2u, round + 1u);
         }
         // one barrier per round: round r reads qn[r % 3] and raises qn[(r + 1) % 3]; the
         // counter round r + 1 raises is lowered here — its last readers passed the previous barrier
