@@ -527,6 +527,13 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
             g_base = t1_er.x;
             // inclusive token test, inl.h:315
             g_deg = (id1 * 32 + lane < n_cur && __uint_as_float(t1_cost) <= cur_cut) ? t1_er.y - t1_er.x : 0u;
+            // the span's arc records are requested a few steps from now: have them in L2 by then
+            // (four in ten come from HBM otherwise, and two steps in flight do not cover that;
+            // measured 47.0 vs 47.9 ms per step)
+            if (g_deg) {
+              prefetch_l2(&g.arcs[g_base]);
+              if (((g_base + g_deg - 1) >> 3) != (g_base >> 3)) prefetch_l2(&g.arcs[g_base + g_deg - 1]);  // (eight per 128-byte line)
+            }
             load_spans(id2);
             id1 = id2;
             id2 = acquire();
