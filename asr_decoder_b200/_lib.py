@@ -47,7 +47,7 @@ class asrd_config(C.Structure):
 class asrd_device_options(C.Structure):
     _fields_ = [("hash_capacity", C.c_int32), ("token_capacity", C.c_int64),
                 ("max_frames", C.c_int32), ("collect_stats", C.c_int32),
-                ("lm_pair_capacity", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("lm_pair_capacity", C.c_int32), ("prune_tokens", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 class asrd_frame_stat(C.Structure):
@@ -126,6 +126,10 @@ def lib():
     L.asrd_host_free.argtypes = [vp]
     L.asrd_launch_count.restype = i64
     L.asrd_last_fallback_frames.restype = i64
+    L.asrd_last_pruned_tokens.restype = i64
+    L.asrd_arena_frame_tokens.argtypes = [vp, vp, i32, vp]
+    L.asrd_arena_frame_tokens.restype = i32
+    L.asrd_last_peak_tokens.restype = i64
     L.asrd_get_counters.argtypes = [vp, i32, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), vp]
     L.asrd_profile_enable.argtypes = [C.c_int]
     L.asrd_profile_get.argtypes = [C.POINTER(C.c_double), C.POINTER(i64)]

@@ -76,7 +76,7 @@ int GetCtx(int device, DeviceCtx **out) {
 }
 
 // Optional per-kernel timing with CUDA events on the launching stream (asrd_profile_*):
-// class 0 = k_expand, 1 = k_post, 2 = k_stream, 3 = unused.  Off by default: events
+// class 0 = k_expand, 1 = k_post, 2 = k_stream, 3 = k_lattice in arena-prune mode.  Off by default: events
 // between launches add gaps.
 std::atomic<int> g_profile{0};
 std::mutex g_prof_mu;
@@ -129,6 +129,8 @@ struct Profiler {
 // its first CUDA call; the library no longer touches the environment when it is loaded.
 
 std::atomic<int64_t> g_last_fallback_frames{0};
+std::atomic<int64_t> g_last_pruned_tokens{0}, g_last_peak_tokens{0};
+std::atomic<int64_t> g_last_prune_cycles[8];
 std::atomic<int64_t> g_last_phase_cycles[6];
 
 int EnvInt(const char *name, int dflt) {
@@ -242,6 +244,7 @@ int CheckBatch(asrd_decoder *const *decs, int n) {
     if (memcmp(&decs[i]->cfg, &decs[0]->cfg, sizeof(asrd_config)) != 0) return ASRD_ERR_BAD_ARG;
     if (decs[i]->opts.hash_capacity != decs[0]->opts.hash_capacity) return ASRD_ERR_BAD_ARG;
     if (decs[i]->opts.collect_stats != decs[0]->opts.collect_stats) return ASRD_ERR_BAD_ARG;
+    if (decs[i]->opts.prune_tokens != decs[0]->opts.prune_tokens) return ASRD_ERR_BAD_ARG;
     if (decs[i]->lm1 != decs[0]->lm1 || decs[i]->lm2 != decs[0]->lm2) return ASRD_ERR_BAD_ARG;
   }
   return ASRD_OK;
@@ -317,6 +320,41 @@ int PlanStream(const asrd_graph *graph, int num_indices, bool biglm, StreamPlan 
   plan->fn = smem_ll ? k_stream<true> : k_stream<false>;
   plan->n_buckets = n_buckets;
   plan->dyn = fixed + (size_t)n_buckets * 32;
+  CU_CHECK(cudaFuncSetAttribute(plan->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->dyn));
+  return ASRD_OK;
+}
+
+// The arena prune (device option prune_tokens): k_prune keeps its lookup map (6 bytes per slot),
+// the extra costs of the frame being swept (4 bytes per token) and two flag bitmaps in shared
+// memory: frames of up to ~20 k tokens.  Streams with a larger frame are taken by the HBM-map
+// sweep (k_lattice in PRUNE mode), launched right behind it (a no-op for the streams k_prune
+// served); ASRD_PRUNE_KERNEL=0 sends every stream there.  ASRD_PRUNE_DEPTH: frames below the
+// previous frontier a sweep goes back (default: prune_interval; -1: to frame 0 every time).
+typedef void (*PruneFn)(StreamState *const *, GraphView, DecoderConfigDev, int, int, uint32_t, uint32_t);
+
+struct PrunePlan {
+  PruneFn fn = nullptr;  // null: k_lattice<false, true> only
+  size_t dyn = 0;
+  uint32_t n_buckets = 0, ex_cap = 0;
+};
+
+int PlanPrune(PrunePlan *plan) {
+  plan->fn = nullptr;
+  if (!EnvInt("ASRD_PRUNE_KERNEL", 1)) return ASRD_OK;
+  cudaFuncAttributes fa;
+  CU_CHECK(cudaFuncGetAttributes(&fa, k_prune));
+  int dev = 0, max_optin = 0;
+  CU_CHECK(cudaGetDevice(&dev));
+  CU_CHECK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  const size_t room = (size_t)max_optin > fa.sharedSizeBytes + 64 ? (size_t)max_optin - fa.sharedSizeBytes - 64 : 0;
+  // per token: 4 + 1/4 bytes of extra cost and flags, 6 bytes per map slot at a load of at most 7/8
+  const uint32_t ex_cap = (uint32_t)std::min<size_t>(20480, room / 12) & ~255u;
+  if (ex_cap < 4096) return ASRD_OK;
+  const uint32_t n_buckets = (uint32_t)std::min<size_t>((room - prune_token_dyn_bytes(ex_cap)) / 24, 16384) & ~1u;  // 4 slots x (4 + 2) bytes
+  plan->fn = k_prune;
+  plan->n_buckets = n_buckets;
+  plan->ex_cap = ex_cap;
+  plan->dyn = (size_t)n_buckets * 24 + prune_token_dyn_bytes(ex_cap);
   CU_CHECK(cudaFuncSetAttribute(plan->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->dyn));
   return ASRD_OK;
 }
@@ -435,9 +473,18 @@ int asrd_graph_create(const asrd_arc *arcs, const uint32_t *num_arcs, const uint
     max_ilabel = std::max(max_ilabel, parc[a].ilabel);
   }
   for (int32_t s2 = 0; s2 < S; ++s2) in_off[s2 + 1] += in_off[s2];
+  // inside a group the eps arcs come first (in_mid: where the emitting ones start): the arena prune
+  // walks the two classes separately (k_prune)
+  std::vector<uint32_t> in_mid((size_t)S, 0u);
   {
-    std::vector<uint32_t> fill(in_off.begin(), in_off.end() - 1);
-    for (int64_t a = 0; a < A; ++a) in_arc[fill[(uint32_t)parc[a].nextstate & kStateMask]++] = (uint32_t)a;
+    for (int64_t a = 0; a < A; ++a)
+      if (parc[a].ilabel == 0) ++in_mid[(uint32_t)parc[a].nextstate & kStateMask];
+    for (int32_t s2 = 0; s2 < S; ++s2) in_mid[s2] += in_off[s2];
+    std::vector<uint32_t> fill_eps(in_off.begin(), in_off.end() - 1), fill_emit(in_mid);
+    for (int64_t a = 0; a < A; ++a) {
+      const uint32_t d = (uint32_t)parc[a].nextstate & kStateMask;
+      in_arc[parc[a].ilabel == 0 ? fill_eps[d]++ : fill_emit[d]++] = (uint32_t)a;
+    }
   }
 
   // eps rows with the first eps arc inline (the closure of k_stream)
@@ -461,12 +508,14 @@ int asrd_graph_create(const asrd_arc *arcs, const uint32_t *num_arcs, const uint
                b_src = sizeof(uint32_t) * src.size(), b_par = sizeof(uint32_t) * par.size(),
                b_eps = sizeof(uint32_t) * epsb.size(), b_erows = sizeof(uint2) * std::max<size_t>(erows.size(), 1),
                b_ioff = sizeof(uint32_t) * in_off.size(), b_iarc = sizeof(uint32_t) * in_arc.size(),
+               b_imid = sizeof(uint32_t) * in_mid.size(),
                b_epsr = sizeof(uint4) * eps_rows.size();
   struct Up { void **dst; const void *src; size_t bytes; };
   const Up ups[] = {{&g->d_arcs, parc.data(), b_arcs}, {&g->d_rows, rows.data(), b_rows},
                     {&g->d_erows, erows.data(), sizeof(uint2) * erows.size()}, {&g->d_arc_src, src.data(), b_src},
                     {&g->d_par, par.data(), b_par}, {&g->d_eps, epsb.data(), b_eps},
                     {&g->d_in_off, in_off.data(), b_ioff}, {&g->d_in_arc, in_arc.data(), b_iarc},
+                    {&g->d_in_mid, in_mid.data(), b_imid},
                     {&g->d_eps_rows, eps_rows.data(), b_epsr}};
   for (const Up &u : ups) {
     if (cudaMalloc(u.dst, std::max<size_t>(u.bytes, 16)) != cudaSuccess) {
@@ -481,7 +530,7 @@ int asrd_graph_create(const asrd_arc *arcs, const uint32_t *num_arcs, const uint
       return ASRD_ERR_CUDA;
     }
   }
-  g->device_bytes = (int64_t)(b_arcs + b_rows + b_erows + b_src + b_par + b_eps + b_ioff + b_iarc + b_epsr);
+  g->device_bytes = (int64_t)(b_arcs + b_rows + b_erows + b_src + b_par + b_eps + b_ioff + b_iarc + b_imid + b_epsr);
   g->view.arcs = (const int4 *)g->d_arcs;
   g->view.rows = (const uint2 *)g->d_rows;
   g->view.erows = (const uint2 *)g->d_erows;
@@ -489,6 +538,7 @@ int asrd_graph_create(const asrd_arc *arcs, const uint32_t *num_arcs, const uint
   g->view.arc_src = (const uint32_t *)g->d_arc_src;
   g->view.in_off = (const uint32_t *)g->d_in_off;
   g->view.in_arc = (const uint32_t *)g->d_in_arc;
+  g->view.in_mid = (const uint32_t *)g->d_in_mid;
   g->view.par_bits = (const uint32_t *)g->d_par;
   g->view.eps_bits = (const uint32_t *)g->d_eps;
   g->view.n_states = S;
@@ -608,6 +658,7 @@ int asrd_graph_destroy(asrd_graph *g) {
   cudaFree(g->d_eps);
   cudaFree(g->d_in_off);
   cudaFree(g->d_in_arc);
+  cudaFree(g->d_in_mid);
   delete g;
   return ASRD_OK;
 }
@@ -677,7 +728,12 @@ static int DecoderCreate(asrd_graph *g, const asrd_config *cfg, const asrd_devic
                b_stats = o.collect_stats ? align(((size_t)o.max_frames + 1) * sizeof(asrd_frame_stat)) : 0,
                b_state = align(sizeof(StreamState));
   const size_t b_lm = b_arc, b_pair = align(pair_cap * 8);
-  const size_t total = b_state + b_hash + 2 * b_bm + 3 * b_list + b_tok + b_arc + 3 * b_off + b_stats + b_lm + b_pair;
+  if (o.prune_tokens && (lm1 || cfg->prune_interval <= 0)) {  // arena pruning: plain decoders, a positive interval
+    delete d;
+    return ASRD_ERR_BAD_ARG;
+  }
+  const size_t b_extra = o.prune_tokens ? align((size_t)o.token_capacity * 4) : 0;
+  const size_t total = b_state + b_hash + 2 * b_bm + 3 * b_list + b_tok + b_arc + 3 * b_off + b_stats + b_lm + b_pair + b_extra;
   if (cudaMalloc(&d->slab, total) != cudaSuccess) {
     cudaGetLastError();
     delete d;
@@ -700,6 +756,7 @@ static int DecoderCreate(asrd_graph *g, const asrd_config *cfg, const asrd_devic
   }
   h.tok_sc = (uint2 *)p; p += b_tok;
   h.tok_arc = lm1 ? (uint32_t *)p : nullptr; p += b_arc;
+  h.tok_extra = o.prune_tokens ? (uint32_t *)p : nullptr; p += b_extra;
   h.frame_off = (uint32_t *)p; p += b_off;
   h.frame_nc = (float *)p; p += b_off;
   h.frame_cur = (float *)p; p += b_off;
@@ -849,6 +906,7 @@ int asrd_init_decoding(asrd_decoder *const *decs, int32_t n, void *stream) {
   CU_CHECK(cudaGetLastError());
   for (int i = 0; i < n; ++i) {
     decs[i]->frames_decoded = 0;
+    decs[i]->last_prune_frame = 0;
     decs[i]->finalized = 0;
     decs[i]->initialized = 1;
   }
@@ -1098,6 +1156,39 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
     }
     CU_CHECK(cudaGetLastError());
   }
+  // ---- PruneActiveTokens (inl.h:438-480, every prune_interval frames at inl.h:660-661): behind the
+  // frame loops of each sub-batch, on its worker stream, so it overlaps the other sub-batches.  The
+  // kernel decides per stream (frames since its last prune); the host only skips the launch when no
+  // stream of the batch can be due.
+  if (decs[0]->opts.prune_tokens && !biglm) {
+    bool due = false;
+    for (int i = 0; i < n && !due; ++i)
+      due = decs[i]->frames_decoded + nf[i] - decs[i]->last_prune_frame >= decs[0]->cfg.prune_interval;
+    if (due) {
+      PrunePlan pplan;
+      if ((rc = PlanPrune(&pplan))) return rc;
+      const int prune_depth = EnvInt("ASRD_PRUNE_DEPTH", decs[0]->cfg.prune_interval);
+      for (int b = 0; b < n_sub; ++b) {
+        cudaStream_t ws = single ? s : ctx->worker[b % n_workers];
+        const int nb = std::min(sub, n - b * sub);
+        prof.Begin(3, ws);
+        if (pplan.fn) {
+          pplan.fn<<<nb, kStreamThreads, pplan.dyn, ws>>>(d_streams + (size_t)b * sub, gv, cfg, decs[0]->cfg.prune_interval,
+                                                          prune_depth, pplan.n_buckets, pplan.ex_cap);
+          ++g_launches;
+        }
+        // (streams k_prune served are no longer due: their CTAs return at once)
+        k_lattice<false, true><<<nb, kStreamThreads, 0, ws>>>(d_streams + (size_t)b * sub, nullptr, gv, cfg, 0, lms,
+                                                               decs[0]->cfg.prune_interval);
+        prof.End(ws);
+        ++g_launches;
+      }
+      CU_CHECK(cudaGetLastError());
+      for (int i = 0; i < n; ++i)
+        if (decs[i]->frames_decoded + nf[i] - decs[i]->last_prune_frame >= decs[0]->cfg.prune_interval)
+          decs[i]->last_prune_frame = decs[i]->frames_decoded + nf[i];
+    }
+  }
   if (!single) {  // join the workers back into the caller's stream
     for (int w = 0; w < n_workers; ++w) {
       tr_mark(tr_join, ctx->worker[w]);
@@ -1243,9 +1334,9 @@ int asrd_get_raw_lattice(asrd_decoder *d, int32_t use_final_probs, asrd_lat_toke
   CU_CHECK(cudaMemsetAsync(maps, 0xFF, 2 * H * sizeof(LatEntry), s));
   CU_CHECK(cudaMemcpyAsync(d_out, &h, sizeof(h), cudaMemcpyHostToDevice, s));
   if (d->lm1)
-    k_lattice<true><<<1, kStreamThreads, 0, s>>>(d_streams, d_out, d->graph->view, DevCfg(d), use_final_probs ? 1 : 0, Lms(d));
+    k_lattice<true, false><<<1, kStreamThreads, 0, s>>>(d_streams, d_out, d->graph->view, DevCfg(d), use_final_probs ? 1 : 0, Lms(d), 0);
   else
-    k_lattice<false><<<1, kStreamThreads, 0, s>>>(d_streams, d_out, d->graph->view, DevCfg(d), use_final_probs ? 1 : 0, Lms(d));
+    k_lattice<false, false><<<1, kStreamThreads, 0, s>>>(d_streams, d_out, d->graph->view, DevCfg(d), use_final_probs ? 1 : 0, Lms(d), 0);
   ++g_launches;
   CU_CHECK(cudaGetLastError());
   LatticeOut r;
@@ -1336,6 +1427,22 @@ int32_t asrd_frame_stats(asrd_decoder *d, asrd_frame_stat *out, int32_t cap, voi
   return n;
 }
 
+int32_t asrd_arena_frame_tokens(asrd_decoder *d, uint32_t *out, int32_t cap, void *stream) {
+  if (!d) return ASRD_ERR_BAD_ARG;
+  const int32_t n = d->initialized ? d->frames_decoded + 1 : 0;
+  if (out && cap > 0 && n > 0) {
+    if (EnsureDevice(d->graph->device)) return ASRD_ERR_CUDA;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int32_t m = std::min(n, cap);
+    std::vector<uint32_t> off((size_t)m + 1);
+    if (cudaMemcpyAsync(off.data(), d->h_state.frame_off, 4 * ((size_t)m + 1), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess)
+      return ASRD_ERR_CUDA;
+    for (int32_t f = 0; f < m; ++f) out[f] = off[f + 1] - off[f];
+  }
+  return n;
+}
+
 int asrd_decoder_status(asrd_decoder *d, void *stream) {
   if (!d) return ASRD_ERR_BAD_ARG;
   int rc = EnsureDevice(d->graph->device);
@@ -1380,22 +1487,30 @@ int asrd_get_counters(asrd_decoder *const *decs, int32_t n, int64_t *arcs_expand
   StreamState **d_streams;
   if ((rc = UploadStreams(decs, n, s, sc, &d_streams))) return rc;
   unsigned long long *d_out;
-  CU_CHECK(sc.Alloc(&d_out, 10));
-  CU_CHECK(cudaMemsetAsync(d_out, 0, 80, s));
+  CU_CHECK(sc.Alloc(&d_out, 20));
+  CU_CHECK(cudaMemsetAsync(d_out, 0, 160, s));
   k_counters<<<(n + 127) / 128, 128, 0, s>>>(d_streams, n, d_out);
   ++g_launches;
-  unsigned long long h[10];
-  CU_CHECK(cudaMemcpyAsync(h, d_out, 80, cudaMemcpyDeviceToHost, s));
+  unsigned long long h[20];
+  CU_CHECK(cudaMemcpyAsync(h, d_out, 160, cudaMemcpyDeviceToHost, s));
   CU_CHECK(cudaStreamSynchronize(s));
   if (arcs_expanded) *arcs_expanded = (int64_t)h[0];
   if (arcs_admitted) *arcs_admitted = (int64_t)h[1];
   if (tokens) *tokens = (int64_t)h[2];
   g_last_fallback_frames.store((int64_t)h[3]);
+  g_last_pruned_tokens.store((int64_t)h[10]);
+  g_last_peak_tokens.store((int64_t)h[11]);
+  for (int k = 0; k < 8; ++k) g_last_prune_cycles[k].store((int64_t)h[12 + k]);
   for (int k = 0; k < 6; ++k) g_last_phase_cycles[k].store((int64_t)h[4 + k]);
   return ASRD_OK;
 }
 
 int64_t asrd_last_fallback_frames(void) { return g_last_fallback_frames.load(); }
+int64_t asrd_last_pruned_tokens(void) { return g_last_pruned_tokens.load(); }
+int64_t asrd_last_peak_tokens(void) { return g_last_peak_tokens.load(); }
+void asrd_last_prune_cycles(int64_t *out8) {
+  for (int k = 0; k < 8; ++k) out8[k] = g_last_prune_cycles[k].load();
+}
 
 void asrd_last_phase_cycles(int64_t *out6) {
   for (int k = 0; k < 6; ++k) out6[k] = g_last_phase_cycles[k].load();

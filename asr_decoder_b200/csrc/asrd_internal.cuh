@@ -54,7 +54,8 @@ struct GraphView {
                            //       state with one eps arc (the common case) is relaxed with a single load
   const uint32_t *arc_src; // [A] source state of every arc
   const uint32_t *in_off;  // [S+1] incoming-arc index: arcs INTO state s are in_arc[in_off[s] .. in_off[s+1])
-  const uint32_t *in_arc;  // [A] arc ids grouped by destination state, ascending inside a group
+  const uint32_t *in_arc;  // [A] arc ids grouped by destination state: the eps arcs first, ascending inside a class
+  const uint32_t *in_mid;  // [S] where the emitting arcs of the group start
   const uint32_t *par_bits;// [ceil(A/32)] arc has a same-class sibling with the same (src, dst)
   const uint32_t *eps_bits;// [ceil(S/32)] state has at least one input-epsilon arc
   int32_t n_states;
@@ -79,6 +80,7 @@ struct StreamState {
   uint32_t *tok_arc;    // biglm: token arena, arc that set the token's cost (kNoArc for the start token);
                         // plain decoders keep {state, cost} only — the trace-back finds the arc through
                         // the graph's incoming-arc index (k_best_path_rev)
+  uint32_t *tok_extra;  // prune_tokens: extra cost of every token as of the last arena prune (change detection)
   uint32_t *frame_off;  // [max_frames + 2] arena offset of every frame's token span
   float *frame_nc;      // [max_frames + 2] final next_cutoff of the step that produced each frame
   float *frame_cur;     // [max_frames + 2] GetCutoff result of each frame (which tokens were expanded)
@@ -100,6 +102,10 @@ struct StreamState {
   unsigned long long tot_arcs_expanded;
   unsigned long long tot_arcs_admitted;
   unsigned long long tot_fallback_frames;  // frames k_stream had to redo through the HBM map
+  int32_t gc_frame;     // frontier frame of the last arena prune (0 after InitDecoding)
+  uint32_t peak_tokens; // high-water mark of the arena (token records)
+  unsigned long long tot_pruned_tokens;    // tokens dropped by the arena prunes of this utterance
+  unsigned long long prune_cycles[8];      // k_prune: SM cycles per phase, frames swept, fixed-point rounds
   unsigned long long phase_cycles[6];      // k_stream: SM cycles per phase (cutoff, row, expand, closure, write-out, fallback)
 };
 
@@ -203,7 +209,7 @@ struct asrd_graph {
   int refs;  // the handle + one per decoder built on it (guarded by g_ref_mu); freed when it reaches 0
   int device;
   asrd::GraphView view;
-  void *d_arcs, *d_rows, *d_erows, *d_eps_rows, *d_arc_src, *d_par, *d_eps, *d_in_off, *d_in_arc;
+  void *d_arcs, *d_rows, *d_erows, *d_eps_rows, *d_arc_src, *d_par, *d_eps, *d_in_off, *d_in_arc, *d_in_mid;
   int32_t max_ilabel;
   int64_t device_bytes;
   int64_t total_arcs;
@@ -222,6 +228,7 @@ struct asrd_decoder {
   float *d_ll_hist;            // allocated at the first AdvanceDecoding (needs num_indices)
   int32_t ll_cols;
   int32_t frames_decoded;      // host-side mirror of StreamState::frame
+  int32_t last_prune_frame;    // host-side mirror of StreamState::gc_frame (prune_tokens)
   int32_t finalized;
   int32_t initialized;
 };

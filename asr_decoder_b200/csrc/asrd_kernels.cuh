@@ -335,6 +335,10 @@ k_init(StreamState *const *streams, FrameDesc *desc, GraphView g, DecoderConfigD
     st->n_cur = 0;
     st->best64 = kInfVal;
     st->tot_arcs_expanded = st->tot_arcs_admitted = st->tot_fallback_frames = 0;
+    st->gc_frame = 0;
+    st->peak_tokens = 0;
+    st->tot_pruned_tokens = 0;
+    for (int k = 0; k < 8; ++k) st->prune_cycles[k] = 0;
     for (int k = 0; k < 6; ++k) st->phase_cycles[k] = 0;
     uint32_t slot;
     bool is_new;
@@ -1010,6 +1014,50 @@ k_post(StreamState *const *streams, FrameDesc *desc, GraphView g, DecoderConfigD
 
 namespace asrd {
 
+// ------------------------------------------------------------------ arena compaction (prune_tokens)
+
+constexpr uint32_t kDeadBit = 0x80000000u;  // tok_sc.x of a token an arena prune dropped (until the compaction)
+
+// Drops the tokens marked kDeadBit from frames lo..F of the arena and rewrites frame_off.  A tile
+// is read into registers before anything of it is written: a token only ever moves towards the
+// front.  Whole-CTA device function.
+template <int NT>
+__device__ __forceinline__ void compact_arena(StreamState *st, int lo, int F, uint32_t *s_scan) {
+  const int tid = threadIdx.x;
+  uint32_t run = st->frame_off[lo], old_b = run;
+  __syncthreads();
+  for (int f = lo; f <= F; ++f) {
+    const uint32_t old_e = st->frame_off[f + 1];
+    const uint32_t n = old_e - old_b, new_b = run;
+    __syncthreads();  // everybody has read frame_off[f + 1] (written by the next round)
+    for (uint32_t i0 = 0; i0 < n; i0 += NT) {
+      const uint32_t i = i0 + tid;
+      uint2 sc = make_uint2(kDeadBit, 0u);
+      uint32_t ex = 0;
+      if (i < n) {
+        sc = st->tok_sc[old_b + i];
+        ex = st->tok_extra[old_b + i];
+      }
+      const uint32_t alive = (sc.x & kDeadBit) ? 0u : 1u;
+      uint32_t total;
+      const uint32_t pos = block_exclusive_scan<NT>(alive, s_scan, total);
+      if (alive) {
+        st->tok_sc[run + pos] = sc;
+        st->tok_extra[run + pos] = ex;
+      }
+      run += total;
+    }
+    if (tid == 0) st->frame_off[f] = new_b;
+    old_b = old_e;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    st->frame_off[F + 1] = run;
+    st->tot_pruned_tokens += old_b - run;
+    st->gc_frame = F;
+  }
+}
+
 // ------------------------------------------------------------------ raw lattice
 
 // GetRawLattice (inl.h:868-975) with the pruning of FinalizeDecoding (inl.h:725-847), one CTA
@@ -1039,23 +1087,54 @@ __device__ __forceinline__ bool lat_find(const LatEntry *m, const uint32_t *mp, 
   return false;
 }
 
-template <bool BIGLM>
+//
+// PRUNE (plain decoders, device option prune_tokens): the same sweep as PruneActiveTokens
+// (inl.h:438-480, called every prune_interval frames at inl.h:660-661) — the frontier frame keeps
+// every token with extra cost 0, nothing is emitted, tokens whose extra cost against the current
+// frontier exceeds lattice_beam are marked dead and the arena is compacted afterwards.  An extra
+// cost can only grow as the frontier moves on (later frontiers are reached THROUGH this one, float
+// addition and min are monotone), so a token dropped here would be dropped by the final sweep too,
+// and a link to it never survives: one-best and raw lattice are bit-identical with and without.
+// The two lookup maps are the halves of the stream's (idle) HBM token map; the sweep stops at the
+// first frame below the previous frontier whose extra costs and survivors did not change — the
+// frames below it cannot change either.
+template <bool BIGLM, bool PRUNE>
 __global__ void __launch_bounds__(kStreamThreads, 2)
 k_lattice(StreamState *const *streams, LatticeOut *outs, GraphView g, DecoderConfigDev cfg, int use_final,
-          LmPair lms) {
+          LmPair lms, int prune_interval) {
+  static_assert(!(BIGLM && PRUNE), "arena pruning: plain decoders only");
   constexpr int NT = kStreamThreads;
   __shared__ unsigned long long s_red64[NT / 32];
-  __shared__ uint32_t s_changed;
+  __shared__ uint32_t s_scan[NT / 32 + 1];
+  __shared__ uint32_t s_changed, s_frame_changed;
   StreamState *st = streams[blockIdx.x];
-  LatticeOut *out = &outs[blockIdx.x];
+  LatticeOut *out = PRUNE ? nullptr : &outs[blockIdx.x];
   const int tid = threadIdx.x;
   const int F = st->frame;
-  if (tid == 0) {
+  if (!PRUNE && tid == 0) {
     out->n_toks = 0;
     out->n_links = 0;
   }
   if (F < 0) return;
-  const uint32_t mask = st->hash_mask, shift = st->hash_shift;
+  uint32_t mask = st->hash_mask, shift = st->hash_shift;
+  LatEntry *pmap[2] = {nullptr, nullptr};
+  int lo = 0;  // PRUNE: lowest frame the sweep changed
+  if (PRUNE) {
+    if (st->status < 0 || F - st->gc_frame < prune_interval) return;  // uniform
+    // the lookup maps are the two halves of the stream's token map (idle between frame-loop
+    // launches, left clean by them and by this kernel); a frame must fit one half at load <= 0.75
+    mask >>= 1;
+    shift += 1;
+    pmap[0] = reinterpret_cast<LatEntry *>(st->hash);
+    pmap[1] = pmap[0] + (mask + 1);
+    uint32_t too_big = 0;
+    for (int f = tid; f <= F; f += NT) too_big |= (st->frame_off[f + 1] - st->frame_off[f]) > (mask + 1) / 4 * 3;
+    if (__syncthreads_or((int)too_big)) return;  // (retried at the next call; the arena just stays larger)
+    if (tid == 0) {
+      const uint32_t used = st->frame_off[F + 1];
+      if (used > st->peak_tokens) st->peak_tokens = used;
+    }
+  }
   const float beam = cfg.lattice_beam;
   uint32_t *slots[2] = {st->queue[0], st->queue[1]};  // slot of token i of the frame in map[f & 1]
 
@@ -1066,7 +1145,7 @@ k_lattice(StreamState *const *streams, LatticeOut *outs, GraphView g, DecoderCon
   // the best cost with final is taken over ALL tokens of the frame.
   float final_best = 0.f;
   bool any_final = false;
-  {
+  if (!PRUNE) {
     const uint32_t b0 = st->frame_off[F], n0 = st->frame_off[F + 1] - b0;
     unsigned long long best_all = kInfVal, best_fin = kInfVal, best_wf = kInfVal;
     for (uint32_t i = tid; i < n0; i += NT) {
@@ -1093,6 +1172,7 @@ k_lattice(StreamState *const *streams, LatticeOut *outs, GraphView g, DecoderCon
   }
 
   auto emit_link = [&](uint32_t src_idx, uint32_t dst_idx, const int4 &arc, float graph_cost, float ac) {
+    if (PRUNE) return;
     const uint32_t p = atomicAdd(&out->n_links, 1u);
     if (p < out->link_cap) {
       asrd_lat_link l;
@@ -1107,8 +1187,8 @@ k_lattice(StreamState *const *streams, LatticeOut *outs, GraphView g, DecoderCon
   };
 
   for (int f = F; f >= 0; --f) {
-    LatEntry *mc = out->map[f & 1];        // this frame
-    LatEntry *mn = out->map[(f + 1) & 1];  // frame f + 1 (complete)
+    LatEntry *mc = PRUNE ? pmap[f & 1] : out->map[f & 1];              // this frame
+    LatEntry *mn = PRUNE ? pmap[(f + 1) & 1] : out->map[(f + 1) & 1];  // frame f + 1 (complete)
     uint32_t *pc = BIGLM ? out->map_pair[f & 1] : nullptr;
     const uint32_t *pn = BIGLM ? out->map_pair[(f + 1) & 1] : nullptr;
     uint32_t *sl = slots[f & 1];
@@ -1119,18 +1199,22 @@ k_lattice(StreamState *const *streams, LatticeOut *outs, GraphView g, DecoderCon
     if (f + 2 <= F) {
       const uint32_t n2 = st->frame_off[f + 3] - st->frame_off[f + 2];
       for (uint32_t i = tid; i < n2; i += NT) {
-        LatEntry e;
-        e.key = kEmptyKey; e.cost_bits = 0; e.extra_ord = kOrdInf; e.idx = 0;
+        LatEntry e;  // (PRUNE: the empty pattern of the token map this memory belongs to)
+        e.key = kEmptyKey; e.cost_bits = PRUNE ? 0xFFFFFFFFu : 0u; e.extra_ord = PRUNE ? 0xFFFFFFFFu : kOrdInf;
+        e.idx = PRUNE ? 0xFFFFFFFFu : 0u;
         mc[sl[i]] = e;
       }
     }
+    if (PRUNE && tid == 0) s_frame_changed = f >= st->gc_frame ? 1u : 0u;  // frames the last prune did not settle
     __syncthreads();
     // ---- insert the frame's tokens
     for (uint32_t i = tid; i < n; i += NT) {
       const uint2 sc = st->tok_sc[b0 + i];
       float init = CUDART_INF_F;
       const uint32_t pair = BIGLM ? tlm[i] : 0u;
-      if (f == F) {  // PruneForwardLinksFinal, inl.h:758-775, 815-816
+      if (PRUNE) {
+        if (f == F) init = 0.f;  // the frontier is not pruned (inl.h:455-470 stops above it)
+      } else if (f == F) {  // PruneForwardLinksFinal, inl.h:758-775, 815-816
         float fc = 0.f;
         if (any_final) fc = (int32_t)sc.x == g.final_state ? (BIGLM ? lm_final(lms, pair_map, pair) : 0.f) : CUDART_INF_F;
         init = __uint_as_float(sc.y) + fc - final_best;
@@ -1217,6 +1301,25 @@ k_lattice(StreamState *const *streams, LatticeOut *outs, GraphView g, DecoderCon
       __syncthreads();
       if (!s_changed) break;
     }
+    if constexpr (PRUNE) {
+      // ---- mark the tokens nothing in the lattice beam hangs on (PruneTokensForFrame, inl.h:591);
+      // remember the extra costs: a frame where nothing changed ends the sweep
+      for (uint32_t i = tid; i < n; i += NT) {
+        const uint32_t ex = __ldcg(&mc[sl[i]].extra_ord);
+        if (ex == kOrdInf) {
+          st->tok_sc[b0 + i].x |= kDeadBit;
+          s_frame_changed = 1;
+        } else if (st->tok_extra[b0 + i] != ex) {
+          st->tok_extra[b0 + i] = ex;
+          s_frame_changed = 1;
+        }
+      }
+      __syncthreads();
+      const uint32_t changed = s_frame_changed;
+      lo = f;
+      __syncthreads();  // (thread 0 resets the flag at the top of the next round)
+      if (!changed) break;  // uniform
+    } else {
     // ---- emit the frame's surviving eps links and tokens
     for (uint32_t i = tid; i < n; i += NT) {
       const uint2 sc = st->tok_sc[b0 + i];
@@ -1253,6 +1356,21 @@ k_lattice(StreamState *const *streams, LatticeOut *outs, GraphView g, DecoderCon
       }
     }
     __syncthreads();
+    }
+  }
+  if (PRUNE) {
+    // ---- hand the token map back clean: the two frames still in the lookup maps are lo and lo + 1
+    __syncthreads();
+    for (int f = lo; f <= min(lo + 1, F); ++f) {
+      const uint32_t n = st->frame_off[f + 1] - st->frame_off[f];
+      const uint32_t *sl = slots[f & 1];
+      for (uint32_t i = tid; i < n; i += NT) {
+        LatEntry e;
+        e.key = e.cost_bits = e.extra_ord = e.idx = 0xFFFFFFFFu;
+        pmap[f & 1][sl[i]] = e;
+      }
+    }
+    compact_arena<NT>(st, lo, F, s_scan);
   }
 }
 
@@ -1266,6 +1384,9 @@ __global__ void k_counters(StreamState *const *streams, int n, unsigned long lon
   atomicAdd(&out[1], st->tot_arcs_admitted);
   atomicAdd(&out[2], (unsigned long long)st->frame_off[st->frame + 1]);
   atomicAdd(&out[3], st->tot_fallback_frames);
+  atomicAdd(&out[10], st->tot_pruned_tokens);
+  for (int k = 0; k < 8; ++k) atomicAdd(&out[12 + k], st->prune_cycles[k]);
+  atomicMax(&out[11], (unsigned long long)max(st->peak_tokens, st->frame_off[st->frame + 1]));
   for (int k = 0; k < 6; ++k) atomicAdd(&out[4 + k], st->phase_cycles[k]);
 }
 
@@ -1682,3 +1803,5 @@ k_best_path_rev(StreamState *const *streams, GraphView g, DecoderConfigDev cfg, 
 }
 
 }  // namespace asrd
+
+#include "asrd_prune_kernel.cuh"  // k_prune: the arena prune with the lookup map in shared memory

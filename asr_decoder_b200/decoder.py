@@ -229,9 +229,12 @@ class CudaDecoderBatch:
 
     def __init__(self, graph: CudaFst, config: LatticeFasterDecoderConfig, n: int,
                  max_frames: int = 0, hash_capacity: int = 0, token_capacity: int = 0,
-                 collect_stats: bool = False, old_lm: "CudaLm" = None, new_lm: "CudaLm" = None):
+                 collect_stats: bool = False, old_lm: "CudaLm" = None, new_lm: "CudaLm" = None,
+                 prune_tokens: bool = False):
         """With ``old_lm``/``new_lm`` the decoders are the biglm variant
-        (``OnlineLatticeDecoderMempoolBiglm(&fst, opt, &lm1, &lm2)``)."""
+        (``OnlineLatticeDecoderMempoolBiglm(&fst, opt, &lm1, &lm2)``).  ``prune_tokens``: drop the
+        tokens outside the lattice beam every ``config.prune_interval`` frames (PruneActiveTokens,
+        inl.h:438-480); ``token_capacity`` then bounds the live tokens instead of the utterance."""
         config.Check()
         L = _lib.lib()
         self.graph = graph
@@ -239,7 +242,7 @@ class CudaDecoderBatch:
         self.config = config
         self.n = n
         cfg = config.to_c()
-        opts = asrd_device_options(hash_capacity, token_capacity, max_frames, int(collect_stats))
+        opts = asrd_device_options(hash_capacity, token_capacity, max_frames, int(collect_stats), 0, int(prune_tokens))
         self.handles = (C.c_void_p * n)()
         self._created = 0
         for i in range(n):
@@ -339,6 +342,17 @@ class CudaDecoderBatch:
                 return None
             check(rc, "asrd_get_raw_lattice")
             return toks[:nt.value].copy(), links[:nl.value].copy()
+
+    def arena_frame_tokens(self, i: int = 0, stream: int = 0) -> np.ndarray:
+        """Token records the arena holds per frame right now (after the prunes, if any)."""
+        L = _lib.lib()
+        n = L.asrd_arena_frame_tokens(self.handles[i], None, 0, stream)
+        if n < 0:
+            raise _lib.AsrdError(n, "asrd_arena_frame_tokens")
+        out = np.zeros(max(n, 1), np.uint32)
+        if n:
+            L.asrd_arena_frame_tokens(self.handles[i], out.ctypes.data, n, stream)
+        return out[:n]
 
     def frame_stats(self, i: int = 0, stream: int = 0) -> np.ndarray:
         L = _lib.lib()

@@ -67,6 +67,10 @@ def parse_args():
                          "deployed = beam 10 / lattice-beam 7 (v2-asrbin/conf/decoder.conf)")
     ap.add_argument("--streams", type=int, default=4096, help="streaming: concurrent streams over ALL GPUs")
     ap.add_argument("--chunk-frames", type=int, default=30)
+    ap.add_argument("--prune-tokens", type=int, default=-1,
+                    help="arena pruning every prune_interval frames (PruneActiveTokens): -1 = on for the streaming "
+                         "workload, off for the others")
+    ap.add_argument("--token-capacity", type=int, default=0, help="token records per stream (0 = sized from the workload)")
     a = ap.parse_args()
     if a.regime == "peaked":
         a.sigma = 3.0
@@ -463,9 +467,13 @@ def run_streaming_arm(a):
     cfg = LatticeFasterDecoderConfig(beam=a.beam, max_active=a.max_active, min_active=a.min_active,
                                      lattice_beam=a.lattice_beam)
     graph = CudaFst(fst, device=local)
-    tok_cap = int((T + 2) * 9000)
+    prune = a.prune_tokens != 0
+    # unpruned: every token of the utterance stays (~9 k per frame); pruned: the frames since the last
+    # prune (one chunk, at most ~15.3 k tokens per frame) plus the thinned-out history
+    tok_cap = a.token_capacity or (int((max(CH, cfg.prune_interval) + 12) * 15300) if prune else int((T + 2) * 9000))
     free0 = torch.cuda.mem_get_info()[0]
-    batch = CudaDecoderBatch(graph, cfg, n, max_frames=T + 8, token_capacity=tok_cap, hash_capacity=a.hash_capacity)
+    batch = CudaDecoderBatch(graph, cfg, n, max_frames=T + 8, token_capacity=tok_cap, hash_capacity=a.hash_capacity,
+                             prune_tokens=prune)
     stream = torch.cuda.current_stream().cuda_stream
     chunks = [(f0, min(CH, T - f0)) for f0 in range(0, T, CH)]
 
@@ -521,6 +529,7 @@ def run_streaming_arm(a):
     ae, aa, tk = C.c_int64(0), C.c_int64(0), C.c_int64(0)
     L.asrd_get_counters(batch.handles, n, C.byref(ae), C.byref(aa), C.byref(tk), stream)
     fallback_frames = int(L.asrd_last_fallback_frames())
+    pruned_tokens, peak_tokens = int(L.asrd_last_pruned_tokens()), int(L.asrd_last_peak_tokens())
     # per-chunk latency (device inputs), then end to end from pinned host memory
     lat = []
     step(dev_args, True, lat)
@@ -553,8 +562,15 @@ def run_streaming_arm(a):
                              "audio_ms_per_chunk": 1e3 * CH * FRAME_SECONDS,
                              "note": "one AdvanceDecoding call over all of this GPU's streams, synchronised"},
         "memory_per_stream_bytes": int(slab_used / max(n, 1)),
-        "memory_note": f"token arena sized for {T}-frame utterances ({tok_cap} records of 8 B) + log-likelihood history + "
-                       "HBM-map fallback structures; grows with utterance length (no arena garbage collection yet)",
+        "token_arena": {"prune_tokens": bool(prune), "prune_interval": cfg.prune_interval, "capacity_records": tok_cap,
+                        "bytes_per_record": 12 if prune else 8, "peak_records_any_stream": peak_tokens,
+                        "records_kept_at_the_end_mean": float(tk.value) / max(n, 1),
+                        "records_pruned_mean": pruned_tokens / max(n, 1)},
+        "memory_note": (f"per stream: token arena ({tok_cap} records) + {T + 8} x {P} log-likelihood history "
+                        f"({(T + 8) * ((P + 3) // 4 * 4) * 4} B) + HBM-map fallback structures (~1.8 MB)"
+                        + ("; the arena holds the frames since the last prune plus the lattice-beam survivors of the "
+                           "history (PruneActiveTokens every prune_interval frames)" if prune else
+                           "; the arena keeps every token of the utterance (prune_tokens off)")),
         "e2e": {"value": audio_all / (ms_e2e / 1e3), "unit": "x realtime", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(n * T * P * 4) * world, "d2h_bytes_per_step": d2h * world,
                 "matches_resident_run": bool(same)},

@@ -76,7 +76,14 @@ typedef struct {
   int32_t lm_pair_capacity;/* biglm: distinct (old LM state, new LM state) pairs one utterance may reach
                             * (DiffArpaLm's state table, src/newlm/diff-lm.h:92-103); rounded up to a
                             * power of two, default 65536 */
-  int32_t reserved[3];
+  int32_t prune_tokens;    /* 1: every config.prune_interval frames the tokens that can no longer reach the
+                            * lattice (extra cost > lattice_beam against the current frontier) are dropped and
+                            * the token arena is compacted — PruneActiveTokens, inl.h:438-480, called at
+                            * inl.h:660-661.  Results do not change (one-best and raw lattice are bit-identical
+                            * with and without); token_capacity then bounds the LIVE tokens, not the
+                            * utterance.  0 (default): the arena keeps every token of the utterance.
+                            * Plain (non-biglm) decoders only. */
+  int32_t reserved[2];
 } asrd_device_options;
 
 /* per-frame statistics; index 0 = after InitDecoding (what the reference logs under
@@ -251,6 +258,18 @@ int asrd_get_counters(asrd_decoder *const *decs, int32_t n, int64_t *arcs_expand
 /* frames the on-chip frame loop had to redo through the HBM map (diagnostic; summed over the
  * streams of the last asrd_get_counters call) */
 int64_t asrd_last_fallback_frames(void);
+/* prune_tokens decoders: token records the arena prunes dropped (summed), and the largest arena
+ * fill any one stream reached (token records), over the streams of the last asrd_get_counters call */
+int64_t asrd_last_pruned_tokens(void);
+/* token records the arena holds for every frame 0..NumFramesDecoded() right now (with prune_tokens:
+ * what the prunes left).  Returns the number of frames, or a negative status; fills min(n, cap).
+ * Synchronises `stream`. */
+int32_t asrd_arena_frame_tokens(asrd_decoder *d, uint32_t *out, int32_t cap, void *stream);
+int64_t asrd_last_peak_tokens(void);
+/* SM cycles the arena prune spent per phase {map build, emitting links, eps rounds, survivors to the
+ * front, closing up, -}, frames swept and eps rounds, summed over the streams of the last
+ * asrd_get_counters call (diagnostic) */
+void asrd_last_prune_cycles(int64_t *out8);
 /* SM cycles the on-chip frame loop spent per phase {cutoff, row load, expansion, eps closure,
  * write-out, HBM-map fallback}, summed over the streams of the last asrd_get_counters call */
 void asrd_last_phase_cycles(int64_t *out6);
