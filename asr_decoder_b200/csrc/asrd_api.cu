@@ -1156,10 +1156,19 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
     }
     CU_CHECK(cudaGetLastError());
   }
-  // ---- PruneActiveTokens (inl.h:438-480, every prune_interval frames at inl.h:660-661): behind the
-  // frame loops of each sub-batch, on its worker stream, so it overlaps the other sub-batches.  The
-  // kernel decides per stream (frames since its last prune); the host only skips the launch when no
-  // stream of the batch can be due.
+  if (!single) {  // join the workers back into the caller's stream
+    for (int w = 0; w < n_workers; ++w) {
+      tr_mark(tr_join, ctx->worker[w]);
+      CU_CHECK(cudaEventRecord(ctx->ev_join[w], ctx->worker[w]));
+      CU_CHECK(cudaStreamWaitEvent(s, ctx->ev_join[w], 0));
+    }
+  }
+  // ---- PruneActiveTokens (inl.h:438-480, every prune_interval frames at inl.h:660-661): ONE launch
+  // over every stream of the call, behind the frame loops.  (A prune takes between a fraction of a
+  // millisecond and several, depending on how wide the stream's recent frames are: launched per
+  // sub-batch, the slowest CTA of each launch held its worker stream while the SMs of the finished
+  // ones sat idle.)  The kernel decides per stream (frames since its last prune); the host only
+  // skips the launch when no stream of the batch can be due.
   if (decs[0]->opts.prune_tokens && !biglm) {
     bool due = false;
     for (int i = 0; i < n && !due; ++i)
@@ -1168,32 +1177,20 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
       PrunePlan pplan;
       if ((rc = PlanPrune(&pplan))) return rc;
       const int prune_depth = EnvInt("ASRD_PRUNE_DEPTH", decs[0]->cfg.prune_interval);
-      for (int b = 0; b < n_sub; ++b) {
-        cudaStream_t ws = single ? s : ctx->worker[b % n_workers];
-        const int nb = std::min(sub, n - b * sub);
-        prof.Begin(3, ws);
-        if (pplan.fn) {
-          pplan.fn<<<nb, kStreamThreads, pplan.dyn, ws>>>(d_streams + (size_t)b * sub, gv, cfg, decs[0]->cfg.prune_interval,
-                                                          prune_depth, pplan.n_buckets, pplan.ex_cap);
-          ++g_launches;
-        }
-        // (streams k_prune served are no longer due: their CTAs return at once)
-        k_lattice<false, true><<<nb, kStreamThreads, 0, ws>>>(d_streams + (size_t)b * sub, nullptr, gv, cfg, 0, lms,
-                                                               decs[0]->cfg.prune_interval);
-        prof.End(ws);
+      prof.Begin(3, s);
+      if (pplan.fn) {
+        pplan.fn<<<n, kStreamThreads, pplan.dyn, s>>>(d_streams, gv, cfg, decs[0]->cfg.prune_interval, prune_depth,
+                                                      pplan.n_buckets, pplan.ex_cap);
         ++g_launches;
       }
+      // (streams k_prune served are no longer due: their CTAs return at once)
+      k_lattice<false, true><<<n, kStreamThreads, 0, s>>>(d_streams, nullptr, gv, cfg, 0, lms, decs[0]->cfg.prune_interval);
+      prof.End(s);
+      ++g_launches;
       CU_CHECK(cudaGetLastError());
       for (int i = 0; i < n; ++i)
         if (decs[i]->frames_decoded + nf[i] - decs[i]->last_prune_frame >= decs[0]->cfg.prune_interval)
           decs[i]->last_prune_frame = decs[i]->frames_decoded + nf[i];
-    }
-  }
-  if (!single) {  // join the workers back into the caller's stream
-    for (int w = 0; w < n_workers; ++w) {
-      tr_mark(tr_join, ctx->worker[w]);
-      CU_CHECK(cudaEventRecord(ctx->ev_join[w], ctx->worker[w]));
-      CU_CHECK(cudaStreamWaitEvent(s, ctx->ev_join[w], 0));
     }
   }
   if (!on_device) {

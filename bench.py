@@ -67,9 +67,10 @@ def parse_args():
                          "deployed = beam 10 / lattice-beam 7 (v2-asrbin/conf/decoder.conf)")
     ap.add_argument("--streams", type=int, default=4096, help="streaming: concurrent streams over ALL GPUs")
     ap.add_argument("--chunk-frames", type=int, default=30)
-    ap.add_argument("--prune-tokens", type=int, default=-1,
-                    help="arena pruning every prune_interval frames (PruneActiveTokens): -1 = on for the streaming "
-                         "workload, off for the others")
+    ap.add_argument("--prune-tokens", type=int, default=0,
+                    help="streaming: 1 = arena pruning every --prune-interval frames (PruneActiveTokens, device option "
+                         "prune_tokens): memory per stream bounded by the live tokens, at the price of the prune sweeps")
+    ap.add_argument("--prune-interval", type=int, default=25, help="LatticeFasterDecoderConfig::prune_interval")
     ap.add_argument("--token-capacity", type=int, default=0, help="token records per stream (0 = sized from the workload)")
     a = ap.parse_args()
     if a.regime == "peaked":
@@ -465,12 +466,13 @@ def run_streaming_arm(a):
         hv[i] = synth.make_loglikes(T, P, a.sigma, seed=1000 + i)
     dev = host.to(f"cuda:{local}")
     cfg = LatticeFasterDecoderConfig(beam=a.beam, max_active=a.max_active, min_active=a.min_active,
-                                     lattice_beam=a.lattice_beam)
+                                     lattice_beam=a.lattice_beam, prune_interval=a.prune_interval)
     graph = CudaFst(fst, device=local)
     prune = a.prune_tokens != 0
     # unpruned: every token of the utterance stays (~9 k per frame); pruned: the frames since the last
     # prune (one chunk, at most ~15.3 k tokens per frame) plus the thinned-out history
-    tok_cap = a.token_capacity or (int((max(CH, cfg.prune_interval) + 12) * 15300) if prune else int((T + 2) * 9000))
+    span = -(-cfg.prune_interval // CH) * CH     # frames between two prunes (a prune runs at the end of a call)
+    tok_cap = a.token_capacity or (int((span + 12) * 11000) if prune else int((T + 2) * 9000))
     free0 = torch.cuda.mem_get_info()[0]
     batch = CudaDecoderBatch(graph, cfg, n, max_frames=T + 8, token_capacity=tok_cap, hash_capacity=a.hash_capacity,
                              prune_tokens=prune)

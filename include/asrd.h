@@ -13,9 +13,13 @@
  * Semantics: the reference's per-frame token set depends on its hash-list visiting
  * order.  This library implements the order-independent
  * ("canonical") semantics: an arc is admitted iff its cost is below the frame's FINAL
- * next_cutoff; equal-cost recombination prefers the lowest arc index.  On inputs where
- * the reference agrees with itself under different token orders, one-best words and
- * alignment are bit-identical to the reference's.
+ * next_cutoff; equal-cost recombination prefers the lowest arc index.  Measured against
+ * the compiled reference under seven token orders (tests/golden/census.json, DESIGN.md
+ * section 5.1): bit-identical one-best on the reference's CPU-sized configuration wherever
+ * the reference agrees with itself; on the 1 M-state configuration, where the reference's
+ * own answer depends on its token order for half of the utterances, the canonical answer
+ * equals one of the reference's answers on 92 % of them and is otherwise within 1 % of the
+ * path cost (cheaper or, on 4 % of the utterances, dearer).
  */
 #ifndef ASRD_H_
 #define ASRD_H_
