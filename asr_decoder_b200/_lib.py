@@ -21,12 +21,13 @@ LIB_PATH = os.path.join(HERE, "libasrd_b200.so")
 SYMBOLS = [
     "asrd_strerror", "asrd_abi_version", "asrd_device_count", "asrd_configure_process",
     "asrd_graph_create", "asrd_graph_read", "asrd_graph_read_const", "asrd_graph_destroy", "asrd_graph_info",
-    "asrd_lm_create", "asrd_lm_destroy",
+    "asrd_lm_create", "asrd_lm_destroy", "asrd_lm_convert_arpa",
     "asrd_decoder_create", "asrd_decoder_create_biglm", "asrd_decoder_destroy",
     "asrd_init_decoding", "asrd_advance_decoding", "asrd_finalize_decoding",
     "asrd_num_frames_decoded", "asrd_get_best_path", "asrd_path_to_vector",
     "asrd_frame_stats", "asrd_decoder_status", "asrd_synchronize",
     "asrd_host_alloc", "asrd_host_free", "asrd_launch_count", "asrd_last_fallback_frames", "asrd_last_phase_cycles",
+    "asrd_last_pruned_tokens", "asrd_last_peak_tokens", "asrd_last_prune_cycles", "asrd_arena_frame_tokens",
     "asrd_get_raw_lattice", "asrd_get_counters", "asrd_profile_enable", "asrd_profile_reset", "asrd_profile_get",
 ]
 
@@ -107,6 +108,7 @@ def lib():
     L.asrd_decoder_destroy.argtypes = [vp]
     L.asrd_lm_create.argtypes = [i32, i32, i32, vp, vp, vp, vp, i64, C.c_int, C.POINTER(vp)]
     L.asrd_lm_destroy.argtypes = [vp]
+    L.asrd_lm_convert_arpa.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p]
     L.asrd_decoder_create_biglm.argtypes = [vp, C.POINTER(asrd_config), C.POINTER(asrd_device_options), vp, vp,
                                             C.POINTER(vp)]
     L.asrd_init_decoding.argtypes = [vp, i32, vp]

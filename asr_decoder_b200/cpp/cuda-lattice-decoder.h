@@ -111,6 +111,10 @@ class CudaLm {
   }
   // ArpaLm::Read(const char*) file format; `scale` = the Rescale() factor applied while loading
   bool Read(const char *file, float scale = 1.0f, int device = 0);
+  // ARPA text -> that file format: what the reference's arpa2fsa tool writes (newlm/arpa2fsa-bin.cc)
+  static bool ConvertArpa(const char *arpa_file, const char *wordlist, const char *out_file) {
+    return asrd_lm_convert_arpa(arpa_file, wordlist, out_file) == ASRD_OK;
+  }
   asrd_lm *handle() const { return lm_; }
 
  private:

@@ -193,7 +193,6 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
   const uint32_t n_slots = n_buckets * 4;
   StreamHot *hot = reinterpret_cast<StreamHot *>(s_dyn);
   SmemMap m;
-#ifdef ASRD_LAYOUT2
   // fixed-size parts first (compile-time offsets from the base), the map — whose size depends on
   // the launch — last
   constexpr uint32_t kOffScratch = sizeof(StreamHot);
@@ -206,15 +205,6 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
   m.cost = m.key + n_slots;
   m.n_buckets = n_buckets;
   m.key_sa = smem_addr(m.key);
-#else
-  m.key = reinterpret_cast<uint32_t *>(s_dyn + sizeof(StreamHot));
-  m.cost = m.key + n_slots;
-  m.n_buckets = n_buckets;
-  m.key_sa = smem_addr(m.key);
-  float *s_ll = reinterpret_cast<float *>(m.cost + n_slots);
-  unsigned char *s_scratch = reinterpret_cast<unsigned char *>(s_ll + (SMEM_LL ? ((num_indices + 3) & ~3) : 0));
-  uint16_t *s_eq = reinterpret_cast<uint16_t *>(s_scratch + NW * kWarpScratch);  // [2][kEpsQueueCap]
-#endif
   uint32_t *s_hist = reinterpret_cast<uint32_t *>(s_scratch);                    // [kHistBins]   (write-out phase only)
   uint32_t *s_cand = s_hist + kHistBins;                                         // [kCandCap]
   // every warp may run ahead of the shared claim counter by what it has not reported yet
@@ -404,12 +394,8 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
       // are kept; flags are folded into values (an arc slot without an arc carries cost +inf) or
       // recomputed from the group ids.)
       const uint32_t base_sa = smem_addr(hot);
-#ifdef ASRD_LAYOUT2
       const uint32_t iring_sa = base_sa + kOffScratch + warp * kWarpScratch;
       const uint32_t cost_sa = m.key_sa + n_buckets * 16u;
-#else
-      const uint32_t iring_sa = smem_addr(s_scratch + warp * kWarpScratch);
-#endif
       constexpr uint32_t kHotClaims = 0, kHotOverflow = 4, kHotBest = 8, kHotQn0 = 24, kHotNextGroup = 36;
       static_assert(offsetof(StreamHot, overflow) == kHotOverflow && offsetof(StreamHot, best_ord) == kHotBest &&
                         offsetof(StreamHot, qn) == kHotQn0 && offsetof(StreamHot, claims) == kHotClaims &&
@@ -417,13 +403,8 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
                     "StreamHot layout");
       auto sring_at = [&](uint32_t i) { return iring_sa + kItemRing * 8 + ((i & (kStageCap - 1)) << 3); };
       auto iring_at = [&](uint32_t i) { return iring_sa + ((i & (kItemRing - 1)) << 3); };
-#ifdef ASRD_LAYOUT2
       auto cost_at = [&](uint32_t slot) { return cost_sa + slot * 4u; };
       auto ll_at = [&](uint32_t c) { return base_sa + kOffLl + c * 4u; };
-#else
-      auto cost_at = [&](uint32_t slot) { return base_sa + (uint32_t)sizeof(StreamHot) + n_buckets * 16u + slot * 4u; };
-      auto ll_at = [&](uint32_t c) { return base_sa + (uint32_t)sizeof(StreamHot) + n_buckets * 32u + c * 4u; };
-#endif
       uint32_t ihead = 0, itail = 0, shead = 0, stail = 0;
       uint32_t expanded = 0, unreported = 0;
       uint32_t my_best = 0xFFFFFFFFu;  // lowest cost this warp has reported to hot->best_ord
@@ -534,9 +515,6 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
       // The group being cut into items keeps its place in registers (a group with more items than
       // the ring has room for is appended slice by slice).
       uint32_t g_cost = 0, g_base = 0, g_deg = 0, g_off = 0, g_total = 0, g_r0 = 0;
-#ifdef ASRD_PF_NEXT
-      bool pf_pending = false, pf_seen = false;
-#endif
       auto top_up = [&]() {  // keep two steps' worth of items in the ring while there are tokens left
         for (;;) {
           const uint32_t avail = itail - ihead;
@@ -557,20 +535,12 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
             g_deg = (id1 * 32 + lane < n_cur && __uint_as_float(t1_cost) <= cur_cut) ? t1_er.y - t1_er.x : 0u;
             // the span's arc records are requested a few steps from now: have them in L2 by then
             // (four in ten come from HBM otherwise, and two steps in flight do not cover that;
-            // measured 47.0 vs 47.9 ms per step)
-#ifndef ASRD_PF_NEXT
+            // measured 47.0 vs 47.9 ms per step.  Prefetching for the NEXT group instead, one step
+            // later when its spans have arrived, was measured too: +0.7 ms)
             if (g_deg) {
               prefetch_l2(&g.arcs[g_base]);
               if (((g_base + g_deg - 1) >> 3) != (g_base >> 3)) prefetch_l2(&g.arcs[g_base + g_deg - 1]);  // (eight per 128-byte line)
             }
-#else
-            if (g_deg && !pf_seen) {  // (the warp's first group: nobody prefetched for it)
-              prefetch_l2(&g.arcs[g_base]);
-              if (((g_base + g_deg - 1) >> 3) != (g_base >> 3)) prefetch_l2(&g.arcs[g_base + g_deg - 1]);
-            }
-            pf_seen = true;
-            pf_pending = true;
-#endif
             load_spans(id2);
             id1 = id2;
             id2 = acquire();
@@ -610,17 +580,6 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
         } else {
           process(sA);
         }
-#ifdef ASRD_PF_NEXT
-        if (pf_pending) {
-          // The spans of the NEXT group (requested when the current one was cut) have arrived by
-          // now: its arc records go to L2 a few steps before they are wanted.
-          pf_pending = false;
-          if (id1 * 32 + lane < n_cur && __uint_as_float(t1_cost) <= cur_cut && t1_er.y > t1_er.x) {
-            prefetch_l2(&g.arcs[t1_er.x]);
-            if (((t1_er.y - 1) >> 3) != (t1_er.x >> 3)) prefetch_l2(&g.arcs[t1_er.y - 1]);
-          }
-        }
-#endif
       }
       while (stail != shead) flush(stail - shead < 32u ? stail - shead : 32u);  // what is still staged
       if (unreported && lane == 0 && atoms_add(base_sa + kHotClaims, unreported) + unreported > claim_limit) raise_overflow(1u);

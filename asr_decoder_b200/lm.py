@@ -4,8 +4,9 @@ The reference keeps an ARPA LM as an FSA (``src/newlm/arpa2fsa.h:217-480``): per
 arc array ``{int word; float weight; int to}`` plus ``{float backoff; int backoff_id}``; state 0
 is the unigram / start state and is direct-indexed by word id (``arpa2fsa.h:211-214``,
 ``arpa2fsa.cc:244-262``).  Weights are natural-log probabilities; cost = -weight
-(``src/newlm/compose-arpalm.cc:52-70``).  This module builds such FSAs directly (the ARPA text
-converter is an offline tool and out of scope), writes / reads the reference's binary format
+(``src/newlm/compose-arpalm.cc:52-70``).  This module builds such FSAs directly, converts ARPA
+text files (``convert_arpa``: the library's restatement of ``arpa2fsa``), writes / reads the
+reference's binary format
 (``ArpaLm::Read`` ``arpa2fsa.h:399-439`` + ``Fsa::Read`` ``arpa2fsa.cc:70-176``), and generates
 seeded synthetic unigram / bigram LMs.
 """
@@ -110,3 +111,12 @@ def make_lm(n_words: int, seed: int, order: int = 2, bigram_density: float = 0.1
             states["backoff_prob"][w] = np.float32(-rng.uniform(0.05, 0.8))
             n_bi += len(nxt)
     return LmFsa(bos, eos, unk, [V, n_bi] if order >= 2 else [V], states, np.concatenate(chunks))
+
+
+def convert_arpa(arpa_path: str, wordlist_path: str, out_path: str) -> LmFsa:
+    """ARPA text LM -> LM FSA file (``asrd_lm_convert_arpa``: the reference's ``arpa2fsa`` tool,
+    ``src/newlm/arpa2fsa.cc:311-739``, byte-identical output); returns the FSA read back."""
+    from . import _lib
+    _lib.check(_lib.lib().asrd_lm_convert_arpa(arpa_path.encode(), wordlist_path.encode(), out_path.encode()),
+               "asrd_lm_convert_arpa")
+    return read_lm(out_path)

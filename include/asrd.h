@@ -162,6 +162,13 @@ int asrd_graph_info(const asrd_graph *g, int32_t *total_states, int64_t *total_a
 
 /* ---- LM: replaces ArpaLm / Fsa for the biglm path (src/newlm/arpa2fsa.h:217-480) -------- */
 
+/* ARPA text LM -> the LM FSA file ArpaLm::Read takes (and CudaLm::Read / lm.read_lm here): what the
+ * reference's arpa2fsa tool does with one thread (src/newlm/arpa2fsa.cc:311-739, arpa2fsa-bin.cc),
+ * byte-identical output.  `wordlist`: "word id" per line with <s>, </s> and <unk>.  n-grams must
+ * come grouped by history (as SRILM writes them): the reference asserts it, this returns
+ * ASRD_ERR_IO.  Host code only — no device is touched. */
+int asrd_lm_convert_arpa(const char *arpa_path, const char *wordlist_path, const char *out_path);
+
 /* The arrays ArpaLm::Read loads (arpa2fsa.h:399-439, arpa2fsa.cc:70-176): per state
  * {arc_num, backoff_prob, backoff_id}, arcs grouped by state and sorted by word; state 0 is the
  * unigram state and MUST hold one arc per word id (direct index, arpa2fsa.h:211-214).  As in the
