@@ -219,6 +219,27 @@ class ClockSampler:
         return out
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this rank's host threads to the CPUs next to its GPU (NVML's ideal affinity) BEFORE the
+    pinned staging memory is allocated: first touch then places the pages on the GPU's NUMA node, so
+    eight ranks do not pull their host->device copies across the socket link (round-1 review: 0.963
+    end-to-end efficiency at 8 GPUs).  Best effort: containers may restrict the cpuset."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w in range(words) for b in range(64) if (mask[w] >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
 def run_b200_arm(a):
     import torch
     import torch.distributed as dist
@@ -231,6 +252,7 @@ def run_b200_arm(a):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
     torch.cuda.set_device(local)
+    numa_cpus = bind_to_gpu_numa_node(local) if world > 1 else 0
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = _lib.lib()
@@ -381,6 +403,7 @@ def run_b200_arm(a):
         "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_value,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "regime": a.regime, "parallelism": f"replica-per-gpu x{world}, streams sharded",
+                   "host_affinity": f"rank 0 bound to the {numa_cpus} CPUs next to its GPU" if numa_cpus else "unbound",
                    "l2": "inputs (1.02 GB of log-likelihoods + per-stream maps) exceed the 126 MB L2; no flush needed",
                    "arena_tokens_per_stream": tok_cap},
         "arcs_expanded_per_s": arcs_all / (ms_value / 1e3),
@@ -389,7 +412,12 @@ def run_b200_arm(a):
         "clocks": clocks,
         "hbm_map_fallback_frames": fallback_frames,
         "roofline": {"bound": "hbm", "kernel": "k_stream" if on_chip else "k_expand", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
+                     "frac": achieved / peak,
+                     # the same bytes over the driver-visible step time (sub-batches overlapped, every SM busy; the
+                     # launch-duration leg above runs one ragged 256-CTA launch at a time on 148 SMs)
+                     "achieved_over_step": 16.0 * float(ae.value) / (ms_value / 1e3) / 1e9,
+                     "frac_over_step": 16.0 * float(ae.value) / (ms_value / 1e3) / 1e9 / peak,
+                     "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
                      "algorithmic_bytes_per_arc": 16, "arcs_per_launch": ae.value / max(1, xn.value),
                      "launch_ms": xm.value / max(1, xn.value), "launches_per_step": int(xn.value),
                      "timing": "CUDA events around every launch of one extra step run without sub-batch overlap",
@@ -601,7 +629,7 @@ def run_side_workload(a):
     stream = torch.cuda.current_stream().cuda_stream
     T, P = a.frames, a.pdfs
     if a.workload == "biglm":
-        n = min(a.utts, 64)
+        n = a.utts
         fst = synth.make_graph(a.states, 5.0, P, seed=12345)
         nw = 20000
         lm1, lm2 = LM.make_lm(nw, seed=1, order=2, bigram_density=0.002), LM.make_lm(nw, seed=2, order=2, bigram_density=0.002)

@@ -115,16 +115,22 @@ def test_config5_many_streams_chunked(big):
     assert all(_same(out[3], out[i]) for i in same_in)
 
 
-def test_config5_4096_streams_in_30_frame_chunks(big):
+@pytest.mark.parametrize("prune", [False, True])
+def test_config5_4096_streams_in_30_frame_chunks(big, prune):
     """BASELINE.json configs[4] at its stated size on one GPU: 4096 concurrent streams on the
     1M-state graph, 30-frame chunks.  Every stream equals the single-stream decode of its input
-    (sampled), equal inputs in different slots give equal outputs, no stream reports an error."""
+    (sampled), equal inputs in different slots give equal outputs, no stream reports an error.
+    prune: with PruneActiveTokens every 25 frames (device option prune_tokens) the same answers come
+    out of a token arena an unpruned decoder overflows."""
     fst, g = big
     n, P, T = 4096, 3000, 75
     base = [synth.make_loglikes(T, P, 2.0 + 0.5 * (k % 3), seed=9900 + k) for k in range(32)]
     lls = [base[i % 32] for i in range(n)]
     cfg = _cfg()
-    dec = CudaDecoderBatch(g, cfg, n, max_frames=T + 5, token_capacity=(T + 2) * 9000, hash_capacity=1 << 15)
+    if prune:
+        dec = CudaDecoderBatch(g, cfg, n, max_frames=T + 5, token_capacity=420000, prune_tokens=True)
+    else:
+        dec = CudaDecoderBatch(g, cfg, n, max_frames=T + 5, token_capacity=(T + 2) * 9000, hash_capacity=1 << 15)
     dec.InitDecoding()
     for f0 in range(0, T, 30):
         dec.AdvanceDecoding([ll[f0:f0 + 30] for ll in lls])
@@ -136,6 +142,16 @@ def test_config5_4096_streams_in_30_frame_chunks(big):
     for k in (0, 1, 2, 31):
         ref = one.Decode([base[k]])[0]
         assert all(_same(ref, out[i]) for i in range(k, n, 32)), k
+    if prune:
+        import ctypes as C
+        from asr_decoder_b200 import _lib
+        L = _lib.lib()
+        tk = C.c_int64(0)
+        L.asrd_get_counters(dec.handles, n, None, None, C.byref(tk), None)
+        assert int(L.asrd_last_peak_tokens()) <= 420000
+        assert tk.value / n < 0.45 * T * 9000      # most of every utterance's tokens are gone
+        small = CudaDecoderBatch(g, cfg, 1, max_frames=T + 5, token_capacity=420000)
+        assert not small.Decode([base[0]])[0].ok   # the same arena without pruning overflows
 
 
 def test_config3_large_graph_lattice(oracle_mod):
