@@ -45,6 +45,13 @@ struct DeviceCtx {
   cudaStream_t worker[kMaxWorkers] = {nullptr};
   cudaEvent_t ev_ready = nullptr, ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[kMaxWorkers] = {nullptr};
+  // Host rows are staged through two device buffers OWNED BY THE CONTEXT (not stream-ordered scratch
+  // of the call): the copy stream may then run ahead of the caller's stream, so the host->device
+  // copies of the NEXT AdvanceDecoding call overlap the search of the current one (a service steps
+  // thousands of streams chunk by chunk: with per-call scratch every call exposed its first copy).
+  float *stage[2] = {nullptr, nullptr};
+  size_t stage_floats = 0;
+  bool stage_busy[2] = {false, false};  // ev_done[b] guards the last scatter that read stage[b]
   std::mutex issue_mu;  // one AdvanceDecoding call at a time ISSUES work on a device (the events above are shared)
 };
 std::mutex g_ctx_mu;
@@ -1000,11 +1007,24 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
   struct CopyRun { int first, count; };
   std::vector<CopyRun> runs;
   if (!on_device) {
-    const int nbuf = max_nf > chunk ? 2 : 1;
-    for (int b = 0; b < nbuf; ++b) CU_CHECK(sc.Alloc(&d_stage[b], (size_t)n * chunk * row));
-    if (nbuf == 1) d_stage[1] = d_stage[0];
-    CU_CHECK(cudaEventRecord(ctx->ev_ready, s));  // staging buffers exist from here on
-    CU_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_ready, 0));
+    const size_t need = (size_t)n * chunk * row;
+    if (ctx->stage_floats < need) {  // (grow-only; rare: every user of the old buffers has to be done)
+      CU_CHECK(cudaDeviceSynchronize());
+      for (int b = 0; b < 2; ++b) {
+        cudaFree(ctx->stage[b]);
+        ctx->stage[b] = nullptr;
+        ctx->stage_busy[b] = false;
+      }
+      ctx->stage_floats = 0;
+      for (int b = 0; b < 2; ++b)
+        if (cudaMalloc((void **)&ctx->stage[b], need * sizeof(float)) != cudaSuccess) {
+          cudaGetLastError();
+          return ASRD_ERR_NOMEM;
+        }
+      ctx->stage_floats = need;
+    }
+    d_stage[0] = ctx->stage[0];
+    d_stage[1] = ctx->stage[1];
     for (int i = 0; i < n;) {
       int j = i + 1;
       if (j < n && stride[i] == num_indices && nf[i] > 0) {
@@ -1076,7 +1096,8 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
     float *stage = d_stage[k & 1];
     // ---- rows of this chunk -> device (copy stream) -> per-stream histories (stream s)
     if (!on_device) {
-      if (k >= 2) CU_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[k & 1], 0));
+      // the buffer's previous rows (of this call or of an earlier one) must be in the histories
+      if (ctx->stage_busy[k & 1]) CU_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[k & 1], 0));
       for (const CopyRun &r : runs) {
         const int i = r.first;
         const int32_t c = hp[(size_t)k * n + i].n_frames;
@@ -1101,7 +1122,10 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
       k_begin_advance<<<dim3(8, (unsigned)n), 256, 0, ps>>>(d_streams, d_params + (size_t)k * n, num_indices);
     ++g_launches;
     // the rows now live in the per-stream histories: the staging buffer may be refilled
-    if (!on_device) CU_CHECK(cudaEventRecord(ctx->ev_done[k & 1], ps));
+    if (!on_device) {
+      CU_CHECK(cudaEventRecord(ctx->ev_done[k & 1], ps));
+      ctx->stage_busy[k & 1] = true;
+    }
     cudaEvent_t ev = nullptr;
     CU_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     ev_rows.push_back(ev);
@@ -1192,10 +1216,6 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
         if (decs[i]->frames_decoded + nf[i] - decs[i]->last_prune_frame >= decs[0]->cfg.prune_interval)
           decs[i]->last_prune_frame = decs[i]->frames_decoded + nf[i];
     }
-  }
-  if (!on_device) {
-    // the copy stream must not run ahead into a later call's (recycled) staging memory
-    CU_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[(n_chunks - 1) & 1], 0));
   }
   for (int i = 0; i < n; ++i) decs[i]->frames_decoded += nf[i];
   if (trace) {
