@@ -54,7 +54,7 @@ int main(int argc, char **argv) {
   LatticeFasterDecoderConfig cfg;
   cfg._beam = 13.0f; cfg._max_active = 7000; cfg._min_active = 200; cfg._lattice_beam = 8.0f;
   int chunk = 0;
-  bool pull = false, lattice = false;
+  bool pull = false, lattice = false, prune = false;
   for (int i = 1; i < argc; ++i) {
     std::string a = argv[i];
     size_t eq = a.find('=');
@@ -68,6 +68,8 @@ int main(int argc, char **argv) {
     else if (k == "--chunk") chunk = atoi(v.c_str());
     else if (k == "--pull") pull = true;
     else if (k == "--lattice") lattice = true;
+    else if (k == "--prune") prune = true;  // PruneActiveTokens every prune_interval frames on the device
+    else if (k == "--prune-interval") cfg._prune_interval = atoi(v.c_str());
     else if (k == "--lm1") lm1f = v;
     else if (k == "--lm2") lm2f = v;
     else { fprintf(stderr, "unknown arg %s\n", a.c_str()); return 2; }
@@ -91,7 +93,7 @@ int main(int argc, char **argv) {
     CudaLm lm1, lm2;  // kaldi-hclg-my-decoder-biglm.cc:55-60: lm1.Read, lm2.Read, lm1.Rescale(-1.0)
     const bool biglm = !lm1f.empty();
     if (biglm && (!lm1.Read(lm1f.c_str(), -1.0f) || !lm2.Read(lm2f.c_str()))) { fprintf(stderr, "load lm error.\n"); return 4; }
-    CudaLatticeDecoder plain(&fst, cfg, max_t + 8);
+    CudaLatticeDecoder plain(&fst, cfg, max_t + 8, NULL, prune);
     CudaLatticeDecoder rescoring(&fst, cfg, biglm ? &lm1 : NULL, biglm ? &lm2 : NULL, max_t + 8);
     DecoderItf *decode = biglm ? &rescoring : &plain;  // everything below goes through the reference interface
     for (int i = 0; i < n; ++i) {

@@ -35,19 +35,19 @@ bool CudaLm::Read(const char *file, float scale, int device) {
 }
 
 CudaLatticeDecoder::CudaLatticeDecoder(CudaFst *graph, const LatticeFasterDecoderConfig &config, int max_frames,
-                                       void *cuda_stream)
+                                       void *cuda_stream, bool prune_tokens)
     : d_(NULL), stream_(cuda_stream), finalized_(false) {
-  Create(graph, config, NULL, NULL, max_frames);
+  Create(graph, config, NULL, NULL, max_frames, prune_tokens);
 }
 
 CudaLatticeDecoder::CudaLatticeDecoder(CudaFst *graph, const LatticeFasterDecoderConfig &config, CudaLm *oldlm,
                                        CudaLm *newlm, int max_frames, void *cuda_stream)
     : d_(NULL), stream_(cuda_stream), finalized_(false) {
-  Create(graph, config, oldlm, newlm, max_frames);
+  Create(graph, config, oldlm, newlm, max_frames, false);
 }
 
 void CudaLatticeDecoder::Create(CudaFst *graph, const LatticeFasterDecoderConfig &config, CudaLm *oldlm,
-                                CudaLm *newlm, int max_frames) {
+                                CudaLm *newlm, int max_frames, bool prune_tokens) {
   config.Check();
   asrd_config c;
   c.beam = config._beam;
@@ -61,6 +61,7 @@ void CudaLatticeDecoder::Create(CudaFst *graph, const LatticeFasterDecoderConfig
   asrd_device_options o = asrd_device_options();
   o.max_frames = max_frames;
   o.collect_stats = 1;
+  o.prune_tokens = prune_tokens ? 1 : 0;  // PruneActiveTokens every config._prune_interval frames (inl.h:660-661)
   if (oldlm || newlm)
     Check(asrd_decoder_create_biglm(graph ? graph->handle() : NULL, &c, &o, oldlm ? oldlm->handle() : NULL,
                                     newlm ? newlm->handle() : NULL, &d_), "asrd_decoder_create_biglm");

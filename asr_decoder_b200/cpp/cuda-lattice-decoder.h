@@ -125,8 +125,11 @@ class CudaLm {
 
 class CudaLatticeDecoder : public DecoderItf {
  public:
+  // prune_tokens: run PruneActiveTokens every config._prune_interval frames like the reference does
+  // (inl.h:438-480, :660-661) — the device memory of a long utterance stays bounded by its live
+  // tokens, at the price of the prune sweeps; results do not change.
   CudaLatticeDecoder(CudaFst *graph, const LatticeFasterDecoderConfig &config, int max_frames = 0,
-                     void *cuda_stream = NULL);
+                     void *cuda_stream = NULL, bool prune_tokens = false);
   // biglm: OnlineLatticeDecoderMempoolBaseBiglm(fst, config, oldlm, newlm) (…-biglm.h:21-30)
   CudaLatticeDecoder(CudaFst *graph, const LatticeFasterDecoderConfig &config, CudaLm *oldlm, CudaLm *newlm,
                      int max_frames = 0, void *cuda_stream = NULL);
@@ -152,7 +155,8 @@ class CudaLatticeDecoder : public DecoderItf {
  private:
   void Check(int status, const char *what) const;  // LOG_ERR -> throw std::runtime_error
   void Upload(AmInterface *decodable, int32 first, int32 count);
-  void Create(CudaFst *graph, const LatticeFasterDecoderConfig &config, CudaLm *oldlm, CudaLm *newlm, int max_frames);
+  void Create(CudaFst *graph, const LatticeFasterDecoderConfig &config, CudaLm *oldlm, CudaLm *newlm, int max_frames,
+              bool prune_tokens);
   asrd_decoder *d_;
   void *stream_;
   bool finalized_;

@@ -180,20 +180,19 @@ k_prune(StreamState *const *streams, GraphView g, DecoderConfigDev cfg, int prun
     __syncthreads();
     phase(0);
     ph[6] += 1;
-    // The link src token i (frame f) -> a destination token (cost dcost, extra cost dextra; EMIT: in
-    // frame f + 1 over an emitting arc, else in frame f over an eps arc) over arc record `arc`: if the
-    // search admitted it, its extra cost goes to the source.
-    auto link = [&](uint32_t i, const int4 &arc, bool EMIT, float dcost, float dextra, uint32_t par) {
-      const float cost = __uint_as_float(__ldcg(&st->tok_sc[b0 + i]).y);
+    // The link src token i (frame f, cost `cost`) -> a destination token (cost dcost, extra cost
+    // dextra; EMIT: in frame f + 1 over an emitting arc whose log-likelihood is llv, else in frame f
+    // over an eps arc) with arc weight w: if the search admitted it, its extra cost goes to the source.
+    auto apply = [&](uint32_t i, float cost, float w, float llv, bool EMIT, float dcost, float dextra, uint32_t par) {
       float tot;
       if (EMIT) {
-        if (!(cost <= cur_cut)) return;                                         // inl.h:315
-        tot = (cost + (-__ldg(&ll[arc.x - 1]))) + __int_as_float(arc.z);        // inl.h:326-329
-        if (!(tot < nc_next)) return;                                           // inl.h:330, final cutoff
+        if (!(cost <= cur_cut)) return;   // inl.h:315
+        tot = (cost + (-llv)) + w;        // inl.h:326-329
+        if (!(tot < nc_next)) return;     // inl.h:330, final cutoff
       } else {
-        if (!(cost < nc_f)) return;                                             // inl.h:391
-        tot = cost + __int_as_float(arc.z);                                     // inl.h:413-414
-        if (!(tot < nc_f)) return;                                              // inl.h:415
+        if (!(cost < nc_f)) return;       // inl.h:391
+        tot = cost + w;                   // inl.h:413-414
+        if (!(tot < nc_f)) return;        // inl.h:415
       }
       float le = dextra + (tot - dcost);  // inl.h:524-526
       if (le > beam) return;              // inl.h:532
@@ -207,33 +206,55 @@ k_prune(StreamState *const *streams, GraphView g, DecoderConfigDev cfg, int prun
         if (!(atomicOr(&s_flag[par][i >> 5], bit) & bit)) wl[par][atomicAdd(&s_nwl[par], 1u)] = (uint16_t)i;
       }
     };
+    auto link = [&](uint32_t i, const int4 &arc, bool EMIT, float dcost, float dextra, uint32_t par) {
+      const float cost = __uint_as_float(__ldcg(&st->tok_sc[b0 + i]).y);
+      apply(i, cost, __int_as_float(arc.z), EMIT ? __ldg(&ll[arc.x - 1]) : 0.f, EMIT, dcost, dextra, par);
+    };
     auto relax_in = [&](uint32_t a, bool EMIT, float dcost, float dextra, uint32_t par) {  // incoming arc a
       const uint32_t i = pm_find(m, __ldg(&g.arc_src[a]));
       if (i != kPruneNone) link(i, __ldg(&g.arcs[a]), EMIT, dcost, dextra, par);
     };
-    // every incoming arc (of the class) of one destination token; hubs are left to the whole CTA
-    auto pull = [&](uint32_t state, uint32_t hub_tag, bool EMIT, float dcost, float dextra, uint32_t par) {
+    // The incoming arcs (of the class) of one destination token, this lane's share of them: lane `sub`
+    // of the `nsub` lanes that work on the destination takes every nsub-th arc.  A prune is a chain of
+    // dependent loads (index -> arc -> source token -> log-likelihood), so everything that can be
+    // requested together is: the ranges, then up to four arc ids, then their source states AND arc
+    // records, then (after the shared-memory lookups) the costs and log-likelihoods of the hits.
+    // Hubs are left to the whole CTA.
+    auto pull = [&](uint32_t state, uint32_t hub_tag, bool EMIT, float dcost, float dextra, uint32_t par,
+                    uint32_t sub, uint32_t nsub) {
       const uint32_t mid = __ldg(&g.in_mid[state]);
       const uint32_t ib = EMIT ? mid : __ldg(&g.in_off[state]), ie = EMIT ? __ldg(&g.in_off[state + 1]) : mid;
       if (ie - ib > (uint32_t)kPruneHubDeg) {
+        if (sub != 0) return;
         const uint32_t h = atomicAdd(&s_nhub, 1u);
         if (h < (uint32_t)kPruneHubCap) {
           s_hub[h] = hub_tag;
           return;
         }
+        nsub = 1;  // (no room in the hub list: this lane walks all of it)
       }
-      for (uint32_t r0 = ib; r0 < ie; r0 += 4) {  // four independent index fetches in flight
-        uint32_t a[4], src[4];
+      for (uint32_t r0 = ib + sub; r0 < ie; r0 += 4 * nsub) {
+        uint32_t a[4], src[4], idx[4];
+        int4 arc[4];
+        float cost[4], llv[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) a[u] = __ldg(&g.in_arc[min(r0 + u, ie - 1)]);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) src[u] = __ldg(&g.arc_src[a[u]]);
+        for (int u = 0; u < 4; ++u) a[u] = __ldg(&g.in_arc[min(r0 + u * nsub, ie - 1)]);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          if (r0 + u >= ie) break;
-          const uint32_t i = pm_find(m, src[u]);
-          if (i != kPruneNone) link(i, __ldg(&g.arcs[a[u]]), EMIT, dcost, dextra, par);
+          src[u] = __ldg(&g.arc_src[a[u]]);
+          arc[u] = __ldg(&g.arcs[a[u]]);
         }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) idx[u] = r0 + u * nsub < ie ? pm_find(m, src[u]) : kPruneNone;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const bool hit = idx[u] != kPruneNone;
+          cost[u] = __uint_as_float(__ldcg(&st->tok_sc[b0 + (hit ? idx[u] : 0u)]).y);
+          llv[u] = EMIT ? __ldg(&ll[hit ? arc[u].x - 1 : 0]) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (idx[u] != kPruneNone) apply(idx[u], cost[u], __int_as_float(arc[u].z), llv[u], EMIT, dcost, dextra, par);
       }
     };
     // Hubs (whole CTA; base: arena offset of the destinations' frame).  A hub with fewer incoming
@@ -267,9 +288,15 @@ k_prune(StreamState *const *streams, GraphView g, DecoderConfigDev cfg, int prun
       }
     };
     // ---- emitting links: the survivors of frame f + 1 pull from their sources in frame f
-    for (uint32_t q = tid; q < k1; q += NT) {
-      const uint2 sc = __ldcg(&st->tok_sc[b1 + q]);
-      pull(sc.x, q, true, __uint_as_float(sc.y), ord2f(__ldcg(&st->tok_extra[b1 + q])), 0u);
+    {
+      // (few survivors: several lanes share one destination, so that the chain of a destination with
+      // many incoming arcs is not what every other warp waits for at the barrier)
+      const uint32_t nsub = k1 > NT / 2 ? 1u : k1 > NT / 4 ? 2u : k1 > NT / 8 ? 4u : 8u;
+      for (uint32_t w = tid; w < k1 * nsub; w += NT) {
+        const uint32_t q = w / nsub;
+        const uint2 sc = __ldcg(&st->tok_sc[b1 + q]);
+        pull(sc.x, q, true, __uint_as_float(sc.y), ord2f(__ldcg(&st->tok_extra[b1 + q])), 0u, w % nsub, nsub);
+      }
     }
     __syncthreads();
     if (s_nhub) {
@@ -289,11 +316,13 @@ k_prune(StreamState *const *streams, GraphView g, DecoderConfigDev cfg, int prun
         s_nhub = 0;
       }
       __syncthreads();
-      for (uint32_t q = tid; q < nq; q += NT) {
-        const uint32_t i = __ldcg(&wl[par][q]);
-        atomicAnd(&s_flag[par][i >> 5], ~(1u << (i & 31)));
+      const uint32_t nsub = nq > NT / 2 ? 1u : nq > NT / 4 ? 2u : nq > NT / 8 ? 4u : 8u;
+      for (uint32_t w = tid; w < nq * nsub; w += NT) {
+        const uint32_t i = __ldcg(&wl[par][w / nsub]);
+        if (w % nsub == 0) atomicAnd(&s_flag[par][i >> 5], ~(1u << (i & 31)));
         const uint2 sc = __ldcg(&st->tok_sc[b0 + i]);
-        pull(sc.x, i, false, __uint_as_float(sc.y), ord2f(*reinterpret_cast<volatile uint32_t *>(&s_ex[i])), par ^ 1u);
+        pull(sc.x, i, false, __uint_as_float(sc.y), ord2f(*reinterpret_cast<volatile uint32_t *>(&s_ex[i])), par ^ 1u,
+             w % nsub, nsub);
       }
       __syncthreads();
       if (s_nhub) {

@@ -15,7 +15,8 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 
 
 @pytest.mark.parametrize("name,extra", [("g1", []), ("g2", ["--chunk=30"]), ("g3", ["--pull"]),
-                                        ("g1", ["--pull", "--chunk=7"])])
+                                        ("g1", ["--pull", "--chunk=7"]),
+                                        ("g2", ["--chunk=10", "--prune", "--prune-interval=10"])])
 def test_decoder_itf_drop_in_matches_reference_golden(name, extra):
     assert os.path.exists(BIN), "build first: python -c 'import __graft_entry__ as g; g.build()'"
     meta = json.load(open(os.path.join(GOLD, name + ".json")))
