@@ -355,8 +355,10 @@ int PlanPrune(PrunePlan *plan) {
   CU_CHECK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   const size_t room = (size_t)max_optin > fa.sharedSizeBytes + 64 ? (size_t)max_optin - fa.sharedSizeBytes - 64 : 0;
   // per token: 4 + 1/4 bytes of extra cost and flags, 6 bytes per map slot at a load of at most 7/8
-  const uint32_t ex_cap = (uint32_t)std::min<size_t>(20480, room / 12) & ~255u;
-  if (ex_cap < 4096) return ASRD_OK;
+  uint32_t ex_cap = (uint32_t)std::min<size_t>(20480, room / 12) & ~255u;
+  const int force = EnvInt("ASRD_PRUNE_CAP", 0);  // (test hook: smaller frames already go to the HBM-map sweep)
+  if (force >= 256 && (uint32_t)force < ex_cap) ex_cap = (uint32_t)force & ~255u;
+  if (ex_cap < 4096 && !force) return ASRD_OK;
   const uint32_t n_buckets = (uint32_t)std::min<size_t>((room - prune_token_dyn_bytes(ex_cap)) / 24, 16384) & ~1u;  // 4 slots x (4 + 2) bytes
   plan->fn = k_prune;
   plan->n_buckets = n_buckets;

@@ -479,6 +479,7 @@ def run_streaming_arm(a):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
     torch.cuda.set_device(local)
+    numa_cpus = bind_to_gpu_numa_node(local) if world > 1 else 0
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = _lib.lib()
@@ -585,6 +586,7 @@ def run_streaming_arm(a):
         "config": {"workload": workload_name(a), "regime": a.regime,
                    "parallelism": f"graph replica per GPU, one pool of {a.streams} streams sharded stream_id mod {world}",
                    "streams_per_gpu": n, "chunks_per_utterance": len(chunks),
+                   "host_affinity": f"rank 0 bound to the {numa_cpus} CPUs next to its GPU" if numa_cpus else "unbound",
                    "l2": "inputs and per-stream state exceed the 126 MB L2; no flush needed"},
         "arcs_expanded_per_s": arcs_all / (ms_value / 1e3), "gpu_launches": int(launches), "clocks": clocks,
         "hbm_map_fallback_frames": fallback_frames,

@@ -120,3 +120,68 @@ def test_prune_options_are_validated():
     opts = _lib.asrd_device_options(0, 0, 32, 0, 0, 1)
     h = C.c_void_p()
     assert L.asrd_decoder_create(g.h, C.byref(cfg), C.byref(opts), C.byref(h)) == -1  # ASRD_ERR_BAD_ARG
+
+
+def test_hub_states_and_mixed_kernels(monkeypatch):
+    """Destinations with thousands of incoming arcs (the super-final state: one eps arc from every
+    final state; here also an emitting hub every 7th state points at) are walked by the whole CTA
+    in k_prune; and with a small on-chip budget (ASRD_PRUNE_CAP) the streams whose frames do not fit
+    go to the HBM-map sweep while the others stay on chip — the answers never change."""
+    import numpy as np
+    from asr_decoder_b200.fstio import Fst
+    base = synth.make_graph(6000, 5.0, 120, seed=5, p_final=0.3)
+    arcs = base.arcs.copy()
+    # redirect the first emitting non-loop arc of every 7th state to one hub state
+    off = np.concatenate([[0], np.cumsum(base.num_arcs.astype(np.int64))])
+    hub = 4321
+    for s in range(0, 6000, 7):
+        for a in range(off[s] + int(base.niepsilons[s]) + 1, off[s + 1]):
+            arcs["nextstate"][a] = hub
+            break
+    fst = Fst(start=base.start, final_state=base.final_state, arcs=arcs, num_arcs=base.num_arcs,
+              niepsilons=base.niepsilons, noepsilons=base.noepsilons)
+    T = 120
+    lls = [synth.make_loglikes(T, 120, 1.5 + 0.5 * (i % 2), seed=40 + i) for i in range(4)]
+    cfg = LatticeFasterDecoderConfig(beam=14.0, max_active=4000, min_active=100, lattice_beam=7.0, prune_interval=20)
+    g = CudaFst(fst)
+    plain = CudaDecoderBatch(g, cfg, len(lls), max_frames=T + 8)
+    want = plain.Decode(lls)
+    want_lat = [plain.GetRawLattice(i) for i in range(len(lls))]
+    for cap in (None, "512"):
+        if cap:
+            monkeypatch.setenv("ASRD_PRUNE_CAP", cap)
+        pr = CudaDecoderBatch(g, cfg, len(lls), max_frames=T + 8, prune_tokens=True)
+        pr.InitDecoding()
+        for k in range(0, T, 20):
+            pr.AdvanceDecoding([ll[k:k + 20] for ll in lls])
+        pr.FinalizeDecoding()
+        got = pr.GetBestPath(True)
+        for w, x in zip(want, got):
+            assert x.ok == w.ok and x.words == w.words and x.ali == w.ali and x.tot_bits == w.tot_bits
+        for i in range(len(lls)):
+            _same_lattice(want_lat[i], pr.GetRawLattice(i))
+        assert _counters(pr)["pruned"] > 0
+
+
+def test_long_utterance_in_a_bounded_arena():
+    """1500 frames (45 s of audio) through an arena sized for ~60 frames: what pruning is for."""
+    fst = synth.make_graph(50000, 5.0, 300, seed=8)
+    T = 1500
+    ll = synth.make_loglikes(T, 300, 2.0, seed=77)
+    cfg = LatticeFasterDecoderConfig(beam=13.0, max_active=3000, min_active=100, lattice_beam=6.0, prune_interval=25)
+    g = CudaFst(fst)
+    big = CudaDecoderBatch(g, cfg, 1, max_frames=T + 8, token_capacity=T * 6000)
+    want = big.Decode([ll])[0]
+    total = _counters(big)["tokens"]
+    cap = 60 * 5000
+    assert total > 8 * cap
+    pr = CudaDecoderBatch(g, cfg, 1, max_frames=T + 8, token_capacity=cap, prune_tokens=True)
+    pr.InitDecoding()
+    for c in _chunks(ll, 30):
+        pr.AdvanceDecoding([c])
+    pr.FinalizeDecoding()
+    got = pr.GetBestPath(True)[0]
+    assert got.ok and got.words == want.words and got.ali == want.ali and got.tot_bits == want.tot_bits
+    c = _counters(pr)
+    assert c["peak"] <= cap, c
+    _same_lattice(big.GetRawLattice(0), pr.GetRawLattice(0))
