@@ -106,7 +106,7 @@ struct StreamState {
   uint32_t peak_tokens; // high-water mark of the arena (token records)
   unsigned long long tot_pruned_tokens;    // tokens dropped by the arena prunes of this utterance
   unsigned long long prune_cycles[8];      // k_prune: SM cycles per phase, frames swept, fixed-point rounds
-  unsigned long long phase_cycles[6];      // k_stream: SM cycles per phase (cutoff, row, expand, closure, write-out, fallback)
+  unsigned long long phase_cycles[6];      // k_stream: SM cycles per phase (prologue, expansion, closure, write-out, next cutoff, fallback)
 };
 
 // Per-stream descriptor of the frame step in flight: everything the grid-wide kernels need, in

@@ -705,7 +705,10 @@ def run_side_workload(a):
     Tl = min(T, 100)
     lls = [synth.make_loglikes(Tl, P, 1.2, seed=50 + i) for i in range(n)]
     graph = CudaFst(fst)
-    batch = CudaDecoderBatch(graph, cfg, n, max_frames=Tl + 8)
+    # --prune-tokens 1: PruneActiveTokens every prune_interval frames while decoding, like the reference
+    # (its GetRawLattice then copies an already thin lattice; here k_lattice then sweeps a thin arena)
+    cfg.prune_interval = a.prune_interval
+    batch = CudaDecoderBatch(graph, cfg, n, max_frames=Tl + 8, prune_tokens=bool(a.prune_tokens))
     batch.Decode(lls)
     t_lat, sizes = [], []
     for rep in range(a.warmup + a.steps):
@@ -722,6 +725,7 @@ def run_side_workload(a):
             "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"lattice: synthetic HCLG {states} states avg-degree 3, {P} pdfs; {n} utts x {Tl} frames, "
                                    f"sigma=1.2; beam={a.beam} max-active={a.max_active} lattice-beam={a.lattice_beam}",
+                       "prune_tokens": bool(a.prune_tokens),
                        "what": "asrd_get_raw_lattice per utterance: k_lattice (link regeneration + lattice-beam prune on the "
                                "device) + D2H of the survivors + host sort"},
             "raw_lattice_states_links_mean": [float(np.mean([s[0] for s in sizes])), float(np.mean([s[1] for s in sizes]))],

@@ -281,8 +281,9 @@ int64_t asrd_last_peak_tokens(void);
  * front, closing up, -}, frames swept and eps rounds, summed over the streams of the last
  * asrd_get_counters call (diagnostic) */
 void asrd_last_prune_cycles(int64_t *out8);
-/* SM cycles the on-chip frame loop spent per phase {cutoff, row load, expansion, eps closure,
- * write-out, HBM-map fallback}, summed over the streams of the last asrd_get_counters call */
+/* SM cycles the on-chip frame loop spent per phase {prologue (row + best-token pre-pass, or the
+ * GetCutoff of a launch's first frame), expansion, eps closure, write-out, GetCutoff of the next
+ * frame, HBM-map fallback frames}, summed over the streams of the last asrd_get_counters call */
 void asrd_last_phase_cycles(int64_t *out6);
 
 /* Per-kernel device timing with CUDA events on the launching stream (measurement aid for

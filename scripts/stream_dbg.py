@@ -24,7 +24,7 @@ L.asrd_get_counters(dec.handles, n, C.byref(ae), C.byref(aa), C.byref(tk), None)
 print('arcs', ae.value, aa.value, 'tokens', tk.value, 'fallback frames', L.asrd_last_fallback_frames(), 'of', n * T, flush=True)
 ph = (C.c_int64 * 6)(); L.asrd_last_phase_cycles(ph)
 totc = sum(ph) or 1
-print('phase share: cutoff %.3f row %.3f expand %.3f closure %.3f writeout %.3f fallback %.3f | us/frame/stream %.1f' % (*[x / totc for x in ph], totc / 1.965e3 / (n * T)), flush=True)
+print('phase share: prologue %.3f expansion %.3f closure %.3f write-out %.3f next-cutoff %.3f fallback %.3f | us/frame/stream %.1f' % (*[x / totc for x in ph], totc / 1.965e3 / (n * T)), flush=True)
 print('raw phase', list(ph), flush=True)
 if os.environ.get('NO_ORACLE'): sys.exit(0)
 og = O.OracleGraph(fst)
