@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(HERE, "libasrd_b200.so")
 # every symbol include/asrd.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
     "asrd_strerror", "asrd_abi_version", "asrd_device_count", "asrd_configure_process",
-    "asrd_graph_create", "asrd_graph_read", "asrd_graph_read_const", "asrd_graph_destroy", "asrd_graph_info",
+    "asrd_graph_create", "asrd_graph_read", "asrd_graph_read_const", "asrd_graph_read_clg", "asrd_graph_destroy", "asrd_graph_info",
     "asrd_lm_create", "asrd_lm_destroy", "asrd_lm_convert_arpa",
     "asrd_decoder_create", "asrd_decoder_create_biglm", "asrd_decoder_destroy",
     "asrd_init_decoding", "asrd_advance_decoding", "asrd_finalize_decoding",
@@ -100,6 +100,7 @@ def lib():
     L.asrd_graph_create.argtypes = [vp, vp, vp, i32, i64, i32, i32, C.c_int, C.POINTER(vp)]
     L.asrd_graph_read.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
     L.asrd_graph_read_const.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
+    L.asrd_graph_read_clg.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(vp)]
     L.asrd_graph_destroy.argtypes = [vp]
     L.asrd_graph_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i64), C.POINTER(i32), C.POINTER(i32),
                                   C.POINTER(i64)]

@@ -50,7 +50,7 @@ unsigned Bits(float f) {
 }  // namespace
 
 int main(int argc, char **argv) {
-  std::string graph, loglikes, lm1f, lm2f;
+  std::string graph, hmm, loglikes, lm1f, lm2f;
   LatticeFasterDecoderConfig cfg;
   cfg._beam = 13.0f; cfg._max_active = 7000; cfg._min_active = 200; cfg._lattice_beam = 8.0f;
   int chunk = 0;
@@ -60,6 +60,7 @@ int main(int argc, char **argv) {
     size_t eq = a.find('=');
     std::string k = a.substr(0, eq), v = eq == std::string::npos ? "" : a.substr(eq + 1);
     if (k == "--graph") graph = v;
+    else if (k == "--hmm") hmm = v;  // --graph is then a CLG graph (ClgFst::Init(clgfst, hmmfst))
     else if (k == "--loglikes") loglikes = v;
     else if (k == "--beam") cfg._beam = atof(v.c_str());
     else if (k == "--max-active") cfg._max_active = atoi(v.c_str());
@@ -89,7 +90,7 @@ int main(int argc, char **argv) {
   fclose(fp);
   try {
     CudaFst fst;
-    if (!fst.ReadFst(graph.c_str())) { fprintf(stderr, "load fst error.\n"); return 4; }
+    if (!(hmm.empty() ? fst.ReadFst(graph.c_str()) : fst.ReadClg(graph.c_str(), hmm.c_str()))) { fprintf(stderr, "load fst error.\n"); return 4; }
     CudaLm lm1, lm2;  // kaldi-hclg-my-decoder-biglm.cc:55-60: lm1.Read, lm2.Read, lm1.Rescale(-1.0)
     const bool biglm = !lm1f.empty();
     if (biglm && (!lm1.Read(lm1f.c_str(), -1.0f) || !lm2.Read(lm2f.c_str()))) { fprintf(stderr, "load lm error.\n"); return 4; }

@@ -64,6 +64,14 @@ class CudaFst {
     g_ = NULL;
     return asrd_graph_read_const(file, device, &g_) == ASRD_OK;
   }
+  // ClgFst::Init(clgfst, hmmfst) (my-decoder/clg-fst.h:17-74): CLG graph + HMM set, written out as one
+  // static device graph; decoders built on it follow the reference's CLG decoder
+  // (OnlineClgLatticeDecoderMempool, --graph-type=clg in kaldi-online-nnet3-my-decoder.h:250-283)
+  bool ReadClg(const char *clg_file, const char *hmm_file, int device = 0) {
+    asrd_graph_destroy(g_);
+    g_ = NULL;
+    return asrd_graph_read_clg(clg_file, hmm_file, device, &g_) == ASRD_OK;
+  }
   // from the arrays an already loaded reference `Fst` holds
   bool FromArrays(const asrd_arc *arcs, const uint32_t *num_arcs, const uint32_t *niepsilons, int32_t states,
                   int64_t n_arcs, int32_t start, int32_t final_state, int device = 0) {

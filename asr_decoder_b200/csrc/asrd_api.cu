@@ -308,7 +308,7 @@ struct StreamPlan {
 // wide to leave a useful map are read from global memory instead.
 int PlanStream(const asrd_graph *graph, int num_indices, bool biglm, StreamPlan *plan) {
   plan->fn = nullptr;
-  if (biglm || !EnvInt("ASRD_STREAM_KERNEL", 1)) return ASRD_OK;
+  if (biglm || graph->view.clg || !EnvInt("ASRD_STREAM_KERNEL", 1)) return ASRD_OK;  // (CLG graphs: HBM-map kernels)
   if (graph->total_arcs >= (int64_t)kMaxStreamArcs) return ASRD_OK;  // work items pack (arc index << 2 | count)
   cudaFuncAttributes fa;
   CU_CHECK(cudaFuncGetAttributes(&fa, k_stream<true>));
@@ -413,9 +413,26 @@ int64_t asrd_launch_count(void) { return g_launches.load(); }
 
 // ------------------------------------------------------------------------- graph
 
+// CLG graphs: per arc (in the order of `arcs`, which must then be eps-first already) the two weights
+// of an arc that leaves a CLG state through an HMM, and which arcs those are
+struct ClgExtras {
+  const float *w_clg, *w_hmm;
+  const unsigned char *two_level;
+};
+
+static int GraphCreate(const asrd_arc *arcs, const uint32_t *num_arcs, const uint32_t *niepsilons,
+                       int32_t total_states, int64_t total_arcs, int32_t start, int32_t final_state,
+                       int device, const ClgExtras *clg, asrd_graph **out);
+
 int asrd_graph_create(const asrd_arc *arcs, const uint32_t *num_arcs, const uint32_t *niepsilons,
                       int32_t total_states, int64_t total_arcs, int32_t start, int32_t final_state,
                       int device, asrd_graph **out) {
+  return GraphCreate(arcs, num_arcs, niepsilons, total_states, total_arcs, start, final_state, device, nullptr, out);
+}
+
+static int GraphCreate(const asrd_arc *arcs, const uint32_t *num_arcs, const uint32_t *niepsilons,
+                       int32_t total_states, int64_t total_arcs, int32_t start, int32_t final_state,
+                       int device, const ClgExtras *clg, asrd_graph **out) {
   if (!arcs || !num_arcs || !niepsilons || !out || total_states <= 0 || total_arcs < 0 ||
       total_arcs >= 0xFFFFFFFFll || start < 0 || start >= total_states)
     return ASRD_ERR_BAD_ARG;
@@ -441,6 +458,9 @@ int asrd_graph_create(const asrd_arc *arcs, const uint32_t *num_arcs, const uint
     uint32_t w = ne;
     for (uint32_t k = 0; k < n; ++k)
       if (arcs[off + k].ilabel != 0) parc[off + w++] = arcs[off + k];
+    if (clg)  // (the per-arc extras follow the caller's order: the rows must be eps-first already)
+      for (uint32_t k = 0; k < n; ++k)
+        if ((arcs[off + k].ilabel == 0) != (k < ne)) return ASRD_ERR_BAD_ARG;
     rows[s] = make_uint2((uint32_t)off, (uint32_t)(off + ne));
     if (ne) epsb[(size_t)s >> 5] |= 1u << (s & 31);
     for (uint32_t k = 0; k < n; ++k) {
@@ -540,6 +560,26 @@ int asrd_graph_create(const asrd_arc *arcs, const uint32_t *num_arcs, const uint
     }
   }
   g->device_bytes = (int64_t)(b_arcs + b_rows + b_erows + b_src + b_par + b_eps + b_ioff + b_iarc + b_imid + b_epsr);
+  if (clg) {
+    std::vector<uint32_t> bits((size_t)(A + 31) / 32 + 1, 0u);
+    for (int64_t a = 0; a < A; ++a)
+      if (clg->two_level[a]) bits[(size_t)a >> 5] |= 1u << (a & 31);
+    const Up cups[] = {{&g->d_w_clg, clg->w_clg, sizeof(float) * (size_t)A}, {&g->d_w_hmm, clg->w_hmm, sizeof(float) * (size_t)A},
+                       {&g->d_clg2, bits.data(), sizeof(uint32_t) * bits.size()}};
+    for (const Up &u : cups) {
+      if (cudaMalloc(u.dst, std::max<size_t>(u.bytes, 16)) != cudaSuccess ||
+          cudaMemcpy(*u.dst, u.src, u.bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaGetLastError();
+        asrd_graph_destroy(g);
+        return ASRD_ERR_NOMEM;
+      }
+      g->device_bytes += (int64_t)u.bytes;
+    }
+    g->view.clg = 1;
+    g->view.w_clg = (const float *)g->d_w_clg;
+    g->view.w_hmm = (const float *)g->d_w_hmm;
+    g->view.clg2_bits = (const uint32_t *)g->d_clg2;
+  }
   g->view.arcs = (const int4 *)g->d_arcs;
   g->view.rows = (const uint2 *)g->d_rows;
   g->view.erows = (const uint2 *)g->d_erows;
@@ -582,6 +622,135 @@ int asrd_graph_read(const char *path, int device, asrd_graph **out) {
     ne[s] = info[(size_t)s * 3 + 1];
   }
   return asrd_graph_create(arcs.data(), na.data(), ne.data(), S, A, hdr[0], hdr[1], device, out);
+}
+
+namespace {
+struct FlatFst {  // one newfst graph as Fst::ReadFst(FILE*) reads it (optimize-fst.h:226-280)
+  int32_t start = 0, final_state = 0, n_states = 0;
+  std::vector<uint32_t> num_arcs, off;
+  std::vector<asrd_arc> arcs;
+};
+
+bool ReadFlat(FILE *fp, FlatFst *f) {
+  int32_t hdr[6];
+  if (fread(hdr, 4, 6, fp) != 6 || hdr[2] <= 0 || hdr[3] < 0) return false;
+  f->start = hdr[0];
+  f->final_state = hdr[1];
+  f->n_states = hdr[2];
+  std::vector<uint32_t> info((size_t)hdr[2] * 3);
+  f->arcs.resize((size_t)hdr[3]);
+  if (fread(info.data(), 12, (size_t)hdr[2], fp) != (size_t)hdr[2]) return false;
+  if (hdr[3] && fread(f->arcs.data(), 16, (size_t)hdr[3], fp) != (size_t)hdr[3]) return false;
+  f->num_arcs.resize((size_t)hdr[2]);
+  f->off.assign((size_t)hdr[2] + 1, 0u);
+  for (int32_t s = 0; s < hdr[2]; ++s) {
+    f->num_arcs[s] = info[(size_t)s * 3];
+    f->off[s + 1] = f->off[s] + f->num_arcs[s];
+  }
+  return f->off[hdr[2]] == (uint32_t)hdr[3];
+}
+}  // namespace
+
+// ClgFst::Init(clgfst, hmmfst) (my-decoder/clg-fst.h:17-74): the CLG graph and the HMM set, written
+// out as ONE static graph over the reference's own two-level state ids — CLG state s keeps its id,
+// the copy of state k of the HMM inside CLG arc a is a + offset * (k + 1), offset = total arcs + 1
+// (GetState / MapClgTokenStateId, clg-fst.h:82-165) — with the arcs in the order the reference's
+// CLG decoder enumerates them (online-clg-decoder-mempool-base.h:122-205):
+//   CLG state, eps arc: unchanged;
+//   CLG state, arc a with HMM id h: one arc per EMITTING arc e of state 0 of HMM h — ilabel of e (a
+//     pdf), olabel of the CLG arc, weight e.w + clg.w, destination a + offset if e is the self-loop
+//     of state 0, else a + 2 offset;
+//   HMM copy (a, k): the arcs of state k of the HMM without olabels (RmOlalel): an emitting arc stays
+//     (self-loop) or goes to (a, k + 1) whatever its target, the eps arc (HMM end) goes to the CLG
+//     arc's destination.
+// Decoders on such a graph follow the reference's CLG decoder (see GraphView::clg).
+int asrd_graph_read_clg(const char *clg_path, const char *hmm_path, int device, asrd_graph **out) {
+  if (!clg_path || !hmm_path || !out) return ASRD_ERR_BAD_ARG;
+  FlatFst clg;
+  std::vector<FlatFst> hmms;
+  {
+    FILE *fp = fopen(clg_path, "rb");
+    if (!fp) return ASRD_ERR_IO;
+    const bool ok = ReadFlat(fp, &clg);
+    fclose(fp);
+    if (!ok) return ASRD_ERR_IO;
+    fp = fopen(hmm_path, "rb");
+    if (!fp) return ASRD_ERR_IO;
+    int32_t n = 0;
+    bool okh = fread(&n, 4, 1, fp) == 1 && n >= 0;
+    hmms.resize(okh ? (size_t)n : 0);
+    for (int32_t i = 0; okh && i < n; ++i) okh = ReadFlat(fp, &hmms[i]);
+    fclose(fp);
+    if (!okh) return ASRD_ERR_IO;
+  }
+  const int64_t A = (int64_t)clg.arcs.size();
+  const int64_t offset = A + 1;
+  int32_t kmax = 1;
+  for (const FlatFst &h : hmms) kmax = std::max(kmax, h.n_states);
+  const int64_t n_ids = offset * ((int64_t)kmax + 1);
+  if (clg.n_states > offset || n_ids >= 0x7FFFFFFFll) return ASRD_ERR_BAD_ARG;  // clg-fst.h:25 asserts the same
+  struct Out { asrd_arc arc; float w_clg, w_hmm; unsigned char two; };
+  std::vector<std::vector<Out>> rows((size_t)n_ids);
+  auto push = [&](int64_t id, int32_t il, int32_t ol, float w, int64_t to, float wc, float wh, bool two) {
+    Out o;
+    o.arc.ilabel = il; o.arc.olabel = ol; o.arc.weight = w; o.arc.nextstate = (int32_t)to;
+    o.w_clg = wc; o.w_hmm = wh; o.two = two ? 1 : 0;
+    rows[(size_t)id].push_back(o);
+  };
+  for (int32_t s = 0; s < clg.n_states; ++s) {
+    for (int pass = 0; pass < 2; ++pass)  // eps arcs first (stable), as the device layout wants them
+      for (uint32_t a = clg.off[s]; a < clg.off[s + 1]; ++a) {
+        const asrd_arc &ca = clg.arcs[a];
+        if ((ca.ilabel == 0) != (pass == 0)) continue;
+        if (ca.ilabel == 0) {
+          push(s, 0, ca.olabel, ca.weight, ca.nextstate, 0.f, ca.weight, false);
+          continue;
+        }
+        if (ca.ilabel < 1 || (size_t)ca.ilabel > hmms.size()) return ASRD_ERR_BAD_ARG;
+        const FlatFst &h = hmms[(size_t)ca.ilabel - 1];
+        for (uint32_t e = h.off[0]; e < h.off[1]; ++e) {
+          const asrd_arc &ea = h.arcs[e];
+          if (ea.ilabel == 0) continue;
+          push(s, ea.ilabel, ca.olabel, ea.weight + ca.weight, ea.nextstate == 0 ? a + offset : a + 2 * offset,
+               ca.weight, ea.weight, true);
+        }
+      }
+    for (uint32_t a = clg.off[s]; a < clg.off[s + 1]; ++a) {
+      const asrd_arc &ca = clg.arcs[a];
+      if (ca.ilabel == 0) continue;
+      const FlatFst &h = hmms[(size_t)ca.ilabel - 1];
+      for (int32_t k = 0; k < h.n_states; ++k) {
+        const int64_t sid = a + offset * ((int64_t)k + 1);
+        for (int pass = 0; pass < 2; ++pass)
+          for (uint32_t e = h.off[k]; e < h.off[k + 1]; ++e) {
+            const asrd_arc &ea = h.arcs[e];
+            if ((ea.ilabel == 0) != (pass == 0)) continue;
+            if (ea.ilabel == 0) push(sid, 0, 0, ea.weight, ca.nextstate, 0.f, ea.weight, false);
+            else push(sid, ea.ilabel, 0, ea.weight, ea.nextstate == k ? sid : sid + offset, 0.f, ea.weight, false);
+          }
+      }
+    }
+  }
+  std::vector<uint32_t> na((size_t)n_ids), ne((size_t)n_ids);
+  int64_t total = 0;
+  for (int64_t i = 0; i < n_ids; ++i) {
+    na[i] = (uint32_t)rows[i].size();
+    uint32_t e = 0;
+    for (const Out &o : rows[i]) e += o.arc.ilabel == 0;
+    ne[i] = e;
+    total += na[i];
+  }
+  std::vector<asrd_arc> arcs((size_t)std::max<int64_t>(total, 1));
+  std::vector<float> wc((size_t)std::max<int64_t>(total, 1)), wh((size_t)std::max<int64_t>(total, 1));
+  std::vector<unsigned char> two((size_t)std::max<int64_t>(total, 1));
+  int64_t p = 0;
+  for (int64_t i = 0; i < n_ids; ++i)
+    for (const Out &o : rows[i]) {
+      arcs[p] = o.arc; wc[p] = o.w_clg; wh[p] = o.w_hmm; two[p] = o.two;
+      ++p;
+    }
+  const ClgExtras ex = {wc.data(), wh.data(), two.data()};
+  return GraphCreate(arcs.data(), na.data(), ne.data(), (int32_t)n_ids, total, clg.start, clg.final_state, device, &ex, out);
 }
 
 int asrd_graph_read_const(const char *path, int device, asrd_graph **out) {
@@ -668,6 +837,9 @@ int asrd_graph_destroy(asrd_graph *g) {
   cudaFree(g->d_in_off);
   cudaFree(g->d_in_arc);
   cudaFree(g->d_in_mid);
+  cudaFree(g->d_w_clg);
+  cudaFree(g->d_w_hmm);
+  cudaFree(g->d_clg2);
   delete g;
   return ASRD_OK;
 }
@@ -737,6 +909,10 @@ static int DecoderCreate(asrd_graph *g, const asrd_config *cfg, const asrd_devic
                b_stats = o.collect_stats ? align(((size_t)o.max_frames + 1) * sizeof(asrd_frame_stat)) : 0,
                b_state = align(sizeof(StreamState));
   const size_t b_lm = b_arc, b_pair = align(pair_cap * 8);
+  if (g->view.clg && (lm1 || o.prune_tokens)) {  // CLG graphs: plain decoders, no arena pruning
+    delete d;
+    return ASRD_ERR_BAD_ARG;
+  }
   if (o.prune_tokens && (lm1 || cfg->prune_interval <= 0)) {  // arena pruning: plain decoders, a positive interval
     delete d;
     return ASRD_ERR_BAD_ARG;

@@ -62,6 +62,16 @@ struct GraphView {
   uint32_t n_arcs;
   int32_t start;
   int32_t final_state;
+  // CLG graphs (asrd_graph_read_clg: the graph ClgFst expands on the fly, written out over the
+  // reference's own two-level state ids).  The reference's CLG decoder compares differently
+  // (my-decoder/online-clg-decoder-mempool-base.h): tokens are expanded when cost < cur_cutoff
+  // (:128, strict), an emitting arc is skipped only when its cost is ABOVE the cutoff (:156), and
+  // the best-token pre-pass adds the CLG-arc and the HMM-arc weight of a two-level arc one after
+  // the other (:91) — w_clg / w_hmm hold them for the arcs flagged in clg2_bits.
+  int32_t clg;
+  const float *w_clg;
+  const float *w_hmm;
+  const uint32_t *clg2_bits;
 };
 
 // Per-stream (per decoder object) state, resident in HBM.
@@ -209,7 +219,7 @@ struct asrd_graph {
   int refs;  // the handle + one per decoder built on it (guarded by g_ref_mu); freed when it reaches 0
   int device;
   asrd::GraphView view;
-  void *d_arcs, *d_rows, *d_erows, *d_eps_rows, *d_arc_src, *d_par, *d_eps, *d_in_off, *d_in_arc, *d_in_mid;
+  void *d_arcs, *d_rows, *d_erows, *d_eps_rows, *d_arc_src, *d_par, *d_eps, *d_in_off, *d_in_arc, *d_in_mid, *d_w_clg, *d_w_hmm, *d_clg2;
   int32_t max_ilabel;
   int64_t device_bytes;
   int64_t total_arcs;

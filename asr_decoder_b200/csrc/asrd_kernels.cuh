@@ -455,7 +455,7 @@ __device__ __forceinline__ void expand_frame(FrameDesc *d, const GraphView &g, c
       const uint2 sc = hints ? ldg_u2(&toks[i], pol_stream) : __ldcg(&toks[i]);
       cost_bits = sc.y;
       if (BIGLM) my_pair = __ldcg(&toks_lm[i]);
-      if (__uint_as_float(sc.y) <= cur_cut) {  // inclusive, inl.h:315
+      if (g.clg ? __uint_as_float(sc.y) < cur_cut : __uint_as_float(sc.y) <= cur_cut) {  // inclusive, inl.h:315 (CLG: strict)
         const uint2 er = hints ? ldg_u2(&g.erows[sc.x], pol_graph) : __ldg(&g.erows[sc.x]);
         base = er.x;
         deg = er.y - er.x;
@@ -505,7 +505,7 @@ __device__ __forceinline__ void expand_frame(FrameDesc *d, const GraphView &g, c
           if (BIGLM && arc[u].y != 0)  // …-biglm.h:377-379: graph_cost = arc weight + LM-difference score
             graph_cost = __int_as_float(arc[u].z) + lm_step(lms, pair_map, tpair[u], arc[u].y, n1, n2);
           tot[u] = (tcost[u] + ac) + graph_cost;  // inl.h:326-329
-          adm[u] = tot[u] < nc && !(flags & 2);   // (flags & 2): measurement aid, no map traffic
+          adm[u] = (g.clg ? tot[u] <= nc : tot[u] < nc) && !(flags & 2);  // inl.h:330 (CLG: skipped only when above); (flags & 2): measurement aid, no map traffic
           if (adm[u]) {
             const float cand = tot[u] + abeam;  // inl.h:332-333
             if (cand < nc) cand_bits = min(cand_bits, f2ord(cand));
@@ -769,6 +769,9 @@ __device__ __forceinline__ void cutoff_prologue(StreamState *st, FrameDesc *d, c
         int32_t n1, n2;
         const float lm_score = lm_step(lms, st->pair_map, bpair, arc.y, n1, n2);
         tot = lm_score + bc + __int_as_float(arc.z) - __ldg(&ll[arc.x - 1]);
+      } else if (g.clg && ((__ldg(&g.clg2_bits[a >> 5]) >> (a & 31)) & 1u)) {
+        // …-clg-decoder-mempool-base.h:91: tok + clgarc.w + arc.w - loglike
+        tot = bc + __ldg(&g.w_clg[a]) + __ldg(&g.w_hmm[a]) - __ldg(&ll[arc.x - 1]);
       } else {
         tot = bc + __int_as_float(arc.z) - __ldg(&ll[arc.x - 1]);
       }
@@ -948,7 +951,7 @@ __device__ __forceinline__ void post_epilogue(StreamState *st, FrameDesc *d, con
             pair = e.y;
             rep = e.z;
             cost = ord2f(e.w);
-            alive = cost < nc;
+            alive = g.clg ? cost <= nc : cost < nc;  // (CLG: an arc AT the cutoff was admitted)
           }
           const unsigned am = __ballot_sync(kFull, alive);
           if (am == 0) continue;
@@ -1240,7 +1243,7 @@ k_lattice(StreamState *const *streams, LatticeOut *outs, GraphView g, DecoderCon
       for (uint32_t i = tid; i < n; i += NT) {
         const uint2 sc = st->tok_sc[b0 + i];
         const float cost = __uint_as_float(sc.y);
-        if (!(cost <= cur_cut)) continue;  // inl.h:315
+        if (g.clg ? !(cost < cur_cut) : !(cost <= cur_cut)) continue;  // inl.h:315 (CLG: strict)
         const uint2 er = __ldg(&g.erows[sc.x]);
         const uint32_t pair = BIGLM ? tlm[i] : 0u;
         float best = CUDART_INF_F;
@@ -1251,7 +1254,7 @@ k_lattice(StreamState *const *streams, LatticeOut *outs, GraphView g, DecoderCon
           int32_t n1 = 0, n2 = 0;
           if (BIGLM && arc.y != 0) graph_cost = __int_as_float(arc.z) + lm_step(lms, pair_map, pair, arc.y, n1, n2);
           const float tot = (cost + ac) + graph_cost;  // inl.h:326-329
-          if (!(tot < nc_next)) continue;              // inl.h:330, final cutoff
+          if (g.clg ? !(tot <= nc_next) : !(tot < nc_next)) continue;  // inl.h:330, final cutoff (CLG: inclusive)
           const uint32_t dpair = (BIGLM && arc.y != 0) ? pair_intern(pair_map, pair_mask, n1, n2, &st->status) : pair;
           uint32_t ds;
           if (!lat_find<BIGLM>(mn, pn, mask, shift, (uint32_t)arc.w & kStateMask, dpair, ds)) continue;
@@ -1737,7 +1740,7 @@ k_best_path_rev(StreamState *const *streams, GraphView g, DecoderConfigDev cfg, 
                 if (!(pc < nc_f)) continue;              // inl.h:391
                 tot = pc + __int_as_float(arc.z);        // inl.h:413-414
               } else {
-                if (!(pc <= cur_prev)) continue;         // inl.h:315
+                if (g.clg ? !(pc < cur_prev) : !(pc <= cur_prev)) continue;  // inl.h:315 (CLG: strict)
                 tot = (pc + (-ll_prev[arc.x - 1])) + __int_as_float(arc.z);  // inl.h:326-329
               }
               if (__float_as_uint(tot) != sc.y) continue;
@@ -1774,7 +1777,7 @@ k_best_path_rev(StreamState *const *streams, GraphView g, DecoderConfigDev cfg, 
         bool admitted;
         if (emitting) {
           tot2 = (pc + (-ll_prev[arc2.x - 1])) + __int_as_float(arc2.z);  // inl.h:326-329
-          admitted = tot2 < nc_f;                                          // inl.h:330
+          admitted = g.clg ? tot2 <= nc_f : tot2 < nc_f;                   // inl.h:330 (CLG: inclusive)
         } else {
           tot2 = pc + __int_as_float(arc2.z);                              // inl.h:413-414
           admitted = pc < nc_f && tot2 < nc_f;                             // inl.h:391,415

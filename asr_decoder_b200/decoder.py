@@ -134,6 +134,22 @@ class CudaFst:
         self.max_ilabel = int(read_const_fst(path).arcs["ilabel"].max())
         return self
 
+    @classmethod
+    def ReadClg(cls, clg_path: str, hmm_path: str, device: int = 0) -> "CudaFst":
+        """``ClgFst::Init(clgfst, hmmfst)`` (my-decoder/clg-fst.h:17-74): the CLG graph and its HMM
+        set as one static device graph (``asrd_graph_read_clg``); decoders on it follow the
+        reference's CLG decoder (``OnlineClgLatticeDecoderMempool``)."""
+        from .fstio import read_hmm_set
+        self = cls.__new__(cls)
+        self.host = None
+        self.device = device
+        h = C.c_void_p()
+        check(_lib.lib().asrd_graph_read_clg(clg_path.encode(), hmm_path.encode(), device, C.byref(h)),
+              "asrd_graph_read_clg")
+        self.h = h
+        self.max_ilabel = max([int(x.arcs["ilabel"].max()) for x in read_hmm_set(hmm_path) if x.total_arcs] + [0])
+        return self
+
     def device_bytes(self) -> int:
         b = C.c_int64(0)
         check(_lib.lib().asrd_graph_info(self.h, None, None, None, None, C.byref(b)), "asrd_graph_info")

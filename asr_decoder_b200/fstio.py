@@ -214,3 +214,107 @@ def write_const_fst(path: str, fst: Fst) -> None:
         f.write(np.array([fst.start, S, arcs.shape[0]], "<i8").tobytes())
         f.write(states.tobytes())
         f.write(np.ascontiguousarray(arcs).tobytes())
+
+
+# --------------------------------------------------------------------------- CLG + HMM set
+
+def write_hmm_set(path: str, hmms) -> None:
+    """``ClgFst::ReadHmm`` format (reference ``src/my-decoder/clg-fst.h:49-74``): int32 count, then
+    that many newfst graphs back to back; HMM ``i`` of the file gets id ``i + 1`` (a CLG arc's
+    ilabel)."""
+    with open(path, "wb") as f:
+        f.write(np.array([len(hmms)], dtype="<i4").tobytes())
+        for h in hmms:
+            hdr = np.array([h.start, h.final_state, h.total_states, h.total_arcs,
+                            int(h.niepsilons.sum()), int(h.noepsilons.sum())], dtype="<i4")
+            info = np.empty(h.total_states, dtype=STATEINFO_DTYPE)
+            info["num_arcs"], info["niepsilons"], info["noepsilons"] = h.num_arcs, h.niepsilons, h.noepsilons
+            f.write(hdr.tobytes())
+            f.write(info.tobytes())
+            f.write(np.ascontiguousarray(h.arcs).tobytes())
+
+
+def read_hmm_set(path: str):
+    out = []
+    with open(path, "rb") as f:
+        n = int(np.frombuffer(f.read(4), "<i4")[0])
+        for _ in range(n):
+            hdr = np.frombuffer(f.read(24), "<i4")
+            ns, na = int(hdr[2]), int(hdr[3])
+            info = np.frombuffer(f.read(12 * ns), STATEINFO_DTYPE)
+            arcs = np.frombuffer(f.read(16 * na), ARC_DTYPE)
+            out.append(Fst(int(hdr[0]), int(hdr[1]), arcs.copy(), info["num_arcs"].copy(),
+                           info["niepsilons"].copy(), info["noepsilons"].copy()))
+    return out
+
+
+@dataclasses.dataclass
+class ClgGraph:
+    """What ``materialize_clg`` returns: the static graph over the reference's own two-level state
+    ids plus, per arc, the two weights the best-token pre-pass adds one after the other."""
+    fst: Fst
+    w_clg: np.ndarray   # f32 [A]: weight of the CLG arc an arc out of a CLG state entered through (else 0)
+    w_hmm: np.ndarray   # f32 [A]: weight of the HMM arc itself
+    from_clg: np.ndarray  # bool [A]: arc leaves a CLG state through an HMM (two-weight arc)
+    offset: int
+
+
+def materialize_clg(clg: Fst, hmms) -> ClgGraph:
+    """The graph ``ClgFst`` (reference ``src/my-decoder/clg-fst.h:9-189``) expands on the fly, written
+    out as one static graph over the SAME state ids: CLG state ``s`` keeps its id; the copy of HMM
+    state ``k`` inside CLG arc ``a`` is ``a + offset * (k + 1)`` with ``offset = total_arcs + 1``
+    (``GetState`` / ``MapClgTokenStateId``, clg-fst.h:82-165).  Arcs, in the order the reference's
+    decoder enumerates them (``online-clg-decoder-mempool-base.h:122-205``):
+
+    * CLG state, eps arc (ilabel 0): unchanged;
+    * CLG state, arc ``a`` with HMM id ``h``: one arc per EMITTING arc ``e`` of state 0 of HMM ``h``
+      — ilabel ``e.ilabel`` (a pdf), olabel of the CLG arc, weight ``e.w + clg.w`` (that order),
+      destination ``a + offset`` when ``e`` is the self-loop of state 0, else ``a + 2 offset``;
+    * HMM copy ``(a, k)``: the arcs of state ``k`` of the HMM, olabels removed (``RmOlalel``):
+      emitting arcs stay (self-loop) or go to ``(a, k + 1)`` whatever their target, the eps arc
+      (HMM end) goes to the CLG arc's destination.
+    Pure Python loops: test infrastructure for small graphs (the library has its own, asrd_graph_read_clg)."""
+    off = clg.row_off
+    A = clg.total_arcs
+    offset = A + 1
+    kmax = max([h.total_states for h in hmms] + [1])
+    n_ids = offset * (kmax + 1)
+    rows = [[] for _ in range(n_ids)]   # (ilabel, olabel, weight, next, w_clg, w_hmm, from_clg)
+    f32 = np.float32
+    for s in range(clg.total_states):
+        for a in range(off[s], off[s + 1]):
+            arc = clg.arcs[a]
+            il = int(arc["ilabel"])
+            if il == 0:
+                rows[s].append((0, int(arc["olabel"]), f32(arc["weight"]), int(arc["nextstate"]), f32(0), f32(arc["weight"]), False))
+                continue
+            h = hmms[il - 1]
+            hoff = h.row_off
+            for e in range(hoff[0], hoff[1]):
+                ea = h.arcs[e]
+                if int(ea["ilabel"]) == 0:
+                    continue
+                dst = a + offset if int(ea["nextstate"]) == 0 else a + 2 * offset
+                rows[s].append((int(ea["ilabel"]), int(arc["olabel"]), f32(f32(ea["weight"]) + f32(arc["weight"])), dst,
+                                f32(arc["weight"]), f32(ea["weight"]), True))
+            for k in range(h.total_states):
+                sid = a + offset * (k + 1)
+                for e in range(hoff[k], hoff[k + 1]):
+                    ea = h.arcs[e]
+                    if int(ea["ilabel"]) == 0:
+                        rows[sid].append((0, 0, f32(ea["weight"]), int(arc["nextstate"]), f32(0), f32(ea["weight"]), False))
+                    else:
+                        dst = sid if int(ea["nextstate"]) == k else sid + offset
+                        rows[sid].append((int(ea["ilabel"]), 0, f32(ea["weight"]), dst, f32(0), f32(ea["weight"]), False))
+    num = np.array([len(r) for r in rows], dtype=np.uint32)
+    nie = np.array([sum(1 for x in r if x[0] == 0) for r in rows], dtype=np.uint32)
+    noe = np.array([sum(1 for x in r if x[1] == 0) for r in rows], dtype=np.uint32)
+    flat = [x for r in rows for x in r]
+    arcs = np.zeros(len(flat), dtype=ARC_DTYPE)
+    arcs["ilabel"] = [x[0] for x in flat]
+    arcs["olabel"] = [x[1] for x in flat]
+    arcs["weight"] = [x[2] for x in flat]
+    arcs["nextstate"] = [x[3] for x in flat]
+    g = Fst(clg.start, clg.final_state, arcs, num, nie, noe)
+    return ClgGraph(g, np.array([x[4] for x in flat], np.float32), np.array([x[5] for x in flat], np.float32),
+                    np.array([x[6] for x in flat], bool), offset)

@@ -89,3 +89,40 @@ def make_tiny_graph(seed: int = 1) -> Fst:
     weights; used by the pure-Python unit checks."""
     return make_graph(40, avg_deg=4.0, n_pdfs=8, seed=seed, n_words=30, p_final=0.1,
                       p_eps=0.35, eps_span=6, near_span=5)
+
+
+def make_clg(n_states: int, n_hmms: int = 40, n_pdfs: int = 60, avg_deg: float = 4.0, seed: int = 7,
+             n_words: int = 500, p_final: float = 0.05, p_eps: float = 0.2):
+    """A seeded CLG graph + HMM set in the shape ``ClgFst`` expects (reference
+    ``src/my-decoder/clg-fst.h:9-189``): the CLG graph is a ``make_graph`` graph whose non-eps
+    ilabels are HMM ids (1..n_hmms); every HMM is a three-state left-to-right model — state k has a
+    self-loop and a forward arc (ilabel = pdf id + 1), the last emitting state ends in an eps arc
+    (``_input == 0`` = "hmm end state", clg-fst.h:124-131) — plus an unused final state.
+    Returns ``(clg, hmms)``."""
+    from .fstio import ARC_DTYPE, Fst
+    clg = make_graph(n_states, avg_deg, n_hmms, seed=seed, n_words=n_words, p_final=p_final, p_eps=p_eps,
+                     eps_span=max(4, n_states // 10), near_span=max(4, min(64, n_states // 4)))
+    rng = np.random.default_rng(seed + 1000)
+    hmms = []
+    for _ in range(n_hmms):
+        rows = []
+        for k in range(3):
+            row = []
+            if k == 2:
+                row.append((0, 0, np.float32(rng.uniform(0.0, 0.7)), 3))          # HMM end (eps first)
+            row.append((int(rng.integers(1, n_pdfs + 1)), 0, np.float32(rng.uniform(0.1, 1.2)), k))   # self-loop
+            if k < 2:
+                row.append((int(rng.integers(1, n_pdfs + 1)), 0, np.float32(rng.uniform(0.1, 1.2)), k + 1))
+            rows.append(row)
+        rows.append([])
+        flat = [x for r in rows for x in r]
+        arcs = np.zeros(len(flat), dtype=ARC_DTYPE)
+        arcs["ilabel"] = [x[0] for x in flat]
+        arcs["olabel"] = [x[1] for x in flat]
+        arcs["weight"] = [x[2] for x in flat]
+        arcs["nextstate"] = [x[3] for x in flat]
+        num = np.array([len(r) for r in rows], np.uint32)
+        nie = np.array([sum(1 for x in r if x[0] == 0) for r in rows], np.uint32)
+        noe = np.array([len(r) for r in rows], np.uint32)
+        hmms.append(Fst(0, 3, arcs, num, nie, noe))
+    return clg, hmms

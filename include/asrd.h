@@ -151,6 +151,15 @@ int asrd_graph_create(const asrd_arc *arcs, const uint32_t *num_arcs, const uint
                       int device, asrd_graph **out);
 /* Fst::ReadFst(const char*), optimize-fst.h:208-219: same file format */
 int asrd_graph_read(const char *path, int device, asrd_graph **out);
+/* ClgFst::Init(clgfst, hmmfst), src/my-decoder/clg-fst.h:17-74: the CLG graph (newfst file whose
+ * non-eps ilabels are HMM ids) and the HMM set (int32 count + that many newfst graphs), which the
+ * reference expands on the fly, are written out as one static device graph over the reference's own
+ * two-level state ids (clg-fst.h:82-165).  Decoders created on such a graph follow the reference's
+ * CLG decoder, OnlineClgLatticeDecoderMempool (src/my-decoder/online-clg-decoder-mempool-base.h:
+ * strict token cutoff :128, an arc is skipped only when above the cutoff :156, two-weight best-token
+ * pre-pass :91); they run the HBM-map kernels, plain (non-biglm) and without prune_tokens. */
+int asrd_graph_read_clg(const char *clg_path, const char *hmm_path, int device, asrd_graph **out);
+
 /* ConstFst<StdArc,int>::Read + Fst(const ConstFst&) (src/newfst/const-fst.h:189-221,
  * src/newfst/optimize-fst.h:82-134): load an OpenFst "const" FST (e.g. a Kaldi HCLG.fst converted
  * with fstconvert --fst_type=const); final weights become leading 0:0 arcs to an appended

@@ -63,6 +63,7 @@ def lib():
         L.orc_graph_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64,
                                        C.c_int32, C.c_int32]
         L.orc_graph_destroy.argtypes = [C.c_void_p]
+        L.orc_graph_set_clg.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_decoder_create.restype = C.c_void_p
         L.orc_decoder_create.argtypes = [C.c_void_p, C.POINTER(OrcConfig), C.c_int]
         L.orc_decoder_destroy.argtypes = [C.c_void_p]
@@ -134,14 +135,23 @@ def path_to_vector(ilabel, olabel, graph, acoustic):
 
 
 class OracleGraph:
-    def __init__(self, fst):
+    def __init__(self, fst, clg=None):
+        """``clg``: an ``fstio.ClgGraph`` — ``fst`` is then its materialised graph and the decoders
+        follow the reference's CLG decoder (see ``orc_graph_set_clg``)."""
         L = lib()
+        if clg is not None:
+            fst = clg.fst
         self._arcs = np.ascontiguousarray(fst.arcs)
         self._off = np.ascontiguousarray(fst.row_off, dtype=np.int64)
         self._ieps = np.ascontiguousarray(fst.niepsilons, dtype=np.uint32)
         self.h = L.orc_graph_create(self._arcs.ctypes.data, self._off.ctypes.data,
                                     self._ieps.ctypes.data, fst.total_states, fst.total_arcs,
                                     fst.start, fst.final_state)
+        if clg is not None:
+            wc = np.ascontiguousarray(clg.w_clg, np.float32)
+            wh = np.ascontiguousarray(clg.w_hmm, np.float32)
+            fc = np.ascontiguousarray(clg.from_clg, np.uint8)
+            L.orc_graph_set_clg(self.h, wc.ctypes.data, wh.ctypes.data, fc.ctypes.data)
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -268,13 +278,22 @@ def have_ref() -> bool:
     return os.path.exists(REF_BIN) and os.access(REF_BIN, os.X_OK)
 
 
+def have_ref_clg() -> bool:
+    return os.path.exists(REF_BIN + "_clg")
+
+
 def run_ref(graph_path: str, loglikes_path: str, stats: bool = True, threads: int = 1, lattice=False,
-            chunk: int = 0, repeat: int = 1, **cfg):
-    """Run the compiled reference decoder; returns (list of per-utterance dicts, summary dict)."""
-    if not have_ref():
+            chunk: int = 0, repeat: int = 1, hmm_path: str = None, **cfg):
+    """Run the compiled reference decoder; returns (list of per-utterance dicts, summary dict).
+    ``hmm_path``: the CLG decoder (``ref_decode_clg``: ClgFst + OnlineClgLatticeDecoderMempool) on the
+    CLG graph ``graph_path`` and that HMM set."""
+    if not have_ref() or (hmm_path and not have_ref_clg()):
         raise RuntimeError("oracle/_ref/ref_decode is not built (run `make -C oracle ref` where "
                            "/root/reference exists)")
-    cmd = [REF_BIN, f"--graph={graph_path}", f"--loglikes={loglikes_path}", f"--threads={threads}"]
+    cmd = [REF_BIN + ("_clg" if hmm_path else ""), f"--graph={graph_path}", f"--loglikes={loglikes_path}",
+           f"--threads={threads}"]
+    if hmm_path:
+        cmd.append(f"--hmm={hmm_path}")
     if stats:
         cmd.append("--stats")
     if lattice:

@@ -27,6 +27,14 @@
 #include <atomic>
 
 #include "src/my-decoder/online-decoder-mempool-base.h"
+#ifdef ASRD_REF_CLG
+// -DASRD_REF_CLG (oracle/_ref/ref_decode_clg): the same driver around the reference's CLG decoder —
+// ClgFst (src/my-decoder/clg-fst.h:9-189: CLG graph + HMM set, expanded on the fly) under
+// OnlineClgLatticeDecoderMempool (src/my-decoder/online-clg-decoder-mempool-base.h:10-281), as
+// OnlineClgLatticeFastDecoder selects it (src/kaldi-nnet3/kaldi-online-nnet3-my-decoder.h:250-283).
+#include "src/my-decoder/clg-fst.h"
+#include "src/my-decoder/online-clg-decoder-mempool-base.h"
+#endif
 #include "src/newfst/lattice-functions.h"
 #include "src/newfst/lattice-determinize-api.h"
 
@@ -70,10 +78,18 @@ struct FrameStat {
   long long ll_calls = 0;  // LogLikelihood calls during this frame
 };
 
-class Probe : public OnlineLatticeDecoderMempool {
+#ifdef ASRD_REF_CLG
+typedef OnlineClgLatticeDecoderMempool RefDecoder;
+typedef ClgFst RefGraph;
+#else
+typedef OnlineLatticeDecoderMempool RefDecoder;
+typedef Fst RefGraph;
+#endif
+
+class Probe : public RefDecoder {
  public:
-  typedef OnlineLatticeDecoderMempool Base;
-  Probe(Fst *fst, const LatticeFasterDecoderConfig &c) : Base(fst, c), collect(false) {}
+  typedef RefDecoder Base;
+  Probe(RefGraph *fst, const LatticeFasterDecoderConfig &c) : Base(fst, c), collect(false) {}
   bool collect;
   int dump_frame = -1;           // debug: print the hash-list key order of this frame to stderr
   std::vector<FrameStat> stats;  // index 0 = after InitDecoding
@@ -136,7 +152,7 @@ struct Result {
 };
 
 struct Options {
-  std::string graph, loglikes, out;
+  std::string graph, hmm, loglikes, out;
   LatticeFasterDecoderConfig cfg;
   int threads = 1;
   bool stats = false;
@@ -270,6 +286,7 @@ int main(int argc, char **argv) {
     };
     const char *v;
     if ((v = val("--graph"))) o.graph = v;
+    else if ((v = val("--hmm"))) o.hmm = v;
     else if ((v = val("--loglikes"))) o.loglikes = v;
     else if ((v = val("--out"))) o.out = v;
     else if ((v = val("--beam"))) o.cfg._beam = atof(v);
@@ -293,8 +310,13 @@ int main(int argc, char **argv) {
                     "[--repeat=N] [--stats] [--lattice]\n");
     return 2;
   }
+#ifdef ASRD_REF_CLG
+  ClgFst fst;
+  if (!fst.Init(o.graph, o.hmm)) return 3;
+#else
   Fst fst;
   if (!fst.ReadFst(o.graph.c_str())) return 3;
+#endif
   std::vector<Utt> utts;
   if (!ReadLoglikes(o.loglikes, &utts)) { fprintf(stderr, "cannot read %s\n", o.loglikes.c_str()); return 3; }
   int n = (int)utts.size();

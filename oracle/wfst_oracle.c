@@ -35,6 +35,12 @@ struct OrcGraph {
   int32_t n_states;
   int64_t n_arcs;
   int32_t start, final_state;
+  /* CLG graphs (orc_graph_set_clg): the reference's CLG decoder compares differently and adds the two
+   * weights of an arc that leaves a CLG state through an HMM one after the other in its best-token
+   * pre-pass (src/my-decoder/online-clg-decoder-mempool-base.h:66-112, :128, :150) */
+  int clg;
+  float *w_clg, *w_hmm;
+  unsigned char *from_clg;
 };
 
 OrcGraph *orc_graph_create(const OrcArc *arcs, const int64_t *row_off, const uint32_t *n_ieps,
@@ -53,8 +59,21 @@ OrcGraph *orc_graph_create(const OrcArc *arcs, const int64_t *row_off, const uin
   return g;
 }
 
+void orc_graph_set_clg(OrcGraph *g, const float *w_clg, const float *w_hmm, const unsigned char *from_clg) {
+  g->clg = 1;
+  g->w_clg = (float *)malloc(sizeof(float) * (size_t)(g->n_arcs ? g->n_arcs : 1));
+  g->w_hmm = (float *)malloc(sizeof(float) * (size_t)(g->n_arcs ? g->n_arcs : 1));
+  g->from_clg = (unsigned char *)malloc((size_t)(g->n_arcs ? g->n_arcs : 1));
+  memcpy(g->w_clg, w_clg, sizeof(float) * (size_t)g->n_arcs);
+  memcpy(g->w_hmm, w_hmm, sizeof(float) * (size_t)g->n_arcs);
+  memcpy(g->from_clg, from_clg, (size_t)g->n_arcs);
+}
+
 void orc_graph_destroy(OrcGraph *g) {
   if (!g) return;
+  free(g->w_clg);
+  free(g->w_hmm);
+  free(g->from_clg);
   free(g->arcs);
   free(g->row_off);
   free(g->n_ieps);
@@ -704,6 +723,9 @@ static float process_emitting(OrcDecoder *d, const float *ll) {
           float lm_score;
           next_lm_state(d, blm, arc->olabel, &lm_score);
           tot_score = lm_score + tok->tot + arc->weight - ll[arc->ilabel - 1];
+        } else if (g->clg && g->from_clg[a]) {
+          /* online-clg-decoder-mempool-base.h:91: tok + clgarc.w + arc.w - loglike */
+          tot_score = tok->tot + g->w_clg[a] + g->w_hmm[a] - ll[arc->ilabel - 1];
         } else {
           tot_score = tok->tot + arc->weight - ll[arc->ilabel - 1];
         }
@@ -717,7 +739,7 @@ static float process_emitting(OrcDecoder *d, const float *ll) {
      * (inl.h:330-333).  Canonical mode computes it first and admits against it. */
     for (Elem *e = final_toks; e; e = e->tail) {
       Tok *tok = e->val;
-      if (tok->tot <= cur_cutoff) {
+      if (g->clg ? tok->tot < cur_cutoff : tok->tot <= cur_cutoff) { /* clg: …-clg-…-base.h:128 */
         const int32_t st = KEY_STATE(e->key), lms = KEY_LM(e->key);
         for (int64_t a = g->row_off[st]; a < g->row_off[st + 1]; ++a) {
           const OrcArc *arc = &g->arcs[a];
@@ -740,7 +762,7 @@ static float process_emitting(OrcDecoder *d, const float *ll) {
   for (Elem *e = final_toks, *e_tail; e; e = e_tail) {
     const int32_t state = KEY_STATE(e->key), lm_state = KEY_LM(e->key);
     Tok *tok = e->val;
-    if (tok->tot <= cur_cutoff) {
+    if (g->clg ? tok->tot < cur_cutoff : tok->tot <= cur_cutoff) {
       for (int64_t a = g->row_off[state]; a < g->row_off[state + 1]; ++a) {
         const OrcArc *arc = &g->arcs[a];
         if (arc->ilabel != 0) {
@@ -756,7 +778,7 @@ static float process_emitting(OrcDecoder *d, const float *ll) {
           float ac_cost = -ll[arc->ilabel - 1];
           float cur_cost = tok->tot;
           float tot_cost = cur_cost + ac_cost + graph_cost;
-          if (tot_cost >= next_cutoff) continue;
+          if (g->clg ? tot_cost > next_cutoff : tot_cost >= next_cutoff) continue; /* clg: …-clg-…-base.h:156 */
           else if (tot_cost + adaptive_beam < next_cutoff)
             next_cutoff = tot_cost + adaptive_beam; /* never fires in canonical mode */
           Elem *nt = find_or_add_token(d, MAKE_KEY(arc->nextstate, next_lm), frame + 1, tot_cost, tok,

@@ -83,6 +83,12 @@ typedef struct OrcDecoder OrcDecoder;
 
 OrcGraph *orc_graph_create(const OrcArc *arcs, const int64_t *row_off, const uint32_t *n_ieps,
                            int32_t n_states, int64_t n_arcs, int32_t start, int32_t final_state);
+/* Marks the graph as a materialised CLG graph (asr_decoder_b200.fstio.materialize_clg): the decoders
+ * built on it follow the reference's CLG decoder (src/my-decoder/online-clg-decoder-mempool-base.h):
+ * tokens are expanded when cost < cur_cutoff (strict, :128), an arc is skipped only when its cost is
+ * ABOVE the cutoff (:156), and the best-token pre-pass adds the CLG-arc and HMM-arc weights of a
+ * two-level arc one after the other (:91). */
+void orc_graph_set_clg(OrcGraph *g, const float *w_clg, const float *w_hmm, const unsigned char *from_clg);
 void orc_graph_destroy(OrcGraph *g);
 
 OrcDecoder *orc_decoder_create(const OrcGraph *g, const OrcConfig *cfg, int mode);

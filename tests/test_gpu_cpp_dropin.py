@@ -96,3 +96,28 @@ def test_biglm_raw_lattice_through_decoder_itf(oracle_mod):
         nt, nl = d.counts()
         assert (r["raw_states"], r["raw_arcs"]) == (nt, nl)
         assert r["raw_finals"] >= 1
+
+
+def test_clg_graph_through_decoder_itf(oracle_mod, tmp_path):
+    """--graph-type=clg: the C++ class on a CLG graph + HMM set (CudaFst::ReadClg = ClgFst::Init)
+    against the compiled reference CLG decoder (ref_decode_clg) — same one-best, in 30-frame chunks."""
+    from asr_decoder_b200 import fstio, synth
+    O = oracle_mod
+    if not O.have_ref_clg():
+        pytest.skip("oracle/_ref/ref_decode_clg not built on this box")
+    clg, hmms = synth.make_clg(400, n_hmms=25, n_pdfs=50, seed=4)
+    lls = [synth.make_loglikes(70, 50, 2.0, seed=10 + i) for i in range(3)]
+    gp, hp, lp = (str(tmp_path / x) for x in ("clg.fst", "hmm.bin", "ll.bin"))
+    fstio.write_fst(gp, clg)
+    fstio.write_hmm_set(hp, hmms)
+    fstio.write_loglikes(lp, lls)
+    cfg = dict(beam=12.0, max_active=300, min_active=20, lattice_beam=6.0)
+    ref = O.run_ref(gp, lp, stats=False, hmm_path=hp, threads=len(lls), **cfg)[0]
+    cmd = [BIN, f"--graph={gp}", f"--hmm={hp}", f"--loglikes={lp}", f"--beam={cfg['beam']}",
+           f"--max-active={cfg['max_active']}", f"--min-active={cfg['min_active']}",
+           f"--lattice-beam={cfg['lattice_beam']}", "--chunk=30"]
+    out = subprocess.run(cmd, check=True, stdout=subprocess.PIPE).stdout.decode()
+    res = [json.loads(l) for l in out.splitlines() if l.startswith("{")]
+    assert len(res) == len(ref)
+    for r, w in zip(res, ref):
+        assert (r["ok"], r["words"], r["ali"], r["tot_bits"]) == (w["ok"], w["words"], w["ali"], w["tot_bits"])
