@@ -308,10 +308,10 @@ struct StreamPlan {
 // wide to leave a useful map are read from global memory instead.
 int PlanStream(const asrd_graph *graph, int num_indices, bool biglm, StreamPlan *plan) {
   plan->fn = nullptr;
-  if (biglm || graph->view.clg || !EnvInt("ASRD_STREAM_KERNEL", 1)) return ASRD_OK;  // (CLG graphs: HBM-map kernels)
+  if (biglm || !EnvInt("ASRD_STREAM_KERNEL", 1)) return ASRD_OK;
   if (graph->total_arcs >= (int64_t)kMaxStreamArcs) return ASRD_OK;  // work items pack (arc index << 2 | count)
   cudaFuncAttributes fa;
-  CU_CHECK(cudaFuncGetAttributes(&fa, k_stream<true>));
+  CU_CHECK(cudaFuncGetAttributes(&fa, k_stream<true, false>));
   int dev = 0, max_optin = 0;
   CU_CHECK(cudaGetDevice(&dev));
   CU_CHECK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -324,7 +324,8 @@ int PlanStream(const asrd_graph *graph, int num_indices, bool biglm, StreamPlan 
   uint32_t n_buckets = (uint32_t)std::min<size_t>((room - fixed) / 32, 16352) & ~31u;
   const int force = EnvInt("ASRD_STREAM_BUCKETS", 0);  // (measurement aid)
   if (force >= 64 && (uint32_t)force < n_buckets) n_buckets = (uint32_t)force & ~31u;
-  plan->fn = smem_ll ? k_stream<true> : k_stream<false>;
+  const bool clg = graph->view.clg != 0;
+  plan->fn = smem_ll ? (clg ? k_stream<true, true> : k_stream<true, false>) : (clg ? k_stream<false, true> : k_stream<false, false>);
   plan->n_buckets = n_buckets;
   plan->dyn = fixed + (size_t)n_buckets * 32;
   CU_CHECK(cudaFuncSetAttribute(plan->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->dyn));

@@ -176,7 +176,12 @@ __device__ __forceinline__ uint32_t smem_find_or_claim(const SmemMap &m, uint32_
   return kNoSlot;
 }
 
-template <bool SMEM_LL>
+// CLG: the graph is a materialised CLG graph (asrd_graph_read_clg) and the loop follows the
+// reference's CLG decoder (my-decoder/online-clg-decoder-mempool-base.h): tokens are expanded when
+// cost < cur_cutoff (strict, :128), an emitting arc is skipped only when ABOVE the cutoff (:156) —
+// so tokens AT the final cutoff survive —, and the best-token pre-pass adds the two weights of an
+// arc that leaves a CLG state through an HMM one after the other (:91).
+template <bool SMEM_LL, bool CLG>
 __global__ void __launch_bounds__(kStreamThreads, 1)
 k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, DecoderConfigDev cfg,
          int num_indices, uint32_t n_buckets) {
@@ -298,7 +303,10 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
         if (SMEM_LL) __syncthreads();
         for (uint32_t a = er.x + tid; a < er.y; a += NT) {
           const int4 arc = __ldg(&g.arcs[a]);
-          const float tot = bc + __int_as_float(arc.z) - (SMEM_LL ? s_ll[arc.x - 1] : __ldg(&llr[arc.x - 1]));
+          const float llv = SMEM_LL ? s_ll[arc.x - 1] : __ldg(&llr[arc.x - 1]);
+          float tot = bc + __int_as_float(arc.z) - llv;
+          if (CLG && ((__ldg(&g.clg2_bits[a >> 5]) >> (a & 31)) & 1u))
+            tot = bc + __ldg(&g.w_clg[a]) + __ldg(&g.w_hmm[a]) - llv;  // …-clg-…-base.h:91
           mn = min(mn, f2ord(tot + h_abeam));
         }
       } else if (SMEM_LL) {
@@ -470,7 +478,7 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
         // (the olabel is not needed, but its register must stay reserved until the record has arrived:
         // ptxas reuses the register of an unused component as a temporary right after the request, and
         // that write waits for the whole fetch.  No olabel is 0x80000001; the test costs one predicate input.)
-        const bool adm = tot < nc && sp.arc.y != (int)0x80000001;  // inl.h:330 (tot is +inf where there is no arc)
+        const bool adm = (CLG ? tot <= nc : tot < nc) && sp.arc.y != (int)0x80000001;  // inl.h:330 (tot is +inf where there is no arc)
         const float cand = adm ? tot + abeam : CUDART_INF_F;       // inl.h:332-333
         if (__any_sync(kFull, cand < nc)) {
           const uint32_t wmin = __reduce_min_sync(kFull, f2ord(cand));
@@ -492,8 +500,8 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
         const float acB = -(SMEM_LL ? lds_f32_ro(ll_at((uint32_t)liB)) : __ldg(&ll[liB]));
         const float totA = (a.tcost + acA) + __int_as_float(a.arc.z);  // inl.h:326-329
         const float totB = (b.tcost + acB) + __int_as_float(b.arc.z);
-        const bool admA = totA < nc && a.arc.y != (int)0x80000001;  // inl.h:330
-        const bool admB = totB < nc && b.arc.y != (int)0x80000001;
+        const bool admA = (CLG ? totA <= nc : totA < nc) && a.arc.y != (int)0x80000001;  // inl.h:330
+        const bool admB = (CLG ? totB <= nc : totB < nc) && b.arc.y != (int)0x80000001;
         const float cand = fminf(admA ? totA + abeam : CUDART_INF_F, admB ? totB + abeam : CUDART_INF_F);  // inl.h:332-333
         if (__any_sync(kFull, cand < nc)) {
           const uint32_t wmin = __reduce_min_sync(kFull, f2ord(cand));
@@ -559,7 +567,10 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
             g_cost = t1_cost;
             g_base = t1_er.x;
             // inclusive token test, inl.h:315
-            g_deg = (id1 * 32 + lane < n_cur && __uint_as_float(t1_cost) <= cur_cut) ? t1_er.y - t1_er.x : 0u;
+            g_deg = (id1 * 32 + lane < n_cur &&
+                     (CLG ? __uint_as_float(t1_cost) < cur_cut : __uint_as_float(t1_cost) <= cur_cut))
+                        ? t1_er.y - t1_er.x
+                        : 0u;
             // the span's arc records are requested a few steps from now: have them in L2 by then
             // (four in ten come from HBM otherwise, and two steps in flight do not cover that;
             // measured 47.0 vs 47.9 ms per step.  Prefetching for the NEXT group instead, one step
@@ -722,7 +733,9 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
           co = *reinterpret_cast<const uint4 *>(&m.cost[s0]);
           *reinterpret_cast<uint4 *>(&m.key[s0]) = make_uint4(kEmptyKey, kEmptyKey, kEmptyKey, kEmptyKey);
           *reinterpret_cast<uint4 *>(&m.cost[s0]) = make_uint4(kFreeCost, kFreeCost, kFreeCost, kFreeCost);
-          cnt = (co.x < nc_ord) + (co.y < nc_ord) + (co.z < nc_ord) + (co.w < nc_ord);
+          // (CLG: an arc AT the cutoff was admitted; a free slot's cost is 0xFFFFFFFF, above +inf's key)
+          const uint32_t lim = CLG ? nc_ord + (nc_ord != 0xFFFFFFFFu ? 1u : 0u) : nc_ord;
+          cnt = (co.x < lim) + (co.y < lim) + (co.z < lim) + (co.w < lim);
         }
         const uint32_t incl = warp_incl_scan(cnt, lane);
         const uint32_t total = __shfl_sync(kFull, incl, 31);
@@ -731,7 +744,7 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
         if (lane == 0) pos = atomicAdd(&hot->alive, total);
         pos = __shfl_sync(kFull, pos, 0) + incl - cnt;
         auto put = [&](uint32_t k, uint32_t c) {
-          if (c < nc_ord) {
+          if (CLG ? (c <= nc_ord && c != kFreeCost) : c < nc_ord) {
             if (pos < cap) out_sc[pos] = make_uint2(k & kStateMask, __float_as_uint(ord2f(c)));
             ++pos;
             if (c == best_ord) atomicMin(&hot->best_state, k & kStateMask);
@@ -831,6 +844,10 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
         }
         (void)keep;
         n_abeam = n_cur_cut - bc + cfg.beam_delta;
+        if (CLG && !(n_cur_cut < beam_cut)) {  // (a survivor AT next_cutoff == best + beam: inl.h:196 does not fire)
+          n_cur_cut = beam_cut;
+          n_abeam = cfg.beam;
+        }
       } else {
         // ---- general case (the adaptive beam of this frame was wider than the beam, or the arena
         // is full): GetCutoff over the survivors in the arena

@@ -71,9 +71,14 @@ def test_oracle_on_the_materialised_graph_equals_the_compiled_clg_reference(orac
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("env", [{}, {"ASRD_STREAM_KERNEL": "0"}, {"ASRD_DEBUG_FLAGS": str(300 << 8)}])
 @pytest.mark.parametrize("seed,sigma,max_active", CASES)
-def test_cuda_clg_equals_canonical_oracle_and_reference(oracle_mod, tmp_path, seed, sigma, max_active):
+def test_cuda_clg_equals_canonical_oracle_and_reference(oracle_mod, tmp_path, monkeypatch, seed, sigma, max_active, env):
+    """Three routes: the on-chip frame loop (k_stream<.., CLG>), the HBM-map kernels, and the on-chip
+    loop with a 300-state budget (frames overflow into the HBM map mid-frame)."""
     from asr_decoder_b200.decoder import CudaDecoderBatch, CudaFst, LatticeFasterDecoderConfig
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
     O = oracle_mod
     clg, hmms, lls, gp, hp, lp = make_case(tmp_path, seed, sigma)
     mg = fstio.materialize_clg(clg, hmms)
