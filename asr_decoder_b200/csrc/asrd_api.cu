@@ -910,7 +910,7 @@ static int DecoderCreate(asrd_graph *g, const asrd_config *cfg, const asrd_devic
                b_stats = o.collect_stats ? align(((size_t)o.max_frames + 1) * sizeof(asrd_frame_stat)) : 0,
                b_state = align(sizeof(StreamState));
   const size_t b_lm = b_arc, b_pair = align(pair_cap * 8);
-  if (g->view.clg && (lm1 || o.prune_tokens)) {  // CLG graphs: plain decoders, no arena pruning
+  if (g->view.clg && lm1) {  // CLG graphs: plain decoders
     delete d;
     return ASRD_ERR_BAD_ARG;
   }

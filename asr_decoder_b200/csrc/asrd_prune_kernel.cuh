@@ -186,9 +186,9 @@ k_prune(StreamState *const *streams, GraphView g, DecoderConfigDev cfg, int prun
     auto apply = [&](uint32_t i, float cost, float w, float llv, bool EMIT, float dcost, float dextra, uint32_t par) {
       float tot;
       if (EMIT) {
-        if (!(cost <= cur_cut)) return;   // inl.h:315
-        tot = (cost + (-llv)) + w;        // inl.h:326-329
-        if (!(tot < nc_next)) return;     // inl.h:330, final cutoff
+        if (g.clg ? !(cost < cur_cut) : !(cost <= cur_cut)) return;     // inl.h:315 (CLG decoder: strict)
+        tot = (cost + (-llv)) + w;                                      // inl.h:326-329
+        if (g.clg ? !(tot <= nc_next) : !(tot < nc_next)) return;       // inl.h:330, final cutoff (CLG: inclusive)
       } else {
         if (!(cost < nc_f)) return;       // inl.h:391
         tot = cost + w;                   // inl.h:413-414

@@ -57,7 +57,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--hash-capacity", type=int, default=0, help="0 = library default (8 x max-active)")
-    ap.add_argument("--workload", default="offline", choices=["offline", "streaming", "biglm", "lattice"],
+    ap.add_argument("--workload", default="offline", choices=["offline", "streaming", "biglm", "lattice", "clg"],
                     help="offline = BASELINE.json configs[1] (the headline); streaming = configs[4]: "
                          "--streams concurrent streams fed in --chunk-frames chunks, sharded over the GPUs; "
                          "biglm = configs[3] (on-the-fly LM-difference composition); lattice = configs[2]'s shape "
@@ -620,7 +620,7 @@ def run_side_workload(a):
     import torch
     from concurrent.futures import ThreadPoolExecutor
     from asr_decoder_b200 import _lib, fstio, synth, lm as LM
-    from asr_decoder_b200.decoder import CudaDecoderBatch, CudaFst, CudaLm, LatticeFasterDecoderConfig
+    from asr_decoder_b200.decoder import CudaDecoderBatch, CudaFst, CudaLm, LatticeFasterDecoderConfig, LatticeToVector
     from oracle import oracle as O
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
@@ -697,6 +697,71 @@ def run_side_workload(a):
                 shutil.rmtree(tmp, ignore_errors=True)
         print(json.dumps(line), flush=True)
         return
+    if a.workload == "clg":
+        # ---- CLG graph + HMM set: what --graph-type=clg decodes.  The CLG graph is
+        # a third of config 2's size because every CLG arc expands into a three-state HMM on the device.
+        n = a.utts
+        n_clg = max(1000, a.states // 3)
+        clg, hmms = synth.make_clg(n_clg, n_hmms=2000, n_pdfs=P, avg_deg=5.0, seed=4321, n_words=20000, p_final=0.02, p_eps=0.15)
+        tmp = tempfile.mkdtemp(prefix="asrd_clg_")
+        try:
+            gp, hp = os.path.join(tmp, "clg.fst"), os.path.join(tmp, "hmm.bin")
+            fstio.write_fst(gp, clg)
+            fstio.write_hmm_set(hp, hmms)
+            graph = CudaFst.ReadClg(gp, hp)
+            lls = [synth.make_loglikes(T, P, a.sigma, seed=1000 + i) for i in range(min(n, 64))]
+            dev = [torch.from_numpy(x).cuda() for x in lls]
+            dev = [dev[i % len(dev)] for i in range(n)]
+            batch = CudaDecoderBatch(graph, cfg, n, max_frames=T + 8, token_capacity=(T + 2) * 12000)
+
+            def step():
+                batch.InitDecoding(stream)
+                batch.AdvanceDecoding(dev, stream=stream)
+                batch.FinalizeDecoding(stream)
+                return batch.GetBestPath(True, stream, vectors=False)
+            for _ in range(a.warmup):
+                res = step()
+            bad = [r.status for r in res if not r.ok and r.status != -7]
+            if bad:
+                raise SystemExit(f"decode failed: statuses {sorted(set(bad))}")
+            torch.cuda.synchronize()
+            l0 = L.asrd_launch_count()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(a.steps):
+                res = step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / a.steps
+            ae, aa, tk = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+            L.asrd_get_counters(batch.handles, n, C.byref(ae), C.byref(aa), C.byref(tk), stream)
+            line = {"metric": "CLG decode RTFx", "value": n * T * FRAME_SECONDS / (ms / 1e3), "unit": "x realtime", "n_gpus": 1,
+                    "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                    "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                    "config": {"workload": f"clg: synthetic CLG {n_clg} states / {clg.total_arcs} arcs + 2000 three-state HMMs over {P} pdfs "
+                                           f"(device graph: {graph.device_bytes() >> 20} MB); {n} utts x {T} frames, sigma={a.sigma}; "
+                                           f"beam={a.beam} max-active={a.max_active}; one-best",
+                               "kernels": "k_stream<SMEM_LL, CLG> (on-chip frame loop)"},
+                    "arcs_expanded_per_s": ae.value / (ms / 1e3), "gpu_launches": int((L.asrd_launch_count() - l0) / a.steps),
+                    "hbm_map_fallback_frames": int(L.asrd_last_fallback_frames()),
+                    "utterances_with_a_best_path": int(sum(r.ok for r in res))}
+            if O.have_ref_clg() and not a.no_cpu_baseline:
+                k = min(cores, len(lls))
+                lp = os.path.join(tmp, "ll.bin")
+                fstio.write_loglikes(lp, lls[:k])
+                ref, summ = O.run_ref(gp, lp, stats=False, hmm_path=hp, threads=k, beam=a.beam, max_active=a.max_active,
+                                      min_active=a.min_active, lattice_beam=a.lattice_beam)
+                line["cpu_baseline"] = {"value": k * T * FRAME_SECONDS / summ["wall_s"], "unit": "x realtime", "cores": k,
+                                        "kind": "reference",
+                                        "sample": f"{k} utterances, OnlineClgLatticeDecoderMempool over ClgFst, one decoder per thread"}
+                same = sum(1 for r, g_ in zip(ref, res)
+                           if (lambda v: v[0] == r["words"] and int(np.float32(v[2]).view(np.uint32)) == r["tot_bits"])(
+                               LatticeToVector(g_.ilabel, g_.olabel, g_.graph, g_.acoustic)))
+                line["parity_vs_reference"] = {"utterances": k, "identical_one_best": same}
+            print(json.dumps(line), flush=True)
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+        return
     # ---- lattice mode: config 3's shape (average degree 3), flat scores so that thousands of tokens survive
     binp = os.path.join(ROOT, "oracle", "_ref", "dropin_nbest")
     states = min(a.states, 2_000_000)
@@ -765,7 +830,7 @@ def main():
         run_reference_arm(a)
     elif a.workload == "streaming":
         run_streaming_arm(a)
-    elif a.workload in ("biglm", "lattice"):
+    elif a.workload in ("biglm", "lattice", "clg"):
         run_side_workload(a)
     else:
         run_b200_arm(a)

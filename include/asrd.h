@@ -157,7 +157,7 @@ int asrd_graph_read(const char *path, int device, asrd_graph **out);
  * two-level state ids (clg-fst.h:82-165).  Decoders created on such a graph follow the reference's
  * CLG decoder, OnlineClgLatticeDecoderMempool (src/my-decoder/online-clg-decoder-mempool-base.h:
  * strict token cutoff :128, an arc is skipped only when above the cutoff :156, two-weight best-token
- * pre-pass :91); plain (non-biglm) decoders without prune_tokens. */
+ * pre-pass :91); plain (non-biglm) decoders only. */
 int asrd_graph_read_clg(const char *clg_path, const char *hmm_path, int device, asrd_graph **out);
 
 /* ConstFst<StdArc,int>::Read + Fst(const ConstFst&) (src/newfst/const-fst.h:189-221,

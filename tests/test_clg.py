@@ -106,7 +106,15 @@ def test_cuda_clg_equals_canonical_oracle_and_reference(oracle_mod, tmp_path, mo
         gt, gl = _canon(toks, links, True)
         ot, ol = _canon(otoks, olinks, False)
         assert gt == ot and gl == ol          # tokens (cost, extra cost) and links bit-identical
-    # a CLG graph takes plain decoders without arena pruning
-    from asr_decoder_b200 import _lib
-    with pytest.raises(_lib.AsrdError):
-        CudaDecoderBatch(g, LatticeFasterDecoderConfig(**cfg), 1, max_frames=80, prune_tokens=True)
+    # ... and with PruneActiveTokens every 20 frames on the device nothing changes
+    pr = CudaDecoderBatch(g, LatticeFasterDecoderConfig(prune_interval=20, **cfg), len(lls), max_frames=80, prune_tokens=True)
+    pr.InitDecoding()
+    for k in range(0, 70, 20):
+        pr.AdvanceDecoding([ll[k:k + 20] for ll in lls])
+    pr.FinalizeDecoding()
+    for a, b in zip(out, pr.GetBestPath(True)):
+        assert (a.ok, a.words, a.ali, a.tot_bits) == (b.ok, b.words, b.ali, b.tot_bits)
+    for i in range(len(lls)):
+        ta, la = dec.GetRawLattice(i)
+        tb, lb = pr.GetRawLattice(i)
+        assert ta.tobytes() == tb.tobytes() and la.tobytes() == lb.tobytes()
