@@ -1529,6 +1529,18 @@ int asrd_get_raw_lattice(asrd_decoder *d, int32_t use_final_probs, asrd_lat_toke
   h.link_cap = (uint32_t)link_cap;
   CU_CHECK(cudaMemsetAsync(maps, 0xFF, 2 * H * sizeof(LatEntry), s));
   CU_CHECK(cudaMemcpyAsync(d_out, &h, sizeof(h), cudaMemcpyHostToDevice, s));
+  if (d->opts.prune_tokens && !d->lm1) {
+    // prune_tokens decoders: bring the frames decoded since the last prune down to their lattice-beam
+    // survivors first (the pull sweep of k_prune, all the way down; always safe: the frontier keeps
+    // every token) — the exact sweep below then walks a thin arena
+    PrunePlan pplan;
+    if ((rc = PlanPrune(&pplan))) return rc;
+    if (pplan.fn) {
+      pplan.fn<<<1, kStreamThreads, pplan.dyn, s>>>(d_streams, d->graph->view, DevCfg(d), 1, -1, pplan.n_buckets, pplan.ex_cap);
+      ++g_launches;
+      d->last_prune_frame = d->frames_decoded;
+    }
+  }
   if (d->lm1)
     k_lattice<true, false><<<1, kStreamThreads, 0, s>>>(d_streams, d_out, d->graph->view, DevCfg(d), use_final_probs ? 1 : 0, Lms(d), 0);
   else

@@ -224,6 +224,8 @@ def bind_to_gpu_numa_node(local):
     pinned staging memory is allocated: first touch then places the pages on the GPU's NUMA node, so
     eight ranks do not pull their host->device copies across the socket link (round-1 review: 0.963
     end-to-end efficiency at 8 GPUs).  Best effort: containers may restrict the cpuset."""
+    if os.environ.get("ASRD_BENCH_NO_BIND"):
+        return 0
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -634,7 +636,9 @@ def run_side_workload(a):
         n = a.utts
         fst = synth.make_graph(a.states, 5.0, P, seed=12345)
         nw = 20000
-        lm1, lm2 = LM.make_lm(nw, seed=1, order=2, bigram_density=0.002), LM.make_lm(nw, seed=2, order=2, bigram_density=0.002)
+        lm_order = int(os.environ.get("ASRD_BENCH_LM_ORDER", "2"))   # (1: unigram LMs — how much of the step the LM look-ups are)
+        lm1 = LM.make_lm(nw, seed=1, order=lm_order, bigram_density=0.002)
+        lm2 = LM.make_lm(nw, seed=2, order=lm_order, bigram_density=0.002)
         lls = [synth.make_loglikes(T, P, a.sigma, seed=1000 + i) for i in range(n)]
         graph = CudaFst(fst)
         batch = CudaDecoderBatch(graph, cfg, n, max_frames=T + 8, token_capacity=(T + 2) * 14000,
