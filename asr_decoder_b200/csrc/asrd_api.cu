@@ -338,10 +338,11 @@ int PlanStream(const asrd_graph *graph, int num_indices, bool biglm, StreamPlan 
 // sweep (k_lattice in PRUNE mode), launched right behind it (a no-op for the streams k_prune
 // served); ASRD_PRUNE_KERNEL=0 sends every stream there.  ASRD_PRUNE_DEPTH: frames below the
 // previous frontier a sweep goes back (default: prune_interval; -1: to frame 0 every time).
-typedef void (*PruneFn)(StreamState *const *, GraphView, DecoderConfigDev, int, int, uint32_t, uint32_t);
+typedef void (*PruneFn)(StreamState *const *, GraphView, DecoderConfigDev, int, int, uint32_t, uint32_t, LatticeOut *, int);
 
 struct PrunePlan {
   PruneFn fn = nullptr;  // null: k_lattice<false, true> only
+  PruneFn emit_fn = nullptr;  // the same sweep as raw-lattice extraction (k_prune<true>)
   size_t dyn = 0;
   uint32_t n_buckets = 0, ex_cap = 0;
 };
@@ -350,7 +351,7 @@ int PlanPrune(PrunePlan *plan) {
   plan->fn = nullptr;
   if (!EnvInt("ASRD_PRUNE_KERNEL", 1)) return ASRD_OK;
   cudaFuncAttributes fa;
-  CU_CHECK(cudaFuncGetAttributes(&fa, k_prune));
+  CU_CHECK(cudaFuncGetAttributes(&fa, k_prune<true>));  // (the larger static footprint of the two)
   int dev = 0, max_optin = 0;
   CU_CHECK(cudaGetDevice(&dev));
   CU_CHECK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -361,11 +362,13 @@ int PlanPrune(PrunePlan *plan) {
   if (force >= 256 && (uint32_t)force < ex_cap) ex_cap = (uint32_t)force & ~255u;
   if (ex_cap < 4096 && !force) return ASRD_OK;
   const uint32_t n_buckets = (uint32_t)std::min<size_t>((room - prune_token_dyn_bytes(ex_cap)) / 24, 16384) & ~1u;  // 4 slots x (4 + 2) bytes
-  plan->fn = k_prune;
+  plan->fn = k_prune<false>;
+  plan->emit_fn = k_prune<true>;
   plan->n_buckets = n_buckets;
   plan->ex_cap = ex_cap;
   plan->dyn = (size_t)n_buckets * 24 + prune_token_dyn_bytes(ex_cap);
   CU_CHECK(cudaFuncSetAttribute(plan->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->dyn));
+  CU_CHECK(cudaFuncSetAttribute(plan->emit_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->dyn));
   return ASRD_OK;
 }
 
@@ -1383,7 +1386,7 @@ int asrd_advance_decoding(asrd_decoder *const *decs, int32_t n, const float *con
       prof.Begin(3, s);
       if (pplan.fn) {
         pplan.fn<<<n, kStreamThreads, pplan.dyn, s>>>(d_streams, gv, cfg, decs[0]->cfg.prune_interval, prune_depth,
-                                                      pplan.n_buckets, pplan.ex_cap);
+                                                      pplan.n_buckets, pplan.ex_cap, nullptr, 0);
         ++g_launches;
       }
       // (streams k_prune served are no longer due: their CTAs return at once)
@@ -1511,42 +1514,51 @@ int asrd_get_raw_lattice(asrd_decoder *d, int32_t use_final_probs, asrd_lat_toke
   LatticeOut h;
   memset(&h, 0, sizeof(h));
   LatticeOut *d_out;
-  LatEntry *maps;
   CU_CHECK(sc.Alloc(&d_out, 1));
-  CU_CHECK(sc.Alloc(&maps, 2 * H));
   CU_CHECK(sc.Alloc(&h.toks, (size_t)std::max<int64_t>(tok_cap, 1)));
   CU_CHECK(sc.Alloc(&h.tok_arena_idx, (size_t)std::max<int64_t>(tok_cap, 1)));
   CU_CHECK(sc.Alloc(&h.links, (size_t)std::max<int64_t>(link_cap, 1)));
-  h.map[0] = maps;
-  h.map[1] = maps + H;
-  if (d->lm1) {
-    uint32_t *pairs;
-    CU_CHECK(sc.Alloc(&pairs, 2 * H));
-    h.map_pair[0] = pairs;
-    h.map_pair[1] = pairs + H;
-  }
   h.tok_cap = (uint32_t)tok_cap;
   h.link_cap = (uint32_t)link_cap;
-  CU_CHECK(cudaMemsetAsync(maps, 0xFF, 2 * H * sizeof(LatEntry), s));
   CU_CHECK(cudaMemcpyAsync(d_out, &h, sizeof(h), cudaMemcpyHostToDevice, s));
-  if (d->opts.prune_tokens && !d->lm1) {
-    // prune_tokens decoders: bring the frames decoded since the last prune down to their lattice-beam
-    // survivors first (the pull sweep of k_prune, all the way down; always safe: the frontier keeps
-    // every token) — the exact sweep below then walks a thin arena
+  // Plain decoders: the pull sweep with its lookup map in shared memory (k_prune<true>: work in
+  // proportion to the tokens that survive, the arena untouched); a stream with a frame beyond that
+  // kernel's capacity, and every biglm decoder, goes through the HBM-map sweep (k_lattice).
+  bool done = false;
+  if (!d->lm1 && EnvInt("ASRD_LATTICE_KERNEL", 1)) {
     PrunePlan pplan;
     if ((rc = PlanPrune(&pplan))) return rc;
-    if (pplan.fn) {
-      pplan.fn<<<1, kStreamThreads, pplan.dyn, s>>>(d_streams, d->graph->view, DevCfg(d), 1, -1, pplan.n_buckets, pplan.ex_cap);
+    if (pplan.emit_fn) {
+      pplan.emit_fn<<<1, kStreamThreads, pplan.dyn, s>>>(d_streams, d->graph->view, DevCfg(d), 0, -1, pplan.n_buckets,
+                                                          pplan.ex_cap, d_out, use_final_probs ? 1 : 0);
       ++g_launches;
-      d->last_prune_frame = d->frames_decoded;
+      CU_CHECK(cudaGetLastError());
+      LatticeOut probe;
+      CU_CHECK(cudaMemcpyAsync(&probe, d_out, sizeof(probe), cudaMemcpyDeviceToHost, s));
+      CU_CHECK(cudaStreamSynchronize(s));
+      done = probe.n_toks != 0xFFFFFFFFu;
     }
   }
-  if (d->lm1)
-    k_lattice<true, false><<<1, kStreamThreads, 0, s>>>(d_streams, d_out, d->graph->view, DevCfg(d), use_final_probs ? 1 : 0, Lms(d), 0);
-  else
-    k_lattice<false, false><<<1, kStreamThreads, 0, s>>>(d_streams, d_out, d->graph->view, DevCfg(d), use_final_probs ? 1 : 0, Lms(d), 0);
-  ++g_launches;
-  CU_CHECK(cudaGetLastError());
+  if (!done) {
+    LatEntry *maps;  // the two per-frame lookup maps of the HBM-map sweep
+    CU_CHECK(sc.Alloc(&maps, 2 * H));
+    h.map[0] = maps;
+    h.map[1] = maps + H;
+    if (d->lm1) {
+      uint32_t *pairs;
+      CU_CHECK(sc.Alloc(&pairs, 2 * H));
+      h.map_pair[0] = pairs;
+      h.map_pair[1] = pairs + H;
+    }
+    CU_CHECK(cudaMemsetAsync(maps, 0xFF, 2 * H * sizeof(LatEntry), s));
+    CU_CHECK(cudaMemcpyAsync(d_out, &h, sizeof(h), cudaMemcpyHostToDevice, s));
+    if (d->lm1)
+      k_lattice<true, false><<<1, kStreamThreads, 0, s>>>(d_streams, d_out, d->graph->view, DevCfg(d), use_final_probs ? 1 : 0, Lms(d), 0);
+    else
+      k_lattice<false, false><<<1, kStreamThreads, 0, s>>>(d_streams, d_out, d->graph->view, DevCfg(d), use_final_probs ? 1 : 0, Lms(d), 0);
+    ++g_launches;
+    CU_CHECK(cudaGetLastError());
+  }
   LatticeOut r;
   CU_CHECK(cudaMemcpyAsync(&r, d_out, sizeof(r), cudaMemcpyDeviceToHost, s));
   CU_CHECK(cudaStreamSynchronize(s));

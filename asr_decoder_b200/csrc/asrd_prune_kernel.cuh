@@ -87,17 +87,36 @@ __device__ __forceinline__ uint32_t pm_find(const PruneMap &m, uint32_t key) {
   return kPruneNone;
 }
 
+// EMIT = the same sweep as GetRawLattice + the pruning of FinalizeDecoding (inl.h:725-847, 868-975),
+// the fast twin of k_lattice for plain decoders: the frontier starts from the final costs
+// (PruneForwardLinksFinal, inl.h:758-816) instead of 0, NOTHING in the arena is touched (no
+// compaction: the seeds of a frame are an index list, the extra costs of frame f + 1 sit in a scratch
+// buffer), and the surviving tokens and links are written to `outs` as they become final — emitting
+// links while they are pulled (the destination's extra cost is final by then), eps links in one more
+// pull over the frame's survivors after its fixed point.  A frame beyond the kernel's capacity
+// reports n_toks = 0xFFFFFFFF and the host falls back to k_lattice.
+template <bool EMIT>
 __global__ void __launch_bounds__(kStreamThreads, 1)
 k_prune(StreamState *const *streams, GraphView g, DecoderConfigDev cfg, int prune_interval, int depth,
-        uint32_t max_buckets, uint32_t ex_cap) {
+        uint32_t max_buckets, uint32_t ex_cap, LatticeOut *outs, int use_final) {
   constexpr int NT = kStreamThreads;
   extern __shared__ __align__(16) unsigned char s_dyn[];
   __shared__ uint32_t s_nalive, s_nwl[2], s_nhub;
   __shared__ uint32_t s_hub[kPruneHubCap];
+  __shared__ unsigned long long s_red64[NT / 32];
   StreamState *st = streams[blockIdx.x];
+  LatticeOut *out = EMIT ? &outs[blockIdx.x] : nullptr;
   const int tid = threadIdx.x;
   const int F = st->frame;
-  if (F < 0 || st->status < 0 || F - st->gc_frame < prune_interval) return;  // uniform
+  if (EMIT) {
+    if (tid == 0) {
+      out->n_toks = 0;
+      out->n_links = 0;
+    }
+    if (F < 0) return;
+  } else if (F < 0 || st->status < 0 || F - st->gc_frame < prune_interval) {
+    return;  // uniform
+  }
   const uint32_t max_slots = max_buckets * 4;
   uint32_t *s_key = reinterpret_cast<uint32_t *>(s_dyn);
   uint16_t *s_idx = reinterpret_cast<uint16_t *>(s_key + max_slots);
@@ -109,7 +128,7 @@ k_prune(StreamState *const *streams, GraphView g, DecoderConfigDev cfg, int prun
   m.key_sa = smem_addr(s_key);
   m.idx_sa = smem_addr(s_idx);
   m.n_buckets = 32;
-  const int lo_limit = depth >= 0 ? max(0, st->gc_frame - depth) : 0;
+  const int lo_limit = (!EMIT && depth >= 0) ? max(0, st->gc_frame - depth) : 0;
   // global scratch (the stream's closure queues, idle between frame-loop launches): worklists and
   // the alive list (u16 token indices), survivors per frame, staging of the survivors of a frame
   const uint32_t H = st->hash_mask + 1;
@@ -118,14 +137,21 @@ k_prune(StreamState *const *streams, GraphView g, DecoderConfigDev cfg, int prun
   wl[0] = reinterpret_cast<uint16_t *>(st->queue[0]);
   wl[1] = wl[0] + cap;
   uint16_t *alive = wl[1] + cap;                      // 3 * cap * 2 <= 2 H bytes
-  uint32_t *keep = st->queue[0] + H / 2;              // [frames swept]
+  uint32_t *keep = st->queue[0] + H / 2;              // [frames swept]  (PRUNE)
   uint2 *stage_sc = reinterpret_cast<uint2 *>(st->queue[1]);
-  uint32_t *stage_ex = st->queue[1] + 2 * (size_t)cap;  // 3 * cap * 4 <= 4 H bytes
+  uint32_t *stage_ex = st->queue[1] + 2 * (size_t)cap;  // 3 * cap * 4 <= 4 H bytes  (PRUNE)
+  // EMIT: nothing is compacted — the survivors of frame f + 1 are an index list (two lists, taking
+  // turns with `alive`), their extra costs a scratch array indexed like the frame
+  uint16_t *alive_alt = alive + cap;                  // 4 * cap * 2 <= 8 H / 3 bytes of queue[0]
+  uint32_t *exn = st->queue[1];                       // [cap] extra costs of frame f + 1
   {
     uint32_t too_big = (uint32_t)(F - lo_limit + 1) > min((uint32_t)kPruneMaxFrames, H / 2) ? 1u : 0u;
     for (int f = lo_limit + tid; f <= F; f += NT) too_big |= (st->frame_off[f + 1] - st->frame_off[f]) > cap;
-    if (__syncthreads_or((int)too_big)) return;  // (the HBM-map sweep launched behind this kernel takes the stream)
-    if (tid == 0) {
+    if (__syncthreads_or((int)too_big)) {  // (the HBM-map sweep takes the stream)
+      if (EMIT && tid == 0) out->n_toks = 0xFFFFFFFFu;
+      return;
+    }
+    if (!EMIT && tid == 0) {
       const uint32_t used = st->frame_off[F + 1];
       if (used > st->peak_tokens) st->peak_tokens = used;
     }
@@ -142,19 +168,39 @@ k_prune(StreamState *const *streams, GraphView g, DecoderConfigDev cfg, int prun
       tph = now;
     }
   };
-  // ---- the frontier is not pruned: extra cost 0 everywhere (inl.h:455-470 stops above it)
-  {
+  // ---- the frontier.  PRUNE: it is not pruned, extra cost 0 everywhere (inl.h:455-470 stops above
+  // it).  EMIT: it is swept like every frame, starting from the final costs (below).
+  float final_best = 0.f;
+  bool any_final = false;
+  if (!EMIT) {
     const uint32_t b0 = st->frame_off[F], n = st->frame_off[F + 1] - b0;
     for (uint32_t i = tid; i < n; i += NT) st->tok_extra[b0 + i] = f2ord(0.f);
     if (tid == 0) keep[F - lo_limit] = n;
+  } else {
+    // ComputeFinalCosts (inl.h:670-720): the token on the super-final state, if any
+    const uint32_t b0 = st->frame_off[F], n0 = st->frame_off[F + 1] - b0;
+    unsigned long long best_all = kInfVal, best_fin = kInfVal;
+    for (uint32_t i = tid; i < n0; i += NT) {
+      const uint2 sc = __ldcg(&st->tok_sc[b0 + i]);
+      const unsigned long long b = ((unsigned long long)f2ord(__uint_as_float(sc.y)) << 32) | sc.x;
+      best_all = b < best_all ? b : best_all;
+      if ((int32_t)sc.x == g.final_state) best_fin = b < best_fin ? b : best_fin;
+    }
+    best_all = block_min_u64<NT>(best_all, s_red64);
+    best_fin = block_min_u64<NT>(best_fin, s_red64);
+    any_final = use_final && best_fin != kInfVal;
+    final_best = ord2f((uint32_t)((any_final ? best_fin : best_all) >> 32));  // inl.h:709-719
   }
-  uint32_t k1 = st->frame_off[F + 1] - st->frame_off[F];  // survivors of frame f + 1 (at the front of its span)
+  uint32_t k1 = st->frame_off[F + 1] - st->frame_off[F];  // survivors of frame f + 1 (PRUNE: at the front of its span)
+  uint16_t *seeds = alive_alt;                             // EMIT: their indices
   __syncthreads();
-  for (int f = F - 1; f >= lo_limit; --f) {
+  for (int f = EMIT ? F : F - 1; f >= lo_limit; --f) {
+    const bool frontier = EMIT && f == F;
     const uint32_t b0 = st->frame_off[f], n = st->frame_off[f + 1] - b0;
     const uint32_t b1 = st->frame_off[f + 1];
-    const float nc_f = st->frame_nc[f], nc_next = st->frame_nc[f + 1], cur_cut = st->frame_cur[f];
-    const float *__restrict__ ll = st->ll_hist + (size_t)f * st->ll_stride;
+    const float nc_f = st->frame_nc[f], nc_next = frontier ? 0.f : st->frame_nc[f + 1], cur_cut = frontier ? 0.f : st->frame_cur[f];
+    const float *__restrict__ ll = st->ll_hist + (size_t)(frontier ? 0 : f) * st->ll_stride;
+    uint16_t *alive_cur = EMIT ? (seeds == alive ? alive_alt : alive) : alive;
     if (tid == 0) {
       s_nalive = 0;
       s_nwl[0] = s_nwl[1] = 0;
@@ -183,9 +229,25 @@ k_prune(StreamState *const *streams, GraphView g, DecoderConfigDev cfg, int prun
     // The link src token i (frame f, cost `cost`) -> a destination token (cost dcost, extra cost
     // dextra; EMIT: in frame f + 1 over an emitting arc whose log-likelihood is llv, else in frame f
     // over an eps arc) with arc weight w: if the search admitted it, its extra cost goes to the source.
-    auto apply = [&](uint32_t i, float cost, float w, float llv, bool EMIT, float dcost, float dextra, uint32_t par) {
+    auto emit_link = [&](uint32_t src_idx, uint32_t dst_idx, int32_t il, int32_t ol, float graph_cost, float ac) {
+      const uint32_t p = atomicAdd(&out->n_links, 1u);
+      if (p < out->link_cap) {
+        asrd_lat_link l;
+        l.src = (int32_t)src_idx;
+        l.dst = (int32_t)dst_idx;
+        l.ilabel = il;
+        l.olabel = ol;
+        l.graph = graph_cost;
+        l.acoustic = ac;
+        out->links[p] = l;
+      }
+    };
+    // (LINKS, EMIT only: the extra costs are final and this is the pass that writes the surviving
+    // eps links — same admission tests, nothing is relaxed)
+    auto apply = [&](uint32_t i, float cost, float w, float llv, bool EMITTING, float dcost, float dextra, uint32_t par,
+                     int32_t il, int32_t ol, uint32_t dst_arena, bool LINKS) {
       float tot;
-      if (EMIT) {
+      if (EMITTING) {
         if (g.clg ? !(cost < cur_cut) : !(cost <= cur_cut)) return;     // inl.h:315 (CLG decoder: strict)
         tot = (cost + (-llv)) + w;                                      // inl.h:326-329
         if (g.clg ? !(tot <= nc_next) : !(tot < nc_next)) return;       // inl.h:330, final cutoff (CLG: inclusive)
@@ -197,22 +259,31 @@ k_prune(StreamState *const *streams, GraphView g, DecoderConfigDev cfg, int prun
       float le = dextra + (tot - dcost);  // inl.h:524-526
       if (le > beam) return;              // inl.h:532
       if (le < 0.f) le = 0.f;             // inl.h:545-551
+      // (EMIT: an emitting link's destination extra cost is final: the link is (inl.h:532 passed))
+      if (EMIT && EMITTING) emit_link(b0 + i, dst_arena, il, ol, w, -llv);
+      if (EMIT && LINKS) {
+        emit_link(b0 + i, dst_arena, il, ol, w, 0.f);
+        return;
+      }
       const uint32_t v = f2ord(le);
       const uint32_t old = atomicMin(&s_ex[i], v);
       if (v < old) {
-        if (old == kOrdInf) alive[atomicAdd(&s_nalive, 1u)] = (uint16_t)i;
+        if (old == kOrdInf) alive_cur[atomicAdd(&s_nalive, 1u)] = (uint16_t)i;
         // its own incoming eps links have to be looked at (again): queue it once per round
         const uint32_t bit = 1u << (i & 31);
         if (!(atomicOr(&s_flag[par][i >> 5], bit) & bit)) wl[par][atomicAdd(&s_nwl[par], 1u)] = (uint16_t)i;
       }
     };
-    auto link = [&](uint32_t i, const int4 &arc, bool EMIT, float dcost, float dextra, uint32_t par) {
+    auto link = [&](uint32_t i, const int4 &arc, bool EMITTING, float dcost, float dextra, uint32_t par, uint32_t dst_arena,
+                    bool LINKS) {
       const float cost = __uint_as_float(__ldcg(&st->tok_sc[b0 + i]).y);
-      apply(i, cost, __int_as_float(arc.z), EMIT ? __ldg(&ll[arc.x - 1]) : 0.f, EMIT, dcost, dextra, par);
+      apply(i, cost, __int_as_float(arc.z), EMITTING ? __ldg(&ll[arc.x - 1]) : 0.f, EMITTING, dcost, dextra, par, arc.x, arc.y,
+            dst_arena, LINKS);
     };
-    auto relax_in = [&](uint32_t a, bool EMIT, float dcost, float dextra, uint32_t par) {  // incoming arc a
+    auto relax_in = [&](uint32_t a, bool EMITTING, float dcost, float dextra, uint32_t par, uint32_t dst_arena,
+                        bool LINKS) {  // incoming arc a
       const uint32_t i = pm_find(m, __ldg(&g.arc_src[a]));
-      if (i != kPruneNone) link(i, __ldg(&g.arcs[a]), EMIT, dcost, dextra, par);
+      if (i != kPruneNone) link(i, __ldg(&g.arcs[a]), EMITTING, dcost, dextra, par, dst_arena, LINKS);
     };
     // The incoming arcs (of the class) of one destination token, this lane's share of them: lane `sub`
     // of the `nsub` lanes that work on the destination takes every nsub-th arc.  A prune is a chain of
@@ -220,10 +291,10 @@ k_prune(StreamState *const *streams, GraphView g, DecoderConfigDev cfg, int prun
     // requested together is: the ranges, then up to four arc ids, then their source states AND arc
     // records, then (after the shared-memory lookups) the costs and log-likelihoods of the hits.
     // Hubs are left to the whole CTA.
-    auto pull = [&](uint32_t state, uint32_t hub_tag, bool EMIT, float dcost, float dextra, uint32_t par,
-                    uint32_t sub, uint32_t nsub) {
+    auto pull = [&](uint32_t state, uint32_t hub_tag, bool EMITTING, float dcost, float dextra, uint32_t par,
+                    uint32_t sub, uint32_t nsub, uint32_t dst_arena, bool LINKS) {
       const uint32_t mid = __ldg(&g.in_mid[state]);
-      const uint32_t ib = EMIT ? mid : __ldg(&g.in_off[state]), ie = EMIT ? __ldg(&g.in_off[state + 1]) : mid;
+      const uint32_t ib = EMITTING ? mid : __ldg(&g.in_off[state]), ie = EMITTING ? __ldg(&g.in_off[state + 1]) : mid;
       if (ie - ib > (uint32_t)kPruneHubDeg) {
         if (sub != 0) return;
         const uint32_t h = atomicAdd(&s_nhub, 1u);
@@ -250,57 +321,78 @@ k_prune(StreamState *const *streams, GraphView g, DecoderConfigDev cfg, int prun
         for (int u = 0; u < 4; ++u) {
           const bool hit = idx[u] != kPruneNone;
           cost[u] = __uint_as_float(__ldcg(&st->tok_sc[b0 + (hit ? idx[u] : 0u)]).y);
-          llv[u] = EMIT ? __ldg(&ll[hit ? arc[u].x - 1 : 0]) : 0.f;
+          llv[u] = EMITTING ? __ldg(&ll[hit ? arc[u].x - 1 : 0]) : 0.f;
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-          if (idx[u] != kPruneNone) apply(idx[u], cost[u], __int_as_float(arc[u].z), llv[u], EMIT, dcost, dextra, par);
+          if (idx[u] != kPruneNone)
+            apply(idx[u], cost[u], __int_as_float(arc[u].z), llv[u], EMITTING, dcost, dextra, par, arc[u].x, arc[u].y, dst_arena,
+                  LINKS);
       }
     };
     // Hubs (whole CTA; base: arena offset of the destinations' frame).  A hub with fewer incoming
     // arcs than the frame has tokens is walked from its side; else the frame's tokens are walked
     // forwards and only their arcs INTO the hub looked at (the super-final state has an incoming
     // arc from every final state of the graph).
-    auto pull_hubs = [&](bool EMIT, uint32_t base, uint32_t par) {
+    auto next_extra = [&](uint32_t j) { return EMIT ? __ldcg(&exn[j]) : __ldcg(&st->tok_extra[b1 + j]); };
+    auto pull_hubs = [&](bool EMITTING, uint32_t base, uint32_t par, bool LINKS) {
       const uint32_t nh = min(s_nhub, (uint32_t)kPruneHubCap);
       for (uint32_t h = 0; h < nh; ++h) {
         const uint32_t j = s_hub[h];
         const uint2 sc = __ldcg(&st->tok_sc[base + j]);
         const float dcost = __uint_as_float(sc.y);
-        const float dextra = ord2f(EMIT ? __ldcg(&st->tok_extra[base + j]) : *reinterpret_cast<volatile uint32_t *>(&s_ex[j]));
+        const float dextra = ord2f(EMITTING ? next_extra(j) : *reinterpret_cast<volatile uint32_t *>(&s_ex[j]));
         const uint32_t mid = __ldg(&g.in_mid[sc.x]);
-        const uint32_t ib = EMIT ? mid : __ldg(&g.in_off[sc.x]), ie = EMIT ? __ldg(&g.in_off[sc.x + 1]) : mid;
+        const uint32_t ib = EMITTING ? mid : __ldg(&g.in_off[sc.x]), ie = EMITTING ? __ldg(&g.in_off[sc.x + 1]) : mid;
         if (ie - ib <= 4u * n) {
-          for (uint32_t r = ib + tid; r < ie; r += NT) relax_in(__ldg(&g.in_arc[r]), EMIT, dcost, dextra, par);
+          for (uint32_t r = ib + tid; r < ie; r += NT) relax_in(__ldg(&g.in_arc[r]), EMITTING, dcost, dextra, par, base + j, LINKS);
         } else {
           for (uint32_t i = tid; i < n; i += NT) {
             const uint2 tk = __ldcg(&st->tok_sc[b0 + i]);
             const float cost = __uint_as_float(tk.y);
-            if (EMIT ? !(cost <= cur_cut) : !(cost < nc_f)) continue;
-            if (!EMIT && !((__ldg(&g.eps_bits[tk.x >> 5]) >> (tk.x & 31)) & 1u)) continue;
-            const uint2 span = EMIT ? __ldg(&g.erows[tk.x]) : __ldg(&g.rows[tk.x]);
+            if (EMITTING ? !(cost <= cur_cut) : !(cost < nc_f)) continue;
+            if (!EMITTING && !((__ldg(&g.eps_bits[tk.x >> 5]) >> (tk.x & 31)) & 1u)) continue;
+            const uint2 span = EMITTING ? __ldg(&g.erows[tk.x]) : __ldg(&g.rows[tk.x]);
             for (uint32_t a = span.x; a < span.y; ++a) {
               const int4 arc = __ldg(&g.arcs[a]);
-              if (((uint32_t)arc.w & kStateMask) == sc.x) link(i, arc, EMIT, dcost, dextra, par);
+              if (((uint32_t)arc.w & kStateMask) == sc.x) link(i, arc, EMITTING, dcost, dextra, par, base + j, LINKS);
             }
           }
         }
       }
     };
-    // ---- emitting links: the survivors of frame f + 1 pull from their sources in frame f
-    {
+    if (!frontier) {
+      // ---- emitting links: the survivors of frame f + 1 pull from their sources in frame f
       // (few survivors: several lanes share one destination, so that the chain of a destination with
       // many incoming arcs is not what every other warp waits for at the barrier)
       const uint32_t nsub = k1 > NT / 2 ? 1u : k1 > NT / 4 ? 2u : k1 > NT / 8 ? 4u : 8u;
       for (uint32_t w = tid; w < k1 * nsub; w += NT) {
         const uint32_t q = w / nsub;
-        const uint2 sc = __ldcg(&st->tok_sc[b1 + q]);
-        pull(sc.x, q, true, __uint_as_float(sc.y), ord2f(__ldcg(&st->tok_extra[b1 + q])), 0u, w % nsub, nsub);
+        const uint32_t j = EMIT ? (uint32_t)__ldcg(&seeds[q]) : q;
+        const uint2 sc = __ldcg(&st->tok_sc[b1 + j]);
+        pull(sc.x, j, true, __uint_as_float(sc.y), ord2f(next_extra(j)), 0u, w % nsub, nsub, b1 + j, false);
       }
-    }
-    __syncthreads();
-    if (s_nhub) {
-      pull_hubs(true, b1, 0u);
+      __syncthreads();
+      if (s_nhub) {
+        pull_hubs(true, b1, 0u, false);
+        __syncthreads();
+      }
+    } else {
+      // ---- EMIT, frame F: PruneForwardLinksFinal (inl.h:758-775, 815-816): a token starts from its cost
+      // with the final cost against the best one, or is dropped when that is beyond the lattice beam
+      for (uint32_t i = tid; i < n; i += NT) {
+        const uint2 sc = __ldcg(&st->tok_sc[b0 + i]);
+        float fc = 0.f;
+        if (any_final) fc = (int32_t)sc.x == g.final_state ? 0.f : CUDART_INF_F;
+        float init = __uint_as_float(sc.y) + fc - final_best;
+        if (init > beam) init = CUDART_INF_F;
+        if (init < CUDART_INF_F) {
+          s_ex[i] = f2ord(init);
+          alive_cur[atomicAdd(&s_nalive, 1u)] = (uint16_t)i;
+          atomicOr(&s_flag[0][i >> 5], 1u << (i & 31));
+          wl[0][atomicAdd(&s_nwl[0], 1u)] = (uint16_t)i;
+        }
+      }
       __syncthreads();
     }
     phase(1);
@@ -322,34 +414,79 @@ k_prune(StreamState *const *streams, GraphView g, DecoderConfigDev cfg, int prun
         if (w % nsub == 0) atomicAnd(&s_flag[par][i >> 5], ~(1u << (i & 31)));
         const uint2 sc = __ldcg(&st->tok_sc[b0 + i]);
         pull(sc.x, i, false, __uint_as_float(sc.y), ord2f(*reinterpret_cast<volatile uint32_t *>(&s_ex[i])), par ^ 1u,
-             w % nsub, nsub);
+             w % nsub, nsub, b0 + i, false);
       }
       __syncthreads();
       if (s_nhub) {
-        pull_hubs(false, b0, par ^ 1u);
+        pull_hubs(false, b0, par ^ 1u, false);
         __syncthreads();
       }
       ph[7] += 1;
     }
     phase(2);
-    // ---- survivors (PruneTokensForFrame, inl.h:591) to the front of the frame's span, through a
-    // staging buffer: the next frame reads them as its seeds, coalesced
     const uint32_t k = s_nalive;
-    for (uint32_t q = tid; q < k; q += NT) {
-      const uint32_t i = __ldcg(&alive[q]);
-      stage_sc[q] = __ldcg(&st->tok_sc[b0 + i]);
-      stage_ex[q] = s_ex[i];
+    if constexpr (EMIT) {
+      // ---- the frame's extra costs are final: its surviving tokens, and — one more pull over them —
+      // its surviving eps links (inl.h:532 with the final extra costs on both ends)
+      for (uint32_t q = tid; q < k; q += NT) {
+        const uint32_t i = __ldcg(&alive_cur[q]);
+        const uint2 sc = __ldcg(&st->tok_sc[b0 + i]);
+        const uint32_t p = atomicAdd(&out->n_toks, 1u);
+        if (p < out->tok_cap) {
+          asrd_lat_token t;
+          t.frame = f;
+          t.state = (int32_t)sc.x;
+          t.cost = __uint_as_float(sc.y);
+          t.extra = ord2f(s_ex[i]);
+          t.is_final = (f == F && (!any_final || (int32_t)sc.x == g.final_state)) ? 1 : 0;  // inl.h:935-951
+          out->toks[p] = t;
+          out->tok_arena_idx[p] = b0 + i;
+        }
+      }
+      if (tid == 0) s_nhub = 0;
+      __syncthreads();
+      {
+        const uint32_t nsub = k > NT / 2 ? 1u : k > NT / 4 ? 2u : k > NT / 8 ? 4u : 8u;
+        for (uint32_t w = tid; w < k * nsub; w += NT) {
+          const uint32_t i = __ldcg(&alive_cur[w / nsub]);
+          const uint2 sc = __ldcg(&st->tok_sc[b0 + i]);
+          pull(sc.x, i, false, __uint_as_float(sc.y), ord2f(s_ex[i]), 0u, w % nsub, nsub, b0 + i, true);
+        }
+      }
+      __syncthreads();
+      if (s_nhub) {
+        pull_hubs(false, b0, 0u, true);
+        __syncthreads();
+      }
+      // the next frame's seeds: this frame's survivors, their extra costs in the scratch array
+      for (uint32_t q = tid; q < k; q += NT) {
+        const uint32_t i = __ldcg(&alive_cur[q]);
+        exn[i] = s_ex[i];
+      }
+      seeds = alive_cur;
+      k1 = k;
+      __syncthreads();
+      phase(3);
+    } else {
+      // ---- survivors (PruneTokensForFrame, inl.h:591) to the front of the frame's span, through a
+      // staging buffer: the next frame reads them as its seeds, coalesced
+      for (uint32_t q = tid; q < k; q += NT) {
+        const uint32_t i = __ldcg(&alive[q]);
+        stage_sc[q] = __ldcg(&st->tok_sc[b0 + i]);
+        stage_ex[q] = s_ex[i];
+      }
+      __syncthreads();
+      for (uint32_t q = tid; q < k; q += NT) {
+        st->tok_sc[b0 + q] = __ldcg(&stage_sc[q]);
+        st->tok_extra[b0 + q] = __ldcg(&stage_ex[q]);
+      }
+      if (tid == 0) keep[f - lo_limit] = k;
+      k1 = k;
+      __syncthreads();
+      phase(3);
     }
-    __syncthreads();
-    for (uint32_t q = tid; q < k; q += NT) {
-      st->tok_sc[b0 + q] = __ldcg(&stage_sc[q]);
-      st->tok_extra[b0 + q] = __ldcg(&stage_ex[q]);
-    }
-    if (tid == 0) keep[f - lo_limit] = k;
-    k1 = k;
-    __syncthreads();
-    phase(3);
   }
+  if constexpr (EMIT) return;
   // ---- close the spans up from frame lo_limit upwards (a tile is read into registers before
   // anything of it is written: tokens only ever move towards the front)
   {

@@ -36,8 +36,10 @@ def _canon(toks, links, gpu):
     return t, l
 
 
+@pytest.mark.parametrize("kernel", ["1", "0"])   # k_prune<EMIT> (pull sweep, map in shared memory) / k_lattice (HBM maps)
 @pytest.mark.parametrize("name", ["g1", "g2", "g3"])
-def test_raw_lattice_equals_canonical_oracle(oracle_mod, name):
+def test_raw_lattice_equals_canonical_oracle(oracle_mod, monkeypatch, name, kernel):
+    monkeypatch.setenv("ASRD_LATTICE_KERNEL", kernel)
     O = oracle_mod
     fst = fstio.read_fst(os.path.join(GOLD, name + ".fst"))
     lls = fstio.read_loglikes(os.path.join(GOLD, name + ".llb"))
