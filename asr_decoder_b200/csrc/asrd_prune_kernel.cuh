@@ -443,6 +443,7 @@ k_prune(StreamState *const *streams, GraphView g, DecoderConfigDev cfg, int prun
           out->tok_arena_idx[p] = b0 + i;
         }
       }
+      __syncthreads();  // (everybody is past the last eps round's look at the hub counter)
       if (tid == 0) s_nhub = 0;
       __syncthreads();
       {
