@@ -33,3 +33,20 @@ gc = CudaFst.ReadClg(tmp + "/c.fst", tmp + "/h.bin")
 c = CudaDecoderBatch(gc, LatticeFasterDecoderConfig(beam=12.0, max_active=300, min_active=20, lattice_beam=6.0), 2, max_frames=48)
 out = c.Decode([synth.make_loglikes(40, 40, 1.5, seed=9 + i) for i in range(2)])
 print("ok", [len(x.words) for x in want], [len(x.ali) for x in out])
+# the HBM-map routes: every frame of the on-chip loop redone through the HBM map, then the
+# k_expand / k_post kernels on their own, then a biglm decoder
+from asr_decoder_b200 import lm as LM
+from asr_decoder_b200.decoder import CudaLm
+for env in ({"ASRD_DEBUG_FLAGS": "8"}, {"ASRD_STREAM_KERNEL": "0"}):
+    os.environ.update(env)
+    d = CudaDecoderBatch(g, cfg, 2, max_frames=48)
+    r = d.Decode(lls)
+    assert all(x.words == y.words and x.tot_bits == y.tot_bits for x, y in zip(want, r)), env
+    for k in env:
+        del os.environ[k]
+lm1, lm2 = LM.make_lm(300, seed=1, order=2, bigram_density=0.05), LM.make_lm(300, seed=2, order=2, bigram_density=0.05)
+fb = synth.make_graph(2000, 5.0, 60, seed=6, n_words=300)
+e = CudaDecoderBatch(CudaFst(fb), cfg, 2, max_frames=48, old_lm=CudaLm(lm1.Rescale(-1.0)), new_lm=CudaLm(lm2))
+rb = e.Decode(lls)
+e.GetRawLattice(0)
+print("ok hbm routes + biglm", [x.status for x in rb])
