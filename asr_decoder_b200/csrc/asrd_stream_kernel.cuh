@@ -722,11 +722,39 @@ k_stream(StreamState *const *streams, const AdvanceParams *params, GraphView g, 
       // GetCutoff (inl.h:138-234) needs the exact max_active-th smallest cost when more tokens than
       // that survive: only possible when more states than that were claimed at all
       const bool want_hist = hot->claims > (uint32_t)cfg.max_active && best_ord != 0xFFFFFFFFu && nc < CUDART_INF_F;
-      for (int i = tid; i < kHistBins; i += NT) s_hist[i] = 0;  // (the warp scratch is idle from here on)
       const uint32_t blocks = n_buckets >> 5;  // n_buckets is a multiple of 32
-      for (uint32_t blk = warp; blk < blocks; blk += NW) {
-        const uint32_t s0 = (blk * 32 + lane) * 4;
-        const uint4 kw = *reinterpret_cast<const uint4 *>(&m.key[s0]);
+      // Fewer claimed states than buckets (the peaked / narrow-beam regimes): most buckets are empty.
+      // Each warp first gathers the occupied buckets of its share into its (idle) scratch and then
+      // walks those, 32 at a time, instead of every bucket (-3 % per step at beam 10, -5 % with peaked
+      // scores; nothing changes for the busy frames, which take the other branch).
+      const bool sparse = !want_hist && hot->claims * 2u < n_buckets;
+      uint32_t n_occ = 0;
+      const uint32_t occ_sa = smem_addr(s_scratch + warp * kWarpScratch);
+      if (sparse) {
+        for (uint32_t blk = warp; blk < blocks; blk += NW) {
+          const uint32_t bkt = blk * 32 + lane;
+          const bool occ = m.key[bkt * 4] != kEmptyKey;
+          const unsigned om = __ballot_sync(kFull, occ);
+          if (occ) sts_u16(occ_sa + (n_occ + (uint32_t)__popc(om & lanemask_lt())) * 2u, bkt);
+          n_occ += (uint32_t)__popc(om);
+        }
+        __syncwarp();
+      } else {
+        for (int i = tid; i < kHistBins; i += NT) s_hist[i] = 0;  // (the warp scratch is idle from here on)
+      }
+      const uint32_t n_iter = sparse ? (n_occ + 31) >> 5 : (blocks > (uint32_t)warp ? (blocks - warp + NW - 1) / NW : 0u);
+      for (uint32_t it = 0; it < n_iter; ++it) {
+        uint32_t s0;
+        bool have = true;
+        if (sparse) {
+          have = it * 32 + lane < n_occ;
+          unsigned short bk = 0;
+          if (have) asm volatile("ld.volatile.shared.u16 %0, [%1];" : "=h"(bk) : "r"(occ_sa + (it * 32 + lane) * 2u) : "memory");
+          s0 = (uint32_t)bk * 4;
+        } else {
+          s0 = ((warp + it * NW) * 32 + lane) * 4;
+        }
+        const uint4 kw = have ? *reinterpret_cast<const uint4 *>(&m.key[s0]) : make_uint4(kEmptyKey, kEmptyKey, kEmptyKey, kEmptyKey);
         uint32_t cnt = 0;
         uint4 co = make_uint4(kFreeCost, kFreeCost, kFreeCost, kFreeCost);
         if (kw.x != kEmptyKey) {  // (slots fill a bucket front to back)
