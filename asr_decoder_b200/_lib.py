@@ -28,7 +28,7 @@ SYMBOLS = [
     "asrd_frame_stats", "asrd_decoder_status", "asrd_synchronize",
     "asrd_host_alloc", "asrd_host_free", "asrd_launch_count", "asrd_last_fallback_frames", "asrd_last_phase_cycles",
     "asrd_last_pruned_tokens", "asrd_last_peak_tokens", "asrd_last_prune_cycles", "asrd_arena_frame_tokens",
-    "asrd_get_raw_lattice", "asrd_get_counters", "asrd_profile_enable", "asrd_profile_reset", "asrd_profile_get",
+    "asrd_get_raw_lattice", "asrd_get_raw_lattice_batch", "asrd_get_counters", "asrd_profile_enable", "asrd_profile_reset", "asrd_profile_get",
 ]
 
 
@@ -119,6 +119,7 @@ def lib():
     L.asrd_num_frames_decoded.restype = i32
     L.asrd_get_best_path.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     L.asrd_get_raw_lattice.argtypes = [vp, i32, vp, i64, vp, i64, C.POINTER(i64), C.POINTER(i64), vp]
+    L.asrd_get_raw_lattice_batch.argtypes = [vp, i32, i32, vp, i64, vp, i64, vp, vp, vp, vp]
     L.asrd_path_to_vector.argtypes = [vp, vp, vp, vp, i32, vp, C.POINTER(i32), vp, C.POINTER(i32),
                                       C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.asrd_frame_stats.argtypes = [vp, vp, i32, vp]

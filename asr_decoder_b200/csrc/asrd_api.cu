@@ -10,6 +10,7 @@
 #include <limits>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "asrd_kernels.cuh"
@@ -1492,100 +1493,23 @@ int asrd_get_best_path(asrd_decoder *const *decs, int32_t n, int32_t use_final_p
   return ASRD_OK;
 }
 
-int asrd_get_raw_lattice(asrd_decoder *d, int32_t use_final_probs, asrd_lat_token *toks, int64_t tok_cap,
-                         asrd_lat_link *links, int64_t link_cap, int64_t *n_toks, int64_t *n_links,
-                         void *stream) {
-  if (!d || !n_toks || !n_links || tok_cap < 0 || link_cap < 0 || tok_cap > 0x7FFFFFFF || link_cap > 0x7FFFFFFF)
-    return ASRD_ERR_BAD_ARG;
-  if (!d->initialized) return ASRD_ERR_STATE;
-  if (d->finalized && !use_final_probs) return ASRD_ERR_STATE;  // inl.h:879-884
-  if (d->frames_decoded <= 0 || !d->d_ll_hist) {
-    *n_toks = *n_links = 0;
-    return ASRD_ERR_NO_TOKENS;
-  }
-  int rc = EnsureDevice(d->graph->device);
-  if (rc) return rc;
-  cudaStream_t s = (cudaStream_t)stream;
-  Scratch sc(s);
-  asrd_decoder *one[1] = {d};
-  StreamState **d_streams;
-  if ((rc = UploadStreams(one, 1, s, sc, &d_streams))) return rc;
-  const size_t H = (size_t)d->opts.hash_capacity;
-  LatticeOut h;
-  memset(&h, 0, sizeof(h));
-  LatticeOut *d_out;
-  CU_CHECK(sc.Alloc(&d_out, 1));
-  CU_CHECK(sc.Alloc(&h.toks, (size_t)std::max<int64_t>(tok_cap, 1)));
-  CU_CHECK(sc.Alloc(&h.tok_arena_idx, (size_t)std::max<int64_t>(tok_cap, 1)));
-  CU_CHECK(sc.Alloc(&h.links, (size_t)std::max<int64_t>(link_cap, 1)));
-  h.tok_cap = (uint32_t)tok_cap;
-  h.link_cap = (uint32_t)link_cap;
-  CU_CHECK(cudaMemcpyAsync(d_out, &h, sizeof(h), cudaMemcpyHostToDevice, s));
-  // Plain decoders: the pull sweep with its lookup map in shared memory (k_prune<true>: work in
-  // proportion to the tokens that survive, the arena untouched); a stream with a frame beyond that
-  // kernel's capacity, and every biglm decoder, goes through the HBM-map sweep (k_lattice).
-  bool done = false;
-  if (!d->lm1 && EnvInt("ASRD_LATTICE_KERNEL", 1)) {
-    PrunePlan pplan;
-    if ((rc = PlanPrune(&pplan))) return rc;
-    if (pplan.emit_fn) {
-      pplan.emit_fn<<<1, kStreamThreads, pplan.dyn, s>>>(d_streams, d->graph->view, DevCfg(d), 0, -1, pplan.n_buckets,
-                                                          pplan.ex_cap, d_out, use_final_probs ? 1 : 0);
-      ++g_launches;
-      CU_CHECK(cudaGetLastError());
-      LatticeOut probe;
-      CU_CHECK(cudaMemcpyAsync(&probe, d_out, sizeof(probe), cudaMemcpyDeviceToHost, s));
-      CU_CHECK(cudaStreamSynchronize(s));
-      done = probe.n_toks != 0xFFFFFFFFu;
-    }
-  }
-  if (!done) {
-    LatEntry *maps;  // the two per-frame lookup maps of the HBM-map sweep
-    CU_CHECK(sc.Alloc(&maps, 2 * H));
-    h.map[0] = maps;
-    h.map[1] = maps + H;
-    if (d->lm1) {
-      uint32_t *pairs;
-      CU_CHECK(sc.Alloc(&pairs, 2 * H));
-      h.map_pair[0] = pairs;
-      h.map_pair[1] = pairs + H;
-    }
-    CU_CHECK(cudaMemsetAsync(maps, 0xFF, 2 * H * sizeof(LatEntry), s));
-    CU_CHECK(cudaMemcpyAsync(d_out, &h, sizeof(h), cudaMemcpyHostToDevice, s));
-    if (d->lm1)
-      k_lattice<true, false><<<1, kStreamThreads, 0, s>>>(d_streams, d_out, d->graph->view, DevCfg(d), use_final_probs ? 1 : 0, Lms(d), 0);
-    else
-      k_lattice<false, false><<<1, kStreamThreads, 0, s>>>(d_streams, d_out, d->graph->view, DevCfg(d), use_final_probs ? 1 : 0, Lms(d), 0);
-    ++g_launches;
-    CU_CHECK(cudaGetLastError());
-  }
-  LatticeOut r;
-  CU_CHECK(cudaMemcpyAsync(&r, d_out, sizeof(r), cudaMemcpyDeviceToHost, s));
-  CU_CHECK(cudaStreamSynchronize(s));
-  *n_toks = r.n_toks;
-  *n_links = r.n_links;
-  if (r.n_toks > h.tok_cap || r.n_links > h.link_cap) return ASRD_ERR_PATH_OVERFLOW;
-  if (r.n_toks == 0) return ASRD_ERR_NO_TOKENS;
-  if (!toks || !links) return ASRD_ERR_BAD_ARG;
-  std::vector<uint32_t> arena(r.n_toks);
-  CU_CHECK(cudaMemcpyAsync(toks, h.toks, sizeof(asrd_lat_token) * r.n_toks, cudaMemcpyDeviceToHost, s));
-  CU_CHECK(cudaMemcpyAsync(arena.data(), h.tok_arena_idx, 4 * (size_t)r.n_toks, cudaMemcpyDeviceToHost, s));
-  if (r.n_links)
-    CU_CHECK(cudaMemcpyAsync(links, h.links, sizeof(asrd_lat_link) * r.n_links, cudaMemcpyDeviceToHost, s));
-  CU_CHECK(cudaStreamSynchronize(s));
-  // Canonical order: tokens by (frame, state), links by (src, dst, arc labels) — the kernel emits
-  // them in scheduling order.  Links carry arena indices; map them to token indices.
-  std::vector<uint32_t> order(r.n_toks);
-  for (uint32_t i = 0; i < r.n_toks; ++i) order[i] = i;
+namespace {
+
+// Canonical order of one stream's raw lattice: tokens by (frame, state), links by (src, dst, arc
+// labels) — the kernels emit them in scheduling order.  Links carry arena indices; map them to
+// token indices.
+int CanonicalLattice(asrd_lat_token *toks, const uint32_t *arena, uint32_t n_toks, asrd_lat_link *links, uint32_t n_links) {
+  std::vector<uint32_t> order(n_toks);
+  for (uint32_t i = 0; i < n_toks; ++i) order[i] = i;
   std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
     if (toks[a].frame != toks[b].frame) return toks[a].frame < toks[b].frame;
     if (toks[a].state != toks[b].state) return toks[a].state < toks[b].state;
     if (toks[a].cost != toks[b].cost) return toks[a].cost < toks[b].cost;  // biglm: several LM states per HCLG state
     return arena[a] < arena[b];
   });
-  std::vector<asrd_lat_token> sorted(r.n_toks);
-  std::vector<std::pair<uint32_t, uint32_t>> a2i(r.n_toks);
-  for (uint32_t i = 0; i < r.n_toks; ++i) {
+  std::vector<asrd_lat_token> sorted(n_toks);
+  std::vector<std::pair<uint32_t, uint32_t>> a2i(n_toks);
+  for (uint32_t i = 0; i < n_toks; ++i) {
     sorted[i] = toks[order[i]];
     a2i[i] = std::make_pair(arena[order[i]], i);
   }
@@ -1595,12 +1519,12 @@ int asrd_get_raw_lattice(asrd_decoder *d, int32_t use_final_probs, asrd_lat_toke
     auto it = std::lower_bound(a2i.begin(), a2i.end(), std::make_pair(arena_idx, 0u));
     return (it != a2i.end() && it->first == arena_idx) ? (int32_t)it->second : -1;
   };
-  for (uint32_t i = 0; i < r.n_links; ++i) {
+  for (uint32_t i = 0; i < n_links; ++i) {
     links[i].src = lookup((uint32_t)links[i].src);
     links[i].dst = lookup((uint32_t)links[i].dst);
     if (links[i].src < 0 || links[i].dst < 0) return ASRD_ERR_STATE;
   }
-  std::sort(links, links + r.n_links, [](const asrd_lat_link &a, const asrd_lat_link &b) {
+  std::sort(links, links + n_links, [](const asrd_lat_link &a, const asrd_lat_link &b) {
     if (a.src != b.src) return a.src < b.src;
     if (a.dst != b.dst) return a.dst < b.dst;
     if (a.ilabel != b.ilabel) return a.ilabel < b.ilabel;
@@ -1608,6 +1532,159 @@ int asrd_get_raw_lattice(asrd_decoder *d, int32_t use_final_probs, asrd_lat_toke
     return a.graph < b.graph;
   });
   return ASRD_OK;
+}
+
+}  // namespace
+
+int asrd_get_raw_lattice_batch(asrd_decoder *const *decs, int32_t n, int32_t use_final_probs, asrd_lat_token *toks,
+                               int64_t tok_cap, asrd_lat_link *links, int64_t link_cap, int64_t *n_toks,
+                               int64_t *n_links, int32_t *status, void *stream) {
+  if (!n_toks || !n_links || !status || tok_cap < 0 || link_cap < 0 || tok_cap > 0x7FFFFFFF || link_cap > 0x7FFFFFFF)
+    return ASRD_ERR_BAD_ARG;
+  int rc = CheckBatch(decs, n);
+  if (rc) return rc;
+  std::vector<asrd_decoder *> act;   // streams with something decoded
+  std::vector<int> act_idx;
+  for (int i = 0; i < n; ++i) {
+    if (!decs[i]->initialized) return ASRD_ERR_STATE;
+    if (decs[i]->finalized && !use_final_probs) return ASRD_ERR_STATE;  // inl.h:879-884
+    n_toks[i] = n_links[i] = 0;
+    status[i] = ASRD_ERR_NO_TOKENS;
+    if (decs[i]->frames_decoded > 0 && decs[i]->d_ll_hist) {
+      act.push_back(decs[i]);
+      act_idx.push_back(i);
+    }
+  }
+  const int m = (int)act.size();
+  if (!m) return ASRD_OK;
+  asrd_decoder *d0 = act[0];
+  if ((rc = EnsureDevice(d0->graph->device))) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  Scratch sc(s);
+  StreamState **d_streams;
+  if ((rc = UploadStreams(act.data(), m, s, sc, &d_streams))) return rc;
+  const size_t H = (size_t)d0->opts.hash_capacity;
+  const size_t tc = (size_t)std::max<int64_t>(tok_cap, 1), lc = (size_t)std::max<int64_t>(link_cap, 1);
+  asrd_lat_token *d_toks;
+  uint32_t *d_arena;
+  asrd_lat_link *d_links;
+  LatticeOut *d_out;
+  CU_CHECK(sc.Alloc(&d_out, (size_t)m));
+  CU_CHECK(sc.Alloc(&d_toks, tc * m));
+  CU_CHECK(sc.Alloc(&d_arena, tc * m));
+  CU_CHECK(sc.Alloc(&d_links, lc * m));
+  std::vector<LatticeOut> h(m), r(m);
+  for (int j = 0; j < m; ++j) {
+    memset(&h[j], 0, sizeof(LatticeOut));
+    h[j].toks = d_toks + tc * j;
+    h[j].tok_arena_idx = d_arena + tc * j;
+    h[j].links = d_links + lc * j;
+    h[j].tok_cap = (uint32_t)tok_cap;
+    h[j].link_cap = (uint32_t)link_cap;
+  }
+  CU_CHECK(cudaMemcpyAsync(d_out, h.data(), sizeof(LatticeOut) * m, cudaMemcpyHostToDevice, s));
+  // Plain decoders: the pull sweep with its lookup map in shared memory (k_prune<true>: work in
+  // proportion to the tokens that survive, the arena untouched), one CTA per stream; a stream with
+  // a frame beyond that kernel's capacity, and every biglm decoder, goes through the HBM-map sweep
+  // (k_lattice).
+  std::vector<int> redo;
+  bool swept = false;
+  if (!d0->lm1 && EnvInt("ASRD_LATTICE_KERNEL", 1)) {
+    PrunePlan pplan;
+    if ((rc = PlanPrune(&pplan))) return rc;
+    if (pplan.emit_fn) {
+      pplan.emit_fn<<<m, kStreamThreads, pplan.dyn, s>>>(d_streams, d0->graph->view, DevCfg(d0), 0, -1, pplan.n_buckets,
+                                                          pplan.ex_cap, d_out, use_final_probs ? 1 : 0);
+      ++g_launches;
+      CU_CHECK(cudaGetLastError());
+      CU_CHECK(cudaMemcpyAsync(r.data(), d_out, sizeof(LatticeOut) * m, cudaMemcpyDeviceToHost, s));
+      CU_CHECK(cudaStreamSynchronize(s));
+      for (int j = 0; j < m; ++j)
+        if (r[j].n_toks == 0xFFFFFFFFu) redo.push_back(j);
+      swept = true;
+    }
+  }
+  if (!swept)
+    for (int j = 0; j < m; ++j) redo.push_back(j);
+  if (!redo.empty()) {
+    const int k = (int)redo.size();
+    LatEntry *maps;  // the two per-frame lookup maps of the HBM-map sweep, per stream
+    uint32_t *pairs = nullptr;
+    CU_CHECK(sc.Alloc(&maps, 2 * H * k));
+    if (d0->lm1) CU_CHECK(sc.Alloc(&pairs, 2 * H * k));
+    CU_CHECK(cudaMemsetAsync(maps, 0xFF, 2 * H * k * sizeof(LatEntry), s));
+    std::vector<LatticeOut> hs(k), rs(k);
+    std::vector<asrd_decoder *> sub(k);
+    for (int q = 0; q < k; ++q) {
+      hs[q] = h[redo[q]];
+      hs[q].map[0] = maps + 2 * H * q;
+      hs[q].map[1] = maps + 2 * H * q + H;
+      if (pairs) {
+        hs[q].map_pair[0] = pairs + 2 * H * q;
+        hs[q].map_pair[1] = pairs + 2 * H * q + H;
+      }
+      sub[q] = act[redo[q]];
+    }
+    StreamState **d_sub;
+    LatticeOut *d_out_sub;
+    if ((rc = UploadStreams(sub.data(), k, s, sc, &d_sub))) return rc;
+    CU_CHECK(sc.Alloc(&d_out_sub, (size_t)k));
+    CU_CHECK(cudaMemcpyAsync(d_out_sub, hs.data(), sizeof(LatticeOut) * k, cudaMemcpyHostToDevice, s));
+    if (d0->lm1)
+      k_lattice<true, false><<<k, kStreamThreads, 0, s>>>(d_sub, d_out_sub, d0->graph->view, DevCfg(d0), use_final_probs ? 1 : 0, Lms(d0), 0);
+    else
+      k_lattice<false, false><<<k, kStreamThreads, 0, s>>>(d_sub, d_out_sub, d0->graph->view, DevCfg(d0), use_final_probs ? 1 : 0, Lms(d0), 0);
+    ++g_launches;
+    CU_CHECK(cudaGetLastError());
+    CU_CHECK(cudaMemcpyAsync(rs.data(), d_out_sub, sizeof(LatticeOut) * k, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(cudaStreamSynchronize(s));
+    for (int q = 0; q < k; ++q) r[redo[q]] = rs[q];
+  }
+  std::vector<std::vector<uint32_t>> arena(m);
+  for (int j = 0; j < m; ++j) {
+    const int i = act_idx[j];
+    n_toks[i] = r[j].n_toks;
+    n_links[i] = r[j].n_links;
+    if (r[j].n_toks > h[j].tok_cap || r[j].n_links > h[j].link_cap) { status[i] = ASRD_ERR_PATH_OVERFLOW; continue; }
+    if (r[j].n_toks == 0) { status[i] = ASRD_ERR_NO_TOKENS; continue; }
+    if (!toks || !links) { status[i] = ASRD_ERR_BAD_ARG; continue; }
+    status[i] = ASRD_OK;
+    arena[j].resize(r[j].n_toks);
+    CU_CHECK(cudaMemcpyAsync(toks + (size_t)tok_cap * i, h[j].toks, sizeof(asrd_lat_token) * r[j].n_toks, cudaMemcpyDeviceToHost, s));
+    CU_CHECK(cudaMemcpyAsync(arena[j].data(), h[j].tok_arena_idx, 4 * (size_t)r[j].n_toks, cudaMemcpyDeviceToHost, s));
+    if (r[j].n_links)
+      CU_CHECK(cudaMemcpyAsync(links + (size_t)link_cap * i, h[j].links, sizeof(asrd_lat_link) * r[j].n_links, cudaMemcpyDeviceToHost, s));
+  }
+  CU_CHECK(cudaStreamSynchronize(s));
+  // host side: one stream's sort is independent of the next one's
+  auto canon = [&](int j) {
+    const int i = act_idx[j];
+    if (status[i] == ASRD_OK)
+      status[i] = CanonicalLattice(toks + (size_t)tok_cap * i, arena[j].data(), r[j].n_toks, links + (size_t)link_cap * i, r[j].n_links);
+  };
+  const int n_thr = std::min<int>({m, (int)std::max(1u, std::thread::hardware_concurrency()), 16});
+  if (n_thr <= 1) {
+    for (int j = 0; j < m; ++j) canon(j);
+  } else {
+    std::atomic<int> next(0);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_thr; ++t)
+      pool.emplace_back([&] {
+        for (int j; (j = next.fetch_add(1)) < m;) canon(j);
+      });
+    for (auto &t : pool) t.join();
+  }
+  return ASRD_OK;
+}
+
+int asrd_get_raw_lattice(asrd_decoder *d, int32_t use_final_probs, asrd_lat_token *toks, int64_t tok_cap,
+                         asrd_lat_link *links, int64_t link_cap, int64_t *n_toks, int64_t *n_links,
+                         void *stream) {
+  if (!d) return ASRD_ERR_BAD_ARG;
+  asrd_decoder *one[1] = {d};
+  int32_t st = ASRD_OK;
+  const int rc = asrd_get_raw_lattice_batch(one, 1, use_final_probs, toks, tok_cap, links, link_cap, n_toks, n_links, &st, stream);
+  return rc ? rc : st;
 }
 
 int asrd_path_to_vector(const int32_t *ilabel, const int32_t *olabel, const float *graph,

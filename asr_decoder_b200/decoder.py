@@ -359,6 +359,33 @@ class CudaDecoderBatch:
             check(rc, "asrd_get_raw_lattice")
             return toks[:nt.value].copy(), links[:nl.value].copy()
 
+    def GetRawLatticeBatch(self, use_final_probs: bool = True, stream: int = 0):
+        """``GetRawLattice`` of every stream in ONE call (``asrd_get_raw_lattice_batch``: one CTA per
+        stream, the host-side ordering on several threads): a list with what ``GetRawLattice(i)``
+        returns for each stream, bit for bit."""
+        L = _lib.lib()
+        tok_cap, link_cap = 1 << 15, 1 << 16
+        while True:
+            toks = np.empty((self.n, tok_cap), LAT_TOKEN_DTYPE)
+            links = np.empty((self.n, link_cap), LAT_LINK_DTYPE)
+            nt, nl = np.zeros(self.n, np.int64), np.zeros(self.n, np.int64)
+            st = np.zeros(self.n, np.int32)
+            check(L.asrd_get_raw_lattice_batch(self.handles, self.n, int(use_final_probs), toks.ctypes.data, tok_cap,
+                                               links.ctypes.data, link_cap, nt.ctypes.data, nl.ctypes.data,
+                                               st.ctypes.data, stream), "asrd_get_raw_lattice_batch")
+            if (st == -8).any():  # ASRD_ERR_PATH_OVERFLOW: retry with what the kernels asked for
+                tok_cap = max(tok_cap, int(nt.max()) + 16)
+                link_cap = max(link_cap, int(nl.max()) + 16)
+                continue
+            out = []
+            for i in range(self.n):
+                if st[i] == -7:
+                    out.append(None)
+                    continue
+                check(int(st[i]), "asrd_get_raw_lattice_batch")
+                out.append((toks[i, :nt[i]].copy(), links[i, :nl[i]].copy()))
+            return out
+
     def arena_frame_tokens(self, i: int = 0, stream: int = 0) -> np.ndarray:
         """Token records the arena holds per frame right now (after the prunes, if any)."""
         L = _lib.lib()

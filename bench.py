@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--max-active", type=int, default=7000)
     ap.add_argument("--min-active", type=int, default=200)
     ap.add_argument("--lattice-beam", type=float, default=8.0)
+    ap.add_argument("--lattice-utts", type=int, default=16, help="utterances of the lattice workload")
     ap.add_argument("--cpu-sample-utts", type=int, default=0, help="0 = 2 x host cores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -770,7 +771,7 @@ def run_side_workload(a):
     binp = os.path.join(ROOT, "oracle", "_ref", "dropin_nbest")
     states = min(a.states, 2_000_000)
     fst = synth.make_graph(states, 3.0, P, seed=777)
-    n = min(a.utts, 16)
+    n = min(a.utts, a.lattice_utts)
     Tl = min(T, 100)
     lls = [synth.make_loglikes(Tl, P, 1.2, seed=50 + i) for i in range(n)]
     graph = CudaFst(fst)
@@ -789,6 +790,16 @@ def run_side_workload(a):
             t_lat.append(1e3 * (time.perf_counter() - t0) / n)
         sizes = [(len(x[0]), len(x[1])) for x in lat]
     d2h = int(np.mean([20 * t + 24 * l for t, l in sizes]))
+    # the same n lattices through ONE call: one CTA per stream, the host-side ordering on several threads
+    t_batch = []
+    for rep in range(a.warmup + a.steps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        lat_b = batch.GetRawLatticeBatch()
+        torch.cuda.synchronize()
+        if rep >= a.warmup:
+            t_batch.append(1e3 * (time.perf_counter() - t0) / n)
+    batch_same = all(x[0].tobytes() == y[0].tobytes() and x[1].tobytes() == y[1].tobytes() for x, y in zip(lat, lat_b))
     line = {"metric": "raw lattice extraction ms per utterance", "value": float(np.mean(t_lat)), "unit": "ms",
             "n_gpus": 1, "steps": a.steps, "warmup": a.warmup, "ms_per_step": float(np.mean(t_lat)) * n,
             "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -798,7 +809,10 @@ def run_side_workload(a):
                        "what": "asrd_get_raw_lattice per utterance: k_lattice (link regeneration + lattice-beam prune on the "
                                "device) + D2H of the survivors + host sort"},
             "raw_lattice_states_links_mean": [float(np.mean([s[0] for s in sizes])), float(np.mean([s[1] for s in sizes]))],
-            "d2h_bytes_per_utterance": d2h}
+            "d2h_bytes_per_utterance": d2h,
+            "batched": {"ms_per_utterance": float(np.mean(t_batch)), "utterances_per_call": n,
+                        "identical_to_the_single_calls": bool(batch_same),
+                        "what": "asrd_get_raw_lattice_batch: all utterances in one launch (one CTA per stream)"}}
     if os.path.exists(binp) and not a.no_cpu_baseline:
         tmp = tempfile.mkdtemp(prefix="asrd_lat_")
         try:

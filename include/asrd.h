@@ -244,6 +244,17 @@ int asrd_get_raw_lattice(asrd_decoder *d, int32_t use_final_probs, asrd_lat_toke
                          asrd_lat_link *links, int64_t link_cap, int64_t *n_toks, int64_t *n_links,
                          void *stream);
 
+/* GetRawLattice for n streams in one call (the reference calls it once per decoder object,
+ * kaldi-nnet3bin/kaldi-hclg-my-decoder.cc:134-139; on the device one stream's sweep occupies one
+ * SM, so a service that finishes many utterances together hands them over together).  Stream i
+ * owns toks[i*tok_cap ..) and links[i*link_cap ..); n_toks[i], n_links[i] and status[i] are what
+ * asrd_get_raw_lattice would return for it (ASRD_ERR_NO_TOKENS = the reference's `false`,
+ * ASRD_ERR_PATH_OVERFLOW = call again with larger windows).  Results are identical to n single
+ * calls.  The return value covers the call itself (arguments, call order, CUDA). */
+int asrd_get_raw_lattice_batch(asrd_decoder *const *decs, int32_t n, int32_t use_final_probs,
+                               asrd_lat_token *toks, int64_t tok_cap, asrd_lat_link *links, int64_t link_cap,
+                               int64_t *n_toks, int64_t *n_links, int32_t *status, void *stream);
+
 /* DecoderItf::GetBestPath (decoder-itf.h:22; inl.h:1071-1200), batched.  For stream i the
  * arcs of the linear best-path lattice are written in path order (start -> end) to
  * ilabel/olabel/graph/acoustic[i*cap .. i*cap + n_arcs[i]), including the label-free arc

@@ -22,10 +22,14 @@ assert all(x.words == y.words and x.tot_bits == y.tot_bits for x, y in zip(want,
 for i in range(2):
     t, l = b.GetRawLattice(i)
     assert t.tobytes() == lat[i][0].tobytes() and l.tobytes() == lat[i][1].tobytes()
+for (t, l), w in zip(a.GetRawLatticeBatch(), lat):     # one launch over both streams
+    assert t.tobytes() == w[0].tobytes() and l.tobytes() == w[1].tobytes()
 os.environ["ASRD_LATTICE_KERNEL"] = "0"
 for i in range(2):
     t, l = a.GetRawLattice(i)
     assert t.tobytes() == lat[i][0].tobytes() and l.tobytes() == lat[i][1].tobytes()
+for (t, l), w in zip(a.GetRawLatticeBatch(), lat):
+    assert t.tobytes() == w[0].tobytes() and l.tobytes() == w[1].tobytes()
 clg, hmms = synth.make_clg(300, n_hmms=20, n_pdfs=40, seed=3)
 tmp = tempfile.mkdtemp()
 fstio.write_fst(tmp + "/c.fst", clg); fstio.write_hmm_set(tmp + "/h.bin", hmms)
@@ -49,4 +53,5 @@ fb = synth.make_graph(2000, 5.0, 60, seed=6, n_words=300)
 e = CudaDecoderBatch(CudaFst(fb), cfg, 2, max_frames=48, old_lm=CudaLm(lm1.Rescale(-1.0)), new_lm=CudaLm(lm2))
 rb = e.Decode(lls)
 e.GetRawLattice(0)
+e.GetRawLatticeBatch()
 print("ok hbm routes + biglm", [x.status for x in rb])

@@ -83,3 +83,39 @@ def test_lattice_contains_the_best_path(oracle_mod):
     assert best_final <= bp.tot + 1e-3
     otoks, olinks = _oracle_lattice(O, O.OracleGraph(fst), cfg, ll)
     assert (len(toks), len(links)) == (len(otoks), len(olinks))
+
+
+def _same_lattice(a, b):
+    if a is None or b is None:
+        return a is None and b is None
+    return a[0].tobytes() == b[0].tobytes() and a[1].tobytes() == b[1].tobytes()
+
+
+@pytest.mark.parametrize("route", ["emit", "hbm", "mixed"])
+def test_batched_raw_lattice_equals_the_single_calls(monkeypatch, route):
+    """asrd_get_raw_lattice_batch: one launch over the streams (one CTA each) returns, stream by
+    stream, the bytes of asrd_get_raw_lattice — through the shared-memory pull sweep, through the
+    HBM-map sweep, and when only SOME streams have a frame beyond the pull sweep's capacity
+    (ASRD_PRUNE_CAP: those alone are redone by k_lattice).  A stream without frames gives None."""
+    if route == "hbm":
+        monkeypatch.setenv("ASRD_LATTICE_KERNEL", "0")
+    if route == "mixed":
+        monkeypatch.setenv("ASRD_PRUNE_CAP", "1024")
+    fst = synth.make_graph(6000, 4.0, 100, seed=77)
+    # flat scores: thousands of tokens per frame (beyond the forced capacity); peaked ones: a few hundred
+    lls = [synth.make_loglikes(t, 100, s, seed=400 + t) for t, s in ((60, 1.0), (45, 5.0), (60, 1.2), (30, 5.0), (52, 1.1))]
+    cfg = LatticeFasterDecoderConfig(beam=13.0, max_active=3000, min_active=100, lattice_beam=7.0)
+    dec = CudaDecoderBatch(CudaFst(fst), cfg, len(lls) + 1, max_frames=64)
+    dec.InitDecoding()
+    dec.AdvanceDecoding(lls + [np.zeros((0, 100), np.float32)])
+    dec.FinalizeDecoding()
+    single = [dec.GetRawLattice(i) for i in range(len(lls) + 1)]
+    batch = dec.GetRawLatticeBatch()
+    assert single[-1] is None and batch[-1] is None
+    assert all(x is not None and len(x[0]) > 10 for x in single[:-1])
+    if route == "mixed":
+        widest = [int(dec.arena_frame_tokens(i).max()) for i in range(len(lls))]
+        assert min(widest) < 1024 < max(widest), widest      # both routes inside one call
+    for i, (a, b) in enumerate(zip(single, batch)):
+        assert _same_lattice(a, b), (route, i)
+    assert all(_same_lattice(a, b) for a, b in zip(batch, dec.GetRawLatticeBatch()))   # repeatable
