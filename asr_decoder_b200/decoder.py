@@ -364,10 +364,13 @@ class CudaDecoderBatch:
         stream, the host-side ordering on several threads): a list with what ``GetRawLattice(i)``
         returns for each stream, bit for bit."""
         L = _lib.lib()
-        tok_cap, link_cap = 1 << 15, 1 << 16
+        # the windows are kept between calls: fresh pages under 256 windows cost more than the call
+        tok_cap, link_cap = getattr(self, "_lat_caps", (1 << 15, 1 << 16))
         while True:
-            toks = np.empty((self.n, tok_cap), LAT_TOKEN_DTYPE)
-            links = np.empty((self.n, link_cap), LAT_LINK_DTYPE)
+            if getattr(self, "_lat_caps", None) != (tok_cap, link_cap):
+                self._lat_buf = (np.empty((self.n, tok_cap), LAT_TOKEN_DTYPE), np.empty((self.n, link_cap), LAT_LINK_DTYPE))
+                self._lat_caps = (tok_cap, link_cap)
+            toks, links = self._lat_buf
             nt, nl = np.zeros(self.n, np.int64), np.zeros(self.n, np.int64)
             st = np.zeros(self.n, np.int32)
             check(L.asrd_get_raw_lattice_batch(self.handles, self.n, int(use_final_probs), toks.ctypes.data, tok_cap,
